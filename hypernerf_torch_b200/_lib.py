@@ -1,0 +1,104 @@
+"""ctypes binding of libhypernerf_b200.so (include/hypernerf_b200.h).
+
+The library is the product: there is no CPU or torch fallback behind these calls.  If the shared object is
+missing, or a call returns non-zero, this module raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhypernerf_b200.so")
+HN_NUM_PARAM_TENSORS = 93
+HN_FLAG_WARP_TRANSLATION = 1
+HN_FLAG_SLICE_BENDY = 2
+HN_COMP_WHITE_BKGD = 1
+HN_COMP_ACC_ALL = 2
+
+EXPORTS = [
+    "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf",
+    "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_fwd", "hn_mlp_bwd", "hn_umma_probe",
+]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("glo_dim", "hyper_dim", "xyz_freqs", "hyper_freqs", "view_freqs", "warp_freqs", "sheet_freqs",
+                 "num_embeddings", "flags")] + [("reserved", C.c_int32 * 7)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [("packed_bytes", C.c_int64), ("saved_bytes", C.c_int64), ("workspace_bytes", C.c_int64),
+                ("flat_param_floats", C.c_int64), ("reserved", C.c_int64 * 4)]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a into libhypernerf_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise NativeLibraryError("building libhypernerf_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    L.hn_abi_version.restype = C.c_int
+    L.hn_last_error.restype = C.c_char_p
+    L.hn_query.argtypes = [C.POINTER(ModelDesc), i64, C.POINTER(Sizes)]
+    L.hn_pack_weights.argtypes = [C.POINTER(ModelDesc), vp, C.POINTER(C.c_int64), i32, vp, vp]
+    L.hn_sample_coarse.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]
+    L.hn_sample_pdf.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    L.hn_composite_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]
+    L.hn_composite_bwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]
+    L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]
+    L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32,
+                             C.POINTER(C.c_int64), vp, vp, vp]
+    L.hn_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("hn_last_error",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().hn_last_error().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeLibraryError("hypernerf_b200 kernels take CUDA tensors only (no CPU path)")
+    if not t.is_contiguous():
+        raise NativeLibraryError("hypernerf_b200 kernels take contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

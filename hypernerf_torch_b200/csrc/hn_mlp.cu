@@ -1,0 +1,945 @@
+// Fused HyperNeRF MLP stack for sm_100a: tcgen05 UMMA with TMEM accumulators, weights streamed from L2 by
+// 1-D bulk async copies through an mbarrier ring, activations resident in shared memory across layers,
+// positional encodings computed in-kernel.
+//
+//   mlp_fwd_kernel    render_samples -> query_template (models.py:587-650, :447-493): GLO lookup, posenc_orig,
+//                     TranslationField, HyperSheetMLP, NerfMLP, noise_regularize, Softplus / Sigmoid.
+//   mlp_dgrad_kernel  the autograd of the above w.r.t. every layer's pre-activation (and the GLO table).
+//   mlp_wgrad_kernel  dW = dY^T X and db = sum dY over all samples, accumulated into the flat gradient.
+//   pack_kernel       fp32 (out,in) nn.Linear weights -> bf16 operand images (forward and transposed).
+//
+// One CTA owns a tile of 128 samples (= UMMA M = TMEM lanes).  Warp roles: warp 0 lane 0 streams weights,
+// warp 1 lane 0 issues UMMAs, warps 2..5 are the epilogue (thread = sample row).  Two CTAs are resident per
+// SM so one CTA's epilogue overlaps the other's MMAs.
+#include <math.h>
+#include "hn_api_internal.h"
+#include "hn_mlp_program.h"
+#include "hn_ptx.cuh"
+
+namespace hn {
+
+// ------------------------------------------------------------------------------------------------------
+// compile-time model shape (cfg-1 family of BASELINE.json)
+// ------------------------------------------------------------------------------------------------------
+template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_>
+struct Shape {
+  static constexpr int G = G_, H = H_, WF = WF_, SF = SF_, XF = XF_, HF = HF_, VF = VF_;
+  static constexpr int PE_W = 3 + 6 * WF, IN_W = PE_W + G, KW = pad16(IN_W);
+  static constexpr int PE_X = 3 + 6 * XF, PE_H = H * (1 + 2 * HF), IN_T = PE_X + PE_H, KT = pad16(IN_T);
+  static constexpr int PE_V = 3 + 6 * VF, KV = pad16(PE_V);
+  static constexpr int IN_CHUNKS = (KW > KT ? (KW > KV ? KW : KV) : (KT > KV ? KT : KV)) / 8;
+  static constexpr int N_RGB0A = pad16(kRgbW + 1);
+};
+using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
+
+// ------------------------------------------------------------------------------------------------------
+// shared memory plan of the fused kernels
+// ------------------------------------------------------------------------------------------------------
+template <class C>
+struct Smem {
+  static constexpr int ACT = 0;                                   // 128 x 256 bf16
+  static constexpr int INB = ACT + 32 * kChunkBytes;              // 128 x (IN_CHUNKS*8) bf16
+  static constexpr int RING = INB + C::IN_CHUNKS * kChunkBytes;   // kRingStages x kStageBytes
+  static constexpr int BARS = RING + kRingStages * kStageBytes;   // full[3], empty[3], acc_full, act_ready
+  static constexpr int TMEMP = BARS + 8 * 8;
+  static constexpr int TOTAL = TMEMP + 16;
+};
+
+struct FwdParams {
+  Program prog;
+  const uint8_t* weights;   // packed blob base + fwd_off
+  const float* bias;        // packed blob base + bias_off
+  const float* glo;         // (E, G) fp32 copy of the GLO table
+  const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
+  float noise_std;
+  int64_t n;                // samples = B * S
+  int S;
+  int n_tiles;
+  int x_total;              // chunks per half tile of the saved-activation slab
+  uint16_t x_in_ws, x_in_t, x_in_v;
+  float* sigma; float* rgb; float* warped;
+  uint8_t* saved;
+};
+
+struct BwdParams {
+  Program prog;
+  const uint8_t* weights;   // packed blob base + bwd_off
+  const int64_t* ids;
+  const float* sigma; const float* rgb; const float* warped;
+  const float* g_sigma; const float* g_rgb; const float* g_warped;
+  const uint8_t* saved;     // forward activations (ReLU gates)
+  uint8_t* dsaved;          // pre-activation gradients for the wgrad kernel
+  float* glo_grad;          // flat_grad + offset of the GLO table
+  int64_t n;
+  int S;
+  int n_tiles;
+  int x_total, d_total;
+  uint16_t d_rgbhead, pad0;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// weight producer and MMA issuer (shared by forward and backward-data kernels)
+// ------------------------------------------------------------------------------------------------------
+struct RingState { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == kRingStages) { slot = 0; phase ^= 1; } } };
+
+__device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
+                                             uint64_t* full, uint64_t* empty, RingState& rs) {
+  for (int oi = 0; oi < prog.nops; ++oi) {
+    const MmaOp& op = prog.ops[oi];
+    const int nchunks = (op.k0 + op.k1) >> 3;
+    const uint8_t* src = weights + (size_t)op.w_off16 * 16;
+    for (int c = 0; c < nchunks; c += op.cps) {
+      int cnt = min((int)op.cps, nchunks - c);
+      uint32_t bytes = (uint32_t)cnt * op.n * 16;
+      mbar_wait(&empty[rs.slot], rs.phase ^ 1);
+      mbar_arrive_expect_tx(&full[rs.slot], bytes);
+      bulk_g2s(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot]);
+      rs.next();
+    }
+  }
+}
+
+__device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, uint32_t act_s, uint32_t inb_s,
+                                            uint32_t ring_s, uint32_t tmem_base, uint64_t* full, uint64_t* empty,
+                                            RingState& rs) {
+  for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
+    const MmaOp& op = prog.ops[oi];
+    const int nchunks = (op.k0 + op.k1) >> 3;
+    const uint32_t idesc = make_idesc_bf16(kTileRows, op.n, 0, 0);
+    const uint32_t a0 = (op.src0 == SRC_ACT ? act_s : inb_s) + op.a0_chunk * kChunkBytes;
+    const uint32_t a1 = (op.src1 == SRC_ACT ? act_s : inb_s) + op.a1_chunk * kChunkBytes;
+    const uint32_t k0_chunks = op.k0 >> 3;
+    const uint32_t b_lbo = op.n * 16;
+    for (int c = 0; c < nchunks; c += op.cps) {
+      int cnt = min((int)op.cps, nchunks - c);
+      mbar_wait(&full[rs.slot], rs.phase);
+      tc_fence_after();
+      const uint32_t stage = ring_s + rs.slot * kStageBytes;
+      for (int j = 0; j < cnt; j += 2) {
+        uint32_t kc = c + j;  // chunk index inside the op's K
+        uint32_t a_addr = kc < k0_chunks ? a0 + kc * kChunkBytes : a1 + (kc - k0_chunks) * kChunkBytes;
+        uint64_t ad = make_smem_desc(a_addr, kChunkBytes, 128);
+        uint64_t bd = make_smem_desc(stage + j * b_lbo, b_lbo, 128);
+        umma_bf16(tmem_base + op.tmem_col, ad, bd, idesc, (kc > 0) | op.acc_init);
+      }
+      umma_commit(&empty[rs.slot]);
+      rs.next();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// positional encoding, posenc_orig (model_utils.py:234-246): [x, sin(2^k x), cos(2^k x)]_k, blocks of NC.
+// sin/cos of the base angle from sincosf, higher octaves by the double-angle recurrence (fp32); the result
+// is consumed as a bf16 operand, the recurrence error (<= 2^k ulp) is far below the bf16 rounding step.
+// ------------------------------------------------------------------------------------------------------
+template <int NC, int NF>
+__device__ __forceinline__ void posenc(const float* x, float* out) {
+  float s[NC], c[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { out[i] = x[i]; sincosf(x[i], &s[i], &c[i]); }
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      out[NC + 2 * NC * k + i] = s[i];
+      out[NC + 2 * NC * k + NC + i] = c[i];
+      float s2 = 2.f * s[i] * c[i];
+      float c2 = 1.f - 2.f * s[i] * s[i];
+      s[i] = s2; c[i] = c2;
+    }
+  }
+}
+// chain rule through posenc: g_x[i] = g[i] + sum_k 2^k (g_sin[k][i] cos_k - g_cos[k][i] sin_k)
+template <int NC, int NF>
+__device__ __forceinline__ void posenc_bwd(const float* x, const float* g, float* gx) {
+  float s[NC], c[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { gx[i] = g[i]; sincosf(x[i], &s[i], &c[i]); }
+  float f = 1.f;
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      gx[i] += f * (g[NC + 2 * NC * k + i] * c[i] - g[NC + 2 * NC * k + NC + i] * s[i]);
+      float s2 = 2.f * s[i] * c[i];
+      float c2 = 1.f - 2.f * s[i] * s[i];
+      s[i] = s2; c[i] = c2;
+    }
+    f *= 2.f;
+  }
+}
+
+// write NCOL (multiple of 8) fp32 features of one row as bf16 packets into an smem operand (and the stash)
+template <int NCOL>
+__device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row, uint4* save_row, int save_chunk) {
+#pragma unroll
+  for (int q = 0; q < NCOL / 8; ++q) {
+    uint4 v;
+    v.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
+    v.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+    v.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
+    v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+    *reinterpret_cast<uint4*>(buf_row + q * kChunkBytes) = v;
+    if (save_row != nullptr) save_row[(save_chunk + q) * (kHalfChunkBytes / 16)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic epilogue blocks: 32 accumulator columns of this thread's row -> bias/activation -> bf16 packets
+// ------------------------------------------------------------------------------------------------------
+template <bool RELU>
+__device__ __forceinline__ void fwd_block32(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
+                                            uint4* save_row, int chunk0, int save_chunk) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[8];
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q);
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q + 1);
+    v[0] = __uint_as_float(r[8 * q + 0]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
+    v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
+    v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
+    v[6] = __uint_as_float(r[8 * q + 6]) + b1.z; v[7] = __uint_as_float(r[8 * q + 7]) + b1.w;
+    uint4 o;
+    if (RELU) {
+      o.x = pack_bf16_relu(v[0], v[1]); o.y = pack_bf16_relu(v[2], v[3]);
+      o.z = pack_bf16_relu(v[4], v[5]); o.w = pack_bf16_relu(v[6], v[7]);
+    } else {
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
+    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+  }
+}
+
+// backward: gate 32 gradient columns by (forward activation > 0) read from the stash
+template <bool MASK>
+__device__ __forceinline__ void bwd_block32(uint32_t taddr, const uint4* __restrict__ mask_row, int mask_chunk,
+                                            uint8_t* dst_row, uint4* save_row, int chunk0, int save_chunk) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  uint4 m[4];
+  if (MASK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = __ldg(mask_row + (mask_chunk + chunk0 + q) * (kHalfChunkBytes / 16));
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * q + j]);
+    if (MASK) {
+      const uint32_t mm[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // post-ReLU bf16 values are >= +0: non-zero bits <=> activation > 0
+        if ((mm[j] & 0x0000FFFFu) == 0) v[2 * j] = 0.f;
+        if ((mm[j] & 0xFFFF0000u) == 0) v[2 * j + 1] = 0.f;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = o;
+    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+  }
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+template <class C>
+__global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using SM = Smem<C>;
+  uint8_t* act = smem + SM::ACT;
+  uint8_t* inb = smem + SM::INB;
+  uint8_t* ring = smem + SM::RING;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* empty = full + kRingStages;
+  uint64_t* acc_full = empty + kRingStages;
+  uint64_t* act_ready = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEMP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(act_ready, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const Program& prog = p.prog;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      RingState rs;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t ph_ready = 0;
+      const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int li = 0; li < prog.nlayers; ++li) {
+          mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
+          tc_fence_after();
+          issue_layer(prog, prog.layers[li], act_s, inb_s, ring_s, tmem_base, full, empty, rs);
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: thread <-> sample row ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* act_row = act + row * 16;
+    uint8_t* inb_row = inb + row * 16;
+    uint32_t ph_acc = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int64_t g = (int64_t)tile * kTileRows + row;
+      const bool valid = g < p.n;
+      const int64_t gc = valid ? g : p.n - 1;
+      const int64_t ray = gc / p.S;
+      uint4* save_row = nullptr;
+      if (p.saved != nullptr)
+        save_row = reinterpret_cast<uint4*>(p.saved + ((size_t)tile * 2 + (row >> 6)) * (size_t)p.x_total * kHalfChunkBytes) +
+                   (row & 63);
+      float pt[3], dir[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dir[i] = __ldg(p.viewdirs + ray * 3 + i);
+        pt[i] = __ldg(p.points + gc * 3 + i);
+      }
+      // prologue: [posenc(points, WF) | GLO | 0] -> INB
+      {
+        float f[C::KW];
+        posenc<3, C::WF>(pt, f);
+        const float* e = p.glo + __ldg(p.ids + ray) * C::G;
+#pragma unroll
+        for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
+#pragma unroll
+        for (int i = C::IN_W; i < C::KW; ++i) f[i] = 0.f;
+        store_features<C::KW>(f, inb_row, save_row, p.x_in_ws);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(act_ready);
+
+      float wp[3 + C::H];  // warped point + hyper coordinates
+      for (int li = 0; li < prog.nlayers; ++li) {
+        const Layer& L = prog.layers[li];
+        const float* bias = p.bias + L.bias_off;
+        mbar_wait(acc_full, ph_acc); ph_acc ^= 1;
+        tc_fence_after();
+        if (L.epi == FE_RELU) {
+          for (int c0 = 0; c0 < L.n_out; c0 += 32)
+            fwd_block32<true>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+        } else if (L.epi == FE_WSHEAD) {
+          uint32_t r[16];
+          tmem_ld16(tlane, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + __ldg(bias + i));
+#pragma unroll
+          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + __ldg(bias + 3 + i);
+          if (valid && p.warped != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 3 + C::H; ++i) p.warped[g * (3 + C::H) + i] = wp[i];
+          }
+          float f[C::KT];
+          posenc<3, C::XF>(wp, f);
+          posenc<C::H, C::HF>(wp + 3, f + C::PE_X);
+#pragma unroll
+          for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
+          store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
+        } else if (L.epi == FE_BOTT) {
+          for (int c0 = 0; c0 < L.n_out; c0 += 32)
+            fwd_block32<false>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+          // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
+          float f[C::KV];
+          posenc<3, C::VF>(dir, f);
+#pragma unroll
+          for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
+          store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
+        } else if (L.epi == FE_RGB0A) {
+          for (int c0 = 0; c0 < kRgbW; c0 += 32)
+            fwd_block32<true>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+          uint32_t r[16];
+          tmem_ld16(tlane + kRgbW, r);
+          tmem_ld_wait();
+          float a = __uint_as_float(r[0]) + __ldg(bias + kRgbW);
+          if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;  // noise_regularize, model_utils.py:312-316
+          if (valid) p.sigma[g] = softplus_f(a);                          // models.py:491
+        } else {  // FE_RGBHEAD
+          uint32_t r[16];
+          tmem_ld16(tlane, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + __ldg(bias + i));
+          }
+        }
+        if (li + 1 < prog.nlayers) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(act_ready);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ======================================================================================================
+// backward-data
+// ======================================================================================================
+template <class C>
+__global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using SM = Smem<C>;
+  uint8_t* act = smem + SM::ACT;
+  uint8_t* inb = smem + SM::INB;
+  uint8_t* ring = smem + SM::RING;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* empty = full + kRingStages;
+  uint64_t* acc_full = empty + kRingStages;
+  uint64_t* act_ready = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEMP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(act_ready, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const Program& prog = p.prog;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      RingState rs;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t ph_ready = 0;
+      const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int li = 0; li < prog.nlayers; ++li) {
+          mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
+          tc_fence_after();
+          issue_layer(prog, prog.layers[li], act_s, inb_s, ring_s, tmem_base, full, empty, rs);
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* act_row = act + row * 16;
+    uint8_t* inb_row = inb + row * 16;
+    uint32_t ph_acc = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int64_t g = (int64_t)tile * kTileRows + row;
+      const bool valid = g < p.n;
+      const int64_t gc = valid ? g : p.n - 1;
+      const int64_t ray = gc / p.S;
+      const size_t half = (size_t)tile * 2 + (row >> 6);
+      const uint4* mask_row = reinterpret_cast<const uint4*>(p.saved + half * (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
+      uint4* save_row = reinterpret_cast<uint4*>(p.dsaved + half * (size_t)p.d_total * kHalfChunkBytes) + (row & 63);
+
+      // prologue: dY of the rgb head = g_rgb * y (1 - y) (Sigmoid, models.py:164)
+      {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float y = __ldg(p.rgb + g * 3 + i);
+            f[i] = __ldg(p.g_rgb + g * 3 + i) * y * (1.f - y);
+          }
+        }
+        store_features<16>(f, act_row, save_row, p.d_rgbhead);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(act_ready);
+
+      for (int li = 0; li < prog.nlayers; ++li) {
+        const Layer& L = prog.layers[li];
+        mbar_wait(acc_full, ph_acc); ph_acc ^= 1;
+        tc_fence_after();
+        if (L.epi == BE_MASK) {
+          for (int c0 = 0; c0 < L.n_out; c0 += 32)
+            bwd_block32<true>(tlane + c0, mask_row, L.mask_chunk, act_row, save_row, c0 >> 3, L.save_chunk);
+        } else if (L.epi == BE_LINEAR) {
+          for (int c0 = 0; c0 < L.n_out; c0 += 32)
+            bwd_block32<false>(tlane + c0, nullptr, 0, act_row, save_row, c0 >> 3, L.save_chunk);
+        } else if (L.epi == BE_RGB1) {
+          for (int c0 = 0; c0 < kRgbW; c0 += 32)
+            bwd_block32<true>(tlane + c0, mask_row, L.mask_chunk, act_row, save_row, c0 >> 3, L.save_chunk);
+          // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
+          store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
+        } else if (L.epi == BE_SKIPSTORE) {
+          for (int c0 = 0; c0 < L.n_out; c0 += 32)
+            bwd_block32<false>(tlane + c0, nullptr, 0, inb_row, nullptr, c0 >> 3, 0);
+        } else if (L.epi == BE_TRUNKIN) {
+          // d(trunk input features) = layer-0 part (TMEM) + skip-layer part (INB, bf16)
+          float gf[C::KT];
+#pragma unroll
+          for (int c0 = 0; c0 < C::KT; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tlane + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 sk = *reinterpret_cast<const uint4*>(inb_row + ((c0 >> 3) + q) * kChunkBytes);
+              const uint32_t ss[4] = {sk.x, sk.y, sk.z, sk.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                gf[c0 + 8 * q + 2 * j] = __uint_as_float(r[8 * q + 2 * j]) + bf16_lo(ss[j]);
+                gf[c0 + 8 * q + 2 * j + 1] = __uint_as_float(r[8 * q + 2 * j + 1]) + bf16_hi(ss[j]);
+              }
+            }
+          }
+          float wp[3 + C::H], gx[3 + C::H];
+#pragma unroll
+          for (int i = 0; i < 3 + C::H; ++i) wp[i] = __ldg(p.warped + gc * (3 + C::H) + i);
+          posenc_bwd<3, C::XF>(wp, gf, gx);
+          posenc_bwd<C::H, C::HF>(wp + 3, gf + C::PE_X, gx + 3);
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 3 + C::H; ++i) {
+              f[i] = gx[i];
+              if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + g * (3 + C::H) + i);
+            }
+          }
+          store_features<16>(f, act_row, save_row, L.save_chunk);
+        } else {  // BE_GLO: d(GLO embedding) of this sample -> per-ray reduction -> atomics on the table gradient
+          uint32_t r[16];
+          tmem_ld16(tlane + kWsW, r);
+          tmem_ld_wait();
+          const int64_t id = __ldg(p.ids + ray);
+          const bool uniform = __all_sync(0xffffffffu, id == __shfl_sync(0xffffffffu, id, 0));
+#pragma unroll
+          for (int i = 0; i < C::G; ++i) {
+            float v = valid ? __uint_as_float(r[i]) : 0.f;
+            if (uniform) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0) atomicAdd(p.glo_grad + id * C::G + i, v);
+            } else {
+              atomicAdd(p.glo_grad + id * C::G + i, v);
+            }
+          }
+        }
+        if (li + 1 < prog.nlayers) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(act_ready);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ======================================================================================================
+// weight gradient: for every job, D[N_j, K_j] += dY^T X over this CTA's half tiles (UMMA with both operands
+// MN-major straight out of the stash layout), bias gradient by column sums on the CUDA cores.
+// ======================================================================================================
+constexpr int kWgStages = 3;
+constexpr int kWgStageA = 256 * kHalfChunkBytes / 8;  // 32 KB: up to 256 dY columns x 64 rows
+constexpr int kWgStageBytes = 2 * kWgStageA;          // + up to 256 X columns
+struct WgSmem {
+  static constexpr int STAGES = 0;
+  static constexpr int BARS = kWgStages * kWgStageBytes;  // full[3], empty[3], acc_full, acc_empty
+  static constexpr int TMEMP = BARS + 8 * 8;
+  static constexpr int TOTAL = TMEMP + 16;
+};
+struct WgradParams {
+  WgradTable tab;
+  const uint8_t* saved; const uint8_t* dsaved;
+  float* flat_grad;
+  int64_t n_half;
+  int x_total, d_total;
+};
+
+__global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WgSmem::BARS);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* acc_full = empty + kWgStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + WgSmem::TMEMP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 4); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // contiguous range of half tiles for this CTA
+  const int64_t per = (p.n_half + gridDim.x - 1) / gridDim.x;
+  const int64_t h0 = (int64_t)blockIdx.x * per;
+  const int64_t h1 = min(h0 + per, p.n_half);
+  const int njobs = p.tab.njobs;
+
+  if (warp == 0) {
+    if (lane == 0 && h0 < h1) {
+      int slot = 0; uint32_t phase = 0;
+      for (int ji = 0; ji < njobs; ++ji) {
+        const WgradJob& J = p.tab.jobs[ji];
+        const uint32_t a_bytes = J.dy_nchunks * kHalfChunkBytes;
+        const uint32_t b0_bytes = J.x0_nchunks * kHalfChunkBytes, b1_bytes = J.x1_nchunks * kHalfChunkBytes;
+        for (int64_t h = h0; h < h1; ++h) {
+          uint8_t* st = smem + slot * kWgStageBytes;
+          mbar_wait(&empty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&full[slot], a_bytes + b0_bytes + b1_bytes);
+          bulk_g2s(st, p.dsaved + ((size_t)h * p.d_total + J.dy_chunk) * kHalfChunkBytes, a_bytes, &full[slot]);
+          bulk_g2s(st + kWgStageA, p.saved + ((size_t)h * p.x_total + J.x0_chunk) * kHalfChunkBytes, b0_bytes, &full[slot]);
+          if (b1_bytes)
+            bulk_g2s(st + kWgStageA + b0_bytes, p.saved + ((size_t)h * p.x_total + J.x1_chunk) * kHalfChunkBytes, b1_bytes,
+                     &full[slot]);
+          if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && h0 < h1) {
+      int slot = 0; uint32_t phase = 0, ph_empty = 0;
+      for (int ji = 0; ji < njobs; ++ji) {
+        const WgradJob& J = p.tab.jobs[ji];
+        const uint32_t ncols = (J.x0_nchunks + J.x1_nchunks) * 8;  // UMMA N
+        const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
+        if (ji > 0) { mbar_wait(acc_empty, ph_empty); ph_empty ^= 1; tc_fence_after(); }
+        for (int64_t h = h0; h < h1; ++h) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + slot * kWgStageBytes);
+          for (int ks = 0; ks < kHalfRows / 16; ++ks) {
+            for (int mb = 0; mb < J.mblocks; ++mb) {
+              // A: dY^T, MN-major: 8 dY columns contiguous (16 B), K = rows (16 B stride); LBO = 8 rows, SBO = chunk
+              uint64_t ad = make_smem_desc(st + mb * 16 * kHalfChunkBytes + ks * 256, 128, kHalfChunkBytes);
+              uint64_t bd = make_smem_desc(st + kWgStageA + ks * 256, 128, kHalfChunkBytes);
+              umma_bf16(tmem_base + mb * ncols, ad, bd, idesc, (h > h0) | (ks > 0));
+            }
+          }
+          umma_commit(&empty[slot]);
+          if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else if (h0 < h1) {
+    // warps 2..5: bias column sums while streaming, TMEM flush at the end of every job
+    const int quarter = warp & 3;
+    const int wr = warp - 2;  // 0..3: which quarter of the dY chunks this warp reduces
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int slot = 0; uint32_t phase = 0, ph_acc = 0;
+    for (int ji = 0; ji < njobs; ++ji) {
+      const WgradJob& J = p.tab.jobs[ji];
+      const int ncols = (J.x0_nchunks + J.x1_nchunks) * 8;
+      // chunks [c_lo, c_hi) of the dY part belong to this warp (<= 8 chunks)
+      const int cpw = (J.dy_nchunks + 3) / 4;
+      const int c_lo = min(wr * cpw, (int)J.dy_nchunks), c_hi = min(c_lo + cpw, (int)J.dy_nchunks);
+      float bs[8][8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bs[a][b] = 0.f;
+      for (int64_t h = h0; h < h1; ++h) {
+        mbar_wait(&full[slot], phase);
+        if (J.nbias) {
+          const uint8_t* st = smem + slot * kWgStageBytes;
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            if (c_lo + a < c_hi) {
+#pragma unroll
+              for (int rr = 0; rr < kHalfRows; rr += 32) {
+                uint4 v = *reinterpret_cast<const uint4*>(st + (c_lo + a) * kHalfChunkBytes + (rr + lane) * 16);
+                bs[a][0] += bf16_lo(v.x); bs[a][1] += bf16_hi(v.x); bs[a][2] += bf16_lo(v.y); bs[a][3] += bf16_hi(v.y);
+                bs[a][4] += bf16_lo(v.z); bs[a][5] += bf16_hi(v.z); bs[a][6] += bf16_lo(v.w); bs[a][7] += bf16_hi(v.w);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+      }
+      // bias gradient: reduce over the 32 lanes (rows), one atomic per column
+      if (J.nbias) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          if (c_lo + a < c_hi) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              float v = bs[a][b];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              const int col = (c_lo + a) * 8 + b;
+              if (lane == 0) {
+                for (int s = 0; s < J.nbias; ++s) {
+                  const BiasSeg& B = J.bias[s];
+                  if (col >= B.col0 && col < B.col0 + B.ncols) atomicAdd(p.flat_grad + B.dst + (col - B.col0), v);
+                }
+              }
+            }
+          }
+        }
+      }
+      // flush the accumulator
+      mbar_wait(acc_full, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      for (int mb = 0; mb < J.mblocks; ++mb) {
+        const int drow = mb * 128 + quarter * 32 + lane;  // row in dY-column space
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tlane + mb * ncols + c0, r);
+          tmem_ld_wait();
+          for (int s = 0; s < J.nflush; ++s) {
+            const FlushSeg& F = J.flush[s];
+            if (drow >= F.row0 && drow < F.row0 + F.nrows) {
+              float* dst = p.flat_grad + F.dst + (int64_t)(drow - F.row0) * F.ld;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                int col = c0 + j;
+                if (col >= F.col0 && col < F.col0 + F.ncols) atomicAdd(dst + (col - F.col0), __uint_as_float(r[j]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ======================================================================================================
+// weight packing
+// ======================================================================================================
+struct PackParams {
+  PackTable tab;
+  const float* flat;
+  uint8_t* blob;
+  int64_t bias_off, glo_off;
+  int64_t glo_src;
+  int glo_floats;
+};
+
+__global__ void pack_kernel(const __grid_constant__ PackParams p) {
+  const int oi = blockIdx.y;
+  if (oi < p.tab.nops) {
+    const PackOp& op = p.tab.ops[oi];
+    const int npk = op.n * (op.k / 8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npk; i += gridDim.x * blockDim.x) {
+      const int chunk = i / op.n, n = i % op.n;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      for (int b = op.blk0; b < op.blk0 + op.nblk; ++b) {
+        const PackBlock& B = p.tab.blocks[b];
+        if (n < B.n0 || n >= B.n0 + B.nn) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int k = chunk * 8 + j;
+          if (k >= B.k0 && k < B.k0 + B.kk) v[j] = __ldg(p.flat + B.src + (int64_t)(n - B.n0) * B.sn + (int64_t)(k - B.k0) * B.sk);
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      reinterpret_cast<uint4*>(p.blob + (size_t)op.w_off16 * 16)[i] = o;
+    }
+  } else {
+    // biases + GLO table copy
+    float* bias = reinterpret_cast<float*>(p.blob + p.bias_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.tab.bias_floats; i += gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (int b = 0; b < p.tab.nbias; ++b) {
+        const BiasBlock& B = p.tab.bias[b];
+        if (i >= B.dst && i < B.dst + B.cnt) v = __ldg(p.flat + B.src + (i - B.dst));
+      }
+      bias[i] = v;
+    }
+    float* glo = reinterpret_cast<float*>(p.blob + p.glo_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.glo_floats; i += gridDim.x * blockDim.x)
+      glo[i] = __ldg(p.flat + p.glo_src + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static int64_t tiles_of(int64_t n) { return (n + kTileRows - 1) / kTileRows; }
+
+template <class K>
+static int set_smem(K kernel, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return set_cuda_error(e, what);
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* out) {
+  if (!desc || !out) return set_error(-2, "hn_query: null pointer");
+  if (int rc = validate_desc(*desc)) return rc;
+  if (n_samples < 0) return set_error(-1, "hn_query: negative n_samples");
+  static thread_local ModelPlan plan;
+  build_plan(*desc, &plan);
+  memset(out, 0, sizeof(*out));
+  const int64_t halves = 2 * tiles_of(n_samples);
+  out->packed_bytes = plan.layout.total;
+  out->saved_bytes = halves * plan.slabs.x_total * kHalfChunkBytes;
+  out->workspace_bytes = halves * plan.slabs.d_total * kHalfChunkBytes;
+  const Dims& m = plan.dims;
+  auto lin = [](int64_t out_f, int64_t in_f) { return out_f * in_f + out_f; };
+  int64_t cnt = (int64_t)desc->num_embeddings * m.G;
+  cnt += lin(kSheetW, m.in_s) + 4 * lin(kSheetW, kSheetW) + lin(kSheetW, kSheetW + m.in_s) + lin(m.H, kSheetW);
+  cnt += lin(kWarpW, m.in_w) + 4 * lin(kWarpW, kWarpW) + lin(kWarpW, kWarpW + m.in_w) + lin(3, kWarpW);
+  int64_t lvl = lin(kTrunkW, m.in_t) + 7 * lin(kTrunkW, kTrunkW) + lin(kTrunkW, kTrunkW + m.in_t) + lin(kRgbW, kTrunkW) +
+                lin(kRgbW, kRgbW + m.pe_v) + 3 * lin(kRgbW, kRgbW) + lin(3, kRgbW) + lin(1, kRgbW);
+  out->flat_param_floats = cnt + 2 * lvl;
+  return 0;
+}
+
+extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_params, const int64_t* param_offsets, int level,
+                               void* packed, void* stream) {
+  if (!desc || !flat_params || !param_offsets || !packed) return set_error(-2, "hn_pack_weights: null pointer");
+  if (level < 0 || level > 1) return set_error(-1, "hn_pack_weights: level must be 0 or 1");
+  if (int rc = validate_desc(*desc)) return rc;
+  static thread_local ModelPlan plan;
+  build_plan(*desc, &plan);
+  build_tables(*desc, level, param_offsets, &plan);
+  PackParams pp;
+  pp.tab = plan.pack;
+  pp.flat = flat_params;
+  pp.blob = (uint8_t*)packed;
+  pp.bias_off = plan.layout.bias_off;
+  pp.glo_off = plan.layout.glo_off;
+  pp.glo_src = param_offsets[P_GLO];
+  pp.glo_floats = desc->num_embeddings * plan.dims.G;
+  dim3 grid(16, plan.pack.nops + 1);
+  pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp);
+  return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
+}
+
+extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
+                          const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
+                          float* rgb, float* warped, void* saved, void* stream) {
+  if (!desc || !packed || !points || !viewdirs || !ids || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
+  if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
+  if (int rc = validate_desc(*desc)) return rc;
+  if (B == 0) return 0;
+  static thread_local ModelPlan plan;
+  build_plan(*desc, &plan);
+  using C = Cfg1;
+  FwdParams fp;
+  fp.prog = plan.fwd;
+  fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
+  fp.bias = (const float*)((const uint8_t*)packed + plan.layout.bias_off);
+  fp.glo = (const float*)((const uint8_t*)packed + plan.layout.glo_off);
+  fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
+  fp.n = B * S; fp.S = S;
+  int64_t nt = tiles_of(fp.n);
+  if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_fwd: too many samples");
+  fp.n_tiles = (int)nt;
+  fp.x_total = plan.slabs.x_total;
+  fp.x_in_ws = plan.slabs.x_in_ws; fp.x_in_t = plan.slabs.x_in_t; fp.x_in_v = plan.slabs.x_in_v;
+  fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
+  if (int rc = set_smem(mlp_fwd_kernel<C>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
+  int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
+  mlp_fwd_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+  return set_cuda_error(cudaGetLastError(), "hn_mlp_fwd");
+}
+
+extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                          const float* rgb, const float* warped, const void* saved, const float* g_sigma,
+                          const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
+                          const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+  if (!desc || !packed || !ids || !sigma || !rgb || !warped || !saved || !g_sigma || !g_rgb || !param_offsets || !flat_grad ||
+      !workspace)
+    return set_error(-2, "hn_mlp_bwd: null pointer");
+  if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_bwd: bad B/S");
+  if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
+  if (int rc = validate_desc(*desc)) return rc;
+  if (B == 0) return 0;
+  static thread_local ModelPlan plan;
+  build_plan(*desc, &plan);
+  build_tables(*desc, level, param_offsets, &plan);
+  using C = Cfg1;
+  BwdParams bp;
+  bp.prog = plan.bwd;
+  bp.weights = (const uint8_t*)packed + plan.layout.bwd_off;
+  bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
+  bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
+  bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
+  bp.glo_grad = flat_grad + param_offsets[P_GLO];
+  bp.n = B * S; bp.S = S;
+  int64_t nt = tiles_of(bp.n);
+  if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_bwd: too many samples");
+  bp.n_tiles = (int)nt;
+  bp.x_total = plan.slabs.x_total; bp.d_total = plan.slabs.d_total;
+  bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
+  if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+  int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
+  mlp_dgrad_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
+  if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: dgrad launch")) return rc;
+
+  WgradParams wp;
+  wp.tab = plan.wgrad;
+  wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
+  wp.flat_grad = flat_grad;
+  wp.n_half = 2 * nt;
+  wp.x_total = plan.slabs.x_total; wp.d_total = plan.slabs.d_total;
+  if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
+  int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
+  mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
+  return set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch");
+}

@@ -1,0 +1,388 @@
+// Host-side construction of the layer programs, pack tables and weight-gradient job tables
+// (see hn_mlp_program.h).  Pure host code.
+#include <string.h>
+#include "hn_api_internal.h"
+#include "hn_mlp_program.h"
+
+namespace hn {
+
+int validate_desc(const hn_model_desc& d) {
+  if ((d.flags & (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY)) != (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY))
+    return set_error(-10, "hn_model_desc: this build implements TranslationField warp + bendy_sheet slicing only");
+  if (d.glo_dim != 8 || d.hyper_dim != 2 || d.xyz_freqs != 10 || d.hyper_freqs != 6 || d.view_freqs != 6 ||
+      d.warp_freqs != 10 || d.sheet_freqs != 7)
+    return set_error(-11,
+                     "hn_model_desc: kernels are instantiated for G=8, H=2, xyz/hyper/view freqs 10/6/6 "
+                     "(warp 10, sheet 7); add an instantiation in hn_mlp.cu for other shapes");
+  if (d.num_embeddings <= 0) return set_error(-12, "hn_model_desc: num_embeddings must be positive");
+  return 0;
+}
+
+namespace {
+
+struct Builder {
+  Program* p;
+  uint32_t w16 = 0;  // running weight offset (16-byte units)
+  void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk) {
+    Layer& L = p->layers[p->nlayers++];
+    L.op0 = (uint8_t)p->nops; L.nops = 0; L.epi = epi; L.pad = 0;
+    L.n_out = (uint16_t)n_out; L.bias_off = (uint16_t)bias_off; L.save_chunk = save_chunk; L.mask_chunk = mask_chunk;
+  }
+  // returns op index
+  int add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
+    MmaOp& o = p->ops[p->nops];
+    o.w_off16 = w16; o.n = (uint16_t)n; o.k0 = (uint16_t)k0; o.k1 = (uint16_t)k1;
+    o.a0_chunk = (uint16_t)(a0_col / 8); o.a1_chunk = (uint16_t)(a1_col / 8);
+    o.tmem_col = (uint16_t)tmem_col; o.src0 = s0; o.src1 = s1; o.acc_init = (uint8_t)acc_init;
+    int cps = (kStageBytes / (n * 16)) & ~1;
+    if (cps < 2) cps = 2;
+    int nchunks = (k0 + k1) / 8;
+    if (cps > nchunks) cps = nchunks;
+    o.cps = (uint8_t)cps;
+    w16 += (uint32_t)n * (uint32_t)(k0 + k1) / 8;  // n * K * 2 bytes / 16
+    p->layers[p->nlayers - 1].nops++;
+    return p->nops++;
+  }
+};
+
+struct Packer {
+  PackTable* t;
+  const int64_t* off;
+  int cur = -1;
+  void op(const MmaOp& o) {
+    cur = t->nops++;
+    PackOp& po = t->ops[cur];
+    po.w_off16 = o.w_off16; po.n = o.n; po.k = (uint16_t)(o.k0 + o.k1); po.blk0 = (uint8_t)t->nblocks; po.nblk = 0; po.pad = 0;
+  }
+  void block(int param, int64_t src_extra, int sn, int sk, int n0, int nn, int k0, int kk) {
+    PackBlock& b = t->blocks[t->nblocks++];
+    b.src = off[param] + src_extra; b.sn = sn; b.sk = sk;
+    b.n0 = (uint16_t)n0; b.nn = (uint16_t)nn; b.k0 = (uint16_t)k0; b.kk = (uint16_t)kk;
+    t->ops[cur].nblk++;
+  }
+  void bias(int param, int dst, int cnt) {
+    BiasBlock& b = t->bias[t->nbias++];
+    b.src = off[param]; b.dst = (uint16_t)dst; b.cnt = (uint16_t)cnt; b.pad = 0;
+  }
+};
+
+}  // namespace
+
+// Forward bias array layout (floats): one run of n_out per layer, in layer order.
+static int fwd_bias_floats(const Dims& m) {
+  return kWsDepth * kWsW + 16 + (kTrunkDepth + 1) * kTrunkW + kRgbW + m.n_rgb0a + (kRgbDepth - 1) * kRgbW + 16;
+}
+
+void build_plan(const hn_model_desc& d, ModelPlan* plan) {
+  memset(plan, 0, sizeof(*plan));
+  const Dims m = make_dims(d);
+  const SlabMap s = make_slabs(m);
+  plan->dims = m;
+  plan->slabs = s;
+
+  // ------------------------------------------------------------------ forward program
+  {
+    Builder b{&plan->fwd};
+    int bias = 0;
+    // warp + sheet, merged to one 192-wide net sharing the input buffer
+    b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone);
+    b.add_op(kWsW, m.KW, SRC_INB, 0, 0, SRC_ACT, 0, 0);
+    bias += kWsW;
+    for (int l = 1; l < kWsDepth; ++l) {
+      b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[l], kNone);
+      bool skip = (l == kSkip + 1);
+      b.add_op(kWarpW, kWarpW, SRC_ACT, 0, skip ? m.KW : 0, SRC_INB, 0, 0);
+      b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, skip ? m.KW : 0, SRC_INB, 0, kWarpW);
+      bias += kWsW;
+    }
+    b.begin_layer(FE_WSHEAD, 16, bias, s.x_in_t, kNone);
+    b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += 16;
+    // trunk
+    b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone);
+    b.add_op(kTrunkW, m.KT, SRC_INB, 0, 0, SRC_ACT, 0, 0);
+    bias += kTrunkW;
+    for (int l = 1; l <= kTrunkDepth; ++l) {  // l == kTrunkDepth is the logit layer (ReLU output, modules.py:230)
+      b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone);
+      bool skip = (l == kSkip + 1);
+      b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, skip ? m.KT : 0, SRC_INB, 0, 0);
+      bias += kTrunkW;
+    }
+    b.begin_layer(FE_BOTT, kRgbW, bias, s.x_bott, kNone);
+    b.add_op(kRgbW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += kRgbW;
+    b.begin_layer(FE_RGB0A, m.n_rgb0a, bias, s.x_r[0], kNone);
+    b.add_op(m.n_rgb0a, kRgbW, SRC_ACT, 0, m.KV, SRC_INB, 0, 0);
+    bias += m.n_rgb0a;
+    for (int l = 1; l < kRgbDepth; ++l) {
+      b.begin_layer(FE_RELU, kRgbW, bias, s.x_r[l], kNone);
+      b.add_op(kRgbW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      bias += kRgbW;
+    }
+    b.begin_layer(FE_RGBHEAD, 16, bias, kNone, kNone);
+    b.add_op(16, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += 16;
+    plan->layout.fwd_off = 0;
+    plan->layout.bwd_off = (int64_t)b.w16 * 16;
+  }
+  // ------------------------------------------------------------------ backward-data program
+  {
+    Builder b{&plan->bwd};
+    // D0: rgb head^T.  A = dY_rgbhead (16 cols, written by the prologue)
+    b.begin_layer(BE_MASK, kRgbW, 0, s.d_r[3], s.x_r[3]);
+    b.add_op(kRgbW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    // D1..D3: rgb3^T, rgb2^T, rgb1^T
+    for (int l = kRgbDepth - 1; l >= 1; --l) {
+      bool last = (l == 1);
+      b.begin_layer(last ? BE_RGB1 : BE_MASK, kRgbW, 0, last ? s.d_rgb0a : s.d_r[l - 1], s.x_r[l - 1]);
+      b.add_op(kRgbW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    }
+    // D4: (rgb0 | alpha)^T -> bottleneck gradient (no activation on the bottleneck, modules.py:232,277)
+    b.begin_layer(BE_LINEAR, kRgbW, 0, s.d_bott, kNone);
+    b.add_op(kRgbW, m.n_rgb0a, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    // D5: bottleneck^T, gated by the trunk output ReLU
+    b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[kTrunkDepth], s.x_t[kTrunkDepth]);
+    b.add_op(kTrunkW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    // trunk layers l = 8 (logit) .. 1: gradient w.r.t. h_{l-1}
+    for (int l = kTrunkDepth; l >= 1; --l) {
+      if (l == kSkip + 1) {
+        // input part of the skip layer first (result parked in INB as bf16), then the hidden part
+        b.begin_layer(BE_SKIPSTORE, m.KT, 0, kNone, kNone);
+        b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      }
+      b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[l - 1], s.x_t[l - 1]);
+      b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    }
+    // trunk layer 0^T -> gradient of the trunk input features -> chain rule through posenc
+    b.begin_layer(BE_TRUNKIN, m.KT, 0, s.d_wshead, kNone);
+    b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    // warp/sheet head^T
+    b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1]);
+    b.add_op(kWsW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    for (int l = kWsDepth - 1; l >= 1; --l) {
+      b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[l - 1], s.x_hws[l - 1]);
+      if (l == kSkip + 1)  // GLO columns of the skip input, parked in TMEM cols [192,208)
+        b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW);
+      b.add_op(kWarpW, kWarpW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, 0, SRC_ACT, 0, kWarpW);
+    }
+    // GLO columns of layer 0, accumulated on top
+    b.begin_layer(BE_GLO, 16, 0, kNone, kNone);
+    b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW, /*acc_init=*/1);
+    plan->layout.bias_off = plan->layout.bwd_off + (int64_t)b.w16 * 16;
+  }
+  plan->layout.glo_off = plan->layout.bias_off + (int64_t)fwd_bias_floats(m) * 4;
+  plan->layout.glo_off = (plan->layout.glo_off + 15) / 16 * 16;
+  plan->layout.total = plan->layout.glo_off + (int64_t)d.num_embeddings * m.G * 4;
+  plan->layout.total = (plan->layout.total + 255) / 256 * 256;
+}
+
+void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPlan* plan) {
+  const Dims& m = plan->dims;
+  const SlabMap& s = plan->slabs;
+  // ------------------------------------------------------------------ pack table
+  PackTable& t = plan->pack;
+  memset(&t, 0, sizeof(t));
+  Packer pk{&t, off};
+  const Program& F = plan->fwd;
+  int oi = 0;
+  const int ldw5 = kWarpW + m.in_w, lds5 = kSheetW + m.in_s;
+  // fwd ws0
+  pk.op(F.ops[oi++]);
+  pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kWarpW, 0, m.in_w);
+  pk.block(P_SHEET_W(0), 0, m.in_s, 1, kWarpW, kSheetW, 0, m.pe_s);
+  pk.block(P_SHEET_W(0), m.pe_s, m.in_s, 1, kWarpW, kSheetW, m.pe_w, m.G);
+  for (int l = 1; l < kWsDepth; ++l) {
+    bool skip = (l == kSkip + 1);
+    pk.op(F.ops[oi++]);
+    pk.block(P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 1, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
+    pk.op(F.ops[oi++]);
+    if (!skip) {
+      pk.block(P_SHEET_W(l), 0, kSheetW, 1, 0, kSheetW, 0, kSheetW);
+    } else {
+      pk.block(P_SHEET_W(l), 0, lds5, 1, 0, kSheetW, 0, kSheetW + m.pe_s);
+      pk.block(P_SHEET_W(l), kSheetW + m.pe_s, lds5, 1, 0, kSheetW, kSheetW + m.pe_w, m.G);
+    }
+  }
+  pk.op(F.ops[oi++]);  // ws head: rows 0..2 warp logit, rows 3..3+H-1 sheet logit
+  pk.block(P_WARP_W(kWsDepth), 0, kWarpW, 1, 0, 3, 0, kWarpW);
+  pk.block(P_SHEET_W(kWsDepth), 0, kSheetW, 1, 3, m.H, kWarpW, kSheetW);
+  pk.op(F.ops[oi++]);  // trunk 0
+  pk.block(P_TRUNK_W(level, 0), 0, m.in_t, 1, 0, kTrunkW, 0, m.in_t);
+  for (int l = 1; l <= kTrunkDepth; ++l) {
+    int ld = (l == kSkip + 1) ? kTrunkW + m.in_t : kTrunkW;
+    pk.op(F.ops[oi++]);
+    pk.block(P_TRUNK_W(level, l), 0, ld, 1, 0, kTrunkW, 0, ld);
+  }
+  pk.op(F.ops[oi++]);  // bottleneck
+  pk.block(P_BOTT_W(level), 0, kTrunkW, 1, 0, kRgbW, 0, kTrunkW);
+  pk.op(F.ops[oi++]);  // rgb0 | alpha
+  pk.block(P_RGB_W(level, 0), 0, kRgbW + m.pe_v, 1, 0, kRgbW, 0, kRgbW + m.pe_v);
+  pk.block(P_ALPHA_W(level), 0, kRgbW, 1, kRgbW, 1, 0, kRgbW);
+  for (int l = 1; l < kRgbDepth; ++l) {
+    pk.op(F.ops[oi++]);
+    pk.block(P_RGB_W(level, l), 0, kRgbW, 1, 0, kRgbW, 0, kRgbW);
+  }
+  pk.op(F.ops[oi++]);  // rgb head
+  pk.block(P_RGB_W(level, kRgbDepth), 0, kRgbW, 1, 0, 3, 0, kRgbW);
+
+  // bwd: dest(n = input feature, k = output feature) = W[k][n]  -> sn = 1, sk = ld
+  const Program& Bp = plan->bwd;
+  const uint32_t bwd16 = (uint32_t)(plan->layout.bwd_off / 16);
+  oi = 0;
+  auto bop = [&](void) { MmaOp o = Bp.ops[oi++]; o.w_off16 += bwd16; pk.op(o); };
+  bop();  // D0 rgb head^T: n < 128, k < 3
+  pk.block(P_RGB_W(level, kRgbDepth), 0, 1, kRgbW, 0, kRgbW, 0, 3);
+  for (int l = kRgbDepth - 1; l >= 1; --l) {
+    bop();
+    pk.block(P_RGB_W(level, l), 0, 1, kRgbW, 0, kRgbW, 0, kRgbW);
+  }
+  bop();  // D4
+  pk.block(P_RGB_W(level, 0), 0, 1, kRgbW + m.pe_v, 0, kRgbW, 0, kRgbW);
+  pk.block(P_ALPHA_W(level), 0, 1, kRgbW, 0, kRgbW, kRgbW, 1);
+  bop();  // D5 bottleneck^T: n < 256, k < 128
+  pk.block(P_BOTT_W(level), 0, 1, kTrunkW, 0, kTrunkW, 0, kRgbW);
+  for (int l = kTrunkDepth; l >= 1; --l) {
+    int ld = (l == kSkip + 1) ? kTrunkW + m.in_t : kTrunkW;
+    if (l == kSkip + 1) {
+      bop();
+      pk.block(P_TRUNK_W(level, l), kTrunkW, 1, ld, 0, m.in_t, 0, kTrunkW);
+    }
+    bop();
+    pk.block(P_TRUNK_W(level, l), 0, 1, ld, 0, kTrunkW, 0, kTrunkW);
+  }
+  bop();  // trunk 0^T
+  pk.block(P_TRUNK_W(level, 0), 0, 1, m.in_t, 0, m.in_t, 0, kTrunkW);
+  bop();  // ws head^T: n < 128 <- warp logit (k < 3); n = 128 + j <- sheet logit (k = 3 + h)
+  pk.block(P_WARP_W(kWsDepth), 0, 1, kWarpW, 0, kWarpW, 0, 3);
+  pk.block(P_SHEET_W(kWsDepth), 0, 1, kSheetW, kWarpW, kSheetW, 3, m.H);
+  for (int l = kWsDepth - 1; l >= 1; --l) {
+    bool skip = (l == kSkip + 1);
+    if (skip) {  // GLO columns: dest(g, k<128) = warpW5[k][128 + pe_w + g]; dest(g, 128 + j) = sheetW5[j][64 + pe_s + g]
+      bop();
+      pk.block(P_WARP_W(l), kWarpW + m.pe_w, 1, ldw5, 0, m.G, 0, kWarpW);
+      pk.block(P_SHEET_W(l), kSheetW + m.pe_s, 1, lds5, 0, m.G, kWarpW, kSheetW);
+    }
+    bop();
+    pk.block(P_WARP_W(l), 0, 1, skip ? ldw5 : kWarpW, 0, kWarpW, 0, kWarpW);
+    bop();
+    pk.block(P_SHEET_W(l), 0, 1, skip ? lds5 : kSheetW, 0, kSheetW, 0, kSheetW);
+  }
+  bop();  // GLO columns of layer 0
+  pk.block(P_WARP_W(0), m.pe_w, 1, m.in_w, 0, m.G, 0, kWarpW);
+  pk.block(P_SHEET_W(0), m.pe_s, 1, m.in_s, 0, m.G, kWarpW, kSheetW);
+
+  // biases, in forward layer order
+  int bo = 0;
+  for (int l = 0; l < kWsDepth; ++l) {
+    pk.bias(P_WARP_B(l), bo, kWarpW);
+    pk.bias(P_SHEET_B(l), bo + kWarpW, kSheetW);
+    bo += kWsW;
+  }
+  pk.bias(P_WARP_B(kWsDepth), bo, 3);
+  pk.bias(P_SHEET_B(kWsDepth), bo + 3, m.H);
+  bo += 16;
+  for (int l = 0; l <= kTrunkDepth; ++l) { pk.bias(P_TRUNK_B(level, l), bo, kTrunkW); bo += kTrunkW; }
+  pk.bias(P_BOTT_B(level), bo, kRgbW); bo += kRgbW;
+  pk.bias(P_RGB_B(level, 0), bo, kRgbW);
+  pk.bias(P_ALPHA_B(level), bo + kRgbW, 1);
+  bo += m.n_rgb0a;
+  for (int l = 1; l < kRgbDepth; ++l) { pk.bias(P_RGB_B(level, l), bo, kRgbW); bo += kRgbW; }
+  pk.bias(P_RGB_B(level, kRgbDepth), bo, 3);
+  bo += 16;
+  t.bias_floats = bo;
+
+  // ------------------------------------------------------------------ weight-gradient jobs
+  WgradTable& w = plan->wgrad;
+  memset(&w, 0, sizeof(w));
+  auto job = [&](int dy_chunk, int dy_cols, int x0_chunk, int x0_cols, int x1_chunk, int x1_cols) -> WgradJob& {
+    WgradJob& j = w.jobs[w.njobs++];
+    j.dy_chunk = (uint16_t)dy_chunk; j.dy_nchunks = (uint16_t)(dy_cols / 8);
+    j.x0_chunk = (uint16_t)x0_chunk; j.x0_nchunks = (uint16_t)(x0_cols / 8);
+    j.x1_chunk = (uint16_t)x1_chunk; j.x1_nchunks = (uint16_t)(x1_cols / 8);
+    j.mblocks = (uint8_t)((dy_cols + 127) / 128);
+    return j;
+  };
+  auto flush = [&](WgradJob& j, int param, int64_t extra, int ld, int row0, int nrows, int col0, int ncols) {
+    FlushSeg& f = j.flush[j.nflush++];
+    f.dst = off[param] + extra; f.ld = ld; f.row0 = (uint16_t)row0; f.nrows = (uint16_t)nrows;
+    f.col0 = (uint16_t)col0; f.ncols = (uint16_t)ncols;
+  };
+  auto bseg = [&](WgradJob& j, int param, int col0, int ncols) {
+    BiasSeg& b = j.bias[j.nbias++];
+    b.dst = off[param]; b.col0 = (uint16_t)col0; b.ncols = (uint16_t)ncols; b.pad = 0;
+  };
+  // warp / sheet layer 0
+  {
+    WgradJob& j = job(s.d_ws[0], kWarpW, s.x_in_ws, m.KW, 0, 0);
+    flush(j, P_WARP_W(0), 0, m.in_w, 0, kWarpW, 0, m.in_w);
+    bseg(j, P_WARP_B(0), 0, kWarpW);
+    WgradJob& k = job(s.d_ws[0] + kWarpW / 8, kSheetW, s.x_in_ws, m.KW, 0, 0);
+    flush(k, P_SHEET_W(0), 0, m.in_s, 0, kSheetW, 0, m.pe_s);
+    flush(k, P_SHEET_W(0), m.pe_s, m.in_s, 0, kSheetW, m.pe_w, m.G);
+    bseg(k, P_SHEET_B(0), 0, kSheetW);
+  }
+  for (int l = 1; l < kWsDepth; ++l) {
+    bool skip = (l == kSkip + 1);
+    WgradJob& j = job(s.d_ws[l], kWarpW, s.x_hws[l - 1], kWarpW, s.x_in_ws, skip ? m.KW : 0);
+    flush(j, P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
+    bseg(j, P_WARP_B(l), 0, kWarpW);
+    WgradJob& k = job(s.d_ws[l] + kWarpW / 8, kSheetW, s.x_hws[l - 1] + kWarpW / 8, kSheetW, s.x_in_ws, skip ? m.KW : 0);
+    if (!skip) {
+      flush(k, P_SHEET_W(l), 0, kSheetW, 0, kSheetW, 0, kSheetW);
+    } else {
+      flush(k, P_SHEET_W(l), 0, lds5, 0, kSheetW, 0, kSheetW + m.pe_s);
+      flush(k, P_SHEET_W(l), kSheetW + m.pe_s, lds5, 0, kSheetW, kSheetW + m.pe_w, m.G);
+    }
+    bseg(k, P_SHEET_B(l), 0, kSheetW);
+  }
+  {
+    WgradJob& j = job(s.d_wshead, 16, s.x_hws[kWsDepth - 1], kWsW, 0, 0);
+    flush(j, P_WARP_W(kWsDepth), 0, kWarpW, 0, 3, 0, kWarpW);
+    flush(j, P_SHEET_W(kWsDepth), 0, kSheetW, 3, m.H, kWarpW, kSheetW);
+    bseg(j, P_WARP_B(kWsDepth), 0, 3);
+    bseg(j, P_SHEET_B(kWsDepth), 3, m.H);
+  }
+  // trunk
+  {
+    WgradJob& j = job(s.d_t[0], kTrunkW, s.x_in_t, m.KT, 0, 0);
+    flush(j, P_TRUNK_W(level, 0), 0, m.in_t, 0, kTrunkW, 0, m.in_t);
+    bseg(j, P_TRUNK_B(level, 0), 0, kTrunkW);
+  }
+  for (int l = 1; l <= kTrunkDepth; ++l) {
+    bool skip = (l == kSkip + 1);
+    int ld = skip ? kTrunkW + m.in_t : kTrunkW;
+    WgradJob& j = job(s.d_t[l], kTrunkW, s.x_t[l - 1], kTrunkW, 0, 0);
+    flush(j, P_TRUNK_W(level, l), 0, ld, 0, kTrunkW, 0, kTrunkW);
+    bseg(j, P_TRUNK_B(level, l), 0, kTrunkW);
+    if (skip) {
+      WgradJob& k = job(s.d_t[l], kTrunkW, s.x_in_t, m.KT, 0, 0);
+      flush(k, P_TRUNK_W(level, l), kTrunkW, ld, 0, kTrunkW, 0, m.in_t);
+    }
+  }
+  {
+    WgradJob& j = job(s.d_bott, kRgbW, s.x_t[kTrunkDepth], kTrunkW, 0, 0);
+    flush(j, P_BOTT_W(level), 0, kTrunkW, 0, kRgbW, 0, kTrunkW);
+    bseg(j, P_BOTT_B(level), 0, kRgbW);
+  }
+  {
+    WgradJob& j = job(s.d_rgb0a, m.n_rgb0a, s.x_bott, kRgbW, s.x_in_v, m.KV);
+    flush(j, P_RGB_W(level, 0), 0, kRgbW + m.pe_v, 0, kRgbW, 0, kRgbW + m.pe_v);
+    flush(j, P_ALPHA_W(level), 0, kRgbW, kRgbW, 1, 0, kRgbW);
+    bseg(j, P_RGB_B(level, 0), 0, kRgbW);
+    bseg(j, P_ALPHA_B(level), kRgbW, 1);
+  }
+  for (int l = 1; l < kRgbDepth; ++l) {
+    WgradJob& j = job(s.d_r[l], kRgbW, s.x_r[l - 1], kRgbW, 0, 0);
+    flush(j, P_RGB_W(level, l), 0, kRgbW, 0, kRgbW, 0, kRgbW);
+    bseg(j, P_RGB_B(level, l), 0, kRgbW);
+  }
+  {
+    WgradJob& j = job(s.d_rgbhead, 16, s.x_r[kRgbDepth - 1], kRgbW, 0, 0);
+    flush(j, P_RGB_W(level, kRgbDepth), 0, kRgbW, 0, 3, 0, kRgbW);
+    bseg(j, P_RGB_B(level, kRgbDepth), 0, 3);
+  }
+  (void)d;
+}
+
+}  // namespace hn

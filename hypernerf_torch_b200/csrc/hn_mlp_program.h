@@ -1,0 +1,207 @@
+// Layer programs for the fused HyperNeRF MLP kernels.
+//
+// The fused forward / backward-data kernels are interpreters of a small table built on the host from
+// hn_model_desc: a list of UMMA "ops" (one accumulation group D[128,N] (+)= A[128,K] * W[N,K]^T, the A
+// operand taken from up to two shared-memory column ranges so that skip concatenations never materialise)
+// grouped into "layers" (ops that share one TMEM epilogue).  The weight-gradient kernel interprets a table
+// of "jobs" (dW = dY^T X over 64-row half tiles).  All of it is plain data so it can be passed by value as
+// a kernel parameter.
+//
+// Topology source: hypernerf/modules.py:99-127 (MLP), :220-252 (NerfMLP), :302-337 (HyperSheetMLP),
+// hypernerf/warping.py:74-88 (TranslationField), hypernerf/models.py:404-493 (conditioning, template query).
+#pragma once
+#include <stdint.h>
+#include "../../include/hypernerf_b200.h"
+
+namespace hn {
+
+constexpr int kTileRows = 128;   // samples per CTA tile (= UMMA M = TMEM lanes)
+constexpr int kHalfRows = 64;    // granularity of the saved-activation layout and of the wgrad K step
+constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-row smem operand
+constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-row global slab
+constexpr int kRingStages = 3;
+constexpr int kStageBytes = 8192;
+constexpr int kMaxOps = 32;
+constexpr int kMaxLayers = 24;
+constexpr int kMaxJobs = 40;
+constexpr uint16_t kNone = 0xFFFF;
+
+constexpr int pad16(int x) { return (x + 15) / 16 * 16; }
+
+// Fixed cfg-1 family widths (models.py:137-141, warping.py:61, modules.py:303).
+constexpr int kTrunkW = 256, kTrunkDepth = 8, kRgbW = 128, kRgbDepth = 4;
+constexpr int kWarpW = 128, kSheetW = 64, kWsDepth = 6, kWsW = kWarpW + kSheetW, kSkip = 4;
+
+// Derived channel counts for a model descriptor.
+struct Dims {
+  int G, H;
+  int pe_w, pe_s, in_w, in_s, KW;  // warp / sheet inputs, shared padded input width
+  int pe_x, pe_h, in_t, KT;        // trunk input
+  int pe_v, KV;                    // view-direction condition
+  int n_rgb0a;                     // rgb layer 0 merged with the alpha head (pad16(128 + 1))
+  int in_max_chunks;               // chunks of the shared input buffer
+};
+inline Dims make_dims(const hn_model_desc& d) {
+  Dims m;
+  m.G = d.glo_dim; m.H = d.hyper_dim;
+  m.pe_w = 3 + 6 * d.warp_freqs; m.pe_s = 3 + 6 * d.sheet_freqs;
+  m.in_w = m.pe_w + m.G; m.in_s = m.pe_s + m.G; m.KW = pad16(m.in_w);
+  m.pe_x = 3 + 6 * d.xyz_freqs; m.pe_h = m.H * (1 + 2 * d.hyper_freqs);
+  m.in_t = m.pe_x + m.pe_h; m.KT = pad16(m.in_t);
+  m.pe_v = 3 + 6 * d.view_freqs; m.KV = pad16(m.pe_v);
+  m.n_rgb0a = pad16(kRgbW + 1);
+  int mx = m.KW > m.KT ? m.KW : m.KT; if (m.KV > mx) mx = m.KV;
+  m.in_max_chunks = mx / 8;
+  return m;
+}
+
+// ---- canonical parameter tensor indices (include/hypernerf_b200.h) -----------------------------------
+constexpr int P_GLO = 0;
+inline int P_SHEET_W(int l) { return 1 + 2 * l; }   // l = 0..5 hidden, 6 = logit
+inline int P_SHEET_B(int l) { return 2 + 2 * l; }
+inline int P_WARP_W(int l) { return 15 + 2 * l; }
+inline int P_WARP_B(int l) { return 16 + 2 * l; }
+inline int P_LEVEL(int level) { return 29 + 32 * level; }
+inline int P_TRUNK_W(int level, int l) { return P_LEVEL(level) + 2 * l; }  // l = 0..7, 8 = logit
+inline int P_TRUNK_B(int level, int l) { return P_LEVEL(level) + 2 * l + 1; }
+inline int P_BOTT_W(int level) { return P_LEVEL(level) + 18; }
+inline int P_BOTT_B(int level) { return P_LEVEL(level) + 19; }
+inline int P_RGB_W(int level, int l) { return P_LEVEL(level) + 20 + 2 * l; }  // l = 0..3, 4 = logit
+inline int P_RGB_B(int level, int l) { return P_LEVEL(level) + 21 + 2 * l; }
+inline int P_ALPHA_W(int level) { return P_LEVEL(level) + 30; }
+inline int P_ALPHA_B(int level) { return P_LEVEL(level) + 31; }
+
+// ---- saved-activation (forward) and pre-activation-gradient (backward) slab offsets, in 8-col chunks ---
+struct SlabMap {
+  // forward activations X (inputs of every linear layer)
+  uint16_t x_in_ws, x_hws[kWsDepth], x_in_t, x_t[kTrunkDepth + 1], x_bott, x_in_v, x_r[kRgbDepth];
+  uint16_t x_total;
+  // gradients w.r.t. every layer's pre-activation output
+  uint16_t d_ws[kWsDepth], d_wshead, d_t[kTrunkDepth + 1], d_bott, d_rgb0a, d_r[kRgbDepth] /* [0] unused */, d_rgbhead;
+  uint16_t d_total;
+};
+inline SlabMap make_slabs(const Dims& m) {
+  SlabMap s{};
+  uint16_t c = 0;
+  s.x_in_ws = c; c += m.KW / 8;
+  for (int l = 0; l < kWsDepth; ++l) { s.x_hws[l] = c; c += kWsW / 8; }
+  s.x_in_t = c; c += m.KT / 8;
+  for (int l = 0; l <= kTrunkDepth; ++l) { s.x_t[l] = c; c += kTrunkW / 8; }
+  s.x_bott = c; c += kRgbW / 8;
+  s.x_in_v = c; c += m.KV / 8;
+  for (int l = 0; l < kRgbDepth; ++l) { s.x_r[l] = c; c += kRgbW / 8; }
+  s.x_total = c;
+  c = 0;
+  for (int l = 0; l < kWsDepth; ++l) { s.d_ws[l] = c; c += kWsW / 8; }
+  s.d_wshead = c; c += 2;
+  for (int l = 0; l <= kTrunkDepth; ++l) { s.d_t[l] = c; c += kTrunkW / 8; }
+  s.d_bott = c; c += kRgbW / 8;
+  s.d_rgb0a = c; c += m.n_rgb0a / 8;
+  s.d_r[0] = kNone;
+  for (int l = 1; l < kRgbDepth; ++l) { s.d_r[l] = c; c += kRgbW / 8; }
+  s.d_rgbhead = c; c += 2;
+  s.d_total = c;
+  return s;
+}
+
+// ---- fused kernel program ----------------------------------------------------------------------------
+enum Src : uint8_t { SRC_ACT = 0, SRC_INB = 1 };
+
+struct MmaOp {
+  uint32_t w_off16;            // weights of this op inside the packed blob, 16-byte units
+  uint16_t n;                  // UMMA N (multiple of 16)
+  uint16_t k0, k1;             // K columns taken from source 0 / source 1 (multiples of 16; k1 may be 0)
+  uint16_t a0_chunk, a1_chunk; // first 8-col chunk inside the source buffers
+  uint16_t tmem_col;           // accumulator column offset
+  uint8_t src0, src1;
+  uint8_t acc_init;            // 1: accumulate onto what TMEM already holds
+  uint8_t cps;                 // 8-col chunks of K per ring stage (even)
+};
+
+enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD };
+enum BwdEpi : uint8_t { BE_MASK = 0, BE_LINEAR, BE_RGB1, BE_SKIPSTORE, BE_TRUNKIN, BE_GLO };
+
+struct Layer {
+  uint8_t op0, nops, epi, pad;
+  uint16_t n_out;       // accumulator columns the epilogue consumes
+  uint16_t bias_off;    // forward: float offset into the bias array
+  uint16_t save_chunk;  // chunk offset where the epilogue's bf16 output is stashed (X slabs fwd, dY slabs bwd)
+  uint16_t mask_chunk;  // backward: chunk offset of the forward activation that gates this gradient
+};
+
+struct Program {
+  int32_t nlayers, nops;
+  Layer layers[kMaxLayers];
+  MmaOp ops[kMaxOps];
+};
+
+// ---- weight packing ----------------------------------------------------------------------------------
+// dest(n, k) of an op's [N x K] bf16 matrix (interleave layout: ((k/8) * N + n) * 8 + k%8) is gathered from
+// flat_params[src + (n - n0) * sn + (k - k0) * sk] for the (n, k) inside a block; everything else is zero.
+struct PackBlock {
+  int64_t src;         // element offset in the flat fp32 parameter buffer
+  int32_t sn, sk;      // source strides (elements)
+  uint16_t n0, nn, k0, kk;
+};
+struct PackOp {
+  uint32_t w_off16;
+  uint16_t n, k;       // padded dims
+  uint8_t blk0, nblk;
+  uint16_t pad;
+};
+constexpr int kMaxPackOps = 64;
+constexpr int kMaxPackBlocks = 96;
+struct BiasBlock { int64_t src; uint16_t dst, cnt; uint32_t pad; };
+constexpr int kMaxBiasBlocks = 40;
+struct PackTable {
+  int32_t nops, nblocks, nbias, bias_floats;
+  PackOp ops[kMaxPackOps];
+  PackBlock blocks[kMaxPackBlocks];
+  BiasBlock bias[kMaxBiasBlocks];
+};
+
+// ---- weight-gradient jobs ----------------------------------------------------------------------------
+struct FlushSeg {
+  int64_t dst;           // element offset in flat_grad of D[row0][col0]
+  int32_t ld;            // destination leading dimension
+  uint16_t row0, nrows;  // rows in dY-column space of the job (row = mblock * 128 + lane row)
+  uint16_t col0, ncols;
+};
+struct BiasSeg { int64_t dst; uint16_t col0, ncols; uint32_t pad; };
+struct WgradJob {
+  uint16_t dy_chunk, dy_nchunks;   // dY columns copied as the A operand
+  uint16_t x0_chunk, x0_nchunks;   // X columns (first range) copied as the B operand
+  uint16_t x1_chunk, x1_nchunks;   // optional second range, placed right after the first
+  uint8_t mblocks;                 // 1 or 2 blocks of 128 dY columns
+  uint8_t nflush, nbias, pad;
+  FlushSeg flush[3];
+  BiasSeg bias[2];
+};
+struct WgradTable {
+  int32_t njobs;
+  int32_t pad;
+  WgradJob jobs[kMaxJobs];
+};
+
+// Layout of one level's packed blob.
+struct PackedLayout {
+  int64_t fwd_off, bwd_off, bias_off, glo_off, total;  // bytes
+};
+
+struct ModelPlan {
+  Dims dims;
+  SlabMap slabs;
+  Program fwd, bwd;
+  PackTable pack;     // needs param_offsets -> built per call
+  WgradTable wgrad;   // needs param_offsets -> built per call
+  PackedLayout layout;
+};
+
+// Validates the descriptor; returns 0 or a negative error code (message through set_error).
+int validate_desc(const hn_model_desc& d);
+// Static part (programs, slabs, blob layout).
+void build_plan(const hn_model_desc& d, ModelPlan* plan);
+// Offset-dependent part for one level.
+void build_tables(const hn_model_desc& d, int level, const int64_t* param_offsets, ModelPlan* plan);
+
+}  // namespace hn

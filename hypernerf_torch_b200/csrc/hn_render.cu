@@ -1,0 +1,559 @@
+// HBM-bound per-ray stages of the HyperNeRF hot path: stratified sampling, inverse-CDF resampling and
+// alpha compositing (forward + reverse).  One warp owns one ray; every lane owns C consecutive samples so
+// global loads are contiguous across the warp and scans are lane-local + one shuffle scan.
+//
+// Reference semantics (cited per kernel): hypernerf/model_utils.py of songrise/HyperNeRF-torch.
+#include "hn_api_internal.h"
+
+namespace hn {
+
+static constexpr int kWarpsPerBlock = 8;
+static constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// hn_sample_coarse — model_utils.py:6-41.  z = lower + (upper-lower)*u, each op separately rounded like the
+// reference's three torch elementwise kernels; points = o + z*d likewise (no FMA contraction).
+// ------------------------------------------------------------------------------------------------
+__global__ void sample_coarse_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                     const float* __restrict__ u, const float* __restrict__ lower,
+                                     const float* __restrict__ upper, int64_t n, int Nc, float* __restrict__ z,
+                                     float* __restrict__ pts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t b = i / Nc;
+  int s = (int)(i - b * Nc);
+  float lo = lower[s];
+  float zz = lo;
+  if (u != nullptr) zz = __fadd_rn(lo, __fmul_rn(__fsub_rn(upper[s], lo), u[i]));
+  z[i] = zz;
+  if (pts != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pts[i * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(zz, d[b * 3 + c]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp scans
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_excl_scan_mul(float v, int lane) {
+  // returns product of v over lanes < lane
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc *= t;
+  }
+  float ex = __shfl_up_sync(kFull, inc, 1);
+  return lane == 0 ? 1.f : ex;
+}
+__device__ __forceinline__ float warp_excl_scan_add(float v, int lane) {
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  float ex = __shfl_up_sync(kFull, inc, 1);
+  return lane == 0 ? 0.f : ex;
+}
+__device__ __forceinline__ float warp_excl_rscan_add(float v, int lane) {
+  // sum of v over lanes > lane
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(kFull, inc, o);
+    if (lane + o < 32) inc += t;
+  }
+  float ex = __shfl_down_sync(kFull, inc, 1);
+  return lane == 31 ? 0.f : ex;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// contiguous per-lane loads of CNT floats with the widest aligned vector
+template <int CNT>
+__device__ __forceinline__ void load_run(const float* __restrict__ p, float* out) {
+  if constexpr (CNT % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT / 4; ++i) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+    }
+  } else if constexpr (CNT % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(p) + i);
+      out[2 * i] = v.x; out[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) out[i] = __ldg(p + i);
+  }
+}
+template <int CNT>
+__device__ __forceinline__ void store_run(float* __restrict__ p, const float* v) {
+  if constexpr (CNT % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT / 4; ++i)
+      reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (CNT % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) p[i] = v[i];
+  }
+}
+
+// Per-lane view of one ray's samples.  EXACT: S == 32*C (vector loads); otherwise guarded scalar loads.
+template <int C, bool EXACT>
+struct RayLane {
+  float sigma[C], z[C], alpha[C], T[C], w[C], dist[C];
+  int base;  // first sample index of this lane
+
+  __device__ __forceinline__ void load(const float* __restrict__ sg, const float* __restrict__ zz, int64_t ray,
+                                       int S, int lane) {
+    base = lane * C;
+    const float* ps = sg + ray * S + base;
+    const float* pz = zz + ray * S + base;
+    if constexpr (EXACT) {
+      load_run<C>(ps, sigma);
+      load_run<C>(pz, z);
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        bool ok = base + j < S;
+        sigma[j] = ok ? __ldg(ps + j) : 0.f;
+        z[j] = ok ? __ldg(pz + j) : 0.f;
+      }
+    }
+  }
+  // alpha, transmittance, weights (model_utils.py:70-87)
+  __device__ __forceinline__ void composite(int S, int lane, float dnorm, float eps, float last_delta) {
+    float znext = __shfl_down_sync(kFull, z[0], 1);
+    float p[C];
+    float run = 1.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int s = base + j;
+      float zn = (j + 1 < C) ? z[j + 1] : znext;
+      float dl = (s == S - 1) ? last_delta : (zn - z[j]);
+      dist[j] = dl * dnorm;
+      float a = 1.f - expf(-sigma[j] * dist[j]);
+      if (s >= S) a = 0.f;
+      alpha[j] = a;
+      p[j] = (s < S) ? (1.f - a + eps) : 1.f;
+      T[j] = run;  // lane-local exclusive product
+      run *= p[j];
+    }
+    float pre = warp_excl_scan_mul(run, lane);
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      T[j] *= pre;
+      w[j] = alpha[j] * T[j];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// hn_composite_fwd — model_utils.py:43-107 + compute_depth_index/compute_depth_map (:319-362)
+// ------------------------------------------------------------------------------------------------
+template <int C, bool EXACT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ z,
+                     const float* __restrict__ dirs, int64_t B, int S, int flags, float eps, float last_delta,
+                     float* __restrict__ out_rgb, float* __restrict__ depth, float* __restrict__ med_depth,
+                     float* __restrict__ acc, float* __restrict__ weights, int64_t* __restrict__ med_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (ray >= B) return;
+  RayLane<C, EXACT> r;
+  r.load(sigma, z, ray, S, lane);
+  float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+  float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  r.composite(S, lane, dnorm, eps, last_delta);
+
+  float col[3 * C];
+  const float* pc = rgb + (ray * S + r.base) * 3;
+  if constexpr (EXACT) {
+    load_run<3 * C>(pc, col);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) col[j] = (r.base + j / 3 < S) ? __ldg(pc + j) : 0.f;
+  }
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f, sall = 0.f, cs = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    float w = r.w[j];
+    sr += w * col[3 * j];
+    sg += w * col[3 * j + 1];
+    sb += w * col[3 * j + 2];
+    sd += w * r.z[j];
+    sall += w;
+    if ((flags & HN_COMP_ACC_ALL) || (r.base + j < S - 1)) sa += w;
+    cs += w;
+  }
+  // median depth: first sample whose inclusive cumsum(w) >= 0.5
+  float pre = warp_excl_scan_add(cs, lane);
+  int first = -1;
+  float run = pre;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    run += r.w[j];
+    if (first < 0 && r.base + j < S && run >= 0.5f) first = j;
+  }
+  unsigned hit = __ballot_sync(kFull, first >= 0);
+  int src = hit ? (__ffs(hit) - 1) : 0;
+  float zsel = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j)
+    if (j == first) zsel = r.z[j];
+  float mz = __shfl_sync(kFull, zsel, src);
+  int mj = __shfl_sync(kFull, first, src);
+  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+  sd = warp_sum(sd); sa = warp_sum(sa); sall = warp_sum(sall);
+
+  if (weights != nullptr) {
+    float* pw = weights + ray * S + r.base;
+    if constexpr (EXACT) {
+      store_run<C>(pw, r.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        if (r.base + j < S) pw[j] = r.w[j];
+    }
+  }
+  if (lane == 0) {
+    if (flags & HN_COMP_WHITE_BKGD) {
+      float bg = 1.f - sall;
+      sr += bg; sg += bg; sb += bg;
+    }
+    out_rgb[ray * 3] = sr; out_rgb[ray * 3 + 1] = sg; out_rgb[ray * 3 + 2] = sb;
+    depth[ray] = sd;
+    acc[ray] = sa;
+    if (med_depth != nullptr) med_depth[ray] = hit ? mz : 0.f;
+    if (med_idx != nullptr) med_idx[ray] = hit ? (int64_t)(src * C + mj) : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hn_composite_bwd — reverse of the above.
+//   G_i = g_rgb . c_i + g_depth z_i + g_acc [i counted] + g_w_i (+ white bkgd: -sum(g_rgb))
+//   dL/dalpha_i = G_i T_i - (sum_{k>i} G_k w_k) / (1 - alpha_i + eps)
+//   dL/dsigma_i = dL/dalpha_i * dist_i * (1 - alpha_i) ;  dL/dc_i = w_i g_rgb
+// ------------------------------------------------------------------------------------------------
+template <int C, bool EXACT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ z,
+                     const float* __restrict__ dirs, int64_t B, int S, int flags, float eps, float last_delta,
+                     const float* __restrict__ g_out_rgb, const float* __restrict__ g_depth,
+                     const float* __restrict__ g_acc, const float* __restrict__ g_weights,
+                     float* __restrict__ g_sigma, float* __restrict__ g_rgb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (ray >= B) return;
+  RayLane<C, EXACT> r;
+  r.load(sigma, z, ray, S, lane);
+  float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+  float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  r.composite(S, lane, dnorm, eps, last_delta);
+
+  float col[3 * C];
+  const float* pc = rgb + (ray * S + r.base) * 3;
+  if constexpr (EXACT) {
+    load_run<3 * C>(pc, col);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) col[j] = (r.base + j / 3 < S) ? __ldg(pc + j) : 0.f;
+  }
+  float gr = 0.f, gg = 0.f, gb = 0.f;
+  if (g_out_rgb != nullptr) {
+    gr = __ldg(g_out_rgb + ray * 3); gg = __ldg(g_out_rgb + ray * 3 + 1); gb = __ldg(g_out_rgb + ray * 3 + 2);
+  }
+  float gd = g_depth ? __ldg(g_depth + ray) : 0.f;
+  float ga = g_acc ? __ldg(g_acc + ray) : 0.f;
+  float gbg = (flags & HN_COMP_WHITE_BKGD) ? -(gr + gg + gb) : 0.f;
+  float gw[C];
+  if (g_weights != nullptr) {
+    const float* pg = g_weights + ray * S + r.base;
+    if constexpr (EXACT) {
+      load_run<C>(pg, gw);
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) gw[j] = (r.base + j < S) ? __ldg(pg + j) : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < C; ++j) gw[j] = 0.f;
+  }
+  float G[C], Gw[C];
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    int s = r.base + j;
+    float g = gr * col[3 * j] + gg * col[3 * j + 1] + gb * col[3 * j + 2] + gd * r.z[j] + gw[j] + gbg;
+    if ((flags & HN_COMP_ACC_ALL) || s < S - 1) g += ga;
+    if (s >= S) g = 0.f;
+    G[j] = g;
+    Gw[j] = g * r.w[j];
+    tot += Gw[j];
+  }
+  float suf = warp_excl_rscan_add(tot, lane);  // sum over later lanes
+  float gs[C], gc[3 * C];
+#pragma unroll
+  for (int j = C - 1; j >= 0; --j) {
+    float p = 1.f - r.alpha[j] + eps;
+    float dalpha = G[j] * r.T[j] - suf / p;
+    gs[j] = dalpha * r.dist[j] * (1.f - r.alpha[j]);
+    suf += Gw[j];
+    gc[3 * j] = r.w[j] * gr; gc[3 * j + 1] = r.w[j] * gg; gc[3 * j + 2] = r.w[j] * gb;
+  }
+  float* ps = g_sigma + ray * S + r.base;
+  float* pr = g_rgb + (ray * S + r.base) * 3;
+  if constexpr (EXACT) {
+    store_run<C>(ps, gs);
+    store_run<3 * C>(pr, gc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (r.base + j < S) {
+        ps[j] = gs[j];
+        pr[3 * j] = gc[3 * j]; pr[3 * j + 1] = gc[3 * j + 1]; pr[3 * j + 2] = gc[3 * j + 2];
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hn_sample_pdf — model_utils.py:160-232 (+ the slicing at models.py:752-755).
+// Arithmetic contract (DESIGN.md "resampling"): w' = fl32(w + 1e-5); S = fl32(sum w') and
+// cdf_j = fl32(sum_{k<=j} pdf_k) with the sums carried in fp64 — exact for these magnitudes, hence
+// independent of summation order, and identical to torch.cumsum on CPU; every other op is a single
+// round-to-nearest fp32 operation (no FMA contraction), like the reference's separate torch kernels.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kPdfMaxN = 512;  // Nc + Nf padded to a power of two must fit
+
+__device__ __forceinline__ void bitonic_sort_warp(float* a, int n2, int lane) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n2; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          float x = a[i], y = a[ixj];
+          bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(4 * 32)
+sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_in, const float* __restrict__ wc,
+                  int64_t w_stride, const float* __restrict__ u, const float* __restrict__ o,
+                  const float* __restrict__ d, int64_t B, int Nc, int nb, int Nf, int n2, float* __restrict__ zf,
+                  float* __restrict__ pts, int32_t* __restrict__ bin_idx) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + wid;
+  if (ray >= B) return;
+  float* bins = sm + (size_t)wid * (2 * (nb + 1) + n2);
+  float* cdf = bins + nb + 1;
+  float* srt = cdf + nb + 1;
+  const float* zr = zc + ray * Nc;
+  const float* wr = wc + ray * w_stride - 1;  // wr[1 + i] = weight of bin i
+  const float eps = 1e-5f;
+
+  for (int i = lane; i < Nc; i += 32) srt[i] = __ldg(zr + i);
+  __syncwarp();
+  if (bins_in != nullptr) {
+    for (int i = lane; i < nb + 1; i += 32) bins[i] = __ldg(bins_in + ray * (nb + 1) + i);
+  } else {
+    for (int i = lane; i < nb + 1; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(srt[i + 1], srt[i]));
+  }
+  // sum of w' in fp64 (exact)
+  double part = 0.0;
+  for (int i = lane; i < nb; i += 32) part += (double)__fadd_rn(__ldg(wr + 1 + i), eps);
+  float Ssum = (float)warp_sum_d(part);
+  // inclusive prefix of pdf in fp64: lane owns a contiguous run of bins
+  const int per = (nb + 31) / 32;
+  const int b0 = lane * per;
+  double loc = 0.0;
+  for (int j = 0; j < per; ++j) {
+    int i = b0 + j;
+    if (i < nb) loc += (double)__fdiv_rn(__fadd_rn(__ldg(wr + 1 + i), eps), Ssum);
+  }
+  double inc = loc;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    double t = __shfl_up_sync(kFull, inc, off);
+    if (lane >= off) inc += t;
+  }
+  double run = inc - loc;  // exclusive prefix of this lane
+  if (lane == 0) cdf[0] = 0.f;
+  for (int j = 0; j < per; ++j) {
+    int i = b0 + j;
+    if (i < nb) {
+      run += (double)__fdiv_rn(__fadd_rn(__ldg(wr + 1 + i), eps), Ssum);
+      cdf[i + 1] = (float)run;
+    }
+  }
+  __syncwarp();
+  const int ncdf = nb + 1;
+  for (int i = lane; i < Nf; i += 32) {
+    float uu = __ldg(u + ray * Nf + i);
+    // searchsorted(cdf, u, right=True): number of entries <= u
+    int lo = 0, hi = ncdf;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    int inds = lo;
+    int below = max(inds - 1, 0), above = min(inds, nb);
+    float c0 = cdf[below], c1 = cdf[above];
+    float g0 = bins[below], g1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < eps) denom = 1.f;
+    float t = __fdiv_rn(__fsub_rn(uu, c0), denom);
+    float smp = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
+    srt[Nc + i] = smp;
+    if (bin_idx != nullptr) bin_idx[ray * Nf + i] = inds;
+  }
+  for (int i = Nc + Nf + lane; i < n2; i += 32) srt[i] = __int_as_float(0x7f800000);
+  __syncwarp();
+  bitonic_sort_warp(srt, n2, lane);
+  const int S = Nc + Nf;
+  float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+  if (pts != nullptr) {
+    ox = __ldg(o + ray * 3); oy = __ldg(o + ray * 3 + 1); oz = __ldg(o + ray * 3 + 2);
+    dx = __ldg(d + ray * 3); dy = __ldg(d + ray * 3 + 1); dz = __ldg(d + ray * 3 + 2);
+  }
+  for (int i = lane; i < S; i += 32) {
+    float zz = srt[i];
+    zf[ray * S + i] = zz;
+    if (pts != nullptr) {
+      float* p = pts + (ray * S + i) * 3;
+      p[0] = __fadd_rn(ox, __fmul_rn(zz, dx));
+      p[1] = __fadd_rn(oy, __fmul_rn(zz, dy));
+      p[2] = __fadd_rn(oz, __fmul_rn(zz, dz));
+    }
+  }
+}
+
+template <int C>
+static int launch_comp_fwd(bool exact, dim3 g, cudaStream_t st, const float* sigma, const float* rgb, const float* z,
+                           const float* dirs, int64_t B, int S, int flags, float eps, float ld, float* o_rgb,
+                           float* depth, float* med, float* acc, float* w, int64_t* mi) {
+  if (exact)
+    composite_fwd_kernel<C, true><<<g, kWarpsPerBlock * 32, 0, st>>>(sigma, rgb, z, dirs, B, S, flags, eps, ld, o_rgb,
+                                                                   depth, med, acc, w, mi);
+  else
+    composite_fwd_kernel<C, false><<<g, kWarpsPerBlock * 32, 0, st>>>(sigma, rgb, z, dirs, B, S, flags, eps, ld,
+                                                                    o_rgb, depth, med, acc, w, mi);
+  return 0;
+}
+template <int C>
+static int launch_comp_bwd(bool exact, dim3 g, cudaStream_t st, const float* sigma, const float* rgb, const float* z,
+                           const float* dirs, int64_t B, int S, int flags, float eps, float ld, const float* g1,
+                           const float* g2, const float* g3, const float* g4, float* gs, float* gc) {
+  if (exact)
+    composite_bwd_kernel<C, true><<<g, kWarpsPerBlock * 32, 0, st>>>(sigma, rgb, z, dirs, B, S, flags, eps, ld, g1, g2,
+                                                                   g3, g4, gs, gc);
+  else
+    composite_bwd_kernel<C, false><<<g, kWarpsPerBlock * 32, 0, st>>>(sigma, rgb, z, dirs, B, S, flags, eps, ld, g1,
+                                                                    g2, g3, g4, gs, gc);
+  return 0;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_sample_coarse(const float* origins, const float* dirs, const float* u, const float* lower,
+                                const float* upper, int64_t B, int Nc, float* z, float* points, void* stream) {
+  if (B < 0 || Nc <= 0) return set_error(-1, "hn_sample_coarse: bad B/Nc");
+  if (!origins || !dirs || !lower || !upper || !z) return set_error(-2, "hn_sample_coarse: null pointer");
+  if (B == 0) return 0;
+  int64_t n = B * Nc;
+  int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  sample_coarse_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(origins, dirs, u, lower, upper, n, Nc,
+                                                                              z, points);
+  return set_cuda_error(cudaGetLastError(), "hn_sample_coarse");
+}
+
+extern "C" int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
+                             const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
+                             float* z_fine, float* points, int32_t* bin_idx, void* stream) {
+  if (B < 0 || Nc < 1 || nb < 1 || Nf <= 0) return set_error(-1, "hn_sample_pdf: need Nc >= 1, nb >= 1, Nf >= 1");
+  if (bins == nullptr && nb != Nc - 2) return set_error(-1, "hn_sample_pdf: in-kernel bins need nb == Nc - 2");
+  if (Nc + Nf > kPdfMaxN || nb + 1 > kPdfMaxN) return set_error(-1, "hn_sample_pdf: Nc + Nf > 512 unsupported");
+  if (!z_coarse || !weights || !u || !z_fine) return set_error(-2, "hn_sample_pdf: null pointer");
+  if (points && (!origins || !dirs)) return set_error(-2, "hn_sample_pdf: points need origins and dirs");
+  if (B == 0) return 0;
+  int n2 = 1;
+  while (n2 < Nc + Nf) n2 <<= 1;
+  size_t smem = (size_t)4 * (2 * (nb + 1) + n2) * sizeof(float);
+  int64_t blocks = (B + 3) / 4;
+  sample_pdf_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(z_coarse, bins, weights, w_stride, u, origins,
+                                                                          dirs, B, Nc, nb, Nf, n2, z_fine, points, bin_idx);
+  return set_cuda_error(cudaGetLastError(), "hn_sample_pdf");
+}
+
+#define HN_DISPATCH_C(FN, ...)                                              \
+  switch (C) {                                                              \
+    case 1: FN<1>(__VA_ARGS__); break;                                      \
+    case 2: FN<2>(__VA_ARGS__); break;                                      \
+    case 3: FN<3>(__VA_ARGS__); break;                                      \
+    case 4: FN<4>(__VA_ARGS__); break;                                      \
+    case 5: FN<5>(__VA_ARGS__); break;                                      \
+    case 6: FN<6>(__VA_ARGS__); break;                                      \
+    case 7: FN<7>(__VA_ARGS__); break;                                      \
+    case 8: FN<8>(__VA_ARGS__); break;                                      \
+    case 12: FN<12>(__VA_ARGS__); break;                                    \
+    default: FN<16>(__VA_ARGS__); break;                                    \
+  }
+
+static int comp_c(int S) {
+  int C = (S + 31) / 32;
+  if (C > 8 && C <= 12) C = 12;
+  else if (C > 12) C = 16;
+  return C;
+}
+
+extern "C" int hn_composite_fwd(const float* sigma, const float* rgb, const float* z, const float* dirs, int64_t B,
+                                int S, int flags, float eps, float last_delta, float* out_rgb, float* depth,
+                                float* med_depth, float* acc, float* weights, int64_t* med_idx, void* stream) {
+  if (B < 0 || S <= 0 || S > 512) return set_error(-1, "hn_composite_fwd: need 1 <= S <= 512");
+  if (!sigma || !rgb || !z || !dirs || !out_rgb || !depth || !acc) return set_error(-2, "hn_composite_fwd: null pointer");
+  if (B == 0) return 0;
+  int C = comp_c(S);
+  bool exact = (S == 32 * C);
+  dim3 g((unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock));
+  HN_DISPATCH_C(launch_comp_fwd, exact, g, (cudaStream_t)stream, sigma, rgb, z, dirs, B, S, flags, eps, last_delta,
+                out_rgb, depth, med_depth, acc, weights, med_idx);
+  return set_cuda_error(cudaGetLastError(), "hn_composite_fwd");
+}
+
+extern "C" int hn_composite_bwd(const float* sigma, const float* rgb, const float* z, const float* dirs, int64_t B,
+                                int S, int flags, float eps, float last_delta, const float* g_out_rgb,
+                                const float* g_depth, const float* g_acc, const float* g_weights, float* g_sigma,
+                                float* g_rgb, void* stream) {
+  if (B < 0 || S <= 0 || S > 512) return set_error(-1, "hn_composite_bwd: need 1 <= S <= 512");
+  if (!sigma || !rgb || !z || !dirs || !g_sigma || !g_rgb) return set_error(-2, "hn_composite_bwd: null pointer");
+  if (B == 0) return 0;
+  int C = comp_c(S);
+  bool exact = (S == 32 * C);
+  dim3 g((unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock));
+  HN_DISPATCH_C(launch_comp_bwd, exact, g, (cudaStream_t)stream, sigma, rgb, z, dirs, B, S, flags, eps, last_delta,
+                g_out_rgb, g_depth, g_acc, g_weights, g_sigma, g_rgb);
+  return set_cuda_error(cudaGetLastError(), "hn_composite_bwd");
+}

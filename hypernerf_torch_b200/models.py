@@ -1,0 +1,343 @@
+"""Drop-in `NerfModel` for songrise/HyperNeRF-torch (hypernerf/models.py:67-780) whose per-ray hot path runs in
+the sm_100a kernels of libhypernerf_b200.so.
+
+Boundary B1 of SURVEY.md §8(b): same constructor, same `forward` signature, same nested output dictionary and
+the same `state_dict()` names / shapes as the reference, so `train.py:48-67,96-114` and `eval.py:77-135` can swap
+the import.  What runs where:
+
+    sample_along_rays        -> hn_sample_coarse           (model_utils.py:6-41)
+    render_samples           -> hn_mlp_fwd (+ hn_mlp_bwd)  (models.py:587-650, 447-493; modules.py; warping.py)
+                                hn_composite_fwd/bwd       (model_utils.py:43-107, 319-362)
+    sample_pdf               -> hn_sample_pdf              (model_utils.py:160-232)
+
+Random draws use the same torch generator calls, in the same order and shapes as the reference
+(SURVEY.md App. A.5), and are handed to the kernels as tensors.
+"""
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, model_utils, modules
+from ._lib import check, lib, ptr, stream
+
+
+def filter_sigma(points, sigma, render_opts):
+    """models.py:35-63 (dust threshold / bounding box); a no-op unless render_opts is given."""
+    if render_opts is None:
+        return sigma
+    if 'dust_threshold' in render_opts:
+        sigma = (sigma >= render_opts.get('dust_threshold', 0.0)) * sigma
+    if 'bounding_box' in render_opts:
+        xmin, xmax, ymin, ymax, zmin, zmax = render_opts['bounding_box']
+        mask = ((points[..., 0] >= xmin) & (points[..., 0] <= xmax) & (points[..., 1] >= ymin) &
+                (points[..., 1] <= ymax) & (points[..., 2] >= zmin) & (points[..., 2] <= zmax))
+        sigma = mask * sigma
+    return sigma
+
+
+class _FusedMlp(torch.autograd.Function):
+    """hn_mlp_fwd / hn_mlp_bwd as one autograd node per level.  Inputs after the fixed arguments are the 93
+    parameter tensors in canonical (state_dict) order; gradients come back as views of one flat fp32 buffer."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, level, points, viewdirs, ids, noise, noise_std, *params):
+        B, S = points.shape[0], points.shape[1]
+        dev = points.device
+        desc = model._desc
+        packed = model._packed_weights(level)
+        pts = points.detach().to(torch.float32).contiguous()
+        vd = viewdirs.detach().to(torch.float32).contiguous()
+        ids = ids.reshape(-1).to(torch.int64).contiguous()
+        if ids.numel() != B:
+            raise ValueError(f"metadata ids must have one entry per ray, got {tuple(ids.shape)} for {B} rays")
+        sigma = torch.empty(B, S, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
+        warped = torch.empty(B, S, 3 + desc.hyper_dim, device=dev, dtype=torch.float32)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        saved = None
+        if need_grad:
+            sizes = model._sizes(B * S)
+            saved = torch.empty(sizes.saved_bytes, device=dev, dtype=torch.uint8)
+        check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
+                               B, S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()), "hn_mlp_fwd")
+        ctx.model, ctx.level, ctx.shape = model, level, (B, S)
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        ctx.save_for_backward(ids, sigma, rgb, warped, saved, packed)
+        ctx.set_materialize_grads(False)
+        return sigma, rgb, warped
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g_sigma, g_rgb, g_warped):
+        ids, sigma, rgb, warped, saved, packed = ctx.saved_tensors
+        model, level = ctx.model, ctx.level
+        B, S = ctx.shape
+        if saved is None:
+            raise RuntimeError("hn_mlp_bwd needs the activation stash; forward ran without grad enabled")
+        dev = sigma.device
+        g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.to(torch.float32).contiguous()
+        g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
+        g_warped = None if g_warped is None else g_warped.to(torch.float32).contiguous()
+        offs, total = model._grad_offsets()
+        flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        sizes = model._sizes(B * S)
+        work = torch.empty(sizes.workspace_bytes, device=dev, dtype=torch.uint8)
+        check(lib().hn_mlp_bwd(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped), ptr(saved),
+                               ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, level, offs, ptr(flat_grad), ptr(work),
+                               stream()), "hn_mlp_bwd")
+        grads = []
+        other = range(*model._level_param_range(1 - level))
+        for i, (shape, n) in enumerate(ctx.param_meta):
+            if i in other or not ctx.needs_input_grad[7 + i]:
+                grads.append(None)
+            else:
+                grads.append(flat_grad[offs[i]:offs[i] + n].view(shape))
+        return (None,) * 7 + tuple(grads)
+
+
+class NerfModel(nn.Module):
+    """Nerf NN Model with both coarse and fine MLPs (reference: hypernerf/models.py:67-780)."""
+
+    def __init__(self, embeddings_dict,
+                 near: float = 0.0, far: float = 1.0,
+                 n_samples_coarse: int = 64,
+                 n_samples_fine: int = 128,
+                 noise_std: float = None,
+                 use_warp: bool = True,
+                 use_nerf_embed: bool = True,
+                 use_alpha_cond: bool = True,
+                 use_rgb_cond: bool = False,
+                 hyper_slice_method: str = None,
+                 hyper_slice_out_dim: int = 4,
+                 GLO_dim: int = 8,
+                 share_GLO: bool = True,
+                 xyz_fourier_dim: int = 10,
+                 hyper_fourier_dim: int = 6,
+                 view_fourier_dim: int = 4):
+        super().__init__()
+        self.embeddings_dict = embeddings_dict
+        self.near, self.far = near, far
+        self.use_viewdirs = True
+        self.noise_std = noise_std
+        self.nerf_trunk_depth, self.nerf_trunk_width = 8, 256
+        self.nerf_rgb_branch_depth, self.nerf_rgb_branch_width = 4, 128
+        self.nerf_skips = [4]
+        self.num_coarse_samples, self.num_fine_samples = n_samples_coarse, n_samples_fine
+        self.use_stratified_sampling = True
+        self.use_white_background = False
+        self.use_linear_disparity = False
+        self.use_sample_at_infinity = True
+        self.alpha_channels, self.rgb_channels = 1, 3
+        if not share_GLO:
+            # the reference leaves nerf_use_warp_embed unbound in this case (models.py:167-174)
+            raise UnboundLocalError("share_GLO=False is not usable in the reference (models.py:167-174)")
+        self.nerf_use_warp_embed = self.hyper_use_warp_embed = use_warp
+        self.use_nerf_embed = use_nerf_embed
+        self.nerf_embed_key = 'warp'
+        self.use_alpha_condition, self.use_rgb_condition = use_alpha_cond, use_rgb_cond
+        self.hyper_slice_method = 'none' if hyper_slice_method is None else hyper_slice_method
+        self.hyper_embed_key = 'time'
+        self.hyper_sheet_out_dim = hyper_slice_out_dim
+        self.use_warp = use_warp
+        self.warp_embed_key = 'time'
+        self.use_original_embed = True
+        self.xyz_freq, self.dir_freq, self.hyper_freq = xyz_fourier_dim, view_fourier_dim, hyper_fourier_dim
+        self.GLO_dim = GLO_dim
+
+        if self.use_nerf_embed and not (self.use_rgb_condition or self.use_alpha_condition):
+            raise ValueError('Template metadata is enabled but none of the condition'
+                             'branches are.')
+        # ---- what the sm_100a kernels of this build implement (cfg 1/2/3 family) -------------
+        if not (use_warp and self.hyper_slice_method == 'bendy_sheet'):
+            raise NotImplementedError(
+                "libhypernerf_b200 implements the TranslationField warp + bendy_sheet path "
+                f"(got use_warp={use_warp}, hyper_slice_method={self.hyper_slice_method!r}); there is no fallback")
+        if use_nerf_embed or use_rgb_cond:
+            raise NotImplementedError("template GLO conditioning (use_nerf_embed / use_rgb_cond) is not built yet")
+
+        n_embed = max(self.embeddings_dict[self.warp_embed_key]) + 1
+        self.warp_embed = modules.GLOEmbed(num_embeddings=n_embed, embedding_dim=GLO_dim)
+        self.hyper_sheet_mlp = modules.HyperSheetMLP(out_ch=self.hyper_sheet_out_dim, in_ch_embed=GLO_dim)
+        self.warp_field = modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
+        self.alpha_default = 0.0
+        self.nerf_in_ch_pos = modules.posenc_channels(3, self.xyz_freq)
+        self.nerf_cond_ch_rgb = modules.posenc_channels(3, self.dir_freq)
+        self.hyper_feat_ch = modules.posenc_channels(self.hyper_sheet_out_dim, self.hyper_freq)
+        self.nerf_in_ch_pos += self.hyper_feat_ch
+
+        def make_nerf_mlp():
+            return modules.NerfMLP(in_ch=self.nerf_in_ch_pos, trunk_depth=self.nerf_trunk_depth,
+                                   trunk_width=self.nerf_trunk_width, rgb_branch_depth=self.nerf_rgb_branch_depth,
+                                   rgb_branch_width=self.nerf_rgb_branch_width, skips=self.nerf_skips,
+                                   alpha_channels=self.alpha_channels, rgb_channels=self.rgb_channels,
+                                   alpha_condition_dim=0, rgb_condition_dim=self.nerf_cond_ch_rgb)
+
+        self.nerf_mlps_coarse = make_nerf_mlp()
+        if self.num_fine_samples > 0:
+            self.nerf_mlps_fine = make_nerf_mlp()
+        else:
+            raise NotImplementedError("n_samples_fine == 0: the reference itself fails here (models.py:292-309)")
+
+        self._desc = _lib.ModelDesc(GLO_dim, hyper_slice_out_dim, xyz_fourier_dim, hyper_fourier_dim, view_fourier_dim,
+                                    modules.TranslationField.n_freq, modules.HyperSheetMLP.n_freq, n_embed,
+                                    _lib.HN_FLAG_WARP_TRANSLATION | _lib.HN_FLAG_SLICE_BENDY)
+        sizes = _lib.Sizes()
+        check(lib().hn_query(C.byref(self._desc), 0, C.byref(sizes)), "hn_query")
+        self._packed_bytes = sizes.packed_bytes
+        n_params = sum(p.numel() for p in self.parameters())
+        if n_params != sizes.flat_param_floats or len(self._canonical_params()) != _lib.HN_NUM_PARAM_TENSORS:
+            raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} parameters, "
+                                          f"library expects {sizes.flat_param_floats}")
+        self._pack_cache = {}
+        self._grad_off_cache = None
+        self._size_cache = {}
+
+    # ------------------------------------------------------------------------------------------------------
+    # native plumbing
+    # ------------------------------------------------------------------------------------------------------
+    def _canonical_params(self):
+        """The 93 parameter tensors in the order include/hypernerf_b200.h documents (= state_dict order)."""
+        out = [self.warp_embed.embed.weight]
+        for mlp in (self.hyper_sheet_mlp.mlp, self.warp_field.mlp):
+            for lin in list(mlp.linears) + [mlp.logit_layer]:
+                out += [lin.weight, lin.bias]
+        for nm in (self.nerf_mlps_coarse, self.nerf_mlps_fine):
+            for lin in list(nm.trunk_mlp.linears) + [nm.trunk_mlp.logit_layer, nm.bottleneck_mlp] + \
+                    list(nm.rgb_mlp.linears) + [nm.rgb_mlp.logit_layer, nm.alpha_mlp]:
+                out += [lin.weight, lin.bias]
+        return out
+
+    @staticmethod
+    def _level_param_range(level):
+        return 29 + 32 * level, 29 + 32 * (level + 1)
+
+    def _grad_offsets(self):
+        if self._grad_off_cache is None:
+            offs, total = [], 0
+            for p in self._canonical_params():
+                offs.append(total)
+                total += (p.numel() + 3) // 4 * 4  # 16-byte aligned slices
+            self._grad_off_cache = ((C.c_int64 * len(offs))(*offs), total)
+        return self._grad_off_cache
+
+    def _sizes(self, n_samples):
+        s = self._size_cache.get(n_samples)
+        if s is None:
+            s = _lib.Sizes()
+            check(lib().hn_query(C.byref(self._desc), n_samples, C.byref(s)), "hn_query")
+            self._size_cache[n_samples] = s
+        return s
+
+    def _packed_weights(self, level):
+        """bf16 kernel-layout weights of one level; re-packed (hn_pack_weights) whenever a parameter changed."""
+        params = self._canonical_params()
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise _lib.NativeLibraryError("NerfModel parameters must live on a CUDA device (no CPU path)")
+        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        hit = self._pack_cache.get(level)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.NativeLibraryError("parameters must be contiguous fp32 tensors")
+        base = min(p.data_ptr() for p in params)
+        offs = (C.c_int64 * len(params))(*[(p.data_ptr() - base) // 4 for p in params])
+        packed = torch.empty(self._packed_bytes, device=dev, dtype=torch.uint8)
+        check(lib().hn_pack_weights(C.byref(self._desc), C.c_void_p(base), offs, level, ptr(packed), stream()),
+              "hn_pack_weights")
+        self._pack_cache[level] = (key, packed)
+        return packed
+
+    # ------------------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def num_warp_embeds(self):
+        return max(self.embeddings_dict[self.warp_embed_key]) + 1
+
+    @property
+    def has_hyper(self):
+        return self.hyper_slice_method != 'none'
+
+    @property
+    def has_hyper_embed(self):
+        return self.has_hyper
+
+    @property
+    def has_embeds(self):
+        return self.has_hyper_embed or self.use_warp or self.use_nerf_embed
+
+    def render_samples(self, level, points, z_vals, directions, viewdirs, metadata, extra_params, use_warp=True,
+                       metadata_encoded=False, return_warp_jacobian=False, use_sample_at_infinity=False,
+                       render_opts=None):
+        """models.py:587-671."""
+        if metadata_encoded:
+            raise NotImplementedError("metadata_encoded=True is not built (callers pass ids; train.py:102, eval.py:86)")
+        if return_warp_jacobian:
+            raise NotImplementedError  # warping.py:121-122
+        if not use_warp:
+            raise NotImplementedError("use_warp=False at call time is not built in this round")
+        if metadata.get('hyper_point') is not None:
+            raise NotImplementedError('hyper_point_override is not implemented.')  # models.py:528-529
+        out = {'points': points}
+        ids = metadata[self.warp_embed_key]
+        B, S = points.shape[0], points.shape[1]
+        noise, noise_std = None, 0.0
+        if (self.noise_std is not None) and self.noise_std > 0.0 and self.use_stratified_sampling:
+            # noise_regularize (model_utils.py:300-317): same draw, same shape, applied inside the kernel
+            noise = torch.randn((B, S, 1), device=points.device, dtype=torch.float32)
+            noise_std = float(self.noise_std)
+        sigma, rgb, warped_points = _FusedMlp.apply(self, 1 if level == 'fine' else 0, points, viewdirs, ids, noise,
+                                                    noise_std, *self._canonical_params())
+        sigma = filter_sigma(points, sigma, render_opts)
+        out['warped_points'] = warped_points
+        comp = model_utils.volumetric_rendering(rgb, sigma, z_vals, directions,
+                                                use_white_background=self.use_white_background,
+                                                sample_at_infinity=use_sample_at_infinity, _return_index=True)
+        depth_indices = comp.pop('_med_idx')
+        out.update(comp)
+        # models.py:664-669: gather with a (B,1,1) index -> channel 0 of the warped point at the median sample
+        out['med_points'] = torch.gather(warped_points, dim=-2, index=depth_indices[..., None, None])
+        return out
+
+    def forward(self, rays_dict: Dict[str, Any], extra_params: Dict[str, Any], metadata_encoded=False, use_warp=True,
+                return_points=False, return_weights=False, return_warp_jacobian=False, near=None, far=None,
+                use_sample_at_infinity=None, render_opts=None, deterministic=False):
+        """models.py:673-780.  Returns {'coarse': {...}, 'fine': {...}} with the reference's keys."""
+        use_warp = self.use_warp and use_warp
+        origins = rays_dict['origins']
+        directions = rays_dict['directions']
+        metadata = rays_dict['metadata']
+        if 'viewdirs' in rays_dict and rays_dict['viewdirs'] is not None:
+            viewdirs = rays_dict['viewdirs']
+        else:
+            viewdirs = directions
+        near = self.near if near is None else near
+        far = self.far if far is None else far
+        if use_sample_at_infinity is None:
+            use_sample_at_infinity = self.use_sample_at_infinity
+
+        z_vals, points = model_utils.sample_along_rays(origins, directions, self.num_coarse_samples, near, far,
+                                                       self.use_stratified_sampling, self.use_linear_disparity)
+        coarse_ret = self.render_samples('coarse', points, z_vals, directions, viewdirs, metadata, extra_params,
+                                         use_warp=use_warp, metadata_encoded=metadata_encoded,
+                                         return_warp_jacobian=return_warp_jacobian,
+                                         use_sample_at_infinity=self.use_sample_at_infinity)
+        out = {'coarse': coarse_ret}
+        if self.num_fine_samples > 0:
+            if self.use_stratified_sampling:
+                z_vals, points = model_utils.sample_pdf_fused(z_vals, coarse_ret['weights'], origins, directions,
+                                                              self.num_fine_samples)
+            else:
+                z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+                z_vals, points = model_utils.sample_pdf(z_mid, coarse_ret['weights'][..., 1:-1], origins, directions,
+                                                        z_vals, self.num_fine_samples, False)
+            out['fine'] = self.render_samples('fine', points, z_vals, directions, viewdirs, metadata, extra_params,
+                                              use_warp=use_warp, metadata_encoded=metadata_encoded,
+                                              return_warp_jacobian=return_warp_jacobian,
+                                              use_sample_at_infinity=use_sample_at_infinity, render_opts=render_opts)
+        return out

@@ -1,0 +1,131 @@
+/* hypernerf_b200 — C-ABI of the B200-native HyperNeRF per-ray hot path.
+ *
+ * This is the drop-in boundary B2 of SURVEY.md §8(b): the reference (songrise/HyperNeRF-torch) has no FFI
+ * of its own — its hot path is Python calling stock torch ops — so each entry point below replaces one
+ * Python function of the reference, cited as file:line into the reference tree.  The Python shim in
+ * hypernerf_torch_b200/ (same class / function names and signatures as the reference) is the only caller.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - every function returns int: 0 = ok, <0 = argument / shape error, >0 = cudaError_t of the launch.
+ *     hn_last_error() returns a thread-local message for the last non-zero return.
+ *   - nothing allocates, synchronises or throws; all buffers are caller-owned; kernels are enqueued on the
+ *     cudaStream_t passed as `void* stream`.
+ *   - all float tensors are fp32 row-major contiguous; ids are int64.
+ */
+#ifndef HYPERNERF_B200_H
+#define HYPERNERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_ABI_VERSION 1
+
+/* Topology of one NerfModel (reference: hypernerf/models.py:111-309).  Round 1 supports the cfg-1 family:
+ * TranslationField warp (warping.py:28-125) + bendy_sheet HyperSheetMLP (modules.py:302-337) + NerfMLP
+ * (modules.py:172-298) with trunk 8x256 skip@4, rgb branch 4x128, warp 6x128 skip@4, sheet 6x64 skip@4. */
+typedef struct hn_model_desc {
+  int32_t glo_dim;        /* G: GLO embedding width (opt.py:99)                                  */
+  int32_t hyper_dim;      /* H: hyper_slice_out_dim (opt.py:92)                                  */
+  int32_t xyz_freqs;      /* template xyz posenc_orig freqs (opt.py:110)                         */
+  int32_t hyper_freqs;    /* template hyper posenc_orig freqs (opt.py:112)                       */
+  int32_t view_freqs;     /* viewdir posenc_orig freqs (opt.py:114)                              */
+  int32_t warp_freqs;     /* TranslationField.n_freq, hard-coded 10 (warping.py:74)              */
+  int32_t sheet_freqs;    /* HyperSheetMLP.n_freq, hard-coded 7 (modules.py:313)                 */
+  int32_t num_embeddings; /* rows of warp_embed.embed.weight (train.py:42-46 -> 100)             */
+  int32_t flags;          /* HN_FLAG_*                                                           */
+  int32_t reserved[7];
+} hn_model_desc;
+
+#define HN_FLAG_WARP_TRANSLATION 1  /* use_warp with TranslationField                            */
+#define HN_FLAG_SLICE_BENDY 2       /* hyper_slice_method == 'bendy_sheet'                       */
+
+/* Canonical parameter order = state_dict order of the reference model:
+ *   0                      warp_embed.embed.weight (E,G)
+ *   1..14                  hyper_sheet_mlp.mlp.linears.{0..5}.{weight,bias}, logit_layer.{weight,bias}
+ *   15..28                 warp_field.mlp.linears.{0..5}.{weight,bias}, logit_layer.{weight,bias}
+ *   29 + 32*level + ...    nerf_mlps_{coarse,fine}: trunk linears 0..7 + logit (18), bottleneck (2),
+ *                          rgb linears 0..3 + logit (10), alpha (2)
+ * Offsets tables give the element offset of tensor i relative to a base pointer; the tensors need not be
+ * contiguous with each other (the Python shim passes base = lowest parameter address). */
+#define HN_NUM_PARAM_TENSORS 93
+
+typedef struct hn_sizes {
+  int64_t packed_bytes;       /* one level's packed bf16 weights (forward + transposed) + fp32 biases */
+  int64_t saved_bytes;        /* activations saved by hn_mlp_fwd for n_samples (training)           */
+  int64_t workspace_bytes;    /* hn_mlp_bwd scratch (pre-activation gradients) for n_samples        */
+  int64_t flat_param_floats;  /* total parameter count                                              */
+  int64_t reserved[4];
+} hn_sizes;
+
+int hn_abi_version(void);
+const char* hn_last_error(void);
+
+/* Buffer sizes for a model and a sample count (n_samples = rays * samples-per-ray of one level). */
+int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* out /* host */);
+
+/* fp32 master parameters -> kernel-layout bf16 blobs of one level (0 = coarse, 1 = fine).
+ * Replaces nothing in the reference (nn.Linear holds (out,in) fp32); it is the per-step re-layout.
+ * param_offsets: HOST array of HN_NUM_PARAM_TENSORS element offsets. */
+int hn_pack_weights(const hn_model_desc* desc, const float* flat_params, const int64_t* param_offsets /* host */,
+                    int level, void* packed, void* stream);
+
+/* model_utils.sample_along_rays (model_utils.py:6-41).  lower/upper: (Nc,) stratum bounds computed by the
+ * caller with the reference's own torch ops (bit-exact linspace); u: (B,Nc) uniform draws or NULL
+ * (non-stratified: z = lower).  Writes z (B,Nc) and points (B,Nc,3) = o + z*d. */
+int hn_sample_coarse(const float* origins, const float* dirs, const float* u, const float* lower,
+                     const float* upper, int64_t B, int Nc, float* z, float* points, void* stream);
+
+/* model_utils.piecewise_constant_pdf + sample_pdf (model_utils.py:160-232).
+ *   bins    (B, nb+1) contiguous, or NULL: computed in-kernel as .5*(z[1:]+z[:-1]) of z_coarse (the
+ *           z_vals_mid of models.py:752; requires nb == Nc-2)
+ *   weights row b starts at weights + b*w_stride and has nb entries (models.py:753 passes the strided view
+ *           coarse_weights[..., 1:-1]: pointer w+1, stride Nc)
+ *   u       (B,Nf) uniform draws (the caller materialises linspace for the non-stratified case)
+ * Writes sorted z_fine (B,Nc+Nf) = sort(cat[z_coarse, samples]), points (B,Nc+Nf,3) (nullable), optional
+ * bin_idx (B,Nf) int32 = searchsorted(cdf,u,right=True). */
+int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride, const float* u,
+                  const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf, float* z_fine,
+                  float* points, int32_t* bin_idx, void* stream);
+
+/* model_utils.volumetric_rendering + compute_depth_index (model_utils.py:43-107, 319-362).
+ * flags: HN_COMP_*.  eps = 1e-5 and last_delta = 1e7 reproduce the HyperNeRF path; the static
+ * models/rendering.py:137-172 path uses 1e-10 / 1e10 and HN_COMP_ACC_ALL. */
+#define HN_COMP_WHITE_BKGD 1
+#define HN_COMP_ACC_ALL 2 /* acc sums every weight (no sample at infinity) */
+int hn_composite_fwd(const float* sigma, const float* rgb, const float* z, const float* dirs, int64_t B, int S,
+                     int flags, float eps, float last_delta, float* out_rgb, float* depth, float* med_depth,
+                     float* acc, float* weights, int64_t* med_idx, void* stream);
+/* Reverse of the above: gradients w.r.t. sigma (B,S) and rgb samples (B,S,3).  g_depth / g_acc / g_weights
+ * may be NULL. */
+int hn_composite_bwd(const float* sigma, const float* rgb, const float* z, const float* dirs, int64_t B, int S,
+                     int flags, float eps, float last_delta, const float* g_out_rgb, const float* g_depth,
+                     const float* g_acc, const float* g_weights, float* g_sigma, float* g_rgb, void* stream);
+
+/* render_samples up to and including query_template (models.py:587-650 -> :447-493): GLO lookup, posenc_orig,
+ * TranslationField, HyperSheetMLP, NerfMLP, noise_regularize, Softplus — one fused tcgen05 kernel.
+ * points (B,S,3); viewdirs (B,3) (the reference passes the raw ray directions, models.py:717-720);
+ * ids: (B,) int64 row of metadata['time']; noise: (B,S) standard-normal draws or NULL; noise_std scales it.
+ * Outputs sigma (B,S) post-softplus, rgb (B,S,3) post-sigmoid, warped (B,S,3+H);
+ * saved: activation stash for hn_mlp_bwd (NULL = inference). */
+int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
+               const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb,
+               float* warped, void* saved, void* stream);
+
+/* autograd of hn_mlp_fwd: accumulates parameter gradients of `level` (and the shared warp / sheet / GLO
+ * gradients) into flat_grad (fp32); grad_offsets: HOST array of HN_NUM_PARAM_TENSORS element offsets into
+ * flat_grad.  g_warped may be NULL.  workspace: hn_sizes.workspace_bytes of scratch. */
+int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma, const float* rgb,
+               const float* warped, const void* saved, const float* g_sigma, const float* g_rgb, const float* g_warped,
+               int64_t B, int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace,
+               void* stream);
+
+/* test hook: one UMMA tile D[128,N] = A * B^T through the shared-memory layouts the MLP kernels use.
+ * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
+int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERNERF_B200_H */

@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE — not product code.  A plain fp32 torch restatement (CPU or GPU tensors) of the reference's
+per-ray HyperNeRF hot path, function by function, with every random draw passed in explicitly.  Only tests/,
+oracle/make_golden.py, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs may import it; the
+product path (hypernerf_torch_b200/) never does and fails loudly without its CUDA library.
+
+Pinning: tests/test_oracle.py checks this restatement against the UNMODIFIED reference imported from
+/root/reference (oracle/ref_loader.py) on identical weights / rays / draws, and against the committed golden vectors
+in tests/golden/ that oracle/make_golden.py generated from that reference.  The reference ships no tests or golden
+vectors of its own, so those two checks are the pin.
+
+All citations are file:line into songrise/HyperNeRF-torch.
+"""
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------------------------
+def posenc_orig(x, n_freqs):
+    """hypernerf/model_utils.py:234-246: [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(F-1) x), cos(2^(F-1) x)]."""
+    out = [x]
+    for k in range(n_freqs):
+        f = float(2 ** k)
+        out += [torch.sin(f * x), torch.cos(f * x)]
+    return torch.cat(out, -1)
+
+
+def mlp(sd, prefix, x, depth, skips=(4,), out_act=None):
+    """hypernerf/modules.py:114-127: x = relu(linear_i(x)); concat [x, inputs] after layer i in skips; logit layer."""
+    inputs = x
+    for i in range(depth):
+        x = F.relu(F.linear(x, sd[f"{prefix}.linears.{i}.weight"], sd[f"{prefix}.linears.{i}.bias"]))
+        if i in skips:
+            x = torch.cat([x, inputs], -1)
+    x = F.linear(x, sd[f"{prefix}.logit_layer.weight"], sd[f"{prefix}.logit_layer.bias"])
+    return out_act(x) if out_act is not None else x
+
+
+def nerf_mlp(sd, prefix, feat, rgb_cond):
+    """hypernerf/modules.py:266-298 without GLO conditioning: trunk (ReLU on the logit layer, :230), bottleneck
+    (no activation), alpha Linear, rgb MLP depth 4 (skip never fires) + Sigmoid (models.py:164)."""
+    x = mlp(sd, f"{prefix}.trunk_mlp", feat, 8, out_act=F.relu)
+    bott = F.linear(x, sd[f"{prefix}.bottleneck_mlp.weight"], sd[f"{prefix}.bottleneck_mlp.bias"])
+    alpha = F.linear(bott, sd[f"{prefix}.alpha_mlp.weight"], sd[f"{prefix}.alpha_mlp.bias"])
+    cond = rgb_cond[:, None, :].expand(-1, bott.shape[1], -1)  # broadcast_condition, modules.py:254-264
+    rgb = mlp(sd, f"{prefix}.rgb_mlp", torch.cat([bott, cond], -1), 4, out_act=torch.sigmoid)
+    return rgb, alpha
+
+
+def sample_along_rays(origins, directions, n, near, far, u):
+    """hypernerf/model_utils.py:6-41 (stratified when u is given)."""
+    t = torch.linspace(0., 1., n, device=origins.device)
+    z = near * (1. - t) + far * t
+    if u is not None:
+        mids = .5 * (z[..., 1:] + z[..., :-1])
+        upper = torch.cat([mids, z[..., -1:]], -1)
+        lower = torch.cat([z[..., :1], mids], -1)
+        z = lower + (upper - lower) * u
+    else:
+        z = z[None].expand(origins.shape[0], n)
+    return z, origins[:, None, :] + z[..., None] * directions[:, None, :]
+
+
+def volumetric_rendering(rgb, sigma, z, dirs, white_bkgd=False, sample_at_infinity=True, eps=1e-5):
+    """hypernerf/model_utils.py:43-107 + compute_opaqueness_mask / depth index / depth map (:319-362)."""
+    last = torch.full_like(z[..., :1], 1e7 if sample_at_infinity else 1e-7)
+    dists = torch.cat([z[..., 1:] - z[..., :-1], last], -1) * torch.norm(dirs[:, None, :], dim=-1)
+    alpha = 1.0 - torch.exp(-sigma * dists)
+    T = torch.cat([torch.ones_like(alpha[..., :1]), torch.cumprod(1.0 - alpha[..., :-1] + eps, -1)], -1)
+    w = alpha * T
+    out_rgb = (w[..., None] * rgb).sum(-2)
+    depth = (w * z).sum(-1)
+    acc = w.sum(-1)
+    if white_bkgd:
+        out_rgb = out_rgb + (1. - acc[..., None])
+    if sample_at_infinity:
+        acc = w[..., :-1].sum(-1)
+    opaque = torch.cumsum(w, -1) >= 0.5
+    mask = torch.logical_xor(opaque, torch.cat([torch.zeros_like(opaque[..., :1]), opaque[..., :-1]], -1)).to(w.dtype)
+    return {'rgb': out_rgb, 'depth': depth, 'med_depth': (mask * z).sum(-1), 'acc': acc, 'weights': w,
+            'med_idx': torch.argmax(mask, -1)}
+
+
+def piecewise_constant_pdf(bins, weights, u):
+    """hypernerf/model_utils.py:160-204 with the arithmetic contract of DESIGN.md made explicit:
+    S = fl32(sum w') and cdf_j = fl32(sum_{k<=j} pdf_k) with the sums carried in fp64 (what torch.cumsum does on
+    CPU); every other op is one fp32 rounding.  Returns (samples, inds)."""
+    eps = 1e-5
+    nb = weights.shape[-1]
+    w = weights + eps
+    S = w.double().sum(-1, keepdim=True).float()
+    pdf = w / S
+    cdf = torch.cumsum(pdf.double(), -1).float()
+    cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    below = torch.clamp_min(inds - 1, 0)
+    above = torch.clamp_max(inds, nb)
+    c0, c1 = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    b0, b1 = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = c1 - c0
+    denom = torch.where(denom < eps, torch.ones_like(denom), denom)
+    samples = b0 + (u - c0) / denom * (b1 - b0)
+    return samples.detach(), inds
+
+
+def sample_pdf(bins, weights, origins, directions, z, u):
+    """hypernerf/model_utils.py:206-232."""
+    samples, inds = piecewise_constant_pdf(bins, weights, u)
+    z_all, _ = torch.sort(torch.cat([z, samples], -1), -1)
+    return z_all, origins[:, None, :] + z_all[..., None] * directions[:, None, :], inds
+
+
+# ------------------------------------------------------------------------------------------------------------
+# model
+# ------------------------------------------------------------------------------------------------------------
+def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None):
+    """map_points + query_template (hypernerf/models.py:545-581, 447-493) for TranslationField + bendy_sheet.
+    Returns (rgb (B,S,3), sigma (B,S), warped_points (B,S,3+H), raw alpha)."""
+    B, S, _ = points.shape
+    embed = sd["warp_embed.embed.weight"][ids.reshape(-1)]            # GLOEmbed, modules.py:155-167
+    embed = embed[:, None, :].expand(B, S, embed.shape[-1])           # models.py:627-632
+    # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
+    warp_in = torch.cat([posenc_orig(points, 10), embed], -1)
+    warped = points + mlp(sd, "warp_field.mlp", warp_in, 6)
+    # HyperSheetMLP on the UNWARPED points, modules.py:331-337 (n_freq 7), models.py:571-572
+    sheet_in = torch.cat([posenc_orig(points, 7), embed], -1)
+    hyper = mlp(sd, "hyper_sheet_mlp.mlp", sheet_in, 6)
+    warped_points = torch.cat([warped, hyper], -1)
+    feat = torch.cat([posenc_orig(warped_points[..., :3], cfg['xyz_freq']),
+                      posenc_orig(warped_points[..., 3:], cfg['hyper_freq'])], -1)   # models.py:458-478
+    rgb_cond = posenc_orig(viewdirs, cfg['view_freq'])                                # models.py:410-419
+    prefix = "nerf_mlps_fine" if level == 'fine' else "nerf_mlps_coarse"
+    rgb, alpha = nerf_mlp(sd, prefix, feat, rgb_cond)
+    if noise is not None:
+        alpha = alpha + noise * cfg['noise_std']                                      # model_utils.py:312-316
+    sigma = F.softplus(alpha.squeeze(-1))                                             # models.py:491
+    return rgb, sigma, warped_points, alpha.squeeze(-1)
+
+
+def render_samples(sd, level, points, z, directions, viewdirs, ids, cfg, noise=None):
+    """hypernerf/models.py:587-671."""
+    rgb, sigma, warped_points, alpha = query_fields(sd, level, points, viewdirs, ids, cfg, noise)
+    out = {'points': points, 'warped_points': warped_points, 'sigma': sigma, 'rgb_samples': rgb}
+    out.update(volumetric_rendering(rgb, sigma, z, directions))
+    out['med_points'] = torch.gather(warped_points, -2, out['med_idx'][..., None, None])   # models.py:664-669
+    return out
+
+
+def forward(sd, origins, directions, ids, draws, cfg, fine_z=None):
+    """hypernerf/models.py:673-780.  draws: dict(u_coarse (B,Nc), noise_coarse (B,Nc,1)|None, u_fine (B,Nf),
+    noise_fine (B,Nc+Nf,1)|None) in the reference's RNG order.
+    cfg: dict(near, far, n_coarse, n_fine, noise_std, xyz_freq, hyper_freq, view_freq).
+    fine_z: stage-isolation hook for tests — evaluate the fine level at these depths instead of the resampled ones."""
+    z, points = sample_along_rays(origins, directions, cfg['n_coarse'], cfg['near'], cfg['far'], draws['u_coarse'])
+    coarse = render_samples(sd, 'coarse', points, z, directions, directions, ids, cfg, draws.get('noise_coarse'))
+    coarse['z_vals'] = z
+    z_mid = .5 * (z[..., 1:] + z[..., :-1])
+    z_f, points_f, inds = sample_pdf(z_mid, coarse['weights'][..., 1:-1].detach(), origins, directions, z,
+                                     draws['u_fine'])
+    if fine_z is not None:
+        z_f = fine_z
+        points_f = origins[:, None, :] + z_f[..., None] * directions[:, None, :]
+    fine = render_samples(sd, 'fine', points_f, z_f, directions, directions, ids, cfg, draws.get('noise_fine'))
+    fine['z_vals'] = z_f
+    fine['pdf_inds'] = inds
+    return {'coarse': coarse, 'fine': fine}
+
+
+def default_cfg(n_fine=64, noise_std=1.0):
+    return dict(near=0., far=1., n_coarse=64, n_fine=n_fine, noise_std=noise_std, xyz_freq=10, hyper_freq=6,
+                view_freq=6)
+
+
+def mse_loss(out, target):
+    """losses.py:9-14."""
+    return F.mse_loss(out['coarse']['rgb'], target) + F.mse_loss(out['fine']['rgb'], target)
