@@ -56,7 +56,7 @@ class _FusedMlp(torch.autograd.Function):
         sigma = torch.empty(B, S, device=dev, dtype=torch.float32)
         rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
         warped = torch.empty(B, S, 3 + desc.hyper_dim, device=dev, dtype=torch.float32)
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad[7:])  # grad mode is off inside forward(); autograd tells us here
         saved = None
         if need_grad:
             sizes = model._sizes(B * S)

@@ -26,25 +26,46 @@ def posenc_orig(x, n_freqs):
     return torch.cat(out, -1)
 
 
-def mlp(sd, prefix, x, depth, skips=(4,), out_act=None):
-    """hypernerf/modules.py:114-127: x = relu(linear_i(x)); concat [x, inputs] after layer i in skips; logit layer."""
+def _ident(x):
+    return x
+
+
+def bf16_ste(x):
+    """Round to bf16 with a straight-through gradient.  Used by the `emulate_bf16` mode, which places a rounding at
+    exactly the points where the sm_100a kernels hold bf16 tensor-core operands (weights, layer inputs, post-ReLU
+    activations, bottleneck), everything else fp32 — the north-star numerics (bf16 operands, fp32 accumulate)."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def _relu(x, gate):
+    """ReLU, or — for tests that must share the kernels' ReLU gates exactly — multiplication by a given 0/1 gate."""
+    return F.relu(x) if gate is None else x * gate.to(x.dtype)
+
+
+def mlp(sd, prefix, x, depth, skips=(4,), out_act=None, q=_ident, gates=None):
+    """hypernerf/modules.py:114-127: x = relu(linear_i(x)); concat [x, inputs] after layer i in skips; logit layer.
+    x must already be q()-rounded by the caller.  gates: optional list of depth (+1 if out_act is relu) masks."""
     inputs = x
     for i in range(depth):
-        x = F.relu(F.linear(x, sd[f"{prefix}.linears.{i}.weight"], sd[f"{prefix}.linears.{i}.bias"]))
+        pre = F.linear(x, q(sd[f"{prefix}.linears.{i}.weight"]), sd[f"{prefix}.linears.{i}.bias"])
+        x = q(_relu(pre, None if gates is None else gates[i]))
         if i in skips:
             x = torch.cat([x, inputs], -1)
-    x = F.linear(x, sd[f"{prefix}.logit_layer.weight"], sd[f"{prefix}.logit_layer.bias"])
+    x = F.linear(x, q(sd[f"{prefix}.logit_layer.weight"]), sd[f"{prefix}.logit_layer.bias"])
+    if out_act is F.relu:
+        return _relu(x, None if gates is None else gates[depth])
     return out_act(x) if out_act is not None else x
 
 
-def nerf_mlp(sd, prefix, feat, rgb_cond):
+def nerf_mlp(sd, prefix, feat, rgb_cond, q=_ident, gates=None):
     """hypernerf/modules.py:266-298 without GLO conditioning: trunk (ReLU on the logit layer, :230), bottleneck
     (no activation), alpha Linear, rgb MLP depth 4 (skip never fires) + Sigmoid (models.py:164)."""
-    x = mlp(sd, f"{prefix}.trunk_mlp", feat, 8, out_act=F.relu)
-    bott = F.linear(x, sd[f"{prefix}.bottleneck_mlp.weight"], sd[f"{prefix}.bottleneck_mlp.bias"])
-    alpha = F.linear(bott, sd[f"{prefix}.alpha_mlp.weight"], sd[f"{prefix}.alpha_mlp.bias"])
-    cond = rgb_cond[:, None, :].expand(-1, bott.shape[1], -1)  # broadcast_condition, modules.py:254-264
-    rgb = mlp(sd, f"{prefix}.rgb_mlp", torch.cat([bott, cond], -1), 4, out_act=torch.sigmoid)
+    g = gates or {}
+    x = q(mlp(sd, f"{prefix}.trunk_mlp", q(feat), 8, out_act=F.relu, q=q, gates=g.get('trunk')))
+    bott = q(F.linear(x, q(sd[f"{prefix}.bottleneck_mlp.weight"]), sd[f"{prefix}.bottleneck_mlp.bias"]))
+    alpha = F.linear(bott, q(sd[f"{prefix}.alpha_mlp.weight"]), sd[f"{prefix}.alpha_mlp.bias"])
+    cond = q(rgb_cond)[:, None, :].expand(-1, bott.shape[1], -1)  # broadcast_condition, modules.py:254-264
+    rgb = mlp(sd, f"{prefix}.rgb_mlp", torch.cat([bott, cond], -1), 4, out_act=torch.sigmoid, q=q, gates=g.get('rgb'))
     return rgb, alpha
 
 
@@ -114,24 +135,26 @@ def sample_pdf(bins, weights, origins, directions, z, u):
 # ------------------------------------------------------------------------------------------------------------
 # model
 # ------------------------------------------------------------------------------------------------------------
-def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None):
+def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None, gates=None):
     """map_points + query_template (hypernerf/models.py:545-581, 447-493) for TranslationField + bendy_sheet.
     Returns (rgb (B,S,3), sigma (B,S), warped_points (B,S,3+H), raw alpha)."""
     B, S, _ = points.shape
+    q = bf16_ste if cfg.get('emulate_bf16') else _ident
     embed = sd["warp_embed.embed.weight"][ids.reshape(-1)]            # GLOEmbed, modules.py:155-167
     embed = embed[:, None, :].expand(B, S, embed.shape[-1])           # models.py:627-632
     # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
-    warp_in = torch.cat([posenc_orig(points, 10), embed], -1)
-    warped = points + mlp(sd, "warp_field.mlp", warp_in, 6)
+    warp_in = q(torch.cat([posenc_orig(points, 10), embed], -1))
+    g = gates or {}
+    warped = points + mlp(sd, "warp_field.mlp", warp_in, 6, q=q, gates=g.get('warp'))
     # HyperSheetMLP on the UNWARPED points, modules.py:331-337 (n_freq 7), models.py:571-572
-    sheet_in = torch.cat([posenc_orig(points, 7), embed], -1)
-    hyper = mlp(sd, "hyper_sheet_mlp.mlp", sheet_in, 6)
+    sheet_in = q(torch.cat([posenc_orig(points, 7), embed], -1))
+    hyper = mlp(sd, "hyper_sheet_mlp.mlp", sheet_in, 6, q=q, gates=g.get('sheet'))
     warped_points = torch.cat([warped, hyper], -1)
     feat = torch.cat([posenc_orig(warped_points[..., :3], cfg['xyz_freq']),
                       posenc_orig(warped_points[..., 3:], cfg['hyper_freq'])], -1)   # models.py:458-478
     rgb_cond = posenc_orig(viewdirs, cfg['view_freq'])                                # models.py:410-419
     prefix = "nerf_mlps_fine" if level == 'fine' else "nerf_mlps_coarse"
-    rgb, alpha = nerf_mlp(sd, prefix, feat, rgb_cond)
+    rgb, alpha = nerf_mlp(sd, prefix, feat, rgb_cond, q=q, gates=gates)
     if noise is not None:
         alpha = alpha + noise * cfg['noise_std']                                      # model_utils.py:312-316
     sigma = F.softplus(alpha.squeeze(-1))                                             # models.py:491
@@ -167,9 +190,9 @@ def forward(sd, origins, directions, ids, draws, cfg, fine_z=None):
     return {'coarse': coarse, 'fine': fine}
 
 
-def default_cfg(n_fine=64, noise_std=1.0):
+def default_cfg(n_fine=64, noise_std=1.0, emulate_bf16=False):
     return dict(near=0., far=1., n_coarse=64, n_fine=n_fine, noise_std=noise_std, xyz_freq=10, hyper_freq=6,
-                view_freq=6)
+                view_freq=6, emulate_bf16=emulate_bf16)
 
 
 def mse_loss(out, target):

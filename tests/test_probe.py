@@ -1,0 +1,28 @@
+"""GPU: pins the UMMA shared-memory descriptor conventions (hn_ptx.cuh) against a plain matmul."""
+import pytest
+import torch
+
+from hypernerf_torch_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(16, 16, 0, 0), (64, 64, 0, 0), (128, 128, 0, 0), (192, 80, 0, 0), (256, 256, 0, 0), (144, 176, 0, 0),
+         (16, 192, 0, 0), (96, 256, 0, 0),
+         (64, 64, 1, 1), (256, 64, 1, 1), (208, 64, 1, 1), (80, 128, 1, 1), (256, 256, 1, 1)]
+
+
+@pytest.mark.parametrize("N,K,a_mn,b_mn", CASES)
+def test_umma_probe(N, K, a_mn, b_mn):
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    ref = A.float() @ B.float().t()
+    Ain = A.t().contiguous() if a_mn else A.contiguous()
+    Bin = B.t().contiguous() if b_mn else B.contiguous()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    _lib.check(_lib.lib().hn_umma_probe(_lib.ptr(Ain), _lib.ptr(Bin), _lib.ptr(D), N, K, a_mn, b_mn, _lib.stream()),
+               "hn_umma_probe")
+    torch.cuda.synchronize()
+    err = (D - ref).abs().max().item()
+    print(f"probe N={N} K={K} a_mn={a_mn} b_mn={b_mn} max_err={err:.3e}")
+    assert err < 1e-2 * max(1.0, ref.abs().max().item() / 16)
