@@ -19,7 +19,8 @@ HN_COMP_ACC_ALL = 2
 
 EXPORTS = [
     "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf",
-    "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_fwd", "hn_mlp_bwd", "hn_umma_probe",
+    "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
+    "hn_umma_probe",
 ]
 
 
@@ -74,6 +75,8 @@ def lib():
     L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]
     L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32,
                              C.POINTER(C.c_int64), vp, vp, vp]
+    L.hn_mlp_bwd_data.argtypes = L.hn_mlp_bwd.argtypes
+    L.hn_mlp_bwd_weights.argtypes = [C.POINTER(ModelDesc), vp, i64, i32, i32, C.POINTER(C.c_int64), vp, vp, vp]
     L.hn_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -81,6 +84,36 @@ def lib():
             fn.restype = C.c_int
     _lib = L
     return L
+
+
+# number of kernels of this library launched so far (bench.py reports the count inside its timed region)
+launches = 0
+# when a list, every MLP kernel call appends (name, n_samples, start_event, end_event) (bench.py roofline leg)
+profile = None
+
+
+def count(n: int):
+    global launches
+    launches += n
+
+
+class timed:
+    """Context manager: CUDA events around one kernel call on the current stream when profiling is on."""
+
+    def __init__(self, name, n_samples):
+        self.name, self.n = name, n_samples
+
+    def __enter__(self):
+        if profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if profile is not None:
+            self.e1.record()
+            profile.append((self.name, self.n, self.e0, self.e1))
 
 
 def check(rc: int, what: str):

@@ -899,12 +899,12 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   return set_cuda_error(cudaGetLastError(), "hn_mlp_fwd");
 }
 
-extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
-                          const float* rgb, const float* warped, const void* saved, const float* g_sigma,
-                          const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
-                          const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
-  if (!desc || !packed || !ids || !sigma || !rgb || !warped || !saved || !g_sigma || !g_rgb || !param_offsets || !flat_grad ||
-      !workspace)
+static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                        const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
+                        const float* g_warped, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
+                        void* workspace, void* stream, bool do_data, bool do_weights) {
+  if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
+  if (do_data && (!packed || !ids || !sigma || !rgb || !warped || !g_sigma || !g_rgb))
     return set_error(-2, "hn_mlp_bwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_bwd: bad B/S");
   if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
@@ -914,32 +914,59 @@ extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const i
   build_plan(*desc, &plan);
   build_tables(*desc, level, param_offsets, &plan);
   using C = Cfg1;
-  BwdParams bp;
-  bp.prog = plan.bwd;
-  bp.weights = (const uint8_t*)packed + plan.layout.bwd_off;
-  bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
-  bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
-  bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
-  bp.glo_grad = flat_grad + param_offsets[P_GLO];
-  bp.n = B * S; bp.S = S;
-  int64_t nt = tiles_of(bp.n);
+  const int64_t n = B * S;
+  const int64_t nt = tiles_of(n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_bwd: too many samples");
-  bp.n_tiles = (int)nt;
-  bp.x_total = plan.slabs.x_total; bp.d_total = plan.slabs.d_total;
-  bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
-  if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-  int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
-  mlp_dgrad_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
-  if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: dgrad launch")) return rc;
+  if (do_data) {
+    BwdParams bp;
+    bp.prog = plan.bwd;
+    bp.weights = (const uint8_t*)packed + plan.layout.bwd_off;
+    bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
+    bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
+    bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
+    bp.glo_grad = flat_grad + param_offsets[P_GLO];
+    bp.n = n; bp.S = S;
+    bp.n_tiles = (int)nt;
+    bp.x_total = plan.slabs.x_total; bp.d_total = plan.slabs.d_total;
+    bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
+    if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+    int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
+    mlp_dgrad_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
+    if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: dgrad launch")) return rc;
+  }
+  if (do_weights) {
+    WgradParams wp;
+    wp.tab = plan.wgrad;
+    wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
+    wp.flat_grad = flat_grad;
+    wp.n_half = 2 * nt;
+    wp.x_total = plan.slabs.x_total; wp.d_total = plan.slabs.d_total;
+    if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
+    int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
+    mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
+    if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch")) return rc;
+  }
+  return 0;
+}
 
-  WgradParams wp;
-  wp.tab = plan.wgrad;
-  wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
-  wp.flat_grad = flat_grad;
-  wp.n_half = 2 * nt;
-  wp.x_total = plan.slabs.x_total; wp.d_total = plan.slabs.d_total;
-  if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
-  int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
-  mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
-  return set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch");
+extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                          const float* rgb, const float* warped, const void* saved, const float* g_sigma,
+                          const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
+                          const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, level, param_offsets,
+                      flat_grad, workspace, stream, true, true);
+}
+
+extern "C" int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                               const float* rgb, const float* warped, const void* saved, const float* g_sigma,
+                               const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
+                               const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, level, param_offsets,
+                      flat_grad, workspace, stream, true, false);
+}
+
+extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
+                                  const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
+                      param_offsets, flat_grad, (void*)workspace, stream, false, true);
 }

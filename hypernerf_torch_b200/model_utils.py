@@ -44,10 +44,12 @@ def sample_along_rays(origins, directions, num_coarse_samples, near, far, use_st
         t_rand = torch.rand([B, num_coarse_samples], device=dev)
         check(lib().hn_sample_coarse(ptr(o), ptr(d), ptr(t_rand), ptr(lower), ptr(upper), B, num_coarse_samples,
                                      ptr(z), ptr(pts), stream()), "hn_sample_coarse")
+        _lib.count(1)
     else:
         zc = z_vals.contiguous()
         check(lib().hn_sample_coarse(ptr(o), ptr(d), None, ptr(zc), ptr(zc), B, num_coarse_samples, ptr(z), ptr(pts),
                                      stream()), "hn_sample_coarse")
+        _lib.count(1)
     return z, pts
 
 
@@ -77,6 +79,7 @@ def _sample_pdf_impl(bins, weights, origins, directions, z_vals, n_new, use_stra
     wptr = C.c_void_p(w.data_ptr())
     check(lib().hn_sample_pdf(ptr(zc), ptr(b), wptr, w.stride(0), ptr(u), ptr(o), ptr(d), B, Nc, nb, n_new, ptr(z_fine),
                               ptr(pts), ptr(inds), stream()), "hn_sample_pdf")
+    _lib.count(1)
     return z_fine, pts, inds
 
 
@@ -103,6 +106,7 @@ def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None,
     wptr = C.c_void_p(w.data_ptr() + 4)  # weights[..., 1:-1]
     check(lib().hn_sample_pdf(ptr(zc), None, wptr, Nc, ptr(u), ptr(o), ptr(d), B, Nc, Nc - 2, n_new, ptr(z_fine),
                               ptr(pts), ptr(inds), stream()), "hn_sample_pdf")
+    _lib.count(1)
     return (z_fine, pts, inds) if want_inds else (z_fine, pts)
 
 
@@ -125,6 +129,7 @@ class _Composite(torch.autograd.Function):
         check(lib().hn_composite_fwd(ptr(sigma_c), ptr(rgb_c), ptr(z_c), ptr(d_c), B, S, flags, eps, last_delta,
                                      ptr(out_rgb), ptr(depth), ptr(med_depth), ptr(acc), ptr(weights), ptr(med_idx),
                                      stream()), "hn_composite_fwd")
+        _lib.count(1)
         ctx.save_for_backward(rgb_c, sigma_c, z_c, d_c)
         ctx.cfg = (flags, eps, last_delta)
         ctx.mark_non_differentiable(med_depth, med_idx)
@@ -144,6 +149,7 @@ class _Composite(torch.autograd.Function):
         check(lib().hn_composite_bwd(ptr(sigma_c), ptr(rgb_c), ptr(z_c), ptr(d_c), B, S, flags, eps, last_delta,
                                      ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
                                      ptr(g_sigma), ptr(g_rgb_s), stream()), "hn_composite_bwd")
+        _lib.count(1)
         return g_rgb_s, g_sigma, None, None, None, None, None
 
 

@@ -61,8 +61,11 @@ class _FusedMlp(torch.autograd.Function):
         if need_grad:
             sizes = model._sizes(B * S)
             saved = torch.empty(sizes.saved_bytes, device=dev, dtype=torch.uint8)
-        check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
-                               B, S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()), "hn_mlp_fwd")
+        with _lib.timed("mlp_fwd", B * S):
+            check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise),
+                                   float(noise_std), B, S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()),
+                  "hn_mlp_fwd")
+        _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
         ctx.param_meta = [(p.shape, p.numel()) for p in params]
         ctx.save_for_backward(ids, sigma, rgb, warped, saved, packed)
@@ -81,13 +84,26 @@ class _FusedMlp(torch.autograd.Function):
         g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.to(torch.float32).contiguous()
         g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
         g_warped = None if g_warped is None else g_warped.to(torch.float32).contiguous()
-        offs, total = model._grad_offsets()
-        flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        direct = model._flat_grads is not None and model._flat_grads.flat.device == dev
+        if direct:
+            # accumulate straight into the bound flat gradient buffer (train.FlatGrads): no per-tensor adds
+            fg = model._flat_grads
+            offs, flat_grad = fg.c_offsets(), fg.flat
+        else:
+            offs, total = model._grad_offsets()
+            flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         sizes = model._sizes(B * S)
         work = torch.empty(sizes.workspace_bytes, device=dev, dtype=torch.uint8)
-        check(lib().hn_mlp_bwd(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped), ptr(saved),
-                               ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, level, offs, ptr(flat_grad), ptr(work),
-                               stream()), "hn_mlp_bwd")
+        with _lib.timed("mlp_dgrad", B * S):
+            check(lib().hn_mlp_bwd_data(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped),
+                                        ptr(saved), ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, level, offs,
+                                        ptr(flat_grad), ptr(work), stream()), "hn_mlp_bwd_data")
+        with _lib.timed("mlp_wgrad", B * S):
+            check(lib().hn_mlp_bwd_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad), ptr(work),
+                                           stream()), "hn_mlp_bwd_weights")
+        _lib.count(2)
+        if direct:
+            return (None,) * (7 + len(ctx.param_meta))
         grads = []
         other = range(*model._level_param_range(1 - level))
         for i, (shape, n) in enumerate(ctx.param_meta):
@@ -192,6 +208,7 @@ class NerfModel(nn.Module):
             raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} parameters, "
                                           f"library expects {sizes.flat_param_floats}")
         self._pack_cache = {}
+        self._flat_grads = None
         self._grad_off_cache = None
         self._size_cache = {}
 
@@ -223,6 +240,15 @@ class NerfModel(nn.Module):
             self._grad_off_cache = ((C.c_int64 * len(offs))(*offs), total)
         return self._grad_off_cache
 
+    def attach_flat_grads(self, flat_grads):
+        """Opt-in: hn_mlp_bwd accumulates directly into `flat_grads.flat` (train.FlatGrads built over
+        `self.parameters()`), bypassing autograd's per-tensor accumulation.  Pass None to detach."""
+        if flat_grads is not None:
+            ps = self._canonical_params()
+            if len(flat_grads.params) != len(ps) or any(a is not b for a, b in zip(flat_grads.params, ps)):
+                raise ValueError("FlatGrads must be built over this model's parameters() in order")
+        self._flat_grads = flat_grads
+
     def _sizes(self, n_samples):
         s = self._size_cache.get(n_samples)
         if s is None:
@@ -249,6 +275,7 @@ class NerfModel(nn.Module):
         packed = torch.empty(self._packed_bytes, device=dev, dtype=torch.uint8)
         check(lib().hn_pack_weights(C.byref(self._desc), C.c_void_p(base), offs, level, ptr(packed), stream()),
               "hn_pack_weights")
+        _lib.count(1)
         self._pack_cache[level] = (key, packed)
         return packed
 

@@ -121,6 +121,17 @@ int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids
                int64_t B, int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace,
                void* stream);
 
+/* The two halves of hn_mlp_bwd, separately callable (hn_mlp_bwd == data then weights on the same stream):
+ *   hn_mlp_bwd_data     back-propagates through every layer (tcgen05, transposed weights), writes the
+ *                       pre-activation gradients to `workspace` and accumulates the GLO-table gradient;
+ *   hn_mlp_bwd_weights  dW = dY^T X and db = sum dY over all samples from `saved` + `workspace`. */
+int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                    const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
+                    const float* g_warped, int64_t B, int S, int level, const int64_t* grad_offsets /* host */,
+                    float* flat_grad, void* workspace, void* stream);
+int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
+                       const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
+
 /* test hook: one UMMA tile D[128,N] = A * B^T through the shared-memory layouts the MLP kernels use.
  * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
 int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);

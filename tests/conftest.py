@@ -35,25 +35,6 @@ def golden_state_dict(fix, shapes_from):
     return sd
 
 
-# state_dict shapes of the cfg-1 model so CPU tests need neither the reference nor CUDA
 def cfg1_shapes():
-    s = {"warp_embed.embed.weight": (100, 8)}
-
-    def mlp(prefix, in_ch, width, depth, out_ch, skip=4):
-        for i in range(depth):
-            fan_in = in_ch if i == 0 else (width + in_ch if (i - 1) == skip else width)
-            s[f"{prefix}.linears.{i}.weight"] = (width, fan_in)
-            s[f"{prefix}.linears.{i}.bias"] = (width,)
-        s[f"{prefix}.logit_layer.weight"] = (out_ch, width)
-        s[f"{prefix}.logit_layer.bias"] = (out_ch,)
-
-    mlp("hyper_sheet_mlp.mlp", 53, 64, 6, 2)
-    mlp("warp_field.mlp", 71, 128, 6, 3)
-    for lvl in ("nerf_mlps_coarse", "nerf_mlps_fine"):
-        mlp(f"{lvl}.trunk_mlp", 89, 256, 8, 256)
-        s[f"{lvl}.bottleneck_mlp.weight"] = (128, 256)
-        s[f"{lvl}.bottleneck_mlp.bias"] = (128,)
-        mlp(f"{lvl}.rgb_mlp", 167, 128, 4, 3)
-        s[f"{lvl}.alpha_mlp.weight"] = (1, 128)
-        s[f"{lvl}.alpha_mlp.bias"] = (1,)
-    return s
+    from hypernerf_torch_b200 import synthetic
+    return synthetic.cfg1_state_dict_shapes()
