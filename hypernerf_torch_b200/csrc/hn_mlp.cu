@@ -8,9 +8,11 @@
 //   mlp_wgrad_kernel  dW = dY^T X and db = sum dY over all samples, accumulated into the flat gradient.
 //   pack_kernel       fp32 (out,in) nn.Linear weights -> bf16 operand images (forward and transposed).
 //
-// One CTA owns a tile of 128 samples (= UMMA M = TMEM lanes).  Warp roles: warp 0 lane 0 streams weights,
-// warp 1 lane 0 issues UMMAs, warps 2..5 are the epilogue (thread = sample row).  Two CTAs are resident per
-// SM so one CTA's epilogue overlaps the other's MMAs.
+// One CTA (one per SM) owns 256 samples as two 128-row sub-tiles (128 = UMMA M = TMEM lanes); both sub-tiles
+// consume every weight stage, so each byte fetched from L2 feeds two UMMAs.  384 threads = 3 warpgroups:
+// warpgroup 0 holds the weight producer (warp 0 lane 0, 6-deep bulk-copy ring) and the UMMA issuer (warp 1 lane 0)
+// and gives its registers away (setmaxnreg 40); warpgroups 1-2 are the epilogue (thread = sample row, one
+// warpgroup per sub-tile, setmaxnreg 216).  TMEM: 512 columns = 2 sub-tiles x 256 fp32 accumulator columns.
 #include <math.h>
 #include "hn_api_internal.h"
 #include "hn_mlp_program.h"
@@ -37,11 +39,14 @@ using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
 // ------------------------------------------------------------------------------------------------------
 template <class C>
 struct Smem {
-  static constexpr int ACT = 0;                                   // 128 x 256 bf16
-  static constexpr int INB = ACT + 32 * kChunkBytes;              // 128 x (IN_CHUNKS*8) bf16
-  static constexpr int RING = INB + C::IN_CHUNKS * kChunkBytes;   // kRingStages x kStageBytes
-  static constexpr int BARS = RING + kRingStages * kStageBytes;   // full[3], empty[3], acc_full, act_ready
-  static constexpr int TMEMP = BARS + 8 * 8;
+  static constexpr int ACT_BYTES = 32 * kChunkBytes;              // 128 x 256 bf16 per sub-tile
+  static constexpr int INB_BYTES = C::IN_CHUNKS * kChunkBytes;    // 128 x (IN_CHUNKS*8) bf16 per sub-tile
+  static constexpr int ACT = 0;
+  static constexpr int INB = ACT + kSubTiles * ACT_BYTES;
+  static constexpr int RING = INB + kSubTiles * INB_BYTES;        // kRingStages x kStageBytes
+  static constexpr int BIAS = RING + kRingStages * kStageBytes;   // 2 x 256 fp32: this / next layer's bias
+  static constexpr int BARS = BIAS + 2 * 256 * 4;                 // full[], empty[], acc_full, act_ready
+  static constexpr int TMEMP = BARS + (2 * kRingStages + 2) * 8;
   static constexpr int TOTAL = TMEMP + 16;
 };
 
@@ -59,6 +64,7 @@ struct FwdParams {
   uint16_t x_in_ws, x_in_t, x_in_v;
   float* sigma; float* rgb; float* warped;
   uint8_t* saved;
+  unsigned long long* dbg;  // optional per-CTA cycle counters (hn_debug_set_timing_buffer)
 };
 
 struct BwdParams {
@@ -75,15 +81,19 @@ struct BwdParams {
   int n_tiles;
   int x_total, d_total;
   uint16_t d_rgbhead, pad0;
+  unsigned long long* dbg;
 };
 
 // ------------------------------------------------------------------------------------------------------
 // weight producer and MMA issuer (shared by forward and backward-data kernels)
 // ------------------------------------------------------------------------------------------------------
+// cycle counters per CTA: [0] producer wait-empty, [1] mma wait-act_ready, [2] mma wait-full, [3] mma total,
+// [4] epilogue wait-acc_full, [5] epilogue work, [6] epilogue prologue, [7] epilogue total
+#define HN_T0() (clock64())
 struct RingState { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == kRingStages) { slot = 0; phase ^= 1; } } };
 
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
-                                             uint64_t* full, uint64_t* empty, RingState& rs) {
+                                             uint64_t* full, uint64_t* empty, RingState& rs, long long& t_wait) {
   for (int oi = 0; oi < prog.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
     const int nchunks = (op.k0 + op.k1) >> 3;
@@ -91,7 +101,9 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
     for (int c = 0; c < nchunks; c += op.cps) {
       int cnt = min((int)op.cps, nchunks - c);
       uint32_t bytes = (uint32_t)cnt * op.n * 16;
+      long long t0 = HN_T0();
       mbar_wait(&empty[rs.slot], rs.phase ^ 1);
+      t_wait += HN_T0() - t0;
       mbar_arrive_expect_tx(&full[rs.slot], bytes);
       bulk_g2s(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot]);
       rs.next();
@@ -100,8 +112,9 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
 }
 
 __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, uint32_t act_s, uint32_t inb_s,
-                                            uint32_t ring_s, uint32_t tmem_base, uint64_t* full, uint64_t* empty,
-                                            RingState& rs) {
+                                            uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s,
+                                            uint32_t tmem_base, uint64_t* full, uint64_t* empty, RingState& rs,
+                                            long long& t_wait) {
   for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
     const int nchunks = (op.k0 + op.k1) >> 3;
@@ -112,17 +125,27 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
     const uint32_t b_lbo = op.n * 16;
     for (int c = 0; c < nchunks; c += op.cps) {
       int cnt = min((int)op.cps, nchunks - c);
+      long long t0 = HN_T0();
       mbar_wait(&full[rs.slot], rs.phase);
+      t_wait += HN_T0() - t0;
       tc_fence_after();
       const uint32_t stage = ring_s + rs.slot * kStageBytes;
+      if (elect_one_sync()) {
       for (int j = 0; j < cnt; j += 2) {
         uint32_t kc = c + j;  // chunk index inside the op's K
-        uint32_t a_addr = kc < k0_chunks ? a0 + kc * kChunkBytes : a1 + (kc - k0_chunks) * kChunkBytes;
-        uint64_t ad = make_smem_desc(a_addr, kChunkBytes, 128);
+        const bool first = kc < k0_chunks;
+        uint32_t a_addr = first ? a0 + kc * kChunkBytes : a1 + (kc - k0_chunks) * kChunkBytes;
+        const uint32_t a_sub = (first ? op.src0 : op.src1) == SRC_ACT ? act_stride : inb_stride;
         uint64_t bd = make_smem_desc(stage + j * b_lbo, b_lbo, 128);
-        umma_bf16(tmem_base + op.tmem_col, ad, bd, idesc, (kc > 0) | op.acc_init);
+#pragma unroll
+        for (int sub = 0; sub < kSubTiles; ++sub) {
+          uint64_t ad = make_smem_desc(a_addr + sub * a_sub, kChunkBytes, 128);
+          umma_bf16(tmem_base + sub * 256 + op.tmem_col, ad, bd, idesc, (kc > 0) | op.acc_init);
+        }
       }
       umma_commit(&empty[rs.slot]);
+      }
+      __syncwarp();
       rs.next();
     }
   }
@@ -186,19 +209,19 @@ __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// generic epilogue blocks: 32 accumulator columns of this thread's row -> bias/activation -> bf16 packets
+// generic epilogue column loops: this thread's row of the accumulator, 32 columns at a time, TMEM loads
+// double-buffered (the load of block b+1 is in flight while block b is converted and stored).
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <bool RELU>
-__device__ __forceinline__ void fwd_block32(uint32_t taddr, const float* __restrict__ bias, uint8_t* act_row,
-                                            uint4* save_row, int chunk0, int save_chunk) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  tmem_ld_wait();
+__device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
+                                            int chunk0, int save_chunk) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q);
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * q + 1);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * q);       // smem broadcast
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * q + 4);
     v[0] = __uint_as_float(r[8 * q + 0]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
     v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
     v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
@@ -216,37 +239,88 @@ __device__ __forceinline__ void fwd_block32(uint32_t taddr, const float* __restr
   }
 }
 
-// backward: gate 32 gradient columns by (forward activation > 0) read from the stash
-template <bool MASK>
-__device__ __forceinline__ void bwd_block32(uint32_t taddr, const uint4* __restrict__ mask_row, int mask_chunk,
-                                            uint8_t* dst_row, uint4* save_row, int chunk0, int save_chunk) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  uint4 m[4];
-  if (MASK) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) m[q] = __ldg(mask_row + (mask_chunk + chunk0 + q) * (kHalfChunkBytes / 16));
+// ncols: multiple of 32
+template <bool RELU>
+__device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, uint8_t* act_row, uint4* save_row,
+                                         int save_chunk, int ncols) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(taddr, ra);
+  for (int c0 = 0; c0 < ncols; c0 += 64) {
+    tmem_ld_wait();
+    const bool more = c0 + 32 < ncols;
+    if (more) tmem_ld32(taddr + c0 + 32, rb);
+    fwd_store32<RELU>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk);
+    if (more) {
+      tmem_ld_wait();
+      if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
+      fwd_store32<RELU>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk);
+    }
   }
-  tmem_ld_wait();
+}
+
+// backward: ReLU gates.  The stash holds post-ReLU bf16 activations (>= +0), so "activation > 0" <=> halfword != 0.
+// 8 activations (one 16-byte packet) -> 8 gate bits; adding 0x7FFF to a halfword <= 0x7FFF sets its bit 15 iff it
+// is non-zero and never carries into the neighbour.
+__device__ __forceinline__ uint32_t gate8(const uint4 x) {
+  const uint32_t t0 = (x.x + 0x7FFF7FFFu) & 0x80008000u, t1 = (x.y + 0x7FFF7FFFu) & 0x80008000u;
+  const uint32_t t2 = (x.z + 0x7FFF7FFFu) & 0x80008000u, t3 = (x.w + 0x7FFF7FFFu) & 0x80008000u;
+  const uint32_t m = (t0 >> 15) | (t1 >> 13) | (t2 >> 11) | (t3 >> 9);
+  return (m | (m >> 15)) & 0xFFu;
+}
+// All gates of one layer for this thread's row: up to 32 independent 16-byte loads (issued while the layer's MMAs
+// run) folded into 8 words.
+__device__ __forceinline__ void load_gates(const uint4* __restrict__ mask_row, int mask_chunk, int ncols, uint32_t* gates) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    gates[w] = 0;
+    if (w * 32 < ncols) {
+      const uint4* p = mask_row + (size_t)(mask_chunk + 4 * w) * (kHalfChunkBytes / 16);
+      const uint4 x0 = __ldg(p), x1 = __ldg(p + kHalfChunkBytes / 16), x2 = __ldg(p + 2 * (kHalfChunkBytes / 16)),
+                  x3 = __ldg(p + 3 * (kHalfChunkBytes / 16));
+      gates[w] = gate8(x0) | (gate8(x1) << 8) | (gate8(x2) << 16) | (gate8(x3) << 24);
+    }
+  }
+}
+
+template <bool MASK>
+__device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t gate, uint8_t* dst_row, uint4* save_row,
+                                            int chunk0, int save_chunk) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * q + j]);
-    if (MASK) {
-      const uint32_t mm[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // post-ReLU bf16 values are >= +0: non-zero bits <=> activation > 0
-        if ((mm[j] & 0x0000FFFFu) == 0) v[2 * j] = 0.f;
-        if ((mm[j] & 0xFFFF0000u) == 0) v[2 * j + 1] = 0.f;
-      }
+    for (int j = 0; j < 8; ++j) {
+      v[j] = __uint_as_float(r[8 * q + j]);
+      if (MASK && !((gate >> (8 * q + j)) & 1u)) v[j] = 0.f;
     }
     uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = o;
     if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+  }
+}
+
+// ncols: multiple of 32; gates[b] holds the 32 gate bits of column block b
+template <bool MASK>
+__device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gates, uint8_t* dst_row, uint4* save_row,
+                                         int save_chunk, int ncols) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(taddr, ra);
+#pragma unroll
+  for (int b = 0; b < 8; b += 2) {
+    const int c0 = b * 32;
+    if (c0 < ncols) {
+      tmem_ld_wait();
+      const bool more = c0 + 32 < ncols;
+      if (more) tmem_ld32(taddr + c0 + 32, rb);
+      bwd_store32<MASK>(ra, gates[b], dst_row, save_row, c0 >> 3, save_chunk);
+      if (more) {
+        tmem_ld_wait();
+        if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
+        bwd_store32<MASK>(rb, gates[b + 1], dst_row, save_row, (c0 + 32) >> 3, save_chunk);
+      }
+    }
   }
 }
 
@@ -257,12 +331,13 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // forward
 // ======================================================================================================
 template <class C>
-__global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
   uint8_t* ring = smem + SM::RING;
+  float* sbias = reinterpret_cast<float*>(smem + SM::BIAS);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* empty = full + kRingStages;
   uint64_t* acc_full = empty + kRingStages;
@@ -273,52 +348,66 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 128);
+    mbar_init(act_ready, 128 * kSubTiles);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const Program& prog = p.prog;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
       RingState rs;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs);
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+      long long tw = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs, tw);
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
+    } else if (warp == 1) {  // whole warp, converged: see elect_one_sync()
       RingState rs;
       uint32_t ph_ready = 0;
+      long long t_ready = 0, t_full = 0;
+      const long long t_begin = HN_T0();
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
+          long long t0 = HN_T0();
           mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
+          t_ready += HN_T0() - t0;
           tc_fence_after();
-          issue_layer(prog, prog.layers[li], act_s, inb_s, ring_s, tmem_base, full, empty, rs);
-          umma_commit(acc_full);
+          issue_layer(prog, prog.layers[li], act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base, full, empty, rs,
+                      t_full);
+          if (elect_one_sync()) umma_commit(acc_full);
+          __syncwarp();
         }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
     }
   } else {
-    // ---------------- epilogue warps: thread <-> sample row ----------------
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* act_row = act + row * 16;
-    uint8_t* inb_row = inb + row * 16;
+    setmaxnreg_inc<216>();
+    const int et = threadIdx.x - 128;  // epilogue thread index 0..255
+    // ---------------- epilogue warps: thread <-> sample row; warps 2..5 sub-tile 0, 6..9 sub-tile 1 ----------------
+    const int sub = (warp - 4) >> 2;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // row inside the sub-tile
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
+    uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
+    uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
     uint32_t ph_acc = 0;
+    long long t_acc = 0, t_pro = 0;
+    const long long t_begin = HN_T0();
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int64_t g = (int64_t)tile * kTileRows + row;
+      const long long t_tile = HN_T0();
+      const int64_t g = (int64_t)tile * kCtaRows + sub * kTileRows + row;
       const bool valid = g < p.n;
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
       uint4* save_row = nullptr;
       if (p.saved != nullptr)
-        save_row = reinterpret_cast<uint4*>(p.saved + ((size_t)tile * 2 + (row >> 6)) * (size_t)p.x_total * kHalfChunkBytes) +
-                   (row & 63);
+        save_row = reinterpret_cast<uint4*>(p.saved + ((size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6)) *
+                                                          (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
       float pt[3], dir[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -339,24 +428,28 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(act_ready);
+      t_pro += HN_T0() - t_tile;
 
       float wp[3 + C::H];  // warped point + hyper coordinates
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
-        const float* bias = p.bias + L.bias_off;
-        mbar_wait(acc_full, ph_acc); ph_acc ^= 1;
+        // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
+        // a per-block __ldg would go to L2 every time); double-buffered by layer parity
+        float* bias = sbias + (li & 1) * 256;
+        if (et < L.n_out) bias[et] = __ldg(p.bias + L.bias_off + et);
+        epi_named_barrier();
+        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == FE_RELU) {
-          for (int c0 = 0; c0 < L.n_out; c0 += 32)
-            fwd_block32<true>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+          fwd_cols<true>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
         } else if (L.epi == FE_WSHEAD) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + __ldg(bias + i));
+          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + bias[i]);
 #pragma unroll
-          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + __ldg(bias + 3 + i);
+          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + bias[3 + i];
           if (valid && p.warped != nullptr) {
 #pragma unroll
             for (int i = 0; i < 3 + C::H; ++i) p.warped[g * (3 + C::H) + i] = wp[i];
@@ -368,8 +461,7 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
           store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
         } else if (L.epi == FE_BOTT) {
-          for (int c0 = 0; c0 < L.n_out; c0 += 32)
-            fwd_block32<false>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+          fwd_cols<false>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
           float f[C::KV];
           posenc<3, C::VF>(dir, f);
@@ -377,12 +469,11 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
-          for (int c0 = 0; c0 < kRgbW; c0 += 32)
-            fwd_block32<true>(tlane + c0, bias + c0, act_row, save_row, c0 >> 3, L.save_chunk);
+          fwd_cols<true>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW);
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
-          float a = __uint_as_float(r[0]) + __ldg(bias + kRgbW);
+          float a = __uint_as_float(r[0]) + bias[kRgbW];
           if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;  // noise_regularize, model_utils.py:312-316
           if (valid) p.sigma[g] = softplus_f(a);                          // models.py:491
         } else {  // FE_RGBHEAD
@@ -391,7 +482,7 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + __ldg(bias + i));
+            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + bias[i]);
           }
         }
         if (li + 1 < prog.nlayers) {
@@ -401,17 +492,22 @@ __global__ void __launch_bounds__(192, 2) mlp_fwd_kernel(const __grid_constant__
         }
       }
     }
+    if (p.dbg && threadIdx.x == 128) {
+      const long long tt = HN_T0() - t_begin;
+      p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;
+      p.dbg[blockIdx.x * 8 + 6] = t_pro; p.dbg[blockIdx.x * 8 + 7] = tt;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ======================================================================================================
 // backward-data
 // ======================================================================================================
 template <class C>
-__global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
   uint8_t* act = smem + SM::ACT;
@@ -427,48 +523,61 @@ __global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 128);
+    mbar_init(act_ready, 128 * kSubTiles);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const Program& prog = p.prog;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
       RingState rs;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs);
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+      long long tw = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) produce_tile(prog, p.weights, ring, full, empty, rs, tw);
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
+    } else if (warp == 1) {  // whole warp, converged: see elect_one_sync()
       RingState rs;
       uint32_t ph_ready = 0;
+      long long t_ready = 0, t_full = 0;
+      const long long t_begin = HN_T0();
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
+          long long t0 = HN_T0();
           mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
+          t_ready += HN_T0() - t0;
           tc_fence_after();
-          issue_layer(prog, prog.layers[li], act_s, inb_s, ring_s, tmem_base, full, empty, rs);
-          umma_commit(acc_full);
+          issue_layer(prog, prog.layers[li], act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base, full, empty, rs,
+                      t_full);
+          if (elect_one_sync()) umma_commit(acc_full);
+          __syncwarp();
         }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
     }
   } else {
+    setmaxnreg_inc<216>();
+    const int sub = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* act_row = act + row * 16;
-    uint8_t* inb_row = inb + row * 16;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
+    uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
+    uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
     uint32_t ph_acc = 0;
+    long long t_acc = 0, t_pro = 0;
+    const long long t_begin = HN_T0();
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int64_t g = (int64_t)tile * kTileRows + row;
+      const long long t_tile = HN_T0();
+      const int64_t g = (int64_t)tile * kCtaRows + sub * kTileRows + row;
       const bool valid = g < p.n;
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
-      const size_t half = (size_t)tile * 2 + (row >> 6);
+      const size_t half = (size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6);
       const uint4* mask_row = reinterpret_cast<const uint4*>(p.saved + half * (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
       uint4* save_row = reinterpret_cast<uint4*>(p.dsaved + half * (size_t)p.d_total * kHalfChunkBytes) + (row & 63);
 
@@ -489,20 +598,21 @@ __global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(act_ready);
+      t_pro += HN_T0() - t_tile;
 
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
-        mbar_wait(acc_full, ph_acc); ph_acc ^= 1;
+        // all ReLU gates of this layer, fetched and compressed while the layer's MMAs run
+        uint32_t gates[8];
+        if (L.epi == BE_MASK || L.epi == BE_RGB1) load_gates(mask_row, L.mask_chunk, L.epi == BE_RGB1 ? kRgbW : L.n_out, gates);
+        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == BE_MASK) {
-          for (int c0 = 0; c0 < L.n_out; c0 += 32)
-            bwd_block32<true>(tlane + c0, mask_row, L.mask_chunk, act_row, save_row, c0 >> 3, L.save_chunk);
+          bwd_cols<true>(tlane, gates, act_row, save_row, L.save_chunk, L.n_out);
         } else if (L.epi == BE_LINEAR) {
-          for (int c0 = 0; c0 < L.n_out; c0 += 32)
-            bwd_block32<false>(tlane + c0, nullptr, 0, act_row, save_row, c0 >> 3, L.save_chunk);
+          bwd_cols<false>(tlane, gates, act_row, save_row, L.save_chunk, L.n_out);
         } else if (L.epi == BE_RGB1) {
-          for (int c0 = 0; c0 < kRgbW; c0 += 32)
-            bwd_block32<true>(tlane + c0, mask_row, L.mask_chunk, act_row, save_row, c0 >> 3, L.save_chunk);
+          bwd_cols<true>(tlane, gates, act_row, save_row, L.save_chunk, kRgbW);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
           float f[16];
 #pragma unroll
@@ -510,8 +620,7 @@ __global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant
           if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
         } else if (L.epi == BE_SKIPSTORE) {
-          for (int c0 = 0; c0 < L.n_out; c0 += 32)
-            bwd_block32<false>(tlane + c0, nullptr, 0, inb_row, nullptr, c0 >> 3, 0);
+          bwd_cols<false>(tlane, gates, inb_row, nullptr, 0, L.n_out);
         } else if (L.epi == BE_TRUNKIN) {
           // d(trunk input features) = layer-0 part (TMEM) + skip-layer part (INB, bf16)
           float gf[C::KT];
@@ -572,10 +681,15 @@ __global__ void __launch_bounds__(192, 2) mlp_dgrad_kernel(const __grid_constant
         }
       }
     }
+    if (p.dbg && threadIdx.x == 128) {
+      const long long tt = HN_T0() - t_begin;
+      p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;
+      p.dbg[blockIdx.x * 8 + 6] = t_pro; p.dbg[blockIdx.x * 8 + 7] = tt;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ======================================================================================================
@@ -646,7 +760,7 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && h0 < h1) {
+    if (h0 < h1) {  // whole warp, converged
       int slot = 0; uint32_t phase = 0, ph_empty = 0;
       for (int ji = 0; ji < njobs; ++ji) {
         const WgradJob& J = p.tab.jobs[ji];
@@ -657,18 +771,22 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
           mbar_wait(&full[slot], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + slot * kWgStageBytes);
-          for (int ks = 0; ks < kHalfRows / 16; ++ks) {
-            for (int mb = 0; mb < J.mblocks; ++mb) {
-              // A: dY^T, MN-major: 8 dY columns contiguous (16 B), K = rows (16 B stride); LBO = 8 rows, SBO = chunk
-              uint64_t ad = make_smem_desc(st + mb * 16 * kHalfChunkBytes + ks * 256, 128, kHalfChunkBytes);
-              uint64_t bd = make_smem_desc(st + kWgStageA + ks * 256, 128, kHalfChunkBytes);
-              umma_bf16(tmem_base + mb * ncols, ad, bd, idesc, (h > h0) | (ks > 0));
+          if (elect_one_sync()) {
+            for (int ks = 0; ks < kHalfRows / 16; ++ks) {
+              for (int mb = 0; mb < J.mblocks; ++mb) {
+                // A: dY^T, MN-major: 8 dY columns contiguous (16 B), K = rows (16 B stride); LBO = 8 rows, SBO = chunk
+                uint64_t ad = make_smem_desc(st + mb * 16 * kHalfChunkBytes + ks * 256, 128, kHalfChunkBytes);
+                uint64_t bd = make_smem_desc(st + kWgStageA + ks * 256, 128, kHalfChunkBytes);
+                umma_bf16(tmem_base + mb * ncols, ad, bd, idesc, (h > h0) | (ks > 0));
+              }
             }
+            umma_commit(&empty[slot]);
           }
-          umma_commit(&empty[slot]);
+          __syncwarp();
           if (++slot == kWgStages) { slot = 0; phase ^= 1; }
         }
-        umma_commit(acc_full);
+        if (elect_one_sync()) umma_commit(acc_full);
+        __syncwarp();
       }
     }
   } else if (h0 < h1) {
@@ -815,7 +933,8 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-static int64_t tiles_of(int64_t n) { return (n + kTileRows - 1) / kTileRows; }
+static unsigned long long* g_dbg = nullptr;
+static int64_t tiles_of(int64_t n) { return (n + kCtaRows - 1) / kCtaRows; }  // CTA tiles (256 rows)
 
 template <class K>
 static int set_smem(K kernel, int bytes, const char* what) {
@@ -834,7 +953,7 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
   static thread_local ModelPlan plan;
   build_plan(*desc, &plan);
   memset(out, 0, sizeof(*out));
-  const int64_t halves = 2 * tiles_of(n_samples);
+  const int64_t halves = 2 * kSubTiles * tiles_of(n_samples);
   out->packed_bytes = plan.layout.total;
   out->saved_bytes = halves * plan.slabs.x_total * kHalfChunkBytes;
   out->workspace_bytes = halves * plan.slabs.d_total * kHalfChunkBytes;
@@ -893,9 +1012,10 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   fp.x_total = plan.slabs.x_total;
   fp.x_in_ws = plan.slabs.x_in_ws; fp.x_in_t = plan.slabs.x_in_t; fp.x_in_v = plan.slabs.x_in_v;
   fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
+  fp.dbg = g_dbg;
   if (int rc = set_smem(mlp_fwd_kernel<C>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
-  int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
-  mlp_fwd_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+  int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
+  mlp_fwd_kernel<C><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
   return set_cuda_error(cudaGetLastError(), "hn_mlp_fwd");
 }
 
@@ -929,9 +1049,10 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.n_tiles = (int)nt;
     bp.x_total = plan.slabs.x_total; bp.d_total = plan.slabs.d_total;
     bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
+    bp.dbg = g_dbg;
     if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-    int grid = (int)std::min<int64_t>(nt, 2 * (int64_t)num_sms());
-    mlp_dgrad_kernel<C><<<grid, 192, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
+    int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
+    mlp_dgrad_kernel<C><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
     if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: dgrad launch")) return rc;
   }
   if (do_weights) {
@@ -939,7 +1060,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.tab = plan.wgrad;
     wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
     wp.flat_grad = flat_grad;
-    wp.n_half = 2 * nt;
+    wp.n_half = 2 * kSubTiles * nt;
     wp.x_total = plan.slabs.x_total; wp.d_total = plan.slabs.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
     int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
@@ -969,4 +1090,11 @@ extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, 
                                   const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
   return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
                       param_offsets, flat_grad, (void*)workspace, stream, false, true);
+}
+
+// debug hook (not part of the drop-in surface): device buffer of 8 x uint64 per CTA that the fused kernels fill with
+// per-role cycle counters; NULL switches it off.
+extern "C" int hn_debug_set_timing_buffer(void* dev_buffer) {
+  g_dbg = (unsigned long long*)dev_buffer;
+  return 0;
 }

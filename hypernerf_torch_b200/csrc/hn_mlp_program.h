@@ -15,12 +15,14 @@
 
 namespace hn {
 
-constexpr int kTileRows = 128;   // samples per CTA tile (= UMMA M = TMEM lanes)
+constexpr int kTileRows = 128;   // samples per sub-tile (= UMMA M = TMEM lanes)
+constexpr int kSubTiles = 2;     // sub-tiles per CTA; they share every weight stage (halves L2 weight traffic)
+constexpr int kCtaRows = kTileRows * kSubTiles;
 constexpr int kHalfRows = 64;    // granularity of the saved-activation layout and of the wgrad K step
 constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-row smem operand
 constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-row global slab
 constexpr int kRingStages = 3;
-constexpr int kStageBytes = 8192;
+constexpr int kStageBytes = 16384;
 constexpr int kMaxOps = 32;
 constexpr int kMaxLayers = 24;
 constexpr int kMaxJobs = 40;

@@ -87,3 +87,124 @@ extern "C" int hn_umma_probe(const void* A, const void* B, float* D, int N, int 
                                                               N, K, a_mn, b_mn);
   return hn::set_cuda_error(cudaGetLastError(), "hn_umma_probe: launch");
 }
+
+// ------------------------------------------------------------------------------------------------------
+// UMMA issue-rate microbenchmark (test hook): back-to-back K=16 UMMAs from resident shared-memory operands,
+// no epilogue.  Reports cycles per UMMA for a layout / shape, so the fused kernels' tensor-pipe time can be
+// separated from everything else.  Operand contents are whatever shared memory holds.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int N, int ksteps, int reps, int swizzle, int nsub, int inner, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x;
+  // zero-fill operands (128 x 256 A per sub, N x 256 B)
+  const int total = nsub * 128 * 256 * 2 + N * 64 * 2;   // A: 128 x 256 per sub; B: N x 64 (4 k-steps, re-used)
+  for (int i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); }
+  if (tid < 32) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid < 32) {  // converged warp; tcgen05 instructions guarded by elect_one_sync()
+    const uint32_t sA = smem_u32(smem), sB = sA + nsub * 128 * 256 * 2;
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one_sync()) {
+      for (int in = 0; in < inner; ++in)
+      for (int ks = 0; ks < ksteps; ++ks) {
+        for (int sub = 0; sub < nsub; ++sub) {
+          uint64_t ad, bd;
+          if (swizzle != 1) {
+            ad = make_smem_desc(sA + sub * 65536 + ks * 4096, 2048, 128);
+            bd = make_smem_desc(sB + (ks % 4) * 2 * N * 16, N * 16, 128);
+          } else {
+            // 128B swizzle, K-major: 64-element (128 B) rows, 8-row atoms of 1024 B; K advance = 32 B inside the atom row
+            ad = make_smem_desc(sA + sub * 65536 + (ks / 4) * 16384 + (ks % 4) * 32, 16, 1024) | ((uint64_t)2 << 61);
+            bd = make_smem_desc(sB + (ks % 4) * 32, 16, 1024) | ((uint64_t)2 << 61);
+          }
+          umma_bf16(tmem_base + sub * 256, ad, bd, idesc, ks > 0);
+        }
+        // swizzle >= 2: also commit (un-waited, on a second barrier) after every (swizzle-1)-th k-step
+        if (swizzle >= 2 && (ks % (swizzle - 1)) == (swizzle - 2)) umma_commit(&bar2);
+      }
+      umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (tid == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+}  // namespace hn
+
+extern "C" int hn_umma_rate(int N, int ksteps, int reps, int swizzle, int nsub, int inner, int grid, void* out_cycles,
+                            void* stream) {
+  if (N < 16 || N > 256 || N % 16 || ksteps < 1 || ksteps > 16 || nsub < 1 || nsub > 2) return hn::set_error(-1, "hn_umma_rate: bad args");
+  size_t smem = (size_t)nsub * 128 * 256 * 2 + (size_t)N * 64 * 2 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(hn::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return hn::set_cuda_error(e, "hn_umma_rate: smem attr");
+  hn::umma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(N, ksteps, reps, swizzle, nsub, inner, (unsigned long long*)out_cycles);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_umma_rate: launch");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// TMEM read-throughput microbenchmark (test hook): nwarps warps each read `cols` accumulator columns of their
+// 32 lanes with tcgen05.ld.32x32b.x32, `reps` times.  mode 0: load+wait per block; 1: two loads in flight.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+__global__ void __launch_bounds__(256, 1) tmem_rate_kernel(int cols, int reps, int mode, unsigned long long* out) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 256;
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0) {
+      for (int c = 0; c < cols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= v[j];
+      }
+    } else {
+      for (int c = 0; c < cols; c += 64) {
+        uint32_t v[32], w[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld32(taddr + c + 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= v[j] ^ w[j];
+      }
+    }
+  }
+  long long t1 = clock64();
+  if (acc == 0x12345678u) out[1] = acc;
+  if (threadIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace hn
+
+extern "C" int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream) {
+  if (nwarps < 1 || nwarps > 8 || cols < 64 || cols > 256 || cols % 64) return hn::set_error(-1, "hn_tmem_rate: bad args");
+  hn::tmem_rate_kernel<<<1, nwarps * 32, 0, (cudaStream_t)stream>>>(cols, reps, mode, (unsigned long long*)out_cycles);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_tmem_rate: launch");
+}

@@ -174,6 +174,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One elected lane of a CONVERGED warp.  The UMMA issuer must run its loop with all 32 lanes (warp-uniform control
+// flow and operands) and guard only the tcgen05 instructions with this predicate: ptxas then keeps descriptors in
+// uniform registers.  Issuing from a divergent `if (lane == 0)` region makes it wrap every UTCHMMA in an
+// ELECT/BRA.U.ANY loop fed by R2UR moves (~240 cycles per instruction, measured with profiles/umma_rate.py).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred;
+}
+
+// register re-balancing between warpgroups (all 4 warps of the warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // pack two fp32 -> bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   uint32_t r;

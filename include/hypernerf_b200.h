@@ -136,6 +136,17 @@ int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, 
  * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
 int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);
 
+/* test hook: cycles for reps x (inner x ksteps x nsub back-to-back K=16 UMMAs (M=128) + one commit/wait) from resident
+ * shared-memory operands; swizzle 0 = un-swizzled interleave layout, 1 = 128B swizzle.  out_cycles: uint64 per CTA. */
+int hn_umma_rate(int N, int ksteps, int reps, int swizzle, int nsub, int inner, int grid, void* out_cycles, void* stream);
+
+/* test hook: cycles for nwarps warps to read `cols` TMEM columns of their 32 lanes `reps` times (tcgen05.ld.32x32b.x32). */
+int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream);
+
+/* profiling hook: device buffer of 8 x uint64 per CTA filled by the fused MLP kernels with per-role cycle counters
+ * (producer wait, UMMA-issuer waits, epilogue wait / work); NULL = off. */
+int hn_debug_set_timing_buffer(void* dev_buffer);
+
 #ifdef __cplusplus
 }
 #endif
