@@ -89,14 +89,21 @@ struct BwdParams {
 // ------------------------------------------------------------------------------------------------------
 // cycle counters per CTA: [0] producer wait-empty, [1] mma wait-act_ready, [2] mma wait-full, [3] mma total,
 // [4] epilogue wait-acc_full, [5] epilogue work, [6] epilogue prologue, [7] epilogue total
+#ifndef HN_ROLE_TIMING
+#define HN_ROLE_TIMING 0   // make EXTRA=-DHN_ROLE_TIMING=1 for profiles/role_timing.py
+#endif
+#if HN_ROLE_TIMING
 #define HN_T0() (clock64())
+#else
+#define HN_T0() (0ll)
+#endif
 struct RingState { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == kRingStages) { slot = 0; phase ^= 1; } } };
 
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
                                              uint64_t* full, uint64_t* empty, RingState& rs, long long& t_wait) {
   for (int oi = 0; oi < prog.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
-    const int nchunks = (op.k0 + op.k1) >> 3;
+    const int nchunks = op.k >> 3;
     const uint8_t* src = weights + (size_t)op.w_off16 * 16;
     for (int c = 0; c < nchunks; c += op.cps) {
       int cnt = min((int)op.cps, nchunks - c);
@@ -111,39 +118,47 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
   }
 }
 
+// The issuing thread's own instruction stream bounds the tensor pipe: measured with profiles/umma_rate{2,3}.py, a
+// UMMA retires at its floor (N/2 cycles for N >= 128) only if the issue loop spends less than that per instruction.
+// So everything that can be hoisted is: per op the descriptors' low words are formed once, and the k-step loop only
+// adds constants to them (address field = bits [0,14) of the low word, in 16-byte units; smem addresses stay below
+// 256 KB so the add never carries into the LBO field).
+constexpr uint32_t kDescHi = (1u << 14) | (128u >> 4);   // descriptor version 1, SBO = 128 B, no swizzle
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
 __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, uint32_t act_s, uint32_t inb_s,
                                             uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s,
                                             uint32_t tmem_base, uint64_t* full, uint64_t* empty, RingState& rs,
                                             long long& t_wait) {
   for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
-    const int nchunks = (op.k0 + op.k1) >> 3;
-    const uint32_t idesc = make_idesc_bf16(kTileRows, op.n, 0, 0);
-    const uint32_t a0 = (op.src0 == SRC_ACT ? act_s : inb_s) + op.a0_chunk * kChunkBytes;
-    const uint32_t a1 = (op.src1 == SRC_ACT ? act_s : inb_s) + op.a1_chunk * kChunkBytes;
-    const uint32_t k0_chunks = op.k0 >> 3;
-    const uint32_t b_lbo = op.n * 16;
-    for (int c = 0; c < nchunks; c += op.cps) {
-      int cnt = min((int)op.cps, nchunks - c);
+    const uint32_t n = op.n, nchunks = op.k >> 3, cps = op.cps;
+    const uint32_t idesc = make_idesc_bf16(kTileRows, n, 0, 0);
+    const bool from_act = op.src == SRC_ACT;
+    // A: K-major, LBO = one 8-column chunk of 128 rows
+    const uint32_t a_base = (((from_act ? act_s : inb_s) + op.a_chunk * kChunkBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16);
+    const uint32_t a_sub = (from_act ? act_stride : inb_stride) >> 4;
+    const uint32_t d0 = tmem_base + op.tmem_col;
+    const uint32_t acc0 = op.acc_init;
+    for (uint32_t c = 0; c < nchunks; c += cps) {
+      const uint32_t cnt = min(cps, nchunks - c);
       long long t0 = HN_T0();
       mbar_wait(&full[rs.slot], rs.phase);
       t_wait += HN_T0() - t0;
       tc_fence_after();
-      const uint32_t stage = ring_s + rs.slot * kStageBytes;
       if (elect_one_sync()) {
-      for (int j = 0; j < cnt; j += 2) {
-        uint32_t kc = c + j;  // chunk index inside the op's K
-        const bool first = kc < k0_chunks;
-        uint32_t a_addr = first ? a0 + kc * kChunkBytes : a1 + (kc - k0_chunks) * kChunkBytes;
-        const uint32_t a_sub = (first ? op.src0 : op.src1) == SRC_ACT ? act_stride : inb_stride;
-        uint64_t bd = make_smem_desc(stage + j * b_lbo, b_lbo, 128);
-#pragma unroll
-        for (int sub = 0; sub < kSubTiles; ++sub) {
-          uint64_t ad = make_smem_desc(a_addr + sub * a_sub, kChunkBytes, 128);
-          umma_bf16(tmem_base + sub * 256 + op.tmem_col, ad, bd, idesc, (kc > 0) | op.acc_init);
+        uint32_t a_lo = a_base + c * (uint32_t)(kChunkBytes >> 4);
+        uint32_t b_lo = ((ring_s + rs.slot * kStageBytes) >> 4) | (n << 16);   // B: K-major, LBO = N * 16 B
+        uint32_t acc = (c > 0) | acc0;
+        for (uint32_t j = 0; j < cnt; j += 2) {
+          const uint64_t bd = desc64(b_lo);
+          umma_bf16(d0, desc64(a_lo), bd, idesc, acc);
+          umma_bf16(d0 + 256, desc64(a_lo + a_sub), bd, idesc, acc);
+          a_lo += 2 * (kChunkBytes >> 4);
+          b_lo += 2 * n;
+          acc = 1;
         }
-      }
-      umma_commit(&empty[rs.slot]);
+        umma_commit(&empty[rs.slot]);
       }
       __syncwarp();
       rs.next();
@@ -359,7 +374,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
   const Program& prog = p.prog;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
+    setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       RingState rs;
       long long tw = 0;
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
   const Program& prog = p.prog;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
+    setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       RingState rs;
       long long tw = 0;
@@ -762,23 +777,30 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
   } else if (warp == 1) {
     if (h0 < h1) {  // whole warp, converged
       int slot = 0; uint32_t phase = 0, ph_empty = 0;
+      // both operands MN-major straight out of the stash layout: 8 columns contiguous (16 B), K = rows (16 B stride);
+      // LBO = 8 rows (128 B), SBO = one chunk (kHalfChunkBytes)
+      constexpr uint32_t kHi = (1u << 14) | (kHalfChunkBytes >> 4);
+      const uint32_t st0 = smem_u32(smem);
       for (int ji = 0; ji < njobs; ++ji) {
         const WgradJob& J = p.tab.jobs[ji];
         const uint32_t ncols = (J.x0_nchunks + J.x1_nchunks) * 8;  // UMMA N
         const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
+        const bool two = J.mblocks == 2;
+        const uint32_t d1 = tmem_base + ncols;
         if (ji > 0) { mbar_wait(acc_empty, ph_empty); ph_empty ^= 1; tc_fence_after(); }
         for (int64_t h = h0; h < h1; ++h) {
           mbar_wait(&full[slot], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + slot * kWgStageBytes);
           if (elect_one_sync()) {
+            const uint32_t a_lo = ((st0 + slot * kWgStageBytes) >> 4) | ((128u >> 4) << 16);
+            const uint32_t b_lo = a_lo + (kWgStageA >> 4);
+            uint32_t acc = h > h0;
+#pragma unroll
             for (int ks = 0; ks < kHalfRows / 16; ++ks) {
-              for (int mb = 0; mb < J.mblocks; ++mb) {
-                // A: dY^T, MN-major: 8 dY columns contiguous (16 B), K = rows (16 B stride); LBO = 8 rows, SBO = chunk
-                uint64_t ad = make_smem_desc(st + mb * 16 * kHalfChunkBytes + ks * 256, 128, kHalfChunkBytes);
-                uint64_t bd = make_smem_desc(st + kWgStageA + ks * 256, 128, kHalfChunkBytes);
-                umma_bf16(tmem_base + mb * ncols, ad, bd, idesc, (h > h0) | (ks > 0));
-              }
+              const uint64_t bd = ((uint64_t)kHi << 32) | (b_lo + ks * 16);
+              umma_bf16(tmem_base, ((uint64_t)kHi << 32) | (a_lo + ks * 16), bd, idesc, acc);
+              if (two) umma_bf16(d1, ((uint64_t)kHi << 32) | (a_lo + ks * 16 + ((16 * kHalfChunkBytes) >> 4)), bd, idesc, acc);
+              acc = 1;
             }
             umma_commit(&empty[slot]);
           }

@@ -22,26 +22,30 @@ namespace {
 
 struct Builder {
   Program* p;
+  LogicalOps* lg;
   uint32_t w16 = 0;  // running weight offset (16-byte units)
   void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk) {
     Layer& L = p->layers[p->nlayers++];
     L.op0 = (uint8_t)p->nops; L.nops = 0; L.epi = epi; L.pad = 0;
     L.n_out = (uint16_t)n_out; L.bias_off = (uint16_t)bias_off; L.save_chunk = save_chunk; L.mask_chunk = mask_chunk;
   }
-  // returns op index
-  int add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
-    MmaOp& o = p->ops[p->nops];
-    o.w_off16 = w16; o.n = (uint16_t)n; o.k0 = (uint16_t)k0; o.k1 = (uint16_t)k1;
-    o.a0_chunk = (uint16_t)(a0_col / 8); o.a1_chunk = (uint16_t)(a1_col / 8);
-    o.tmem_col = (uint16_t)tmem_col; o.src0 = s0; o.src1 = s1; o.acc_init = (uint8_t)acc_init;
+  void emit(int n, int k, Src s, int a_col, int tmem_col, int acc_init) {
+    MmaOp& o = p->ops[p->nops++];
+    o.w_off16 = w16; o.n = (uint16_t)n; o.k = (uint16_t)k; o.a_chunk = (uint16_t)(a_col / 8);
+    o.tmem_col = (uint16_t)tmem_col; o.src = s; o.acc_init = (uint8_t)acc_init; o.pad = 0;
     int cps = (kStageBytes / (n * 16)) & ~1;
     if (cps < 2) cps = 2;
-    int nchunks = (k0 + k1) / 8;
-    if (cps > nchunks) cps = nchunks;
+    if (cps > k / 8) cps = k / 8;
     o.cps = (uint8_t)cps;
-    w16 += (uint32_t)n * (uint32_t)(k0 + k1) / 8;  // n * K * 2 bytes / 16
+    w16 += (uint32_t)n * (uint32_t)k / 8;  // n * K * 2 bytes / 16
     p->layers[p->nlayers - 1].nops++;
-    return p->nops++;
+  }
+  // One logical [n x (k0 + k1)] matrix; the K range is split over two source buffers when k1 > 0.
+  void add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
+    LogicalOp& l = lg->ops[lg->n++];
+    l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k0 + k1);
+    emit(n, k0, s0, a0_col, tmem_col, acc_init);
+    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1);
   }
 };
 
@@ -49,10 +53,10 @@ struct Packer {
   PackTable* t;
   const int64_t* off;
   int cur = -1;
-  void op(const MmaOp& o) {
+  void op(const LogicalOp& o) {
     cur = t->nops++;
     PackOp& po = t->ops[cur];
-    po.w_off16 = o.w_off16; po.n = o.n; po.k = (uint16_t)(o.k0 + o.k1); po.blk0 = (uint8_t)t->nblocks; po.nblk = 0; po.pad = 0;
+    po.w_off16 = o.w_off16; po.n = o.n; po.k = o.k; po.blk0 = (uint8_t)t->nblocks; po.nblk = 0; po.pad = 0;
   }
   void block(int param, int64_t src_extra, int sn, int sk, int n0, int nn, int k0, int kk) {
     PackBlock& b = t->blocks[t->nblocks++];
@@ -82,7 +86,7 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
 
   // ------------------------------------------------------------------ forward program
   {
-    Builder b{&plan->fwd};
+    Builder b{&plan->fwd, &plan->fwd_logical};
     int bias = 0;
     // warp + sheet, merged to one 192-wide net sharing the input buffer
     b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone);
@@ -127,7 +131,7 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   }
   // ------------------------------------------------------------------ backward-data program
   {
-    Builder b{&plan->bwd};
+    Builder b{&plan->bwd, &plan->bwd_logical};
     // D0: rgb head^T.  A = dY_rgbhead (16 cols, written by the prologue)
     b.begin_layer(BE_MASK, kRgbW, 0, s.d_r[3], s.x_r[3]);
     b.add_op(kRgbW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
@@ -184,7 +188,7 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   PackTable& t = plan->pack;
   memset(&t, 0, sizeof(t));
   Packer pk{&t, off};
-  const Program& F = plan->fwd;
+  const LogicalOps& F = plan->fwd_logical;
   int oi = 0;
   const int ldw5 = kWarpW + m.in_w, lds5 = kSheetW + m.in_s;
   // fwd ws0
@@ -227,10 +231,10 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   pk.block(P_RGB_W(level, kRgbDepth), 0, kRgbW, 1, 0, 3, 0, kRgbW);
 
   // bwd: dest(n = input feature, k = output feature) = W[k][n]  -> sn = 1, sk = ld
-  const Program& Bp = plan->bwd;
+  const LogicalOps& Bp = plan->bwd_logical;
   const uint32_t bwd16 = (uint32_t)(plan->layout.bwd_off / 16);
   oi = 0;
-  auto bop = [&](void) { MmaOp o = Bp.ops[oi++]; o.w_off16 += bwd16; pk.op(o); };
+  auto bop = [&](void) { LogicalOp o = Bp.ops[oi++]; o.w_off16 += bwd16; pk.op(o); };
   bop();  // D0 rgb head^T: n < 128, k < 3
   pk.block(P_RGB_W(level, kRgbDepth), 0, 1, kRgbW, 0, kRgbW, 0, 3);
   for (int l = kRgbDepth - 1; l >= 1; --l) {

@@ -23,7 +23,7 @@ constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-
 constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-row global slab
 constexpr int kRingStages = 3;
 constexpr int kStageBytes = 16384;
-constexpr int kMaxOps = 32;
+constexpr int kMaxOps = 40;
 constexpr int kMaxLayers = 24;
 constexpr int kMaxJobs = 40;
 constexpr uint16_t kNone = 0xFFFF;
@@ -112,12 +112,19 @@ enum Src : uint8_t { SRC_ACT = 0, SRC_INB = 1 };
 struct MmaOp {
   uint32_t w_off16;            // weights of this op inside the packed blob, 16-byte units
   uint16_t n;                  // UMMA N (multiple of 16)
-  uint16_t k0, k1;             // K columns taken from source 0 / source 1 (multiples of 16; k1 may be 0)
-  uint16_t a0_chunk, a1_chunk; // first 8-col chunk inside the source buffers
+  uint16_t k;                  // K columns (multiple of 16), all taken from one source buffer
+  uint16_t a_chunk;            // first 8-col chunk inside the source buffer
   uint16_t tmem_col;           // accumulator column offset
-  uint8_t src0, src1;
+  uint8_t src;
   uint8_t acc_init;            // 1: accumulate onto what TMEM already holds
   uint8_t cps;                 // 8-col chunks of K per ring stage (even)
+  uint8_t pad;
+};
+// A weight matrix as the packer sees it: one [n x k] operand image; a skip layer's matrix is consumed by two
+// consecutive MmaOps (hidden part, then input part accumulating on top).
+struct LogicalOp {
+  uint32_t w_off16;
+  uint16_t n, k;
 };
 
 enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD };
@@ -135,6 +142,10 @@ struct Program {
   int32_t nlayers, nops;
   Layer layers[kMaxLayers];
   MmaOp ops[kMaxOps];
+};
+struct LogicalOps {
+  int32_t n;
+  LogicalOp ops[kMaxOps];
 };
 
 // ---- weight packing ----------------------------------------------------------------------------------
@@ -194,6 +205,7 @@ struct ModelPlan {
   Dims dims;
   SlabMap slabs;
   Program fwd, bwd;
+  LogicalOps fwd_logical, bwd_logical;
   PackTable pack;     // needs param_offsets -> built per call
   WgradTable wgrad;   // needs param_offsets -> built per call
   PackedLayout layout;

@@ -208,3 +208,189 @@ extern "C" int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_
   hn::tmem_rate_kernel<<<1, nwarps * 32, 0, (cudaStream_t)stream>>>(cols, reps, mode, (unsigned long long*)out_cycles);
   return hn::set_cuda_error(cudaGetLastError(), "hn_tmem_rate: launch");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// Second issue-rate microbenchmark (test hook): separates the per-UMMA cost by accumulator rotation, M, operand
+// source (A from shared memory or TMEM) and CTA pairing (cta_group::1 vs ::2 on a 2-CTA cluster).
+//   nacc   accumulators rotated (N * nacc <= 512 columns minus the TMEM A operand)
+//   order  0: k-step outer, accumulator inner (adjacent UMMAs hit different accumulators)
+//          1: accumulator outer, k-step inner (16 chained UMMAs per accumulator)
+//   a_src  0: A from shared memory, distinct K slice per step; 1: same A slice every step; 2: A from TMEM (.ts)
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+template <int CG>
+__device__ __forceinline__ void umma2(uint32_t d, uint64_t ad, uint32_t a_tmem, bool a_in_tmem, uint64_t bd, uint32_t idesc,
+                                      uint32_t acc) {
+  if (CG == 1) {
+    if (!a_in_tmem)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                   ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+  } else {
+    if (!a_in_tmem)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                   ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+umma_rate2_kernel(int M, int N, int nacc, int order, int a_src, int reps, int inner, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x;
+  uint32_t rank = 0;
+  if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int total = 128 * 256 * 2 + 256 * 64 * 2;   // A: 128 x 256; B: up to 256 x 64 (4 k-steps, re-used)
+  for (int i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) {
+    if (CG == 1) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid < 32 && rank == 0) {
+    const uint32_t sA = smem_u32(smem), sB = sA + 128 * 256 * 2;
+    const uint32_t idesc = make_idesc_bf16(M, N, 0, 0);
+    const uint32_t nb = (CG == 2) ? N / 2 : N;  // B rows held by this CTA
+    const uint32_t a_tmem = tmem_base + 384;    // 128 columns of packed bf16 A (K = 256)
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one_sync()) {
+        for (int in = 0; in < inner; ++in) {
+          const int n_outer = order == 0 ? 16 : nacc, n_inner = order == 0 ? nacc : 16;
+          for (int o = 0; o < n_outer; ++o)
+            for (int i2 = 0; i2 < n_inner; ++i2) {
+              const int ks = order == 0 ? o : i2, acc = order == 0 ? i2 : o;
+              const uint64_t ad = make_smem_desc(sA + (a_src == 1 ? 0 : ks * 4096), 2048, 128);
+              const uint64_t bd = make_smem_desc(sB + (ks % 4) * 2 * nb * 16, nb * 16, 128);
+              umma2<CG>(tmem_base + acc * N, ad, a_tmem + ks * 8, a_src == 2, bd, idesc, ks > 0);
+            }
+        }
+        if (CG == 1) umma_commit(&bar);
+        else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (tid == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+  if (tid < 32) {
+    if (CG == 1) tmem_dealloc(tmem_base, 512);
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+}  // namespace hn
+
+extern "C" int hn_umma_rate2(int cta_group, int M, int N, int nacc, int order, int a_src, int reps, int inner, int grid,
+                             void* out_cycles, void* stream) {
+  if (N < 16 || N > 256 || N % 16 || nacc < 1 || N * nacc > 384 || (cta_group != 1 && cta_group != 2))
+    return hn::set_error(-1, "hn_umma_rate2: bad args");
+  size_t smem = 128 * 256 * 2 + 256 * 64 * 2 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e;
+  if (cta_group == 1) {
+    e = cudaFuncSetAttribute(hn::umma_rate2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, hn::umma_rate2_kernel<1>, M, N, nacc, order, a_src, reps, inner, (unsigned long long*)out_cycles);
+  } else {
+    e = cudaFuncSetAttribute(hn::umma_rate2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, hn::umma_rate2_kernel<2>, M, N, nacc, order, a_src, reps, inner, (unsigned long long*)out_cycles);
+  }
+  return hn::set_cuda_error(e, "hn_umma_rate2: launch");
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Third issue-rate microbenchmark: the same UMMA stream as a fully unrolled, straight-line sequence with
+// descriptors advanced by compile-time constants (no per-instruction descriptor arithmetic), to separate the
+// tensor pipe's own rate from the cost of the issuing thread's loop.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+template <int N, int NACC>
+__global__ void __launch_bounds__(128, 1) umma_rate3_kernel(int reps, int inner, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x;
+  const int total = NACC * 128 * 256 * 2 + 256 * 64 * 2;
+  for (int i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid < 32) {
+    const uint32_t sA = smem_u32(smem), sB = sA + NACC * 128 * 256 * 2;
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint64_t ad0 = make_smem_desc(sA, 2048, 128), bd0 = make_smem_desc(sB, N * 16, 128);
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one_sync()) {
+        for (int in = 0; in < inner; ++in) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              umma_bf16(tmem_base + a * 256, ad0 + (uint64_t)((a * 65536 + ks * 4096) >> 4), bd0 + (uint64_t)(((ks % 4) * 2 * N * 16) >> 4),
+                        idesc, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (tid == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+template <int N, int NACC>
+static cudaError_t launch_rate3(int reps, int inner, int grid, unsigned long long* out, cudaStream_t st) {
+  size_t smem = (size_t)NACC * 128 * 256 * 2 + 256 * 64 * 2 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_rate3_kernel<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  umma_rate3_kernel<N, NACC><<<grid, 128, smem, st>>>(reps, inner, out);
+  return cudaGetLastError();
+}
+}  // namespace hn
+
+extern "C" int hn_umma_rate3(int N, int nacc, int reps, int inner, int grid, void* out_cycles, void* stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  unsigned long long* o = (unsigned long long*)out_cycles;
+  cudaStream_t st = (cudaStream_t)stream;
+#define HN_R3(n, a) if (N == n && nacc == a) e = hn::launch_rate3<n, a>(reps, inner, grid, o, st);
+  HN_R3(256, 1) HN_R3(256, 2) HN_R3(128, 1) HN_R3(128, 2) HN_R3(64, 1) HN_R3(64, 2) HN_R3(16, 1) HN_R3(16, 2)
+#undef HN_R3
+  return hn::set_cuda_error(e, "hn_umma_rate3");
+}

@@ -140,6 +140,14 @@ int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K
  * shared-memory operands; swizzle 0 = un-swizzled interleave layout, 1 = 128B swizzle.  out_cycles: uint64 per CTA. */
 int hn_umma_rate(int N, int ksteps, int reps, int swizzle, int nsub, int inner, int grid, void* out_cycles, void* stream);
 
+/* test hook: per-UMMA cost by accumulator rotation (nacc, order), M, A source (0 smem, 1 same smem slice, 2 TMEM) and
+ * CTA pairing (cta_group 1, or 2 on a 2-CTA cluster); reps x (inner x 16 x nacc UMMAs + commit/wait). */
+int hn_umma_rate2(int cta_group, int M, int N, int nacc, int order, int a_src, int reps, int inner, int grid,
+                  void* out_cycles, void* stream);
+
+/* test hook: as hn_umma_rate but a fully unrolled issue sequence (N in {16,64,128,256}, nacc in {1,2}). */
+int hn_umma_rate3(int N, int nacc, int reps, int inner, int grid, void* out_cycles, void* stream);
+
 /* test hook: cycles for nwarps warps to read `cols` TMEM columns of their 32 lanes `reps` times (tcgen05.ld.32x32b.x32). */
 int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream);
 

@@ -32,6 +32,9 @@ def report(tag):
     torch.cuda.synchronize()
     v = dbg.view(148, 8).double()
     tot = v[:, 3].mean().item()
+    if tot == 0:
+        print(tag, '(library built without -DHN_ROLE_TIMING=1: no role counters)')
+        return
     print(tag, " ".join(f"{n}={v[:, i].mean().item() / tot:.3f}" for i, n in enumerate(names)), f"cycles={tot:.3e}")
     dbg.zero_()
 
