@@ -10,7 +10,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhypernerf_b200.so")
+LIB_PATH = os.environ.get("HN_LIB") or os.path.join(_HERE, "libhypernerf_b200.so")  # HN_LIB: profiling build
 HN_NUM_PARAM_TENSORS = 93
 HN_FLAG_WARP_TRANSLATION = 1
 HN_FLAG_SLICE_BENDY = 2

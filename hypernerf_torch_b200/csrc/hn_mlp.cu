@@ -273,70 +273,65 @@ __device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, ui
   }
 }
 
-// backward: ReLU gates.  The stash holds post-ReLU bf16 activations (>= +0), so "activation > 0" <=> halfword != 0.
-// 8 activations (one 16-byte packet) -> 8 gate bits; adding 0x7FFF to a halfword <= 0x7FFF sets its bit 15 iff it
-// is non-zero and never carries into the neighbour.
-__device__ __forceinline__ uint32_t gate8(const uint4 x) {
-  const uint32_t t0 = (x.x + 0x7FFF7FFFu) & 0x80008000u, t1 = (x.y + 0x7FFF7FFFu) & 0x80008000u;
-  const uint32_t t2 = (x.z + 0x7FFF7FFFu) & 0x80008000u, t3 = (x.w + 0x7FFF7FFFu) & 0x80008000u;
-  const uint32_t m = (t0 >> 15) | (t1 >> 13) | (t2 >> 11) | (t3 >> 9);
-  return (m | (m >> 15)) & 0xFFu;
-}
-// All gates of one layer for this thread's row: up to 32 independent 16-byte loads (issued while the layer's MMAs
-// run) folded into 8 words.
-__device__ __forceinline__ void load_gates(const uint4* __restrict__ mask_row, int mask_chunk, int ncols, uint32_t* gates) {
+// backward: ReLU gates.  All stash packets that gate one layer are requested before the epilogue waits for the
+// accumulator (they are L2 hits: the prefetch warp pulled the slab in a layer ahead) and folded to byte masks
+// (2 words per 8 columns, see gate_bytes in hn_ptx.cuh); the packed gradient is then masked with 2 integer ops per
+// 2 columns.
+template <int NCOLS>
+__device__ __forceinline__ void load_gates(const uint4* __restrict__ mask_row, int mask_chunk, uint32_t* gm) {
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    gates[w] = 0;
-    if (w * 32 < ncols) {
-      const uint4* p = mask_row + (size_t)(mask_chunk + 4 * w) * (kHalfChunkBytes / 16);
-      const uint4 x0 = __ldg(p), x1 = __ldg(p + kHalfChunkBytes / 16), x2 = __ldg(p + 2 * (kHalfChunkBytes / 16)),
-                  x3 = __ldg(p + 3 * (kHalfChunkBytes / 16));
-      gates[w] = gate8(x0) | (gate8(x1) << 8) | (gate8(x2) << 16) | (gate8(x3) << 24);
+  for (int b = 0; b < NCOLS / 64; ++b) {  // batches of 8 packets = 64 columns
+    uint4 x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = __ldg(mask_row + (size_t)(mask_chunk + b * 8 + q) * (kHalfChunkBytes / 16));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      gm[(b * 8 + q) * 2] = gate_bytes(x[q].x, x[q].y);
+      gm[(b * 8 + q) * 2 + 1] = gate_bytes(x[q].z, x[q].w);
     }
   }
 }
 
+// one 32-column block: r = accumulator row slice, gm = byte masks of the block's 4 packets (8 words)
 template <bool MASK>
-__device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t gate, uint8_t* dst_row, uint4* save_row,
+__device__ __forceinline__ void bwd_store32(const uint32_t* r, const uint32_t* gm, uint8_t* dst_row, uint4* save_row,
                                             int chunk0, int save_chunk) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = __uint_as_float(r[8 * q + j]);
-      if (MASK && !((gate >> (8 * q + j)) & 1u)) v[j] = 0.f;
-    }
     uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    o.x = pack_bf16(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
+    o.y = pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
+    o.z = pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
+    o.w = pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+    if (MASK) {
+      o.x &= gate_half<0>(gm[2 * q]); o.y &= gate_half<1>(gm[2 * q]);
+      o.z &= gate_half<0>(gm[2 * q + 1]); o.w &= gate_half<1>(gm[2 * q + 1]);
+    }
     *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = o;
     if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
   }
 }
-
-// ncols: multiple of 32; gates[b] holds the 32 gate bits of column block b
-template <bool MASK>
-__device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gates, uint8_t* dst_row, uint4* save_row,
-                                         int save_chunk, int ncols) {
-  uint32_t ra[32], rb[32];
-  tmem_ld32(taddr, ra);
+// NCOLS: multiple of 32 (<= 256), compile time so that gm[] and both row buffers stay in registers
+template <bool MASK, int NCOLS>
+__device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gm, uint8_t* dst_row, uint4* save_row, int save_chunk) {
+  uint32_t r[2][32];
+  tmem_ld32(taddr, r[0]);
 #pragma unroll
-  for (int b = 0; b < 8; b += 2) {
-    const int c0 = b * 32;
-    if (c0 < ncols) {
-      tmem_ld_wait();
-      const bool more = c0 + 32 < ncols;
-      if (more) tmem_ld32(taddr + c0 + 32, rb);
-      bwd_store32<MASK>(ra, gates[b], dst_row, save_row, c0 >> 3, save_chunk);
-      if (more) {
-        tmem_ld_wait();
-        if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
-        bwd_store32<MASK>(rb, gates[b + 1], dst_row, save_row, (c0 + 32) >> 3, save_chunk);
-      }
-    }
+  for (int b = 0; b < NCOLS / 32; ++b) {
+    tmem_ld_wait();
+    if (b + 1 < NCOLS / 32) tmem_ld32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+    bwd_store32<MASK>(r[b & 1], gm + b * 8, dst_row, save_row, b * 4, save_chunk);
   }
+}
+// masked layer of width NCOLS: gate fetch, accumulator wait, masked store
+template <int NCOLS>
+__device__ __forceinline__ void bwd_masked_layer(uint32_t tlane, const uint4* __restrict__ mask_row, int mask_chunk, uint8_t* dst_row,
+                                                 uint4* save_row, int save_chunk, uint64_t* acc_full, uint32_t& ph_acc, long long& t_acc) {
+  uint32_t gm[NCOLS / 4];
+  load_gates<NCOLS>(mask_row, mask_chunk, gm);
+  { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
+  tc_fence_after();
+  bwd_cols<true, NCOLS>(tlane, gm, dst_row, save_row, save_chunk);
 }
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -574,6 +569,30 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
         }
       }
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
+    } else if (warp == 2 && lane == 0) {
+      // gate prefetcher: keeps the stash slabs that gate the next kPrefetchAhead layers resident in L2 (bulk L2
+      // prefetch, no registers or shared memory), paced by the accumulator barrier so that it never runs more than
+      // that far ahead of the epilogue (a whole tile's stash times 148 CTAs would not fit in L2).
+      constexpr int kPrefetchAhead = 2;
+      uint32_t ph = 0;
+      auto prefetch_layer = [&](int tile, int li) {
+        const Layer& L = prog.layers[li];
+        if (L.mask_chunk == kNone) return;
+        const uint32_t bytes = (uint32_t)(L.epi == BE_RGB1 ? kRgbW : L.n_out) / 8 * kHalfChunkBytes;
+#pragma unroll
+        for (int hh = 0; hh < 2 * kSubTiles; ++hh)
+          bulk_prefetch_l2(p.saved + (((size_t)tile * (2 * kSubTiles) + hh) * (size_t)p.x_total + L.mask_chunk) * kHalfChunkBytes, bytes);
+      };
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        if (tile == (int)blockIdx.x)
+          for (int li = 0; li < kPrefetchAhead && li < prog.nlayers; ++li) prefetch_layer(tile, li);
+        for (int li = 0; li < prog.nlayers; ++li) {
+          const int lj = li + kPrefetchAhead;
+          if (lj < prog.nlayers) prefetch_layer(tile, lj);
+          else if (tile + (int)gridDim.x < p.n_tiles) prefetch_layer(tile + gridDim.x, lj - prog.nlayers);
+          mbar_wait(acc_full, ph); ph ^= 1;
+        }
+      }
     }
   } else {
     setmaxnreg_inc<216>();
@@ -617,25 +636,30 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
 
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
-        // all ReLU gates of this layer, fetched and compressed while the layer's MMAs run
-        uint32_t gates[8];
-        if (L.epi == BE_MASK || L.epi == BE_RGB1) load_gates(mask_row, L.mask_chunk, L.epi == BE_RGB1 ? kRgbW : L.n_out, gates);
-        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
-        tc_fence_after();
         if (L.epi == BE_MASK) {
-          bwd_cols<true>(tlane, gates, act_row, save_row, L.save_chunk, L.n_out);
-        } else if (L.epi == BE_LINEAR) {
-          bwd_cols<false>(tlane, gates, act_row, save_row, L.save_chunk, L.n_out);
-        } else if (L.epi == BE_RGB1) {
-          bwd_cols<true>(tlane, gates, act_row, save_row, L.save_chunk, kRgbW);
+          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          else bwd_masked_layer<kRgbW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); mbar_arrive(act_ready); }
+          continue;
+        }
+        if (L.epi == BE_RGB1) {
+          bwd_masked_layer<kRgbW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
+          fence_proxy_async_smem(); tc_fence_before(); mbar_arrive(act_ready);
+          continue;
+        }
+        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
+        tc_fence_after();
+        if (L.epi == BE_LINEAR) {
+          bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
         } else if (L.epi == BE_SKIPSTORE) {
-          bwd_cols<false>(tlane, gates, inb_row, nullptr, 0, L.n_out);
+          bwd_cols<false, C::KT>(tlane, nullptr, inb_row, nullptr, 0);
         } else if (L.epi == BE_TRUNKIN) {
           // d(trunk input features) = layer-0 part (TMEM) + skip-layer part (INB, bf16)
           float gf[C::KT];

@@ -74,6 +74,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// bulk L2 prefetch of a contiguous global range (bytes: multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // bulk async copy shared -> global (bulk group completion)
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
@@ -204,6 +208,22 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+// ReLU gates from stashed post-ReLU bf16 activations (>= +0): "activation > 0" <=> halfword != 0.  Adding 0x7FFF to a
+// halfword <= 0x7FFF sets its bit 15 iff it is non-zero and never carries into the neighbour; PRMT with selector
+// nibbles 8|b replicates the top bit of byte b over a result byte.  gate_bytes: 4 activations (two packed words) ->
+// one word of 0x00/0xFF bytes; gate_half<0|1>: the byte pair of columns (0,1) / (2,3) widened to halfword masks.
+__device__ __forceinline__ uint32_t gate_bytes(uint32_t x01, uint32_t x23) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(m) : "r"(x01 + 0x7FFF7FFFu), "r"(x23 + 0x7FFF7FFFu));
+  return m;
+}
+template <int HI>
+__device__ __forceinline__ uint32_t gate_half(uint32_t gb) {
+  uint32_t m;
+  if (HI) asm("prmt.b32 %0, %1, %1, 0x3322;" : "=r"(m) : "r"(gb));
+  else asm("prmt.b32 %0, %1, %1, 0x1100;" : "=r"(m) : "r"(gb));
+  return m;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
