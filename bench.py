@@ -244,7 +244,9 @@ def run_gpu_arm(args):
         k = kernels[dom]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
+            # ncu dram bytes per sample of this kernel x the average samples per launch of the timed region
+            traffic = tr["dram_bytes_per_sample"] * per[dom][2] / per[dom][1]
         except Exception:
             pass
         roof = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
