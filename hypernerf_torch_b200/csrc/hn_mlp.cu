@@ -229,7 +229,7 @@ __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row,
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <bool RELU>
+template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
                                             int chunk0, int save_chunk) {
 #pragma unroll
@@ -250,12 +250,12 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
       o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
     }
     *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
-    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+    if (STASH) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
   }
 }
 
 // ncols: multiple of 32
-template <bool RELU>
+template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, uint8_t* act_row, uint4* save_row,
                                          int save_chunk, int ncols) {
   uint32_t ra[32], rb[32];
@@ -264,11 +264,11 @@ __device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, ui
     tmem_ld_wait();
     const bool more = c0 + 32 < ncols;
     if (more) tmem_ld32(taddr + c0 + 32, rb);
-    fwd_store32<RELU>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk);
+    fwd_store32<RELU, STASH>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk);
     if (more) {
       tmem_ld_wait();
       if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
-      fwd_store32<RELU>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk);
+      fwd_store32<RELU, STASH>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk);
     }
   }
 }
@@ -340,7 +340,9 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // ======================================================================================================
 // forward
 // ======================================================================================================
-template <class C>
+// STASH = false (inference, hn_mlp_fwd with saved == NULL) compiles every stash store out: even predicated-off
+// st.global instructions in the drain loop cost 23 % of the kernel (2.67 -> 2.06 ms per 1 M samples, measured).
+template <class C, bool STASH>
 __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
         { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == FE_RELU) {
-          fwd_cols<true>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
+          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
         } else if (L.epi == FE_WSHEAD) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
           store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
         } else if (L.epi == FE_BOTT) {
-          fwd_cols<false>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
+          fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
           float f[C::KV];
           posenc<3, C::VF>(dir, f);
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
-          fwd_cols<true>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW);
+          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW);
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
@@ -1059,9 +1061,14 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   fp.x_in_ws = plan.slabs.x_in_ws; fp.x_in_t = plan.slabs.x_in_t; fp.x_in_v = plan.slabs.x_in_v;
   fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
   fp.dbg = g_dbg;
-  if (int rc = set_smem(mlp_fwd_kernel<C>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
   int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
-  mlp_fwd_kernel<C><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+  if (saved != nullptr) {
+    if (int rc = set_smem(mlp_fwd_kernel<C, true>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
+    mlp_fwd_kernel<C, true><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+  } else {
+    if (int rc = set_smem(mlp_fwd_kernel<C, false>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
+    mlp_fwd_kernel<C, false><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+  }
   return set_cuda_error(cudaGetLastError(), "hn_mlp_fwd");
 }
 

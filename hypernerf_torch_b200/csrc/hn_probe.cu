@@ -394,3 +394,116 @@ extern "C" int hn_umma_rate3(int N, int nacc, int reps, int inner, int grid, voi
 #undef HN_R3
   return hn::set_cuda_error(e, "hn_umma_rate3");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// Epilogue microbenchmark (test hook): 8 warps drain a 256-column fp32 accumulator (thread = row) `reps` times with
+// a selectable subset of the forward epilogue's work, to find which pipe bounds it.
+//   bit 0: convert (F2FP.RELU pack)       bit 1: st.shared 16 B packets (next layer's operand)
+//   bit 2: st.global 16 B packets (stash) bit 3: bias from shared memory (8 x LDS.128 + 32 FADD per 32 columns)
+//   bit 4: two TMEM loads in flight        bit 5: 64 B per thread contiguous global stores instead of 16 B
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+template <int mode>
+__global__ void __launch_bounds__(256, 1) epi_rate_kernel(int reps, uint8_t* gout, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sbias[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  sbias[threadIdx.x] = 0.001f * threadIdx.x;
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int sub = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
+  const uint32_t taddr = tmem_base_s + ((uint32_t)(quarter * 32) << 16) + sub * 256;
+  uint8_t* act_row = smem + sub * 65536 + row * 16;
+  uint4* save_row = reinterpret_cast<uint4*>(gout + ((size_t)blockIdx.x * 4 + sub * 2 + (row >> 6)) * 32 * 1024) + (row & 63);
+  uint32_t sink = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32(taddr, ra);
+    if (mode & (64 | 128)) {   // previous layer's bulk stores must have finished reading the rows we overwrite
+      bulk_wait_read<0>();
+      if (mode & 128) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncwarp();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 64) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t* cur = h ? rb : ra;
+        uint32_t* nxt = h ? ra : rb;
+        tmem_ld_wait();
+        const int c = c0 + 32 * h;
+        if (c + 32 < 256 && (mode & 16)) tmem_ld32(taddr + c + 32, nxt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(cur[8 * q + j]);
+          if (mode & 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + 8 * q);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 8 * q + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          uint4 o;
+          if (mode & 1) {
+            o.x = pack_bf16_relu(v[0], v[1]); o.y = pack_bf16_relu(v[2], v[3]);
+            o.z = pack_bf16_relu(v[4], v[5]); o.w = pack_bf16_relu(v[6], v[7]);
+          } else {
+            o.x = __float_as_uint(v[0]) ^ __float_as_uint(v[1]); o.y = __float_as_uint(v[2]) ^ __float_as_uint(v[3]);
+            o.z = __float_as_uint(v[4]) ^ __float_as_uint(v[5]); o.w = __float_as_uint(v[6]) ^ __float_as_uint(v[7]);
+          }
+          if (mode & 2) *reinterpret_cast<uint4*>(act_row + ((c >> 3) + q) * 2048) = o;
+          if (mode & 4) {
+            if (mode & 32) reinterpret_cast<uint4*>(gout + ((size_t)blockIdx.x * 256 + threadIdx.x) * 512)[(c >> 3) + q] = o;
+            else save_row[((c >> 3) + q) * 64] = o;
+          }
+          sink ^= o.x ^ o.y ^ o.z ^ o.w;
+        }
+        if (c + 32 < 256 && !(mode & 16)) tmem_ld32(taddr + c + 32, nxt);
+      }
+    }
+    if (mode & 64) {          // per warp: 32 copies of 512 B (lane = chunk)
+      fence_proxy_async_smem();
+      __syncwarp();
+      bulk_s2g(gout + ((size_t)blockIdx.x * 4 + sub * 2 + (quarter >> 1)) * 32 * 1024 + lane * 1024 + (quarter & 1) * 512,
+               smem + sub * 65536 + lane * 2048 + quarter * 512, 512);
+      bulk_commit();
+    }
+    if (mode & 128) {         // per sub tile: one copy of 64 KB
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if ((threadIdx.x & 127) == 0) {
+        bulk_s2g(gout + ((size_t)blockIdx.x * 2 + sub) * 65536, smem + sub * 65536, 65536);
+        bulk_commit();
+      }
+    }
+  }
+  if (mode & (64 | 128)) bulk_wait_read<0>();
+  long long t1 = clock64();
+  if (sink == 0x12345678u) out[1] = sink;
+  if (threadIdx.x == 0) out[blockIdx.x * 2] = (unsigned long long)(t1 - t0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace hn
+
+extern "C" int hn_epi_rate(int mode, int reps, int grid, void* gout /* grid * 128 KB */, void* out_cycles, void* stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  const int smem = 131072 + 1024;
+#define HN_EPI(m)                                                                                              \
+  if (mode == m) {                                                                                             \
+    e = cudaFuncSetAttribute(hn::epi_rate_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+    if (e == cudaSuccess) {                                                                                    \
+      hn::epi_rate_kernel<m><<<grid, 256, smem, (cudaStream_t)stream>>>(reps, (uint8_t*)gout, (unsigned long long*)out_cycles); \
+      e = cudaGetLastError();                                                                                  \
+    }                                                                                                          \
+  }
+  HN_EPI(0) HN_EPI(16) HN_EPI(17) HN_EPI(19) HN_EPI(21) HN_EPI(23) HN_EPI(31) HN_EPI(27) HN_EPI(20) HN_EPI(52) HN_EPI(18) HN_EPI(24) HN_EPI(25) HN_EPI(7) HN_EPI(55) HN_EPI(83) HN_EPI(147) HN_EPI(91) HN_EPI(155)
+#undef HN_EPI
+  return hn::set_cuda_error(e, "hn_epi_rate");
+}

@@ -318,8 +318,13 @@ class NerfModel(nn.Module):
             # noise_regularize (model_utils.py:300-317): same draw, same shape, applied inside the kernel
             noise = torch.randn((B, S, 1), device=points.device, dtype=torch.float32)
             noise_std = float(self.noise_std)
+        params = self._canonical_params()
+        if not torch.is_grad_enabled():
+            # autograd.Function reports needs_input_grad for parameters even under no_grad; detached parameters make
+            # the eval path (eval.py:77 @torch.no_grad) take the inference kernel, which writes no activation stash
+            params = [q.detach() for q in params]
         sigma, rgb, warped_points = _FusedMlp.apply(self, 1 if level == 'fine' else 0, points, viewdirs, ids, noise,
-                                                    noise_std, *self._canonical_params())
+                                                    noise_std, *params)
         sigma = filter_sigma(points, sigma, render_opts)
         out['warped_points'] = warped_points
         comp = model_utils.volumetric_rendering(rgb, sigma, z_vals, directions,

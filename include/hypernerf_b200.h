@@ -148,6 +148,9 @@ int hn_umma_rate2(int cta_group, int M, int N, int nacc, int order, int a_src, i
 /* test hook: as hn_umma_rate but a fully unrolled issue sequence (N in {16,64,128,256}, nacc in {1,2}). */
 int hn_umma_rate3(int N, int nacc, int reps, int inner, int grid, void* out_cycles, void* stream);
 
+/* test hook: cycles for 8 warps to drain a 256-column accumulator with a selectable subset of the epilogue's work. */
+int hn_epi_rate(int mode, int reps, int grid, void* gout, void* out_cycles, void* stream);
+
 /* test hook: cycles for nwarps warps to read `cols` TMEM columns of their 32 lanes `reps` times (tcgen05.ld.32x32b.x32). */
 int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream);
 
