@@ -64,6 +64,8 @@ struct FwdParams {
   uint16_t x_in_ws, x_in_t, x_in_v;
   float* sigma; float* rgb; float* warped;
   uint8_t* saved;
+  uint32_t* gates;          // ReLU gate words: [half tile][g_total][64 rows] (inside `saved`, after the X slabs)
+  int g_total;
   unsigned long long* dbg;  // optional per-CTA cycle counters (hn_debug_set_timing_buffer)
 };
 
@@ -73,7 +75,9 @@ struct BwdParams {
   const int64_t* ids;
   const float* sigma; const float* rgb; const float* warped;
   const float* g_sigma; const float* g_rgb; const float* g_warped;
-  const uint8_t* saved;     // forward activations (ReLU gates)
+  const uint8_t* saved;     // forward stash (X slabs; only its gate-word region is read here)
+  const uint32_t* gates;    // ReLU gate words written by the forward: [half tile][g_total][64 rows]
+  int g_total;
   uint8_t* dsaved;          // pre-activation gradients for the wgrad kernel
   float* glo_grad;          // flat_grad + offset of the GLO table
   int64_t n;
@@ -227,11 +231,19 @@ __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row,
 // generic epilogue column loops: this thread's row of the accumulator, 32 columns at a time, TMEM loads
 // double-buffered (the load of block b+1 is in flight while block b is converted and stored).
 // ------------------------------------------------------------------------------------------------------
+// One mbarrier arrival per warp instead of 32: every lane has fenced its own writes, __syncwarp orders them before
+// lane 0's (release) arrive.  256 individual arrivals on one shared-memory word serialise for several hundred cycles on
+// the critical path between a layer's epilogue and the next layer's first UMMA.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
-                                            int chunk0, int save_chunk) {
+                                            int chunk0, int save_chunk, uint32_t* gate_dst) {
+  uint32_t ge = 0, go = 0;   // sign bits of the even / odd columns of this 32-column block (hn_ptx.cuh: gate_push)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
@@ -245,6 +257,10 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
     if (RELU) {
       o.x = pack_bf16_relu(v[0], v[1]); o.y = pack_bf16_relu(v[2], v[3]);
       o.z = pack_bf16_relu(v[4], v[5]); o.w = pack_bf16_relu(v[6], v[7]);
+      if (STASH) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ge = gate_push(ge, v[2 * j]); go = gate_push(go, v[2 * j + 1]); }
+      }
     } else {
       o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
       o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
@@ -252,86 +268,78 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
     *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
     if (STASH) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
   }
+  if (RELU && STASH) gate_dst[(chunk0 >> 2) * kHalfRows] = gate_word_of(ge, go);
 }
 
 // ncols: multiple of 32
 template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, uint8_t* act_row, uint4* save_row,
-                                         int save_chunk, int ncols) {
+                                         int save_chunk, int ncols, uint32_t* gate_dst) {
   uint32_t ra[32], rb[32];
   tmem_ld32(taddr, ra);
   for (int c0 = 0; c0 < ncols; c0 += 64) {
     tmem_ld_wait();
     const bool more = c0 + 32 < ncols;
     if (more) tmem_ld32(taddr + c0 + 32, rb);
-    fwd_store32<RELU, STASH>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk);
+    fwd_store32<RELU, STASH>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk, gate_dst);
     if (more) {
       tmem_ld_wait();
       if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
-      fwd_store32<RELU, STASH>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk);
+      fwd_store32<RELU, STASH>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk, gate_dst);
     }
   }
 }
 
-// backward: ReLU gates.  All stash packets that gate one layer are requested before the epilogue waits for the
-// accumulator (they are L2 hits: the prefetch warp pulled the slab in a layer ahead) and folded to byte masks
-// (2 words per 8 columns, see gate_bytes in hn_ptx.cuh); the packed gradient is then masked with 2 integer ops per
-// 2 columns.
+// backward: ReLU gates from the gate words the forward wrote (one uint32 per row per 32 columns, hn_ptx.cuh), so the
+// data gradient never re-reads the 8.6 KB/sample activation stash.  The words of a layer (<= 8 per row) are requested
+// before the epilogue waits for the accumulator; the packed gradient pair j of a block is masked with 3 integer ops.
 template <int NCOLS>
-__device__ __forceinline__ void load_gates(const uint4* __restrict__ mask_row, int mask_chunk, uint32_t* gm) {
+__device__ __forceinline__ void load_gates(const uint32_t* __restrict__ gate_row, int gate_word, uint32_t* gw) {
 #pragma unroll
-  for (int b = 0; b < NCOLS / 64; ++b) {  // batches of 8 packets = 64 columns
-    uint4 x[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) x[q] = __ldg(mask_row + (size_t)(mask_chunk + b * 8 + q) * (kHalfChunkBytes / 16));
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      gm[(b * 8 + q) * 2] = gate_bytes(x[q].x, x[q].y);
-      gm[(b * 8 + q) * 2 + 1] = gate_bytes(x[q].z, x[q].w);
-    }
-  }
+  for (int b = 0; b < NCOLS / 32; ++b) gw[b] = __ldg(gate_row + (size_t)(gate_word + b) * kHalfRows);
 }
 
-// one 32-column block: r = accumulator row slice, gm = byte masks of the block's 4 packets (8 words)
+// one 32-column block: r = accumulator row slice, w = the block's gate word
 template <bool MASK>
-__device__ __forceinline__ void bwd_store32(const uint32_t* r, const uint32_t* gm, uint8_t* dst_row, uint4* save_row,
-                                            int chunk0, int save_chunk) {
+__device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t w, uint8_t* dst_row, uint4* save_row, int chunk0,
+                                            int save_chunk) {
+  uint32_t o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+  if (MASK) {
+    o[0] &= ~gate_pair_closed<0>(w); o[1] &= ~gate_pair_closed<1>(w); o[2] &= ~gate_pair_closed<2>(w); o[3] &= ~gate_pair_closed<3>(w);
+    o[4] &= ~gate_pair_closed<4>(w); o[5] &= ~gate_pair_closed<5>(w); o[6] &= ~gate_pair_closed<6>(w); o[7] &= ~gate_pair_closed<7>(w);
+    o[8] &= ~gate_pair_closed<8>(w); o[9] &= ~gate_pair_closed<9>(w); o[10] &= ~gate_pair_closed<10>(w); o[11] &= ~gate_pair_closed<11>(w);
+    o[12] &= ~gate_pair_closed<12>(w); o[13] &= ~gate_pair_closed<13>(w); o[14] &= ~gate_pair_closed<14>(w); o[15] &= ~gate_pair_closed<15>(w);
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 o;
-    o.x = pack_bf16(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
-    o.y = pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
-    o.z = pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
-    o.w = pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
-    if (MASK) {
-      o.x &= gate_half<0>(gm[2 * q]); o.y &= gate_half<1>(gm[2 * q]);
-      o.z &= gate_half<0>(gm[2 * q + 1]); o.w &= gate_half<1>(gm[2 * q + 1]);
-    }
-    *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = o;
-    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+    const uint4 v = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = v;
+    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = v;
   }
 }
-// NCOLS: multiple of 32 (<= 256), compile time so that gm[] and both row buffers stay in registers
+// NCOLS: multiple of 32 (<= 256), compile time so that gw[] and both row buffers stay in registers
 template <bool MASK, int NCOLS>
-__device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gm, uint8_t* dst_row, uint4* save_row, int save_chunk) {
+__device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gw, uint8_t* dst_row, uint4* save_row, int save_chunk) {
   uint32_t r[2][32];
   tmem_ld32(taddr, r[0]);
 #pragma unroll
   for (int b = 0; b < NCOLS / 32; ++b) {
     tmem_ld_wait();
     if (b + 1 < NCOLS / 32) tmem_ld32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
-    bwd_store32<MASK>(r[b & 1], gm + b * 8, dst_row, save_row, b * 4, save_chunk);
+    bwd_store32<MASK>(r[b & 1], MASK ? gw[b] : 0u, dst_row, save_row, b * 4, save_chunk);
   }
 }
 // masked layer of width NCOLS: gate fetch, accumulator wait, masked store
 template <int NCOLS>
-__device__ __forceinline__ void bwd_masked_layer(uint32_t tlane, const uint4* __restrict__ mask_row, int mask_chunk, uint8_t* dst_row,
+__device__ __forceinline__ void bwd_masked_layer(uint32_t tlane, const uint32_t* __restrict__ gate_row, int gate_word, uint8_t* dst_row,
                                                  uint4* save_row, int save_chunk, uint64_t* acc_full, uint32_t& ph_acc, long long& t_acc) {
-  uint32_t gm[NCOLS / 4];
-  load_gates<NCOLS>(mask_row, mask_chunk, gm);
+  uint32_t gw[NCOLS / 32];
+  load_gates<NCOLS>(gate_row, gate_word, gw);
   { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
   tc_fence_after();
-  bwd_cols<true, NCOLS>(tlane, gm, dst_row, save_row, save_chunk);
+  bwd_cols<true, NCOLS>(tlane, gw, dst_row, save_row, save_chunk);
 }
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 128 * kSubTiles);
+    mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -417,9 +425,12 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
       uint4* save_row = nullptr;
-      if (p.saved != nullptr)
-        save_row = reinterpret_cast<uint4*>(p.saved + ((size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6)) *
-                                                          (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
+      uint32_t* gate_row = nullptr;   // this row's column of the half tile's gate words
+      if (p.saved != nullptr) {
+        const size_t half = (size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6);
+        save_row = reinterpret_cast<uint4*>(p.saved + half * (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
+        gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
+      }
       float pt[3], dir[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(act_ready);
+      warp_arrive(act_ready);
       t_pro += HN_T0() - t_tile;
 
       float wp[3 + C::H];  // warped point + hyper coordinates
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
         { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == FE_RELU) {
-          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
+          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
         } else if (L.epi == FE_WSHEAD) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
@@ -473,7 +484,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
           store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
         } else if (L.epi == FE_BOTT) {
-          fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out);
+          fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, nullptr);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
           float f[C::KV];
           posenc<3, C::VF>(dir, f);
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
           for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
-          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW);
+          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW, gate_row + (size_t)L.gate_word * kHalfRows);
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
         if (li + 1 < prog.nlayers) {
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(act_ready);
+          warp_arrive(act_ready);
         }
       }
     }
@@ -535,7 +546,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
-    mbar_init(act_ready, 128 * kSubTiles);
+    mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -571,30 +582,6 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
         }
       }
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
-    } else if (warp == 2 && lane == 0) {
-      // gate prefetcher: keeps the stash slabs that gate the next kPrefetchAhead layers resident in L2 (bulk L2
-      // prefetch, no registers or shared memory), paced by the accumulator barrier so that it never runs more than
-      // that far ahead of the epilogue (a whole tile's stash times 148 CTAs would not fit in L2).
-      constexpr int kPrefetchAhead = 2;
-      uint32_t ph = 0;
-      auto prefetch_layer = [&](int tile, int li) {
-        const Layer& L = prog.layers[li];
-        if (L.mask_chunk == kNone) return;
-        const uint32_t bytes = (uint32_t)(L.epi == BE_RGB1 ? kRgbW : L.n_out) / 8 * kHalfChunkBytes;
-#pragma unroll
-        for (int hh = 0; hh < 2 * kSubTiles; ++hh)
-          bulk_prefetch_l2(p.saved + (((size_t)tile * (2 * kSubTiles) + hh) * (size_t)p.x_total + L.mask_chunk) * kHalfChunkBytes, bytes);
-      };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (tile == (int)blockIdx.x)
-          for (int li = 0; li < kPrefetchAhead && li < prog.nlayers; ++li) prefetch_layer(tile, li);
-        for (int li = 0; li < prog.nlayers; ++li) {
-          const int lj = li + kPrefetchAhead;
-          if (lj < prog.nlayers) prefetch_layer(tile, lj);
-          else if (tile + (int)gridDim.x < p.n_tiles) prefetch_layer(tile + gridDim.x, lj - prog.nlayers);
-          mbar_wait(acc_full, ph); ph ^= 1;
-        }
-      }
     }
   } else {
     setmaxnreg_inc<216>();
@@ -614,7 +601,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
       const size_t half = (size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6);
-      const uint4* mask_row = reinterpret_cast<const uint4*>(p.saved + half * (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
+      const uint32_t* gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
       uint4* save_row = reinterpret_cast<uint4*>(p.dsaved + half * (size_t)p.d_total * kHalfChunkBytes) + (row & 63);
 
       // prologue: dY of the rgb head = g_rgb * y (1 - y) (Sigmoid, models.py:164)
@@ -633,27 +620,27 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(act_ready);
+      warp_arrive(act_ready);
       t_pro += HN_T0() - t_tile;
 
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         if (L.epi == BE_MASK) {
-          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          else bwd_masked_layer<kRgbW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); mbar_arrive(act_ready); }
+          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          else bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); warp_arrive(act_ready); }
           continue;
         }
         if (L.epi == BE_RGB1) {
-          bwd_masked_layer<kRgbW>(tlane, mask_row, L.mask_chunk, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
-          fence_proxy_async_smem(); tc_fence_before(); mbar_arrive(act_ready);
+          fence_proxy_async_smem(); tc_fence_before(); warp_arrive(act_ready);
           continue;
         }
         { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
@@ -718,7 +705,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
         if (li + 1 < prog.nlayers) {
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(act_ready);
+          warp_arrive(act_ready);
         }
       }
     }
@@ -1003,7 +990,8 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
   memset(out, 0, sizeof(*out));
   const int64_t halves = 2 * kSubTiles * tiles_of(n_samples);
   out->packed_bytes = plan.layout.total;
-  out->saved_bytes = halves * plan.slabs.x_total * kHalfChunkBytes;
+  // X slabs, then the ReLU gate words ([half tile][g_total][64 rows] uint32)
+  out->saved_bytes = halves * plan.slabs.x_total * kHalfChunkBytes + halves * plan.slabs.g_total * kHalfRows * 4;
   out->workspace_bytes = halves * plan.slabs.d_total * kHalfChunkBytes;
   const Dims& m = plan.dims;
   auto lin = [](int64_t out_f, int64_t in_f) { return out_f * in_f + out_f; };
@@ -1060,6 +1048,8 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   fp.x_total = plan.slabs.x_total;
   fp.x_in_ws = plan.slabs.x_in_ws; fp.x_in_t = plan.slabs.x_in_t; fp.x_in_v = plan.slabs.x_in_v;
   fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
+  fp.g_total = plan.slabs.g_total;
+  fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.slabs.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
   int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
   if (saved != nullptr) {
@@ -1097,6 +1087,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
     bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
     bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
+    bp.g_total = plan.slabs.g_total;
+    bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.slabs.x_total * kHalfChunkBytes);
     bp.glo_grad = flat_grad + param_offsets[P_GLO];
     bp.n = n; bp.S = S;
     bp.n_tiles = (int)nt;

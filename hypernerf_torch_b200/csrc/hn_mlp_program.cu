@@ -24,10 +24,11 @@ struct Builder {
   Program* p;
   LogicalOps* lg;
   uint32_t w16 = 0;  // running weight offset (16-byte units)
-  void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk) {
+  void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk, uint16_t gate_word = kNone) {
     Layer& L = p->layers[p->nlayers++];
     L.op0 = (uint8_t)p->nops; L.nops = 0; L.epi = epi; L.pad = 0;
     L.n_out = (uint16_t)n_out; L.bias_off = (uint16_t)bias_off; L.save_chunk = save_chunk; L.mask_chunk = mask_chunk;
+    L.gate_word = gate_word; L.pad2 = 0;
   }
   void emit(int n, int k, Src s, int a_col, int tmem_col, int acc_init) {
     MmaOp& o = p->ops[p->nops++];
@@ -89,11 +90,11 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     Builder b{&plan->fwd, &plan->fwd_logical};
     int bias = 0;
     // warp + sheet, merged to one 192-wide net sharing the input buffer
-    b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone);
+    b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone, s.g_hws[0]);
     b.add_op(kWsW, m.KW, SRC_INB, 0, 0, SRC_ACT, 0, 0);
     bias += kWsW;
     for (int l = 1; l < kWsDepth; ++l) {
-      b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[l], kNone);
+      b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[l], kNone, s.g_hws[l]);
       bool skip = (l == kSkip + 1);
       b.add_op(kWarpW, kWarpW, SRC_ACT, 0, skip ? m.KW : 0, SRC_INB, 0, 0);
       b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, skip ? m.KW : 0, SRC_INB, 0, kWarpW);
@@ -103,11 +104,11 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     bias += 16;
     // trunk
-    b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone);
+    b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone, s.g_t[0]);
     b.add_op(kTrunkW, m.KT, SRC_INB, 0, 0, SRC_ACT, 0, 0);
     bias += kTrunkW;
     for (int l = 1; l <= kTrunkDepth; ++l) {  // l == kTrunkDepth is the logit layer (ReLU output, modules.py:230)
-      b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone);
+      b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone, s.g_t[l]);
       bool skip = (l == kSkip + 1);
       b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, skip ? m.KT : 0, SRC_INB, 0, 0);
       bias += kTrunkW;
@@ -115,11 +116,11 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     b.begin_layer(FE_BOTT, kRgbW, bias, s.x_bott, kNone);
     b.add_op(kRgbW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     bias += kRgbW;
-    b.begin_layer(FE_RGB0A, m.n_rgb0a, bias, s.x_r[0], kNone);
+    b.begin_layer(FE_RGB0A, m.n_rgb0a, bias, s.x_r[0], kNone, s.g_r[0]);
     b.add_op(m.n_rgb0a, kRgbW, SRC_ACT, 0, m.KV, SRC_INB, 0, 0);
     bias += m.n_rgb0a;
     for (int l = 1; l < kRgbDepth; ++l) {
-      b.begin_layer(FE_RELU, kRgbW, bias, s.x_r[l], kNone);
+      b.begin_layer(FE_RELU, kRgbW, bias, s.x_r[l], kNone, s.g_r[l]);
       b.add_op(kRgbW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
       bias += kRgbW;
     }
@@ -133,19 +134,19 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   {
     Builder b{&plan->bwd, &plan->bwd_logical};
     // D0: rgb head^T.  A = dY_rgbhead (16 cols, written by the prologue)
-    b.begin_layer(BE_MASK, kRgbW, 0, s.d_r[3], s.x_r[3]);
+    b.begin_layer(BE_MASK, kRgbW, 0, s.d_r[3], s.x_r[3], s.g_r[3]);
     b.add_op(kRgbW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     // D1..D3: rgb3^T, rgb2^T, rgb1^T
     for (int l = kRgbDepth - 1; l >= 1; --l) {
       bool last = (l == 1);
-      b.begin_layer(last ? BE_RGB1 : BE_MASK, kRgbW, 0, last ? s.d_rgb0a : s.d_r[l - 1], s.x_r[l - 1]);
+      b.begin_layer(last ? BE_RGB1 : BE_MASK, kRgbW, 0, last ? s.d_rgb0a : s.d_r[l - 1], s.x_r[l - 1], s.g_r[l - 1]);
       b.add_op(kRgbW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     }
     // D4: (rgb0 | alpha)^T -> bottleneck gradient (no activation on the bottleneck, modules.py:232,277)
     b.begin_layer(BE_LINEAR, kRgbW, 0, s.d_bott, kNone);
     b.add_op(kRgbW, m.n_rgb0a, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     // D5: bottleneck^T, gated by the trunk output ReLU
-    b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[kTrunkDepth], s.x_t[kTrunkDepth]);
+    b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[kTrunkDepth], s.x_t[kTrunkDepth], s.g_t[kTrunkDepth]);
     b.add_op(kTrunkW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     // trunk layers l = 8 (logit) .. 1: gradient w.r.t. h_{l-1}
     for (int l = kTrunkDepth; l >= 1; --l) {
@@ -154,17 +155,17 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
         b.begin_layer(BE_SKIPSTORE, m.KT, 0, kNone, kNone);
         b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
       }
-      b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[l - 1], s.x_t[l - 1]);
+      b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[l - 1], s.x_t[l - 1], s.g_t[l - 1]);
       b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     }
     // trunk layer 0^T -> gradient of the trunk input features -> chain rule through posenc
     b.begin_layer(BE_TRUNKIN, m.KT, 0, s.d_wshead, kNone);
     b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     // warp/sheet head^T
-    b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1]);
+    b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1], s.g_hws[kWsDepth - 1]);
     b.add_op(kWsW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     for (int l = kWsDepth - 1; l >= 1; --l) {
-      b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[l - 1], s.x_hws[l - 1]);
+      b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[l - 1], s.x_hws[l - 1], s.g_hws[l - 1]);
       if (l == kSkip + 1)  // GLO columns of the skip input, parked in TMEM cols [192,208)
         b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW);
       b.add_op(kWarpW, kWarpW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);

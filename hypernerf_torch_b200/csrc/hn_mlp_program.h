@@ -81,6 +81,10 @@ struct SlabMap {
   // gradients w.r.t. every layer's pre-activation output
   uint16_t d_ws[kWsDepth], d_wshead, d_t[kTrunkDepth + 1], d_bott, d_rgb0a, d_r[kRgbDepth] /* [0] unused */, d_rgbhead;
   uint16_t d_total;
+  // ReLU gate words (one uint32 per row per 32 output columns of every ReLU layer), written by the forward epilogue
+  // next to the X slabs and read by the data gradient instead of the activations themselves
+  uint16_t g_hws[kWsDepth], g_t[kTrunkDepth + 1], g_r[kRgbDepth];
+  uint16_t g_total;
 };
 inline SlabMap make_slabs(const Dims& m) {
   SlabMap s{};
@@ -103,6 +107,11 @@ inline SlabMap make_slabs(const Dims& m) {
   for (int l = 1; l < kRgbDepth; ++l) { s.d_r[l] = c; c += kRgbW / 8; }
   s.d_rgbhead = c; c += 2;
   s.d_total = c;
+  c = 0;
+  for (int l = 0; l < kWsDepth; ++l) { s.g_hws[l] = c; c += kWsW / 32; }
+  for (int l = 0; l <= kTrunkDepth; ++l) { s.g_t[l] = c; c += kTrunkW / 32; }
+  for (int l = 0; l < kRgbDepth; ++l) { s.g_r[l] = c; c += kRgbW / 32; }
+  s.g_total = c;
   return s;
 }
 
@@ -135,7 +144,9 @@ struct Layer {
   uint16_t n_out;       // accumulator columns the epilogue consumes
   uint16_t bias_off;    // forward: float offset into the bias array
   uint16_t save_chunk;  // chunk offset where the epilogue's bf16 output is stashed (X slabs fwd, dY slabs bwd)
-  uint16_t mask_chunk;  // backward: chunk offset of the forward activation that gates this gradient
+  uint16_t mask_chunk;  // backward: chunk offset of the forward activation that gates this gradient (kNone: no gate)
+  uint16_t gate_word;   // first ReLU gate word of this layer's output (forward: written, backward: read); kNone: none
+  uint16_t pad2;
 };
 
 struct Program {

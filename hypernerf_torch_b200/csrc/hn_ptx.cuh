@@ -218,20 +218,18 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-// ReLU gates from stashed post-ReLU bf16 activations (>= +0): "activation > 0" <=> halfword != 0.  Adding 0x7FFF to a
-// halfword <= 0x7FFF sets its bit 15 iff it is non-zero and never carries into the neighbour; PRMT with selector
-// nibbles 8|b replicates the top bit of byte b over a result byte.  gate_bytes: 4 activations (two packed words) ->
-// one word of 0x00/0xFF bytes; gate_half<0|1>: the byte pair of columns (0,1) / (2,3) widened to halfword masks.
-__device__ __forceinline__ uint32_t gate_bytes(uint32_t x01, uint32_t x23) {
+// ReLU gate words.  The forward epilogue records, per row and per block of 32 output columns, the SIGN bits of the 32
+// fp32 pre-activations (sign set <=> ReLU closed; relu(+0) = 0 either way): even columns 0,2,..,30 in bits 15..0
+// (column 2j at bit 15-j), odd columns 1,3,..,31 in bits 31..16 (column 2j+1 at bit 31-j).  gate_push shifts one sign
+// in with a single funnel shift; after 16 pushes per half the word is complete.  The data gradient masks the packed
+// bf16 pair j with gate_pair_mask: (w << j) puts the pair's signs at bits 15 and 31, PRMT (selector nibble 8|b =
+// "replicate the top bit of byte b") widens them to halfword masks of the CLOSED gates.
+__device__ __forceinline__ uint32_t gate_push(uint32_t acc, float v) { return __funnelshift_l(__float_as_uint(v), acc, 1); }
+__device__ __forceinline__ uint32_t gate_word_of(uint32_t even_bits, uint32_t odd_bits) { return __byte_perm(even_bits, odd_bits, 0x5410); }
+template <int J>
+__device__ __forceinline__ uint32_t gate_pair_closed(uint32_t w) {
   uint32_t m;
-  asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(m) : "r"(x01 + 0x7FFF7FFFu), "r"(x23 + 0x7FFF7FFFu));
-  return m;
-}
-template <int HI>
-__device__ __forceinline__ uint32_t gate_half(uint32_t gb) {
-  uint32_t m;
-  if (HI) asm("prmt.b32 %0, %1, %1, 0x3322;" : "=r"(m) : "r"(gb));
-  else asm("prmt.b32 %0, %1, %1, 0x1100;" : "=r"(m) : "r"(gb));
+  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(w << J));
   return m;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }

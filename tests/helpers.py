@@ -27,8 +27,8 @@ def to_dev(sd, device="cuda"):
 
 def decode_slab(saved, n_rows, chunk0, ncols, total_chunks=X_TOTAL):
     """uint8 stash -> (n_rows, ncols) fp32 of the slab starting at chunk0 (layout: [half tile][chunk][64 rows][8])."""
-    halves = saved.numel() // (total_chunks * 1024)
-    v = saved.view(torch.bfloat16).view(halves, total_chunks, 64, 8)
+    halves = (n_rows + 255) // 256 * 4   # CTA tiles of 256 rows = 4 half tiles; the gate words follow the X slabs
+    v = saved[:halves * total_chunks * 1024].view(torch.bfloat16).view(halves, total_chunks, 64, 8)
     x = v[:, chunk0:chunk0 + ncols // 8]                      # (halves, c, 64, 8)
     x = x.permute(0, 2, 1, 3).reshape(halves * 64, ncols)
     return x[:n_rows].float()

@@ -35,7 +35,9 @@ def test_query_matches_reference_parameter_count():
     s = _lib.Sizes()
     assert _lib.lib().hn_query(C.byref(_desc()), 1024 * 64, C.byref(s)) == 0
     assert s.flat_param_floats == n_ref
-    assert s.saved_bytes == (1024 * 64 // 64) * 540 * 1024      # 4320 bf16 columns per sample
+    halves = 1024 * 64 // 64
+    # 4320 bf16 columns per sample + 124 ReLU gate words per sample
+    assert s.saved_bytes == halves * 540 * 1024 + halves * 124 * 64 * 4
     assert s.workspace_bytes == (1024 * 64 // 64) * 518 * 1024
     assert s.packed_bytes % 256 == 0 and s.packed_bytes > 2 * 2 * 700000
 
