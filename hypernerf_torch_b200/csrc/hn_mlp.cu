@@ -46,7 +46,7 @@ struct Smem {
   static constexpr int RING = INB + kSubTiles * INB_BYTES;        // kRingStages x kStageBytes
   static constexpr int BIAS = RING + kRingStages * kStageBytes;   // 2 x 256 fp32: this / next layer's bias
   static constexpr int BARS = BIAS + 2 * 256 * 4;                 // full[], empty[], acc_full, act_ready
-  static constexpr int TMEMP = BARS + (2 * kRingStages + 2) * 8;
+    static constexpr int TMEMP = BARS + (2 * kRingStages + 2) * 8;
   static constexpr int TOTAL = TMEMP + 16;
 };
 
@@ -156,8 +156,8 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
         uint32_t acc = (c > 0) | acc0;
         for (uint32_t j = 0; j < cnt; j += 2) {
           const uint64_t bd = desc64(b_lo);
-          umma_bf16(d0, desc64(a_lo), bd, idesc, acc);
-          umma_bf16(d0 + 256, desc64(a_lo + a_sub), bd, idesc, acc);
+#pragma unroll
+          for (int sub = 0; sub < kSubTiles; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
           a_lo += 2 * (kChunkBytes >> 4);
           b_lo += 2 * n;
           acc = 1;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
-__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(128 * kSubTiles) : "memory"); }
 
 template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
@@ -351,7 +351,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // STASH = false (inference, hn_mlp_fwd with saved == NULL) compiles every stash store out: even predicated-off
 // st.global instructions in the drain loop cost 23 % of the kernel (2.67 -> 2.06 ms per 1 M samples, measured).
 template <class C, bool STASH>
-__global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
   uint8_t* act = smem + SM::ACT;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
     mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 256 * kSubTiles); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
   const Program& prog = p.prog;
 
   if (warp < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<kSubTiles == 2 ? 56 : 40>();
     if (warp == 0 && lane == 0) {
       RingState rs;
       long long tw = 0;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
     }
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
     const int et = threadIdx.x - 128;  // epilogue thread index 0..255
     // ---------------- epilogue warps: thread <-> sample row; warps 2..5 sub-tile 0, 6..9 sub-tile 1 ----------------
     const int sub = (warp - 4) >> 2;
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
         float* bias = sbias + (li & 1) * 256;
-        if (et < L.n_out) bias[et] = __ldg(p.bias + L.bias_off + et);
+        for (int i = et; i < L.n_out; i += 128 * kSubTiles) bias[i] = __ldg(p.bias + L.bias_off + i);
         epi_named_barrier();
         { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
@@ -523,14 +523,14 @@ __global__ void __launch_bounds__(384, 1) mlp_fwd_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256 * kSubTiles);
 }
 
 // ======================================================================================================
 // backward-data
 // ======================================================================================================
 template <class C>
-__global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
   uint8_t* act = smem + SM::ACT;
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
     mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr, 256 * kSubTiles); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
   const Program& prog = p.prog;
 
   if (warp < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<kSubTiles == 2 ? 56 : 40>();
     if (warp == 0 && lane == 0) {
       RingState rs;
       long long tw = 0;
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
     }
   } else {
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
     const int sub = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(384, 1) mlp_dgrad_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256 * kSubTiles);
 }
 
 // ======================================================================================================
@@ -1051,13 +1051,13 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   fp.g_total = plan.slabs.g_total;
   fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.slabs.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
-  int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
+  int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
   if (saved != nullptr) {
     if (int rc = set_smem(mlp_fwd_kernel<C, true>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
-    mlp_fwd_kernel<C, true><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+    mlp_fwd_kernel<C, true><<<grid, kMlpThreads, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
   } else {
     if (int rc = set_smem(mlp_fwd_kernel<C, false>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
-    mlp_fwd_kernel<C, false><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
+    mlp_fwd_kernel<C, false><<<grid, kMlpThreads, Smem<C>::TOTAL, (cudaStream_t)stream>>>(fp);
   }
   return set_cuda_error(cudaGetLastError(), "hn_mlp_fwd");
 }
@@ -1096,8 +1096,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
     bp.dbg = g_dbg;
     if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-    int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms());
-    mlp_dgrad_kernel<C><<<grid, 384, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
+    int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
+    mlp_dgrad_kernel<C><<<grid, kMlpThreads, Smem<C>::TOTAL, (cudaStream_t)stream>>>(bp);
     if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: dgrad launch")) return rc;
   }
   if (do_weights) {

@@ -15,14 +15,25 @@
 
 namespace hn {
 
+// HN_SUBTILES = 2: one CTA per SM owns 256 samples as two 128-row sub-tiles that share every weight stage.
+// HN_SUBTILES = 1: two CTAs per SM of 128 samples each (half the shared memory / TMEM / registers per CTA): the two
+//                  CTAs run out of phase, so one's UMMAs overlap the other's epilogue and stash stores, at the price
+//                  of streaming the weights from L2 once per 128 instead of once per 256 samples.
+// Measured (profiles/README.md): with the 2 x 8 KB ring that fits next to a second CTA the weight stream starves the
+// UMMAs (fwd 2.83 -> 4.06 ms, dgrad 2.78 -> 3.92 ms per 1 M samples), so 2 is the shipped configuration.
+#ifndef HN_SUBTILES
+#define HN_SUBTILES 2
+#endif
 constexpr int kTileRows = 128;   // samples per sub-tile (= UMMA M = TMEM lanes)
-constexpr int kSubTiles = 2;     // sub-tiles per CTA; they share every weight stage (halves L2 weight traffic)
+constexpr int kSubTiles = HN_SUBTILES;
+constexpr int kCtasPerSm = kSubTiles == 2 ? 1 : 2;
+constexpr int kMlpThreads = 128 + 128 * kSubTiles;   // warpgroup 0: producer + UMMA issuer; then one epilogue warpgroup per sub-tile
 constexpr int kCtaRows = kTileRows * kSubTiles;
 constexpr int kHalfRows = 64;    // granularity of the saved-activation layout and of the wgrad K step
 constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-row smem operand
 constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-row global slab
-constexpr int kRingStages = 3;
-constexpr int kStageBytes = 16384;
+constexpr int kRingStages = kSubTiles == 2 ? 3 : 2;   // two co-resident CTAs only have room for a 2-stage ring
+constexpr int kStageBytes = kSubTiles == 2 ? 16384 : 8192;
 constexpr int kMaxOps = 40;
 constexpr int kMaxLayers = 24;
 constexpr int kMaxJobs = 40;

@@ -9,6 +9,7 @@ EXTRA = dict(nerf_alpha=None, warp_alpha=None, hyper_alpha=None, hyper_sheet_alp
 EMB = {'warp': list(range(100)), 'camera': [0], 'appearance': list(range(100)), 'time': list(range(100))}
 
 # saved-activation slab map (hn_mlp_program.h make_slabs, cfg-1 shape), in 8-column chunks
+TILE_ROWS = 256   # rows per CTA tile (hn_mlp_program.h: kTileRows * HN_SUBTILES)
 X_IN_WS, X_HWS, X_IN_T, X_T, X_BOTT, X_IN_V, X_R, X_TOTAL = 0, 10, 154, 166, 454, 470, 476, 540
 
 
@@ -27,7 +28,7 @@ def to_dev(sd, device="cuda"):
 
 def decode_slab(saved, n_rows, chunk0, ncols, total_chunks=X_TOTAL):
     """uint8 stash -> (n_rows, ncols) fp32 of the slab starting at chunk0 (layout: [half tile][chunk][64 rows][8])."""
-    halves = (n_rows + 255) // 256 * 4   # CTA tiles of 256 rows = 4 half tiles; the gate words follow the X slabs
+    halves = (n_rows + TILE_ROWS - 1) // TILE_ROWS * (TILE_ROWS // 64)   # whole CTA tiles; the gate words follow the X slabs
     v = saved[:halves * total_chunks * 1024].view(torch.bfloat16).view(halves, total_chunks, 64, 8)
     x = v[:, chunk0:chunk0 + ncols // 8]                      # (halves, c, 64, 8)
     x = x.permute(0, 2, 1, 3).reshape(halves * 64, ncols)
