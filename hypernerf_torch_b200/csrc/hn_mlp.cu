@@ -37,6 +37,20 @@ using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
 // ------------------------------------------------------------------------------------------------------
 // shared memory plan of the fused kernels
 // ------------------------------------------------------------------------------------------------------
+// HN_PINGPONG = 1: the two sub-tiles of a CTA run half a step out of phase: each has its own accumulator /
+// activation barriers and makes its own pass over a layer's weight stages, so sub-tile 0's epilogue (TMEM drain,
+// stash stores) runs under sub-tile 1's UMMAs and vice versa.  Price: every weight stage is fetched from L2 once per
+// 128 instead of once per 256 samples.  HN_PINGPONG = 0: both sub-tiles consume each stage in lock step.
+// Measured: the 128-row passes need 64 B/clk of weights per SM while their UMMAs run; the 48 KB ring over the L2
+// latency sustains ~48, the issuer then waits 27 % of the time for stages and the gain from the overlap is lost
+// (fwd 2.79 vs 2.83 ms, dgrad 2.76 vs 2.78 ms per 1 M samples), so lock step stays the default.
+#ifndef HN_PINGPONG
+#define HN_PINGPONG 0
+#endif
+constexpr bool kPingPong = HN_PINGPONG && kSubTiles == 2;
+constexpr int kChains = kPingPong ? kSubTiles : 1;          // independently synchronised sub-tile groups
+constexpr int kSubsPerChain = kSubTiles / kChains;
+
 template <class C>
 struct Smem {
   static constexpr int ACT_BYTES = 32 * kChunkBytes;              // 128 x 256 bf16 per sub-tile
@@ -105,19 +119,24 @@ struct RingState { int slot = 0; uint32_t phase = 0; __device__ void next() { if
 
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
                                              uint64_t* full, uint64_t* empty, RingState& rs, long long& t_wait) {
-  for (int oi = 0; oi < prog.nops; ++oi) {
-    const MmaOp& op = prog.ops[oi];
-    const int nchunks = op.k >> 3;
-    const uint8_t* src = weights + (size_t)op.w_off16 * 16;
-    for (int c = 0; c < nchunks; c += op.cps) {
-      int cnt = min((int)op.cps, nchunks - c);
-      uint32_t bytes = (uint32_t)cnt * op.n * 16;
-      long long t0 = HN_T0();
-      mbar_wait(&empty[rs.slot], rs.phase ^ 1);
-      t_wait += HN_T0() - t0;
-      mbar_arrive_expect_tx(&full[rs.slot], bytes);
-      bulk_g2s(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot]);
-      rs.next();
+  for (int li = 0; li < prog.nlayers; ++li) {
+    const Layer& L = prog.layers[li];
+    for (int chain = 0; chain < kChains; ++chain) {   // ping-pong: every sub-tile makes its own pass over the layer
+      for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
+        const MmaOp& op = prog.ops[oi];
+        const int nchunks = op.k >> 3;
+        const uint8_t* src = weights + (size_t)op.w_off16 * 16;
+        for (int c = 0; c < nchunks; c += op.cps) {
+          int cnt = min((int)op.cps, nchunks - c);
+          uint32_t bytes = (uint32_t)cnt * op.n * 16;
+          long long t0 = HN_T0();
+          mbar_wait(&empty[rs.slot], rs.phase ^ 1);
+          t_wait += HN_T0() - t0;
+          mbar_arrive_expect_tx(&full[rs.slot], bytes);
+          bulk_g2s(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot]);
+          rs.next();
+        }
+      }
     }
   }
 }
@@ -130,7 +149,7 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
 constexpr uint32_t kDescHi = (1u << 14) | (128u >> 4);   // descriptor version 1, SBO = 128 B, no swizzle
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
-__device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, uint32_t act_s, uint32_t inb_s,
+__device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, int sub0, uint32_t act_s, uint32_t inb_s,
                                             uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s,
                                             uint32_t tmem_base, uint64_t* full, uint64_t* empty, RingState& rs,
                                             long long& t_wait) {
@@ -140,9 +159,9 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
     const uint32_t idesc = make_idesc_bf16(kTileRows, n, 0, 0);
     const bool from_act = op.src == SRC_ACT;
     // A: K-major, LBO = one 8-column chunk of 128 rows
-    const uint32_t a_base = (((from_act ? act_s : inb_s) + op.a_chunk * kChunkBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16);
     const uint32_t a_sub = (from_act ? act_stride : inb_stride) >> 4;
-    const uint32_t d0 = tmem_base + op.tmem_col;
+    const uint32_t a_base = ((((from_act ? act_s : inb_s) + op.a_chunk * kChunkBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16)) + sub0 * a_sub;
+    const uint32_t d0 = tmem_base + op.tmem_col + sub0 * 256;
     const uint32_t acc0 = op.acc_init;
     for (uint32_t c = 0; c < nchunks; c += cps) {
       const uint32_t cnt = min(cps, nchunks - c);
@@ -157,7 +176,7 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
         for (uint32_t j = 0; j < cnt; j += 2) {
           const uint64_t bd = desc64(b_lo);
 #pragma unroll
-          for (int sub = 0; sub < kSubTiles; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
+          for (int sub = 0; sub < kSubsPerChain; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
           a_lo += 2 * (kChunkBytes >> 4);
           b_lo += 2 * n;
           acc = 1;
@@ -238,7 +257,10 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
-__device__ __forceinline__ void epi_named_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(128 * kSubTiles) : "memory"); }
+// named barrier of one chain's epilogue threads (ids 1, 2; barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_named_barrier(int chain) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * kSubsPerChain) : "memory");
+}
 
 template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
@@ -360,15 +382,14 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   float* sbias = reinterpret_cast<float*>(smem + SM::BIAS);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* empty = full + kRingStages;
-  uint64_t* acc_full = empty + kRingStages;
-  uint64_t* act_ready = acc_full + 1;
+  uint64_t* acc_full = empty + kRingStages;   // [2]: one per chain
+  uint64_t* act_ready = acc_full + 2;         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEMP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * kSubsPerChain); }  // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 256 * kSubTiles); tmem_relinquish(); }
@@ -393,21 +414,24 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
-          long long t0 = HN_T0();
-          mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
-          t_ready += HN_T0() - t0;
-          tc_fence_after();
-          issue_layer(prog, prog.layers[li], act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base, full, empty, rs,
-                      t_full);
-          if (elect_one_sync()) umma_commit(acc_full);
-          __syncwarp();
+          for (int chain = 0; chain < kChains; ++chain) {
+            long long t0 = HN_T0();
+            mbar_wait(&act_ready[chain], ph_ready);
+            t_ready += HN_T0() - t0;
+            tc_fence_after();
+            issue_layer(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
+                        full, empty, rs, t_full);
+            if (elect_one_sync()) umma_commit(&acc_full[chain]);
+            __syncwarp();
+          }
+          ph_ready ^= 1;
         }
       }
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
     }
   } else {
     setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
-    const int et = threadIdx.x - 128;  // epilogue thread index 0..255
+    const int et = (threadIdx.x - 128) & (128 * kSubsPerChain - 1);  // index inside this chain's epilogue threads
     // ---------------- epilogue warps: thread <-> sample row; warps 2..5 sub-tile 0, 6..9 sub-tile 1 ----------------
     const int sub = (warp - 4) >> 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -415,6 +439,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
     uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
+    const int chain = kPingPong ? sub : 0;
+    uint64_t* my_acc = &acc_full[chain];
+    uint64_t* my_ready = &act_ready[chain];
     uint32_t ph_acc = 0;
     long long t_acc = 0, t_pro = 0;
     const long long t_begin = HN_T0();
@@ -450,7 +477,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      warp_arrive(act_ready);
+      warp_arrive(my_ready);
       t_pro += HN_T0() - t_tile;
 
       float wp[3 + C::H];  // warped point + hyper coordinates
@@ -458,10 +485,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         const Layer& L = prog.layers[li];
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
-        float* bias = sbias + (li & 1) * 256;
-        for (int i = et; i < L.n_out; i += 128 * kSubTiles) bias[i] = __ldg(p.bias + L.bias_off + i);
-        epi_named_barrier();
-        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
+        float* bias = kPingPong ? sbias + chain * 256 : sbias + (li & 1) * 256;
+        if (kPingPong) epi_named_barrier(chain);   // single buffer per chain: everyone is done with the previous layer's bias
+        for (int i = et; i < L.n_out; i += 128 * kSubsPerChain) bias[i] = __ldg(p.bias + L.bias_off + i);
+        epi_named_barrier(chain);
+        { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == FE_RELU) {
           fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
@@ -511,7 +539,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         if (li + 1 < prog.nlayers) {
           fence_proxy_async_smem();
           tc_fence_before();
-          warp_arrive(act_ready);
+          warp_arrive(my_ready);
         }
       }
     }
@@ -538,15 +566,14 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   uint8_t* ring = smem + SM::RING;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* empty = full + kRingStages;
-  uint64_t* acc_full = empty + kRingStages;
-  uint64_t* act_ready = acc_full + 1;
+  uint64_t* acc_full = empty + kRingStages;   // [2]: one per chain
+  uint64_t* act_ready = acc_full + 2;         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEMP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(act_ready, 4 * kSubTiles);  // one arrival per epilogue warp (warp_arrive)
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * kSubsPerChain); }  // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr, 256 * kSubTiles); tmem_relinquish(); }
@@ -571,14 +598,17 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
-          long long t0 = HN_T0();
-          mbar_wait(act_ready, ph_ready); ph_ready ^= 1;
-          t_ready += HN_T0() - t0;
-          tc_fence_after();
-          issue_layer(prog, prog.layers[li], act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base, full, empty, rs,
-                      t_full);
-          if (elect_one_sync()) umma_commit(acc_full);
-          __syncwarp();
+          for (int chain = 0; chain < kChains; ++chain) {
+            long long t0 = HN_T0();
+            mbar_wait(&act_ready[chain], ph_ready);
+            t_ready += HN_T0() - t0;
+            tc_fence_after();
+            issue_layer(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
+                        full, empty, rs, t_full);
+            if (elect_one_sync()) umma_commit(&acc_full[chain]);
+            __syncwarp();
+          }
+          ph_ready ^= 1;
         }
       }
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin; }
@@ -591,6 +621,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
     uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
+    const int chain = kPingPong ? sub : 0;
+    uint64_t* my_acc = &acc_full[chain];
+    uint64_t* my_ready = &act_ready[chain];
     uint32_t ph_acc = 0;
     long long t_acc = 0, t_pro = 0;
     const long long t_begin = HN_T0();
@@ -620,30 +653,30 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      warp_arrive(act_ready);
+      warp_arrive(my_ready);
       t_pro += HN_T0() - t_tile;
 
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         if (L.epi == BE_MASK) {
-          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          else bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
-          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); warp_arrive(act_ready); }
+          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          else bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); warp_arrive(my_ready); }
           continue;
         }
         if (L.epi == BE_RGB1) {
-          bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, acc_full, ph_acc, t_acc);
+          bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
-          fence_proxy_async_smem(); tc_fence_before(); warp_arrive(act_ready);
+          fence_proxy_async_smem(); tc_fence_before(); warp_arrive(my_ready);
           continue;
         }
-        { long long t0 = HN_T0(); mbar_wait(acc_full, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
+        { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == BE_LINEAR) {
           bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
@@ -705,7 +738,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
         if (li + 1 < prog.nlayers) {
           fence_proxy_async_smem();
           tc_fence_before();
-          warp_arrive(act_ready);
+          warp_arrive(my_ready);
         }
       }
     }
