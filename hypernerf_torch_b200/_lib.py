@@ -20,7 +20,7 @@ HN_COMP_ACC_ALL = 2
 EXPORTS = [
     "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf",
     "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
-    "hn_umma_probe", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_epi_rate", "hn_tmem_rate", "hn_debug_set_timing_buffer",
+    "hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4", "hn_epi_rate", "hn_tmem_rate", "hn_debug_set_timing_buffer",
 ]
 
 
@@ -83,6 +83,8 @@ def lib():
     L.hn_umma_rate2.argtypes = [i32] * 9 + [vp, vp]
     L.hn_umma_rate3.argtypes = [i32] * 5 + [vp, vp]
     L.hn_epi_rate.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.hn_umma_probe2.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.hn_umma_rate4.argtypes = [i32] * 5 + [vp, vp]
     L.hn_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -34,7 +34,8 @@ struct Builder {
     MmaOp& o = p->ops[p->nops++];
     o.w_off16 = w16; o.n = (uint16_t)n; o.k = (uint16_t)k; o.a_chunk = (uint16_t)(a_col / 8);
     o.tmem_col = (uint16_t)tmem_col; o.src = s; o.acc_init = (uint8_t)acc_init; o.pad = 0;
-    int cps = (kStageBytes / (n * 16)) & ~1;
+    const int rows_here = kPair ? n / 2 : n;   // pair mode: each CTA stages half of the N rows of every chunk
+    int cps = (kStageBytes / (rows_here * 16)) & ~1;
     if (cps < 2) cps = 2;
     if (cps > k / 8) cps = k / 8;
     o.cps = (uint8_t)cps;

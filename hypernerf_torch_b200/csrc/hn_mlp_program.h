@@ -24,6 +24,19 @@ namespace hn {
 #ifndef HN_SUBTILES
 #define HN_SUBTILES 2
 #endif
+// HN_PAIR = 1: the fused kernels run on 2-CTA clusters.  A UMMA spans the pair (cta_group::2, M = 256 = one 128-row
+// sub-tile of each CTA) and takes half of every weight stage from each CTA's shared memory, so a pass over a layer's
+// weights serves 256 rows while each SM only ingests half of it; that makes the out-of-phase (ping-pong) schedule of
+// the two sub-tiles affordable: sub-tile 0's epilogue of both CTAs runs under sub-tile 1's UMMAs and vice versa.
+// Status: functionally complete (all GPU parity tests pass with HN_PAIR=1) but not the default.  The leader's issuer
+// has to learn that the OTHER CTA's half of a stage has landed; without tensor-map TMA (whose cta_group::2 form can
+// signal the leader's mbarrier directly) that takes a relay thread and a remote arrive per stage, the refill round
+// trip grows to ~2 000 cycles, and the 48 KB ring then covers only ~75 % of it: the issuer waits 41 % of its time
+// for the peer (profiles/README.md), fwd 3.27 / dgrad 3.36 ms per 1 M samples against 2.83 / 2.78 in lock step.
+#ifndef HN_PAIR
+#define HN_PAIR 0
+#endif
+constexpr bool kPair = HN_PAIR && HN_SUBTILES == 2;
 constexpr int kTileRows = 128;   // samples per sub-tile (= UMMA M = TMEM lanes)
 constexpr int kSubTiles = HN_SUBTILES;
 constexpr int kCtasPerSm = kSubTiles == 2 ? 1 : 2;

@@ -507,3 +507,147 @@ extern "C" int hn_epi_rate(int mode, int reps, int grid, void* gout /* grid * 12
 #undef HN_EPI
   return hn::set_cuda_error(e, "hn_epi_rate");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// CTA-pair UMMA probe (test hook): D[256 x N] = A[256 x K] * B[N x K]^T on a 2-CTA cluster with cta_group::2.
+// CTA r stages A rows [128 r, 128 r + 128) and B rows [r N/2, (r + 1) N/2) in the un-swizzled K-major interleave
+// layout at the same shared-memory offsets; the leader issues, the commit is multicast to both CTAs, each CTA drains
+// its own 128 accumulator rows.  Pins the operand split that the pair mode of the fused kernels relies on.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_probe2_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, NH = N / 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (uint32_t)(k / 8) * (128 * 16) + r * 16 + (k % 8) * 2) = A[(size_t)(rank * 128 + r) * K + k];
+  }
+  for (int i = tid; i < NH * K; i += 128) {
+    const int n = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (uint32_t)(k / 8) * (NH * 16) + n * 16 + (k % 8) * 2) = B[(size_t)(rank * NH + n) * K + k];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) { tmem_alloc2(&tmem_base_s, 256); tmem_relinquish2(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (rank == 0 && tid < 32) {
+    const uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
+    if (elect_one_sync()) {
+      for (int ks = 0; ks < K / 16; ++ks) {
+        uint64_t ad = make_smem_desc(smem_u32(sA) + ks * 2 * 128 * 16, 128 * 16, 128);
+        uint64_t bd = make_smem_desc(smem_u32(sB) + ks * 2 * NH * 16, NH * 16, 128);
+        umma2_bf16(tmem_base, ad, bd, idesc, ks > 0);
+      }
+      umma2_commit_mc(&bar, 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int warp = tid / 32, lane = tid % 32;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[(size_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (tid < 32) tmem_dealloc2(tmem_base, 256);
+}
+}  // namespace hn
+
+extern "C" int hn_umma_probe2(const void* A, const void* B, float* D, int N, int K, void* stream) {
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K > 256 || K % 16) return hn::set_error(-1, "hn_umma_probe2: bad N/K");
+  size_t smem = (size_t)(128 + N / 2) * K * 2;
+  cudaError_t e = cudaFuncSetAttribute(hn::umma_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return hn::set_cuda_error(e, "hn_umma_probe2: smem attr");
+  hn::umma_probe2_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_umma_probe2: launch");
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Unrolled issue-rate microbenchmark for the CTA-pair form (cta_group::2, M = 256, each CTA holding N/2 rows of B).
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+template <int N, int NACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate4_kernel(int reps, int inner, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int total = NACC * 128 * 256 * 2 + 128 * 64 * 2;
+  for (int i = tid * 16; i < total; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 32) { tmem_alloc2(&tmem_base_s, 512); tmem_relinquish2(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid < 32 && rank == 0) {
+    const uint32_t sA = smem_u32(smem), sB = sA + NACC * 128 * 256 * 2;
+    constexpr uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
+    const uint64_t ad0 = make_smem_desc(sA, 2048, 128), bd0 = make_smem_desc(sB, (N / 2) * 16, 128);
+    long long t0 = clock64();
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one_sync()) {
+        for (int in = 0; in < inner; ++in) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              umma2_bf16(tmem_base + a * 256, ad0 + (uint64_t)((a * 65536 + ks * 4096) >> 4), bd0 + (uint64_t)(((ks % 4) * 2 * (N / 2) * 16) >> 4),
+                         idesc, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma2_commit_mc(&bar, 1);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (tid == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (tid < 32) tmem_dealloc2(tmem_base, 512);
+}
+template <int N, int NACC>
+static cudaError_t launch_rate4(int reps, int inner, int grid, unsigned long long* out, cudaStream_t st) {
+  size_t smem = (size_t)NACC * 128 * 256 * 2 + 128 * 64 * 2 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_rate4_kernel<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  umma_rate4_kernel<N, NACC><<<grid, 128, smem, st>>>(reps, inner, out);
+  return cudaGetLastError();
+}
+}  // namespace hn
+
+extern "C" int hn_umma_rate4(int N, int nacc, int reps, int inner, int grid, void* out_cycles, void* stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  unsigned long long* o = (unsigned long long*)out_cycles;
+  cudaStream_t st = (cudaStream_t)stream;
+#define HN_R4(n, a) if (N == n && nacc == a) e = hn::launch_rate4<n, a>(reps, inner, grid, o, st);
+  HN_R4(256, 1) HN_R4(256, 2) HN_R4(128, 1) HN_R4(128, 2) HN_R4(64, 1) HN_R4(64, 2) HN_R4(16, 1) HN_R4(16, 2)
+#undef HN_R4
+  return hn::set_cuda_error(e, "hn_umma_rate4");
+}

@@ -136,6 +136,9 @@ int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, 
  * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
 int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);
 
+/* test hook: D[256,N] = A[256,K] * B[N,K]^T on a 2-CTA cluster with cta_group::2 (A, B row-major [rows][K]). */
+int hn_umma_probe2(const void* A_bf16, const void* B_bf16, float* D, int N, int K, void* stream);
+
 /* test hook: cycles for reps x (inner x ksteps x nsub back-to-back K=16 UMMAs (M=128) + one commit/wait) from resident
  * shared-memory operands; swizzle 0 = un-swizzled interleave layout, 1 = 128B swizzle.  out_cycles: uint64 per CTA. */
 int hn_umma_rate(int N, int ksteps, int reps, int swizzle, int nsub, int inner, int grid, void* out_cycles, void* stream);
@@ -150,6 +153,9 @@ int hn_umma_rate3(int N, int nacc, int reps, int inner, int grid, void* out_cycl
 
 /* test hook: cycles for 8 warps to drain a 256-column accumulator with a selectable subset of the epilogue's work. */
 int hn_epi_rate(int mode, int reps, int grid, void* gout, void* out_cycles, void* stream);
+
+/* test hook: as hn_umma_rate3 for the CTA-pair form (cta_group::2, M = 256 on 2-CTA clusters). */
+int hn_umma_rate4(int N, int nacc, int reps, int inner, int grid, void* out_cycles, void* stream);
 
 /* test hook: cycles for nwarps warps to read `cols` TMEM columns of their 32 lanes `reps` times (tcgen05.ld.32x32b.x32). */
 int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream);
