@@ -78,7 +78,7 @@ def run_reference_arm(args):
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -221,6 +221,26 @@ def run_gpu_arm(args):
     e2e_step()
     secs_e2e, _, _ = timed_loop(e2e_step, args.steps)
 
+    # secondary metric of BASELINE.json ("render Mrays/s", configs[2]): one 1008x756 frame, 64+128 samples, no_grad,
+    # random-init weights, rows of the frame sharded over the ranks (no collective); device time, max over ranks
+    render = None
+    if not args.no_render:
+        rmodel = NerfModel(emb, near=0., far=1., n_samples_coarse=64, n_samples_fine=128, noise_std=None,
+                           hyper_slice_method='bendy_sheet', hyper_slice_out_dim=2, use_warp=True, use_nerf_embed=False,
+                           use_alpha_cond=False, use_rgb_cond=False, GLO_dim=8, share_GLO=True, xyz_fourier_dim=10,
+                           hyper_fourier_dim=6, view_fourier_dim=6)
+        rmodel.load_state_dict(model.state_dict())
+        rmodel = rmodel.to(dev).eval()
+        frame = synthetic.frame_rays(image_id=3, seed=0)
+        flo, fhi = hn_train.shard_bounds(frame.shape[0], rank, world)
+        frame_d = frame[flo:fhi].contiguous().to(dev)
+        hn_train.render_rays(rmodel, frame_d[:32768], chunk=32768)       # warm-up (packs the weights)
+        secs_r, launches_r, _ = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=32768), 2)
+        render = {"value": frame.shape[0] * 2 / secs_r / 1e6, "unit": "Mrays/s", "rays_per_frame": int(frame.shape[0]),
+                  "samples": "64+128", "ms_per_frame": 1e3 * secs_r / 2, "frames_timed": 2,
+                  "workload": "cfg3: full-frame eval render 1008x756, random-init weights, no_grad"}
+        del rmodel, frame_d
+
     # roofline of the dominant kernel from the per-kernel events recorded inside the timed region
     per = {}
     for name, n, a, b in prof or []:
@@ -233,12 +253,19 @@ def run_gpu_arm(args):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
-        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    peak_hbm = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json (bf16_tflops_sustained / hbm_gbs: kernels timed inside a long step)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained, 6.65 TB/s (B200_PROFILING.md)"
+    # Which roofline bounds each kernel: the fused forward and data-gradient kernels are dense
+    # contractions (tensor pipe); the weight-gradient kernel streams both activation stashes once and is HBM bound.
+    # Algorithmic HBM bytes per sample: X stash 8640 B + dY stash 8288 B read once by wgrad.
+    ALG_BYTES = {"mlp_wgrad": 8640 + 8288}
     for name, (t, cnt, nsamp) in per.items():
         flops = FWD_FLOP_PER_EVAL * nsamp          # fwd, dgrad and wgrad each count 1x forward FLOPs (bwd = 2x fwd)
         kernels[name] = {"launches": cnt, "seconds": t, "tflops": flops / t / 1e12 if t > 0 else None,
                          "share_of_step": t / (secs if secs > 0 else 1)}
+        if name in ALG_BYTES and t > 0:
+            kernels[name]["hbm_gbs"] = ALG_BYTES[name] * nsamp / t / 1e9
     if kernels:
         dom = max(kernels, key=lambda k: kernels[k]["seconds"])
         k = kernels[dom]
@@ -249,9 +276,17 @@ def run_gpu_arm(args):
             traffic = tr["dram_bytes_per_sample"] * per[dom][2] / per[dom][1]
         except Exception:
             pass
-        roof = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": k["tflops"] / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": 1e3 * k["seconds"] / k["launches"], "kernels": kernels}
+        if dom in ALG_BYTES:
+            roof = {"kernel": dom, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
+                    "frac": k["hbm_gbs"] / peak_hbm, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ALG_BYTES[dom] * per[dom][2] / per[dom][1],
+                    "avg_launch_ms": 1e3 * k["seconds"] / k["launches"], "kernels": kernels}
+        else:
+            roof = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": k["tflops"] / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_ms": 1e3 * k["seconds"] / k["launches"], "kernels": kernels}
+        # the whole step against the tensor roofline, for the north-star utilisation target
+        roof["step_tensor_frac"] = (GLOBAL_RAYS * EVALS_PER_RAY * FWD_FLOP_PER_EVAL * 3 * args.steps / secs / 1e12) / (peak_tf * world)
 
     if rank == 0:
         cpu = None
@@ -271,14 +306,31 @@ def run_gpu_arm(args):
             "model_tflops": total_flop * args.steps / secs / 1e12,
             "e2e": {"value": GLOBAL_RAYS * args.steps / secs_e2e, "unit": "rays/s",
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the process's real stdout; everything else any library prints on
+    fd 1 during the run (e.g. NCCL's version banner at N > 1) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -286,6 +338,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=8192, help="rays per forward/backward chunk on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the secondary full-frame render measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
