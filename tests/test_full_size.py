@@ -1,0 +1,118 @@
+"""GPU: properties of the fused path at BASELINE.json sizes, where the fp32 oracle would take minutes.
+
+* chunk invariance: a ray's outputs and the accumulated gradient do not depend on how the batch is cut into chunks
+  or which tile / CTA a ray lands in (8 192 rays in one call vs 5 uneven calls; same draws);
+* the inference and training instantiations of the forward kernel agree bit for bit;
+* compositing invariants on the full 65 536-ray batch: weights in [0, 1], sum(weights) <= 1, acc / depth bounds,
+  sorted fine samples, finite everything;
+* gradient linearity: grad of (a * loss) == a * grad of loss (the backward kernels accumulate into the flat buffer).
+"""
+import pytest
+import torch
+
+import helpers as H
+from hypernerf_torch_b200 import model_utils as mu
+from hypernerf_torch_b200 import synthetic
+from hypernerf_torch_b200 import train as hn_train
+from oracle import ref_loader
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(noise_std=1.0, n_fine=64):
+    sd = synthetic.make_state_dict(synthetic.cfg1_state_dict_shapes(), seed=0, boosted=True)
+    return H.make_model(n_fine=n_fine, noise_std=noise_std, sd=sd)
+
+
+def _draws(B, Nc, Nf, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return [torch.rand(B, Nc, device=DEV, generator=g), torch.randn(B, Nc, 1, device=DEV, generator=g),
+            torch.rand(B, Nf, device=DEV, generator=g), torch.randn(B, Nc + Nf, 1, device=DEV, generator=g)]
+
+
+def _forward(model, rays, draws):
+    with ref_loader._DrawTape(draws):
+        return model(mu.prepare_ray_dict(rays), dict(H.EXTRA))
+
+
+def test_chunk_invariance_of_outputs_and_gradients():
+    B, Nc, Nf = 8192, 64, 64
+    model = _model()
+    rays, rgbs = synthetic.train_rays(B, seed=3, device=DEV)
+    draws = _draws(B, Nc, Nf, seed=11)
+    fg = hn_train.FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+
+    def run(cuts):
+        fg.zero()
+        outs = []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            out = _forward(model, rays[lo:hi], [d[lo:hi] for d in draws])
+            loss = (torch.nn.functional.mse_loss(out['coarse']['rgb'], rgbs[lo:hi], reduction='sum') +
+                    torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs[lo:hi], reduction='sum')) / (3.0 * B)
+            loss.backward()
+            outs.append({k: out['fine'][k].detach() for k in ('rgb', 'depth', 'acc', 'weights')})
+        return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}, fg.flat.clone()
+
+    whole, g_whole = run([0, B])
+    parts, g_parts = run([0, 1000, 1001, 4097, 7777, B])
+    for k in whole:                      # per-ray results are position independent: bit-identical
+        assert torch.equal(whole[k], parts[k]), k
+    # gradients are sums over samples in a different order (atomics / tile partition): equal up to fp32 rounding
+    rel = (g_whole - g_parts).norm() / g_whole.norm()
+    assert rel < 1e-5, rel
+    assert torch.isfinite(g_whole).all() and g_whole.abs().sum() > 0
+
+
+def test_inference_and_training_forward_agree():
+    B = 4096
+    model = _model(noise_std=None)
+    rays, _ = synthetic.train_rays(B, seed=5, device=DEV)
+    d4 = _draws(B, 64, 64, seed=2)
+    draws = [d4[0], d4[2]]                          # no sigma noise: only the two uniform draws are consumed
+    with torch.no_grad():
+        a = _forward(model, rays, draws)            # inference instantiation (no stash)
+    b = _forward(model, rays, draws)                # training instantiation (stash + gate words)
+    for lvl in ('coarse', 'fine'):
+        for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
+            assert torch.equal(a[lvl][k], b[lvl][k].detach()), (lvl, k)
+
+
+def test_full_batch_invariants():
+    B = 65536
+    model = _model()
+    rays, _ = synthetic.train_rays(B, seed=0, device=DEV)
+    outs = []
+    with torch.no_grad():
+        for i in range(0, B, 16384):
+            outs.append(model(mu.prepare_ray_dict(rays[i:i + 16384]), dict(H.EXTRA)))
+    for lvl, S in (('coarse', 64), ('fine', 128)):
+        w = torch.cat([o[lvl]['weights'] for o in outs])
+        rgb = torch.cat([o[lvl]['rgb'] for o in outs])
+        depth = torch.cat([o[lvl]['depth'] for o in outs])
+        acc = torch.cat([o[lvl]['acc'] for o in outs])
+        assert w.shape == (B, S) and torch.isfinite(w).all() and torch.isfinite(rgb).all()
+        assert (w >= 0).all() and (w <= 1 + 1e-5).all()
+        assert (w.sum(-1) <= 1 + 1e-3).all()            # sum alpha_i T_i <= 1 (up to the +1e-5 inside the cumprod)
+        assert (acc >= 0).all() and (acc <= w.sum(-1) + 1e-6).all()   # acc excludes the sample at infinity
+        assert (rgb >= 0).all() and (rgb <= 1 + 1e-3).all()          # convex-ish combination of sigmoids
+        assert (depth >= 0).all() and (depth <= 1 + 1e-3).all()      # near = 0, far = 1
+
+
+def test_gradient_is_linear_in_the_loss_scale():
+    B = 2048
+    model = _model()
+    rays, rgbs = synthetic.train_rays(B, seed=9, device=DEV)
+    draws = _draws(B, 64, 64, seed=4)
+    fg = hn_train.FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+    grads = []
+    for scale in (1.0, 4.0):
+        fg.zero()
+        out = _forward(model, rays, draws)
+        loss = torch.nn.functional.mse_loss(out['coarse']['rgb'], rgbs) + torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs)
+        (scale * loss).backward()
+        grads.append(fg.flat.clone())
+    rel = (4.0 * grads[0] - grads[1]).norm() / grads[1].norm()
+    assert rel < 2e-2, rel    # dY is rounded to bf16 before it enters the UMMAs, so scaling is linear up to bf16 rounding
