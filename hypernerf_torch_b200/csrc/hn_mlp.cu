@@ -14,6 +14,8 @@
 // and gives its registers away (setmaxnreg 40); warpgroups 1-2 are the epilogue (thread = sample row, one
 // warpgroup per sub-tile, setmaxnreg 216).  TMEM: 512 columns = 2 sub-tiles x 256 fp32 accumulator columns.
 #include <math.h>
+#include <cuda.h>          // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>
 #include "hn_api_internal.h"
 #include "hn_mlp_program.h"
 #include "hn_ptx.cuh"
@@ -70,8 +72,14 @@ struct Smem {
   static constexpr int TOTAL = TMEMP + 16;
 };
 
+// pair mode: 3-D tensor maps over the packed blob viewed as [128-byte block][8 rows][8 bf16]; map i moves a contiguous
+// run of 2^i blocks (128 B .. 32 KB) in one request
+struct PairMaps { CUtensorMap m[kPair ? 9 : 1]; };
+
 struct FwdParams {
   Program prog;
+  PairMaps maps;
+  uint32_t w_row0;          // pair mode: first 16-byte row of `weights` inside the blob the tensor maps cover
   const uint8_t* weights;   // packed blob base + fwd_off
   const float* bias;        // packed blob base + bias_off
   const float* glo;         // (E, G) fp32 copy of the GLO table
@@ -91,6 +99,8 @@ struct FwdParams {
 
 struct BwdParams {
   Program prog;
+  PairMaps maps;
+  uint32_t w_row0;
   const uint8_t* weights;   // packed blob base + bwd_off
   const int64_t* ids;
   const float* sigma; const float* rgb; const float* warped;
@@ -196,9 +206,16 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
 }
 
 // ---- pair mode (HN_PAIR): see hn_mlp_program.h -------------------------------------------------------------------
+// HN_PAIR_DIRECT = 1: the non-leader CTA's weight copies complete_tx on the LEADER's full[] barrier (its shared::cluster
+// address), so the issuer learns from one local barrier that both halves of a stage have landed; 0: relay thread +
+// remote arrive on peer_full[].
+#ifndef HN_PAIR_DIRECT
+#define HN_PAIR_DIRECT 1
+#endif
 // Producer of CTA `rank`: per stage, its half (rows [rank N/2, (rank+1) N/2) of every 8-column chunk) of the weights.
-__device__ __forceinline__ void produce_tile_pair(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
-                                                  uint64_t* full, uint64_t* empty, RingState& rs, uint32_t rank) {
+__device__ __forceinline__ void produce_tile_pair(const Program& prog, const PairMaps& maps, uint32_t w_row0,
+                                                  const uint8_t* __restrict__ weights, uint8_t* ring,
+                                                  uint64_t* full, uint64_t* empty, RingState& rs, uint32_t rank, long long& t_wait) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
     for (int chain = 0; chain < kChains; ++chain) {
@@ -206,14 +223,29 @@ __device__ __forceinline__ void produce_tile_pair(const Program& prog, const uin
         const MmaOp& op = prog.ops[oi];
         const int nchunks = op.k >> 3;
         const uint32_t half_bytes = (uint32_t)(op.n >> 1) * 16;   // one chunk's rows held by this CTA
-        const uint8_t* src = weights + (size_t)op.w_off16 * 16 + (size_t)rank * half_bytes;
+        // pair layout of the packed weights: [rank][chunk][N/2 rows][8] -> this CTA's chunks are contiguous
+        const uint32_t nh = op.n >> 1;
+        const uint32_t row_base = (op.w_off16 - (uint32_t)op.n * op.kc0)                 // the logical matrix
+                                  + rank * (uint32_t)op.kc_total * nh + (uint32_t)op.kc0 * nh;   // 16-byte rows inside `weights`
         for (int c = 0; c < nchunks; c += op.cps) {
           const int cnt = min((int)op.cps, nchunks - c);
-          mbar_wait(&empty[rs.slot], rs.phase ^ 1);
-          mbar_arrive_expect_tx(&full[rs.slot], cnt * half_bytes);
+          { long long t0 = HN_T0(); mbar_wait(&empty[rs.slot], rs.phase ^ 1); t_wait += HN_T0() - t0; }
           uint8_t* dst = ring + rs.slot * kStageBytes;
-          for (int j = 0; j < cnt; ++j)
-            bulk_g2s(dst + j * half_bytes, src + (size_t)(c + j) * op.n * 16, half_bytes, &full[rs.slot]);
+          const uint32_t bytes = cnt * half_bytes;
+          const uint32_t row0 = row_base + (uint32_t)c * (op.n >> 1);
+#if HN_PAIR_DIRECT
+          // both CTAs' halves complete_tx on the leader's full[slot]; the leader expects the bytes of both
+          if (rank == 0) mbar_arrive_expect_tx(&full[rs.slot], 2 * bytes);
+          uint32_t blk = (w_row0 + row0) >> 3, nblk = bytes >> 7, off = 0;   // 128-byte blocks
+          while (nblk) {
+            const int i = 31 - __clz(nblk > 256u ? 256u : nblk);             // largest power of two that fits
+            tma_g2s_3d_pair(dst + off, &maps.m[i], (int32_t)blk, &full[rs.slot]);
+            blk += 1u << i; nblk -= 1u << i; off += 128u << i;
+          }
+#else
+          mbar_arrive_expect_tx(&full[rs.slot], bytes);
+          bulk_g2s(dst, weights + (size_t)row0 * 16, bytes, &full[rs.slot]);
+#endif
           rs.next();
         }
       }
@@ -254,10 +286,16 @@ __device__ __forceinline__ void issue_layer_pair(const Program& prog, const Laye
     for (uint32_t c = 0; c < nchunks; c += cps) {
       const uint32_t cnt = min(cps, nchunks - c);
       long long t0 = HN_T0();
+#if HN_PAIR_DIRECT
+      mbar_wait_cluster(&full[rs.slot], rs.phase);
+      t_wait += HN_T0() - t0;
+      (void)peer_full; (void)t_peer;
+#else
       mbar_wait(&full[rs.slot], rs.phase);
       long long t1 = HN_T0();
       mbar_wait_cluster(&peer_full[rs.slot], rs.phase);
       t_wait += t1 - t0; t_peer += HN_T0() - t1;
+#endif
       tc_fence_after();
       if (elect_one_sync()) {
         uint32_t a_lo = a_base + c * (uint32_t)(kChunkBytes >> 4);
@@ -505,11 +543,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       RingState rs;
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (kPair) produce_tile_pair(prog, p.weights, ring, full, empty, rs, rank);
+        if (kPair) produce_tile_pair(prog, p.maps, p.w_row0, p.weights, ring, full, empty, rs, rank, tw);
         else produce_tile(prog, p.weights, ring, full, empty, rs, tw);
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
-    } else if (kPair && warp == kRelayWarp && lane == 0 && rank == 1) {
+    } else if (kPair && !HN_PAIR_DIRECT && warp == kRelayWarp && lane == 0 && rank == 1) {
       RingState rs;
       const uint32_t leader_peer_full = mapa_u32(peer_full, 0);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) relay_tile_pair(prog, full, leader_peer_full, rs);
@@ -542,7 +580,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       }
       if (p.dbg && lane == 0) {
         p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin;
-        if (kPair) p.dbg[blockIdx.x * 8 + 0] = t_peer;   // pair mode: slot 0 = issuer's wait for the other CTA's half stage
+        if (kPair && !HN_PAIR_DIRECT) p.dbg[blockIdx.x * 8 + 0] = t_peer;   // relay variant: issuer's wait for the other CTA's half stage
       }
     }
   } else {
@@ -714,11 +752,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       RingState rs;
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (kPair) produce_tile_pair(prog, p.weights, ring, full, empty, rs, rank);
+        if (kPair) produce_tile_pair(prog, p.maps, p.w_row0, p.weights, ring, full, empty, rs, rank, tw);
         else produce_tile(prog, p.weights, ring, full, empty, rs, tw);
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
-    } else if (kPair && warp == kRelayWarp && lane == 0 && rank == 1) {
+    } else if (kPair && !HN_PAIR_DIRECT && warp == kRelayWarp && lane == 0 && rank == 1) {
       RingState rs;
       const uint32_t leader_peer_full = mapa_u32(peer_full, 0);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) relay_tile_pair(prog, full, leader_peer_full, rs);
@@ -751,7 +789,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       }
       if (p.dbg && lane == 0) {
         p.dbg[blockIdx.x * 8 + 1] = t_ready; p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = HN_T0() - t_begin;
-        if (kPair) p.dbg[blockIdx.x * 8 + 0] = t_peer;   // pair mode: slot 0 = issuer's wait for the other CTA's half stage
+        if (kPair && !HN_PAIR_DIRECT) p.dbg[blockIdx.x * 8 + 0] = t_peer;   // relay variant: issuer's wait for the other CTA's half stage
       }
     }
   } else {
@@ -1106,8 +1144,11 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
   if (oi < p.tab.nops) {
     const PackOp& op = p.tab.ops[oi];
     const int npk = op.n * (op.k / 8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npk; i += gridDim.x * blockDim.x) {
-      const int chunk = i / op.n, n = i % op.n;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < npk; i0 += gridDim.x * blockDim.x) {
+      const int chunk = i0 / op.n, n = i0 % op.n;
+      // pair mode: [rank][chunk][N/2 rows] so that each CTA's half of consecutive chunks is one contiguous run
+      const int nh = op.n >> 1;
+      const int i = kPair ? ((n / nh) * (op.k / 8) + chunk) * nh + (n % nh) : i0;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -1151,6 +1192,37 @@ static int64_t tiles_of(int64_t n) {
   int64_t t = (n + kCtaRows - 1) / kCtaRows;
   return kPair ? (t + 1) / 2 * 2 : t;
 }
+// pair mode: tensor maps over one packed blob (cached per blob pointer: the encoder is a host-side driver call)
+static int build_pair_maps(const void* blob, int64_t blob_bytes, PairMaps* out) {
+  if (!kPair) return 0;
+  static thread_local const void* cached_blob = nullptr;
+  static thread_local int64_t cached_bytes = 0;
+  static thread_local PairMaps cached;
+  if (blob == cached_blob && blob_bytes == cached_bytes) { *out = cached; return 0; }
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (enc == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess)
+      return set_error(-20, "pair mode: cuTensorMapEncodeTiled is not available from this driver");
+    enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const cuuint64_t dims[3] = {8, 8, (cuuint64_t)(blob_bytes / 128)};
+  const cuuint64_t strides[2] = {16, 128};
+  const cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < 9; ++i) {
+    const cuuint32_t box[3] = {8, 8, (cuuint32_t)(1u << i)};
+    CUresult r = enc(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(blob), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-21, "pair mode: cuTensorMapEncodeTiled failed");
+  }
+  cached_blob = blob; cached_bytes = blob_bytes;
+  *out = cached;
+  return 0;
+}
+
 template <class K, class P>
 static cudaError_t launch_mlp(K kernel, int grid, int smem, cudaStream_t stream, const P& params) {
   cudaLaunchConfig_t cfg = {};
@@ -1229,6 +1301,8 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   FwdParams fp;
   fp.prog = plan.fwd;
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
+  fp.w_row0 = (uint32_t)(plan.layout.fwd_off / 16);
+  if (int rc = build_pair_maps(packed, plan.layout.total, &fp.maps)) return rc;
   fp.bias = (const float*)((const uint8_t*)packed + plan.layout.bias_off);
   fp.glo = (const float*)((const uint8_t*)packed + plan.layout.glo_off);
   fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
@@ -1273,6 +1347,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     BwdParams bp;
     bp.prog = plan.bwd;
     bp.weights = (const uint8_t*)packed + plan.layout.bwd_off;
+    bp.w_row0 = (uint32_t)(plan.layout.bwd_off / 16);
+    if (int rc = build_pair_maps(packed, plan.layout.total, &bp.maps)) return rc;
     bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
     bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
     bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;

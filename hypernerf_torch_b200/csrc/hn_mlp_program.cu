@@ -30,8 +30,9 @@ struct Builder {
     L.n_out = (uint16_t)n_out; L.bias_off = (uint16_t)bias_off; L.save_chunk = save_chunk; L.mask_chunk = mask_chunk;
     L.gate_word = gate_word; L.pad2 = 0;
   }
-  void emit(int n, int k, Src s, int a_col, int tmem_col, int acc_init) {
+  void emit(int n, int k, Src s, int a_col, int tmem_col, int acc_init, int kc0, int kc_total) {
     MmaOp& o = p->ops[p->nops++];
+    o.kc0 = (uint16_t)kc0; o.kc_total = (uint16_t)kc_total;
     o.w_off16 = w16; o.n = (uint16_t)n; o.k = (uint16_t)k; o.a_chunk = (uint16_t)(a_col / 8);
     o.tmem_col = (uint16_t)tmem_col; o.src = s; o.acc_init = (uint8_t)acc_init; o.pad = 0;
     const int rows_here = kPair ? n / 2 : n;   // pair mode: each CTA stages half of the N rows of every chunk
@@ -46,8 +47,8 @@ struct Builder {
   void add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
     LogicalOp& l = lg->ops[lg->n++];
     l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k0 + k1);
-    emit(n, k0, s0, a0_col, tmem_col, acc_init);
-    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1);
+    emit(n, k0, s0, a0_col, tmem_col, acc_init, 0, (k0 + k1) / 8);
+    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1, k0 / 8, (k0 + k1) / 8);
   }
 };
 

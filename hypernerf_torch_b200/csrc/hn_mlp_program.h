@@ -28,11 +28,14 @@ namespace hn {
 // sub-tile of each CTA) and takes half of every weight stage from each CTA's shared memory, so a pass over a layer's
 // weights serves 256 rows while each SM only ingests half of it; that makes the out-of-phase (ping-pong) schedule of
 // the two sub-tiles affordable: sub-tile 0's epilogue of both CTAs runs under sub-tile 1's UMMAs and vice versa.
-// Status: functionally complete (all GPU parity tests pass with HN_PAIR=1) but not the default.  The leader's issuer
-// has to learn that the OTHER CTA's half of a stage has landed; without tensor-map TMA (whose cta_group::2 form can
-// signal the leader's mbarrier directly) that takes a relay thread and a remote arrive per stage, the refill round
-// trip grows to ~2 000 cycles, and the 48 KB ring then covers only ~75 % of it: the issuer waits 41 % of its time
-// for the peer (profiles/README.md), fwd 3.27 / dgrad 3.36 ms per 1 M samples against 2.83 / 2.78 in lock step.
+// Status: functionally complete (GPU parity tests pass with HN_PAIR=1; tests/helpers.py TILE_ROWS = 512) but not the
+// default.  Two variants were measured (profiles/README.md): (a) relay thread + remote arrive to tell the leader that
+// the peer's half stage landed, (b) HN_PAIR_DIRECT: tensor-map TMA loads whose cta_group::2 form signals the leader's
+// mbarrier directly, with a pair-friendly packed layout so that a half stage is one request.  In both the weight
+// refill round trip (UMMA commit multicast to both CTAs -> producers -> TMA -> complete_tx across the pair) is
+// ~3 000 cycles against ~1 200 in the single-CTA schedule, and the 48 KB ring that fits next to the 2 x 64 KB of
+// resident activations only holds ~1 500 cycles of UMMA work: the issuer waits ~40 % of its time for stages
+// (fwd 3.33 / dgrad 3.32 ms per 1 M samples against 2.77 / 2.71 in lock step).
 #ifndef HN_PAIR
 #define HN_PAIR 0
 #endif
@@ -152,6 +155,7 @@ struct MmaOp {
   uint8_t acc_init;            // 1: accumulate onto what TMEM already holds
   uint8_t cps;                 // 8-col chunks of K per ring stage (even)
   uint8_t pad;
+  uint16_t kc0, kc_total;      // first chunk of this op inside its logical weight matrix / that matrix's chunk count
 };
 // A weight matrix as the packer sees it: one [n x k] operand image; a skip layer's matrix is consumed by two
 // consecutive MmaOps (hidden part, then input part accumulating on top).

@@ -74,6 +74,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Tensor-map TMA load of a contiguous run of 128-byte blocks (3-D view [block][8 rows][8 bf16], box = 2^i blocks) into this CTA's shared memory whose completion (complete_tx) is signalled
+// on the LEADER CTA's mbarrier: the cta_group::2 form accepts the barrier of the pair's other CTA (bit 24 of the
+// shared::cluster address selects the CTA; cute/arch/copy_sm100_tma.hpp, SM100_TMA_2SM_LOAD_2D).  The plain
+// cp.async.bulk form faults when given a remote barrier (tried), hence the tensor map.
+__device__ __forceinline__ void tma_g2s_3d_pair(void* smem_dst, const void* tensor_map, int32_t block, uint64_t* bar_same_offset) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar_same_offset) & 0xFEFFFFFFu), "r"(0), "r"(0), "r"(block)
+               : "memory");
+}
 // bulk L2 prefetch of a contiguous global range (bytes: multiple of 16)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
