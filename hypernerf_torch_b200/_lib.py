@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("HN_LIB") or os.path.join(_HERE, "libhypernerf_b200.so
 HN_NUM_PARAM_TENSORS = 93
 HN_FLAG_WARP_TRANSLATION = 1
 HN_FLAG_SLICE_BENDY = 2
+HN_FLAG_STATIC_NERF = 4
+HN_NUM_STATIC_PARAM_TENSORS = 24
 HN_COMP_WHITE_BKGD = 1
 HN_COMP_ACC_ALL = 2
 

@@ -25,8 +25,9 @@ namespace hn {
 // ------------------------------------------------------------------------------------------------------
 // compile-time model shape (cfg-1 family of BASELINE.json)
 // ------------------------------------------------------------------------------------------------------
-template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_>
+template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_, bool STATIC_ = false>
 struct Shape {
+  static constexpr bool STATIC = STATIC_;   // static baseline models/nerf.py: no GLO / warp / sheet / hyper coordinates
   static constexpr int G = G_, H = H_, WF = WF_, SF = SF_, XF = XF_, HF = HF_, VF = VF_;
   static constexpr int PE_W = 3 + 6 * WF, IN_W = PE_W + G, KW = pad16(IN_W);
   static constexpr int PE_X = 3 + 6 * XF, PE_H = H * (1 + 2 * HF), IN_T = PE_X + PE_H, KT = pad16(IN_T);
@@ -35,6 +36,7 @@ struct Shape {
   static constexpr int N_RGB0A = pad16(kRgbW + 1);
 };
 using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
+using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (-> K 64), dir PE 27 (-> K 32)
 
 // ------------------------------------------------------------------------------------------------------
 // shared memory plan of the fused kernels
@@ -114,7 +116,7 @@ struct BwdParams {
   int S;
   int n_tiles;
   int x_total, d_total;
-  uint16_t d_rgbhead, pad0;
+  uint16_t d_rgbhead, d_sigma;
   unsigned long long* dbg;
 };
 
@@ -619,13 +621,15 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         dir[i] = __ldg(p.viewdirs + ray * 3 + i);
         pt[i] = __ldg(p.points + gc * 3 + i);
       }
-      // prologue: [posenc(points, WF) | GLO | 0] -> INB
+      // prologue: [posenc(points, WF) | GLO | 0] -> INB   (static baseline: [Embedding(xyz) | 0], nerf.py:21-38)
       {
         float f[C::KW];
         posenc<3, C::WF>(pt, f);
-        const float* e = p.glo + __ldg(p.ids + ray) * C::G;
+        if constexpr (!C::STATIC) {
+          const float* e = p.glo + __ldg(p.ids + ray) * C::G;
 #pragma unroll
-        for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
+          for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
+        }
 #pragma unroll
         for (int i = C::IN_W; i < C::KW; ++i) f[i] = 0.f;
         store_features<C::KW>(f, inb_row, save_row, p.x_in_ws);
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
       t_pro += HN_T0() - t_tile;
 
-      float wp[3 + C::H];  // warped point + hyper coordinates
+      float wp[3 + C::H + (C::STATIC ? 1 : 0)];  // warped point + hyper coordinates
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
@@ -649,6 +653,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         if (L.epi == FE_RELU) {
           fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
         } else if (L.epi == FE_WSHEAD) {
+          if constexpr (!C::STATIC) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
@@ -666,6 +671,15 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
 #pragma unroll
           for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
           store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
+          }
+        } else if (L.epi == FE_SIGMA) {
+          // static baseline: raw sigma = Linear(W, 1)(h8) (nerf.py:109); rendering.py:150 uses relu(sigma + noise)
+          uint32_t r[16];
+          tmem_ld16(tlane, r);
+          tmem_ld_wait();
+          float a = __uint_as_float(r[0]) + bias[0];
+          if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;
+          if (valid) p.sigma[g] = fmaxf(a, 0.f);
         } else if (L.epi == FE_BOTT) {
           fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, nullptr);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
@@ -675,6 +689,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
+          if constexpr (!C::STATIC) {
           fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW, gate_row + (size_t)L.gate_word * kHalfRows);
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
@@ -682,6 +697,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           float a = __uint_as_float(r[0]) + bias[kRgbW];
           if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;  // noise_regularize, model_utils.py:312-316
           if (valid) p.sigma[g] = softplus_f(a);                          // models.py:491
+          }
         } else {  // FE_RGBHEAD
           uint32_t r[16];
           tmem_ld16(tlane, r);
@@ -830,6 +846,14 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           }
         }
         store_features<16>(f, act_row, save_row, p.d_rgbhead);
+        if constexpr (C::STATIC) {
+          // dY of the sigma head: sigma = relu(raw + noise) (rendering.py:150) -> gate on the stored sigma; kept in INB
+          // as the A operand of the sigma^T op that accumulates onto final^T, and stashed for the weight gradient
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          if (valid && __ldg(p.sigma + g) > 0.f) f[0] = __ldg(p.g_sigma + g);
+          store_features<16>(f, inb_row, save_row, p.d_sigma);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -845,7 +869,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); } }
           continue;
         }
-        if (L.epi == BE_RGB1) {
+        if (!C::STATIC && L.epi == BE_RGB1) {
           bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
           float f[16];
@@ -859,8 +883,10 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == BE_LINEAR) {
-          bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
-        } else if (L.epi == BE_SKIPSTORE) {
+          if (L.n_out == kTrunkW) bwd_cols<false, kTrunkW>(tlane, nullptr, act_row, save_row, L.save_chunk);
+          else bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
+        } else if constexpr (!C::STATIC) {   // (the static program only has BE_MASK / BE_LINEAR layers)
+        if (L.epi == BE_SKIPSTORE) {
           bwd_cols<false, C::KT>(tlane, nullptr, inb_row, nullptr, 0);
         } else if (L.epi == BE_TRUNKIN) {
           // d(trunk input features) = layer-0 part (TMEM) + skip-layer part (INB, bf16)
@@ -914,6 +940,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
               atomicAdd(p.glo_grad + id * C::G + i, v);
             }
           }
+        }
         }
         if (li + 1 < prog.nlayers) {
           fence_proxy_async_smem();
@@ -1254,10 +1281,15 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
   const int64_t halves = 2 * kSubTiles * tiles_of(n_samples);
   out->packed_bytes = plan.layout.total;
   // X slabs, then the ReLU gate words ([half tile][g_total][64 rows] uint32)
-  out->saved_bytes = halves * plan.slabs.x_total * kHalfChunkBytes + halves * plan.slabs.g_total * kHalfRows * 4;
-  out->workspace_bytes = halves * plan.slabs.d_total * kHalfChunkBytes;
+  out->saved_bytes = halves * plan.info.x_total * kHalfChunkBytes + halves * plan.info.g_total * kHalfRows * 4;
+  out->workspace_bytes = halves * plan.info.d_total * kHalfChunkBytes;
   const Dims& m = plan.dims;
   auto lin = [](int64_t out_f, int64_t in_f) { return out_f * in_f + out_f; };
+  if (is_static(*desc)) {   // NeRF(D=8, W=256): 595 844 parameters at the default 63 / 27 input channels
+    out->flat_param_floats = lin(kTrunkW, m.pe_x) + 6 * lin(kTrunkW, kTrunkW) + lin(kTrunkW, kTrunkW + m.pe_x) + lin(1, kTrunkW) +
+                             lin(kTrunkW, kTrunkW) + lin(kRgbW, kTrunkW + m.pe_v) + lin(3, kRgbW);
+    return 0;
+  }
   int64_t cnt = (int64_t)desc->num_embeddings * m.G;
   cnt += lin(kSheetW, m.in_s) + 4 * lin(kSheetW, kSheetW) + lin(kSheetW, kSheetW + m.in_s) + lin(m.H, kSheetW);
   cnt += lin(kWarpW, m.in_w) + 4 * lin(kWarpW, kWarpW) + lin(kWarpW, kWarpW + m.in_w) + lin(3, kWarpW);
@@ -1281,8 +1313,8 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   pp.blob = (uint8_t*)packed;
   pp.bias_off = plan.layout.bias_off;
   pp.glo_off = plan.layout.glo_off;
-  pp.glo_src = param_offsets[P_GLO];
-  pp.glo_floats = desc->num_embeddings * plan.dims.G;
+  pp.glo_src = is_static(*desc) ? 0 : param_offsets[P_GLO];
+  pp.glo_floats = plan.info.glo_floats;
   dim3 grid(16, plan.pack.nops + 1);
   pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp);
   return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
@@ -1291,13 +1323,14 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
 extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
                           const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
                           float* rgb, float* warped, void* saved, void* stream) {
-  if (!desc || !packed || !points || !viewdirs || !ids || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
+  if (!desc || !packed || !points || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
   if (int rc = validate_desc(*desc)) return rc;
+  const bool stat = is_static(*desc);
+  if (!stat && !ids) return set_error(-2, "hn_mlp_fwd: null ids");
   if (B == 0) return 0;
   static thread_local ModelPlan plan;
   build_plan(*desc, &plan);
-  using C = Cfg1;
   FwdParams fp;
   fp.prog = plan.fwd;
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
@@ -1310,19 +1343,22 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   int64_t nt = tiles_of(fp.n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_fwd: too many samples");
   fp.n_tiles = (int)nt;
-  fp.x_total = plan.slabs.x_total;
-  fp.x_in_ws = plan.slabs.x_in_ws; fp.x_in_t = plan.slabs.x_in_t; fp.x_in_v = plan.slabs.x_in_v;
+  fp.x_total = plan.info.x_total;
+  fp.x_in_ws = plan.info.x_in0; fp.x_in_t = plan.info.x_in_t; fp.x_in_v = plan.info.x_in_v;
   fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
-  fp.g_total = plan.slabs.g_total;
-  fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.slabs.x_total * kHalfChunkBytes) : nullptr;
+  fp.g_total = plan.info.g_total;
+  fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
   int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
-  if (saved != nullptr) {
-    if (int rc = set_smem(mlp_fwd_kernel<C, true>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
-    return set_cuda_error(launch_mlp(mlp_fwd_kernel<C, true>, grid, Smem<C>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd");
-  }
-  if (int rc = set_smem(mlp_fwd_kernel<C, false>, Smem<C>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;
-  return set_cuda_error(launch_mlp(mlp_fwd_kernel<C, false>, grid, Smem<C>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd");
+#define HN_LAUNCH_FWD(CFG, ST)                                                                                              \
+  do {                                                                                                                      \
+    if (int rc = set_smem(mlp_fwd_kernel<CFG, ST>, Smem<CFG>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;                   \
+    return set_cuda_error(launch_mlp(mlp_fwd_kernel<CFG, ST>, grid, Smem<CFG>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd"); \
+  } while (0)
+  if (stat) { if (saved != nullptr) HN_LAUNCH_FWD(CfgStatic, true); else HN_LAUNCH_FWD(CfgStatic, false); }
+  if (saved != nullptr) HN_LAUNCH_FWD(Cfg1, true);
+  HN_LAUNCH_FWD(Cfg1, false);
+#undef HN_LAUNCH_FWD
 }
 
 static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
@@ -1330,7 +1366,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
                         const float* g_warped, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
                         void* workspace, void* stream, bool do_data, bool do_weights) {
   if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
-  if (do_data && (!packed || !ids || !sigma || !rgb || !warped || !g_sigma || !g_rgb))
+  const bool stat = desc && is_static(*desc);
+  if (do_data && (!packed || !sigma || !rgb || !g_sigma || !g_rgb || (!stat && (!ids || !warped))))
     return set_error(-2, "hn_mlp_bwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_bwd: bad B/S");
   if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
@@ -1339,7 +1376,6 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
   static thread_local ModelPlan plan;
   build_plan(*desc, &plan);
   build_tables(*desc, level, param_offsets, &plan);
-  using C = Cfg1;
   const int64_t n = B * S;
   const int64_t nt = tiles_of(n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_bwd: too many samples");
@@ -1352,17 +1388,22 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
     bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
     bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
-    bp.g_total = plan.slabs.g_total;
-    bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.slabs.x_total * kHalfChunkBytes);
-    bp.glo_grad = flat_grad + param_offsets[P_GLO];
+    bp.g_total = plan.info.g_total;
+    bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes);
+    bp.glo_grad = stat ? nullptr : flat_grad + param_offsets[P_GLO];
     bp.n = n; bp.S = S;
     bp.n_tiles = (int)nt;
-    bp.x_total = plan.slabs.x_total; bp.d_total = plan.slabs.d_total;
-    bp.d_rgbhead = plan.slabs.d_rgbhead; bp.pad0 = 0;
+    bp.x_total = plan.info.x_total; bp.d_total = plan.info.d_total;
+    bp.d_rgbhead = plan.info.d_rgbhead; bp.d_sigma = plan.info.d_sigma;
     bp.dbg = g_dbg;
-    if (int rc = set_smem(mlp_dgrad_kernel<C>, Smem<C>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
     int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
-    if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<C>, grid, Smem<C>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
+    if (stat) {
+      if (int rc = set_smem(mlp_dgrad_kernel<CfgStatic>, Smem<CfgStatic>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<CfgStatic>, grid, Smem<CfgStatic>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
+    } else {
+      if (int rc = set_smem(mlp_dgrad_kernel<Cfg1>, Smem<Cfg1>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<Cfg1>, grid, Smem<Cfg1>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
+    }
   }
   if (do_weights) {
     WgradParams wp;
@@ -1370,7 +1411,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
     wp.flat_grad = flat_grad;
     wp.n_half = 2 * kSubTiles * nt;
-    wp.x_total = plan.slabs.x_total; wp.d_total = plan.slabs.d_total;
+    wp.x_total = plan.info.x_total; wp.d_total = plan.info.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
     int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
     mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);

@@ -7,6 +7,11 @@
 namespace hn {
 
 int validate_desc(const hn_model_desc& d) {
+  if (is_static(d)) {
+    if (d.xyz_freqs != 10 || d.view_freqs != 4)
+      return set_error(-11, "hn_model_desc: the static NeRF kernels are instantiated for xyz / dir freqs 10 / 4 (models/nerf.py defaults)");
+    return 0;
+  }
   if ((d.flags & (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY)) != (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY))
     return set_error(-10, "hn_model_desc: this build implements TranslationField warp + bendy_sheet slicing only");
   if (d.glo_dim != 8 || d.hyper_dim != 2 || d.xyz_freqs != 10 || d.hyper_freqs != 6 || d.view_freqs != 6 ||
@@ -80,8 +85,12 @@ static int fwd_bias_floats(const Dims& m) {
   return kWsDepth * kWsW + 16 + (kTrunkDepth + 1) * kTrunkW + kRgbW + m.n_rgb0a + (kRgbDepth - 1) * kRgbW + 16;
 }
 
+static void build_plan_static(const hn_model_desc& d, ModelPlan* plan);
+static void build_tables_static(const int64_t* off, ModelPlan* plan);
+
 void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   memset(plan, 0, sizeof(*plan));
+  if (is_static(d)) { build_plan_static(d, plan); return; }
   const Dims m = make_dims(d);
   const SlabMap s = make_slabs(m);
   plan->dims = m;
@@ -182,9 +191,15 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   plan->layout.glo_off = (plan->layout.glo_off + 15) / 16 * 16;
   plan->layout.total = plan->layout.glo_off + (int64_t)d.num_embeddings * m.G * 4;
   plan->layout.total = (plan->layout.total + 255) / 256 * 256;
+  PlanInfo& I = plan->info;
+  I.x_total = s.x_total; I.d_total = s.d_total; I.g_total = s.g_total;
+  I.x_in0 = s.x_in_ws; I.x_in_t = s.x_in_t; I.x_in_v = s.x_in_v;
+  I.d_rgbhead = s.d_rgbhead; I.d_sigma = kNone;
+  I.n_params = HN_NUM_PARAM_TENSORS; I.glo_floats = d.num_embeddings * m.G;
 }
 
 void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPlan* plan) {
+  if (is_static(d)) { build_tables_static(off, plan); return; }
   const Dims& m = plan->dims;
   const SlabMap& s = plan->slabs;
   // ------------------------------------------------------------------ pack table
@@ -390,6 +405,218 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
     bseg(j, P_RGB_B(level, kRgbDepth), 0, 3);
   }
   (void)d;
+}
+
+
+// ======================================================================================================================
+// static baseline: models/nerf.py:41-123 (NeRF(D=8, W=256, in_channels_xyz=63, in_channels_dir=27, skips=[4]))
+// ======================================================================================================================
+namespace {
+struct StaticSlabs {
+  uint16_t x_in_x, x_t[kStaticDepth], x_final, x_in_v, x_dir, x_total;
+  uint16_t d_t[kStaticDepth], d_final, d_dir, d_rgbhead, d_sigma, d_total;
+  uint16_t g_t[kStaticDepth], g_dir, g_total;
+  int KX, KV, pe_x, pe_v;
+};
+StaticSlabs make_static_slabs(const hn_model_desc& d) {
+  StaticSlabs s{};
+  s.pe_x = 3 + 6 * d.xyz_freqs; s.pe_v = 3 + 6 * d.view_freqs;
+  s.KX = pad16(s.pe_x); s.KV = pad16(s.pe_v);
+  uint16_t c = 0;
+  s.x_in_x = c; c += s.KX / 8;
+  for (int l = 0; l < kStaticDepth; ++l) { s.x_t[l] = c; c += kTrunkW / 8; }
+  s.x_final = c; c += kTrunkW / 8;
+  s.x_in_v = c; c += s.KV / 8;
+  s.x_dir = c; c += kRgbW / 8;
+  s.x_total = c;
+  c = 0;
+  for (int l = 0; l < kStaticDepth; ++l) { s.d_t[l] = c; c += kTrunkW / 8; }
+  s.d_final = c; c += kTrunkW / 8;
+  s.d_dir = c; c += kRgbW / 8;
+  s.d_rgbhead = c; c += 2;
+  s.d_sigma = c; c += 2;
+  s.d_total = c;
+  c = 0;
+  for (int l = 0; l < kStaticDepth; ++l) { s.g_t[l] = c; c += kTrunkW / 32; }
+  s.g_dir = c; c += kRgbW / 32;
+  s.g_total = c;
+  return s;
+}
+int static_bias_floats() { return kStaticDepth * kTrunkW + 16 + kTrunkW + kRgbW + 16; }
+}  // namespace
+
+static void build_plan_static(const hn_model_desc& d, ModelPlan* plan) {
+  const StaticSlabs s = make_static_slabs(d);
+  // ---------------------------------------------------------------- forward (nerf.py:84-123)
+  {
+    Builder b{&plan->fwd, &plan->fwd_logical};
+    int bias = 0;
+    b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone, s.g_t[0]);
+    b.add_op(kTrunkW, s.KX, SRC_INB, 0, 0, SRC_ACT, 0, 0);
+    bias += kTrunkW;
+    for (int l = 1; l < kStaticDepth; ++l) {
+      b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone, s.g_t[l]);
+      // skip: cat([input_xyz, h]) (nerf.py:104-106); the hidden part comes first in OUR K order, the packer remaps
+      b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, l == kStaticSkip ? s.KX : 0, SRC_INB, 0, 0);
+      bias += kTrunkW;
+    }
+    b.begin_layer(FE_SIGMA, 16, bias, kNone, kNone);          // sigma = Linear(W, 1)(h8)        nerf.py:109
+    b.add_op(16, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += 16;
+    b.begin_layer(FE_BOTT, kTrunkW, bias, s.x_final, kNone);  // xyz_encoding_final, no activation nerf.py:113
+    b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += kTrunkW;
+    b.begin_layer(FE_RELU, kRgbW, bias, s.x_dir, kNone, s.g_dir);   // dir_encoding on cat([final, dir PE]) nerf.py:115-116
+    b.add_op(kRgbW, kTrunkW, SRC_ACT, 0, s.KV, SRC_INB, 0, 0);
+    bias += kRgbW;
+    b.begin_layer(FE_RGBHEAD, 16, bias, kNone, kNone);        // rgb = Sigmoid(Linear(W/2, 3))   nerf.py:117
+    b.add_op(16, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    bias += 16;
+    plan->layout.fwd_off = 0;
+    plan->layout.bwd_off = (int64_t)b.w16 * 16;
+  }
+  // ---------------------------------------------------------------- backward-data
+  {
+    Builder b{&plan->bwd, &plan->bwd_logical};
+    b.begin_layer(BE_MASK, kRgbW, 0, s.d_dir, s.x_dir, s.g_dir);           // rgb^T, A = dY_rgbhead (prologue)
+    b.add_op(kRgbW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    b.begin_layer(BE_LINEAR, kTrunkW, 0, s.d_final, kNone);                // dir_encoding^T (hidden part)
+    b.add_op(kTrunkW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[kStaticDepth - 1], s.x_t[kStaticDepth - 1], s.g_t[kStaticDepth - 1]);
+    b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);              // final^T
+    b.add_op(kTrunkW, 16, SRC_INB, 0, 0, SRC_ACT, 0, 0, /*acc_init=*/1);   // + sigma^T, A = dY_sigma (prologue, INB)
+    for (int l = kStaticDepth - 1; l >= 1; --l) {
+      b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[l - 1], s.x_t[l - 1], s.g_t[l - 1]);
+      b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    }
+    plan->layout.bias_off = plan->layout.bwd_off + (int64_t)b.w16 * 16;
+  }
+  plan->layout.glo_off = (plan->layout.bias_off + (int64_t)static_bias_floats() * 4 + 15) / 16 * 16;
+  plan->layout.total = (plan->layout.glo_off + 255) / 256 * 256;
+  PlanInfo& I = plan->info;
+  I.x_total = s.x_total; I.d_total = s.d_total; I.g_total = s.g_total;
+  I.x_in0 = s.x_in_x; I.x_in_t = kNone; I.x_in_v = s.x_in_v;
+  I.d_rgbhead = s.d_rgbhead; I.d_sigma = s.d_sigma;
+  I.n_params = HN_NUM_STATIC_PARAM_TENSORS; I.glo_floats = 0;
+  // the descriptor is needed again by build_tables_static: keep the derived sizes in dims (unused otherwise)
+  plan->dims.KW = s.KX; plan->dims.KV = s.KV; plan->dims.pe_x = s.pe_x; plan->dims.pe_v = s.pe_v;
+}
+
+static void build_tables_static(const int64_t* off, ModelPlan* plan) {
+  hn_model_desc d{};
+  d.xyz_freqs = (plan->dims.pe_x - 3) / 6; d.view_freqs = (plan->dims.pe_v - 3) / 6;
+  const StaticSlabs s = make_static_slabs(d);
+  const int pe_x = s.pe_x, pe_v = s.pe_v;
+  const int ld_skip = kTrunkW + pe_x, ld_dir = kTrunkW + pe_v;
+  PackTable& t = plan->pack;
+  memset(&t, 0, sizeof(t));
+  Packer pk{&t, off};
+  const LogicalOps& F = plan->fwd_logical;
+  int oi = 0;
+  pk.op(F.ops[oi++]);
+  pk.block(SP_TRUNK_W(0), 0, pe_x, 1, 0, kTrunkW, 0, pe_x);
+  for (int l = 1; l < kStaticDepth; ++l) {
+    pk.op(F.ops[oi++]);
+    if (l == kStaticSkip) {   // weight columns: [0, pe_x) input_xyz, [pe_x, pe_x + W) hidden
+      pk.block(SP_TRUNK_W(l), pe_x, ld_skip, 1, 0, kTrunkW, 0, kTrunkW);
+      pk.block(SP_TRUNK_W(l), 0, ld_skip, 1, 0, kTrunkW, kTrunkW, pe_x);
+    } else {
+      pk.block(SP_TRUNK_W(l), 0, kTrunkW, 1, 0, kTrunkW, 0, kTrunkW);
+    }
+  }
+  pk.op(F.ops[oi++]);
+  pk.block(SP_SIGMA_W, 0, kTrunkW, 1, 0, 1, 0, kTrunkW);
+  pk.op(F.ops[oi++]);
+  pk.block(SP_FINAL_W, 0, kTrunkW, 1, 0, kTrunkW, 0, kTrunkW);
+  pk.op(F.ops[oi++]);
+  pk.block(SP_DIR_W, 0, ld_dir, 1, 0, kRgbW, 0, ld_dir);
+  pk.op(F.ops[oi++]);
+  pk.block(SP_RGB_W, 0, kRgbW, 1, 0, 3, 0, kRgbW);
+
+  // backward: dest(n = input feature, k = output feature) = W[k][n]
+  const LogicalOps& Bp = plan->bwd_logical;
+  const uint32_t bwd16 = (uint32_t)(plan->layout.bwd_off / 16);
+  oi = 0;
+  auto bop = [&](void) { LogicalOp o = Bp.ops[oi++]; o.w_off16 += bwd16; pk.op(o); };
+  bop();  // rgb^T
+  pk.block(SP_RGB_W, 0, 1, kRgbW, 0, kRgbW, 0, 3);
+  bop();  // dir^T, hidden columns
+  pk.block(SP_DIR_W, 0, 1, ld_dir, 0, kTrunkW, 0, kRgbW);
+  bop();  // final^T
+  pk.block(SP_FINAL_W, 0, 1, kTrunkW, 0, kTrunkW, 0, kTrunkW);
+  bop();  // sigma^T
+  pk.block(SP_SIGMA_W, 0, 1, kTrunkW, 0, kTrunkW, 0, 1);
+  for (int l = kStaticDepth - 1; l >= 1; --l) {
+    bop();
+    if (l == kStaticSkip) pk.block(SP_TRUNK_W(l), pe_x, 1, ld_skip, 0, kTrunkW, 0, kTrunkW);
+    else pk.block(SP_TRUNK_W(l), 0, 1, kTrunkW, 0, kTrunkW, 0, kTrunkW);
+  }
+  // biases, forward layer order
+  int bo = 0;
+  for (int l = 0; l < kStaticDepth; ++l) { pk.bias(SP_TRUNK_B(l), bo, kTrunkW); bo += kTrunkW; }
+  pk.bias(SP_SIGMA_B, bo, 1); bo += 16;
+  pk.bias(SP_FINAL_B, bo, kTrunkW); bo += kTrunkW;
+  pk.bias(SP_DIR_B, bo, kRgbW); bo += kRgbW;
+  pk.bias(SP_RGB_B, bo, 3); bo += 16;
+  t.bias_floats = bo;
+
+  // weight-gradient jobs
+  WgradTable& w = plan->wgrad;
+  memset(&w, 0, sizeof(w));
+  auto job = [&](int dy_chunk, int dy_cols, int x0_chunk, int x0_cols) -> WgradJob& {
+    WgradJob& j = w.jobs[w.njobs++];
+    j.dy_chunk = (uint16_t)dy_chunk; j.dy_nchunks = (uint16_t)(dy_cols / 8);
+    j.x0_chunk = (uint16_t)x0_chunk; j.x0_nchunks = (uint16_t)(x0_cols / 8);
+    j.x1_chunk = 0; j.x1_nchunks = 0;
+    j.mblocks = (uint8_t)((dy_cols + 127) / 128);
+    return j;
+  };
+  auto flush = [&](WgradJob& j, int param, int64_t extra, int ld, int row0, int nrows, int col0, int ncols) {
+    FlushSeg& f = j.flush[j.nflush++];
+    f.dst = off[param] + extra; f.ld = ld; f.row0 = (uint16_t)row0; f.nrows = (uint16_t)nrows;
+    f.col0 = (uint16_t)col0; f.ncols = (uint16_t)ncols;
+  };
+  auto bseg = [&](WgradJob& j, int param, int col0, int ncols) {
+    BiasSeg& b = j.bias[j.nbias++];
+    b.dst = off[param]; b.col0 = (uint16_t)col0; b.ncols = (uint16_t)ncols; b.pad = 0;
+  };
+  {
+    WgradJob& j = job(s.d_t[0], kTrunkW, s.x_in_x, s.KX);
+    flush(j, SP_TRUNK_W(0), 0, pe_x, 0, kTrunkW, 0, pe_x);
+    bseg(j, SP_TRUNK_B(0), 0, kTrunkW);
+  }
+  for (int l = 1; l < kStaticDepth; ++l) {
+    const bool skip = l == kStaticSkip;
+    WgradJob& j = job(s.d_t[l], kTrunkW, s.x_t[l - 1], kTrunkW);
+    flush(j, SP_TRUNK_W(l), skip ? pe_x : 0, skip ? ld_skip : kTrunkW, 0, kTrunkW, 0, kTrunkW);
+    bseg(j, SP_TRUNK_B(l), 0, kTrunkW);
+    if (skip) {
+      WgradJob& k = job(s.d_t[l], kTrunkW, s.x_in_x, s.KX);
+      flush(k, SP_TRUNK_W(l), 0, ld_skip, 0, kTrunkW, 0, pe_x);
+    }
+  }
+  {
+    WgradJob& j = job(s.d_sigma, 16, s.x_t[kStaticDepth - 1], kTrunkW);
+    flush(j, SP_SIGMA_W, 0, kTrunkW, 0, 1, 0, kTrunkW);
+    bseg(j, SP_SIGMA_B, 0, 1);
+  }
+  {
+    WgradJob& j = job(s.d_final, kTrunkW, s.x_t[kStaticDepth - 1], kTrunkW);
+    flush(j, SP_FINAL_W, 0, kTrunkW, 0, kTrunkW, 0, kTrunkW);
+    bseg(j, SP_FINAL_B, 0, kTrunkW);
+  }
+  {
+    WgradJob& j = job(s.d_dir, kRgbW, s.x_final, kTrunkW);
+    flush(j, SP_DIR_W, 0, ld_dir, 0, kRgbW, 0, kTrunkW);
+    bseg(j, SP_DIR_B, 0, kRgbW);
+    WgradJob& k = job(s.d_dir, kRgbW, s.x_in_v, s.KV);
+    flush(k, SP_DIR_W, kTrunkW, ld_dir, 0, kRgbW, 0, pe_v);
+  }
+  {
+    WgradJob& j = job(s.d_rgbhead, 16, s.x_dir, kRgbW);
+    flush(j, SP_RGB_W, 0, kRgbW, 0, 3, 0, kRgbW);
+    bseg(j, SP_RGB_B, 0, 3);
+  }
 }
 
 }  // namespace hn

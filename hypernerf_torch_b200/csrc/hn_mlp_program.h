@@ -164,7 +164,7 @@ struct LogicalOp {
   uint16_t n, k;
 };
 
-enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD };
+enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD, FE_SIGMA };
 enum BwdEpi : uint8_t { BE_MASK = 0, BE_LINEAR, BE_RGB1, BE_SKIPSTORE, BE_TRUNKIN, BE_GLO };
 
 struct Layer {
@@ -240,9 +240,26 @@ struct PackedLayout {
   int64_t fwd_off, bwd_off, bias_off, glo_off, total;  // bytes
 };
 
+// What the host launch code needs to know about a plan, whichever model family built it.
+struct PlanInfo {
+  uint16_t x_total, d_total, g_total;   // chunks per half tile of the X / dY stashes, gate words per row
+  uint16_t x_in0, x_in_t, x_in_v;       // X slabs written by the prologue / trunk-input / view-direction PE
+  uint16_t d_rgbhead, d_sigma;          // dY slabs written by the data-gradient prologue
+  int32_t n_params;                     // canonical parameter tensors
+  int32_t glo_floats;
+};
+
+// static baseline (models/nerf.py): canonical parameter indices = state_dict order
+inline int SP_TRUNK_W(int l) { return 2 * l; }   // l = 0..7: xyz_encoding_{l+1}.0
+inline int SP_TRUNK_B(int l) { return 2 * l + 1; }
+constexpr int SP_FINAL_W = 16, SP_FINAL_B = 17, SP_DIR_W = 18, SP_DIR_B = 19, SP_SIGMA_W = 20, SP_SIGMA_B = 21,
+              SP_RGB_W = 22, SP_RGB_B = 23;
+constexpr int kStaticDepth = 8, kStaticSkip = 4;   // NeRF(D=8, W=256, skips=[4])
+
 struct ModelPlan {
   Dims dims;
   SlabMap slabs;
+  PlanInfo info;
   Program fwd, bwd;
   LogicalOps fwd_logical, bwd_logical;
   PackTable pack;     // needs param_offsets -> built per call
@@ -250,6 +267,7 @@ struct ModelPlan {
   PackedLayout layout;
 };
 
+inline bool is_static(const hn_model_desc& d) { return (d.flags & HN_FLAG_STATIC_NERF) != 0; }
 // Validates the descriptor; returns 0 or a negative error code (message through set_error).
 int validate_desc(const hn_model_desc& d);
 // Static part (programs, slabs, blob layout).

@@ -111,3 +111,21 @@ def cfg1_state_dict_shapes():
         s[f"{lvl}.alpha_mlp.weight"] = (1, 128)
         s[f"{lvl}.alpha_mlp.bias"] = (1,)
     return s
+
+
+def static_state_dict_shapes():
+    """state_dict names / shapes of one static NeRF (models/nerf.py: D=8, W=256, 63 / 27 input channels, skips=[4])."""
+    s = {}
+    for i in range(8):
+        fan_in = 63 if i == 0 else (256 + 63 if i == 4 else 256)
+        s[f"xyz_encoding_{i + 1}.0.weight"] = (256, fan_in)
+        s[f"xyz_encoding_{i + 1}.0.bias"] = (256,)
+    s["xyz_encoding_final.weight"] = (256, 256)
+    s["xyz_encoding_final.bias"] = (256,)
+    s["dir_encoding.0.weight"] = (128, 256 + 27)
+    s["dir_encoding.0.bias"] = (128,)
+    s["sigma.weight"] = (1, 256)
+    s["sigma.bias"] = (1,)
+    s["rgb.0.weight"] = (3, 128)
+    s["rgb.0.bias"] = (3,)
+    return s

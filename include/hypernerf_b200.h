@@ -40,6 +40,13 @@ typedef struct hn_model_desc {
 
 #define HN_FLAG_WARP_TRANSLATION 1  /* use_warp with TranslationField                            */
 #define HN_FLAG_SLICE_BENDY 2       /* hyper_slice_method == 'bendy_sheet'                       */
+#define HN_FLAG_STATIC_NERF 4       /* static baseline models/nerf.py:41-123 (one NeRF per blob; xyz_freqs 10,
+                                       view_freqs 4; glo/hyper/warp/sheet fields ignored).  hn_mlp_fwd then returns
+                                       sigma = relu(raw + noise * noise_std) (rendering.py:150) and rgb; ids / warped
+                                       may be NULL; `level` is ignored.  Canonical parameter order = state_dict order
+                                       of NeRF: xyz_encoding_{1..8}.0.{weight,bias}, xyz_encoding_final.{weight,bias},
+                                       dir_encoding.0.{weight,bias}, sigma.{weight,bias}, rgb.0.{weight,bias}          */
+#define HN_NUM_STATIC_PARAM_TENSORS 24
 
 /* Canonical parameter order = state_dict order of the reference model:
  *   0                      warp_embed.embed.weight (E,G)

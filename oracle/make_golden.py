@@ -48,7 +48,45 @@ def make(name, n_rays, n_fine, noise_std, boosted, seed):
     print(name, 'loss', float(loss), os.path.getsize(path) // 1024, 'KiB')
 
 
+STATIC_SMALL_GRADS = ["sigma.weight", "sigma.bias", "rgb.0.weight", "rgb.0.bias", "xyz_encoding_1.0.bias",
+                      "xyz_encoding_5.0.bias", "dir_encoding.0.bias", "xyz_encoding_final.bias"]
+
+
+def make_static(name, n_rays, n_samples, n_importance, perturb, noise_std, seed):
+    """Static baseline (BASELINE.json configs[3]): models/nerf.py + models/rendering.py of the unmodified reference."""
+    torch.set_num_threads(8)
+    ref_loader.load_reference()
+    from models.nerf import Embedding, NeRF          # the reference's modules (sys.path set by load_reference)
+    from models.rendering import render_rays
+    models = [NeRF(), NeRF()]
+    sds = [synthetic.make_state_dict(synthetic.static_state_dict_shapes(), seed=seed + i) for i in range(2)]
+    for m, sd in zip(models, sds):
+        m.load_state_dict(sd)
+    emb = [Embedding(3, 10), Embedding(3, 4)]
+    rays9, rgbs = synthetic.train_rays(n_rays, seed=seed + 10)
+    rays = rays9[:, :8].contiguous()
+    torch.manual_seed(1234)
+    with ref_loader._DrawTape() as tape:
+        out = render_rays(models, emb, rays, N_samples=n_samples, perturb=perturb, noise_std=noise_std,
+                          N_importance=n_importance, chunk=1 << 15)
+    loss = torch.nn.functional.mse_loss(out['rgb_coarse'], rgbs) + torch.nn.functional.mse_loss(out['rgb_fine'], rgbs)
+    loss.backward()
+    fix = {'name': name, 'n_samples': n_samples, 'n_importance': n_importance, 'perturb': perturb, 'noise_std': noise_std,
+           'weight_seed': seed, 'rays': rays, 'rgbs': rgbs, 'draws': tape.tape, 'loss': float(loss.detach()),
+           'weight_checksum': [float(sum(v.double().abs().sum() for v in sd.values())) for sd in sds],
+           'out': {k: v.detach().clone() for k, v in out.items()},
+           'grad_norms': [{k: float(p.grad.double().norm()) for k, p in m.named_parameters()} for m in models],
+           'grad_small': [{k: dict(m.named_parameters())[k].grad.detach().clone() for k in STATIC_SMALL_GRADS} for m in models]}
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.pt')
+    torch.save(fix, path)
+    print(name, 'loss', float(loss), os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'static':
+        make_static('static_train_b32', 32, 64, 64, 1.0, 1.0, 20)       # training shape: perturbed, sigma noise
+        make_static('static_eval_b16', 16, 64, 128, 0, 0.0, 30)         # eval shape: deterministic sampling, no noise
+        sys.exit(0)
     make('cfg1_refinit_b32', 32, 64, 1.0, False, 0)      # reference-style init, train config (noise on)
     make('cfg1_boosted_b32', 32, 64, 1.0, True, 1)       # warp / sheet branches carry signal
     make('cfg3_boosted_b16', 16, 128, None, True, 2)     # render config: 64+128, no noise
