@@ -241,6 +241,37 @@ def run_gpu_arm(args):
                   "workload": "cfg3: full-frame eval render 1008x756, random-init weights, no_grad"}
         del rmodel, frame_d
 
+    # secondary workload (BASELINE.json configs[3]): static NeRF baseline (models/nerf.py x2 + render_rays), 262 144-ray
+    # batch sharded over the ranks, 128+128 samples, perturb=1, noise_std=1, forward + backward (no optimizer)
+    static = None
+    if not args.no_static:
+        from hypernerf_torch_b200.nerf import Embedding, NeRF
+        from hypernerf_torch_b200.rendering import render_rays as static_render_rays
+        smodels = [NeRF().to(dev), NeRF().to(dev)]
+        semb = [Embedding(3, 10), Embedding(3, 4)]
+        n_static = 262144
+        slo, shi = hn_train.shard_bounds(n_static, rank, world)
+        srays9, srgbs = synthetic.train_rays(shi - slo, seed=7 + rank, device=dev)
+        srays = srays9[:, :8].contiguous()
+
+        def static_step():
+            for m in smodels:
+                m.zero_grad(set_to_none=True)
+            for i in range(0, srays.shape[0], 32768):
+                out = static_render_rays(smodels, semb, srays[i:i + 32768], N_samples=128, perturb=1.0, noise_std=1.0,
+                                         N_importance=128)
+                tgt = srgbs[i:i + 32768]
+                loss = (torch.nn.functional.mse_loss(out['rgb_coarse'], tgt, reduction='sum') +
+                        torch.nn.functional.mse_loss(out['rgb_fine'], tgt, reduction='sum')) / (3.0 * n_static)
+                loss.backward()
+
+        static_step()
+        secs_s, _, _ = timed_loop(static_step, 2)
+        static = {"value": n_static * 2 / secs_s, "unit": "rays/s", "rays_per_step": n_static, "samples": "128+128",
+                  "ms_per_step": 1e3 * secs_s / 2, "steps_timed": 2,
+                  "workload": "cfg4: static NeRF baseline, 262144-ray batch, perturb=1, noise_std=1, fwd+bwd"}
+        del smodels, srays, srgbs
+
     # roofline of the dominant kernel from the per-kernel events recorded inside the timed region
     per = {}
     for name, n, a, b in prof or []:
@@ -306,7 +337,7 @@ def run_gpu_arm(args):
             "model_tflops": total_flop * args.steps / secs / 1e12,
             "e2e": {"value": GLOBAL_RAYS * args.steps / secs_e2e, "unit": "rays/s",
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render,
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render, "static_nerf": static,
         }
         emit(line)
     if world > 1:
@@ -339,6 +370,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=8192, help="rays per forward/backward chunk on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary full-frame render measurement")
+    ap.add_argument("--no-static", action="store_true", help="skip the secondary static-NeRF (cfg4) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

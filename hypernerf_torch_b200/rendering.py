@@ -11,8 +11,9 @@ __all__ = ['render_rays', 'sample_pdf']
 
 
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
-    """models/rendering.py:14-55 (torch ops on the GPU: < 0.5 % of the path; the reference calls the third-party
-    `torchsearchsorted.searchsorted(cdf, u, side='right')` here, i.e. torch.searchsorted(right=True))."""
+    """models/rendering.py:14-55 as a stand-alone utility (torch ops; the reference calls the third-party
+    `torchsearchsorted.searchsorted(cdf, u, side='right')` here, i.e. torch.searchsorted(right=True)).  render_rays does
+    not use it: it runs the whole resampling step in the hn_sample_pdf kernel."""
     N_rays, N_samples_ = weights.shape
     weights = weights + eps
     pdf = weights / torch.sum(weights, -1, keepdim=True)
@@ -85,10 +86,10 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
         result = {'rgb_coarse': rgb_coarse, 'depth_coarse': depth_coarse, 'opacity_coarse': weights_coarse.sum(1)}
 
     if N_importance > 0:
-        z_vals_mid = 0.5 * (z_vals[:, :-1] + z_vals[:, 1:])
-        z_vals_ = sample_pdf(z_vals_mid, weights_coarse[:, 1:-1], N_importance, det=(perturb == 0)).detach()
-        z_vals, _ = torch.sort(torch.cat([z_vals, z_vals_], -1), -1)
-        xyz_fine = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * z_vals.unsqueeze(2)
+        # rendering.py:223-233 in one launch (hn_sample_pdf): z_vals_mid, weights_coarse[:, 1:-1], inverse-CDF samples
+        # (searchsorted right=True), sort(cat([z_vals, samples])) and the fine sample points; detached like the reference
+        u = None if perturb > 0 else torch.linspace(0, 1, N_importance, device=rays.device).expand(N_rays, N_importance)
+        z_vals, xyz_fine = mu.sample_pdf_fused(z_vals, weights_coarse.detach(), rays_o, rays_d, N_importance, u=u)
         if _taps is not None:
             _taps['z_fine'] = z_vals.detach().clone()
         rgb_fine, depth_fine, weights_fine = inference(models[1], xyz_fine, z_vals.contiguous())
