@@ -557,3 +557,53 @@ extern "C" int hn_composite_bwd(const float* sigma, const float* rgb, const floa
                 g_out_rgb, g_depth, g_acc, g_weights, g_sigma, g_rgb);
   return set_cuda_error(cudaGetLastError(), "hn_composite_bwd");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// hn_mse_loss — losses.py:9-14 (MSE(coarse.rgb) + MSE(fine.rgb), mean reduction) fused with its gradient seed
+// and the fine-level MSE that metrics.py:4-13 turns into PSNR.  One pass over (B,3) predictions: sums[0] +=
+// sum (c - t)^2, sums[1] += sum (f - t)^2 (fp32 block partials, one atomic per block and level) and
+// g_level = 2 (pred - t) * grad_scale (grad_scale = upstream_grad / (3 B_global)).
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ pc, const float* __restrict__ pf,
+                                                       const float* __restrict__ tg, int64_t n, float grad_scale,
+                                                       float* __restrict__ sums, float* __restrict__ gc, float* __restrict__ gf) {
+  float sc = 0.f, sf = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = __ldg(tg + i);
+    const float dc = __ldg(pc + i) - t;
+    sc += dc * dc;
+    if (gc != nullptr) gc[i] = 2.f * dc * grad_scale;
+    if (pf != nullptr) {
+      const float df = __ldg(pf + i) - t;
+      sf += df * df;
+      if (gf != nullptr) gf[i] = 2.f * df * grad_scale;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(kFull, sc, o); sf += __shfl_xor_sync(kFull, sf, o); }
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = sc; red[1][wid] = sf; }
+  __syncthreads();
+  if (wid == 0) {
+    sc = lane < 8 ? red[0][lane] : 0.f;
+    sf = lane < 8 ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { sc += __shfl_xor_sync(kFull, sc, o); sf += __shfl_xor_sync(kFull, sf, o); }
+    if (lane == 0) { atomicAdd(sums, sc); if (pf != nullptr) atomicAdd(sums + 1, sf); }
+  }
+}
+}  // namespace hn
+
+extern "C" int hn_mse_loss(const float* rgb_coarse, const float* rgb_fine, const float* targets, int64_t B, float grad_scale,
+                           float* sums, float* g_coarse, float* g_fine, void* stream) {
+  if (!rgb_coarse || !targets || !sums) return hn::set_error(-2, "hn_mse_loss: null pointer");
+  if (B < 0) return hn::set_error(-1, "hn_mse_loss: negative B");
+  if (B == 0) return 0;
+  const int64_t n = B * 3;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)hn::num_sms());
+  hn::mse_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb_coarse, rgb_fine, targets, n, grad_scale, sums, g_coarse, g_fine);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_mse_loss");
+}

@@ -10,9 +10,8 @@ ShardedDDP gradient reduction (train.py:224-229) do, without Lightning.
 """
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
-from . import model_utils
+from . import losses, model_utils
 
 EXTRA_PARAMS = {'nerf_alpha': None, 'warp_alpha': None, 'hyper_alpha': None, 'hyper_sheet_alpha': None}
 
@@ -68,9 +67,9 @@ def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, opti
         rows = rays[i:i + chunk]
         tgt = rgbs[i:i + chunk]
         out = model(model_utils.prepare_ray_dict(rows), dict(EXTRA_PARAMS))
-        # mean over the global batch: mse(reduction='sum') / (3 * global_rays)
-        loss = (F.mse_loss(out['coarse']['rgb'], tgt, reduction='sum') +
-                F.mse_loss(out['fine']['rgb'], tgt, reduction='sum')) / (3.0 * global_rays)
+        # mean over the global batch: (sum_sq(coarse) + sum_sq(fine)) / (3 * global_rays), one fused kernel that also
+        # seeds both levels' gradients (losses.py:9-14)
+        loss, _ = losses.mse_coarse_fine(out, tgt, global_count=3.0 * global_rays)
         loss.backward()
         total += loss.detach()
     flat_grads.all_reduce()

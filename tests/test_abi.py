@@ -64,3 +64,20 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("no CPU or torch fallback", ""), fn
+
+
+def test_checkpoint_prefix_stripping(tmp_path):
+    """utils/__init__.py:66-88: Lightning checkpoints store the model under 'nerf.'; names must round-trip."""
+    import torch
+    from hypernerf_torch_b200 import synthetic, utils
+    sd = synthetic.make_state_dict(synthetic.static_state_dict_shapes(), seed=1)
+    ckpt = {'state_dict': {('nerf.' + k): v for k, v in sd.items()} | {'other.weight': torch.zeros(1)}}
+    path = tmp_path / "ckpt.pt"
+    torch.save(ckpt, path)
+    got = utils.extract_model_state_dict(str(path), model_name='nerf')
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+
+    from hypernerf_torch_b200.nerf import NeRF
+    m = NeRF()
+    utils.load_ckpt(m, str(path), model_name='nerf')
+    assert all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)

@@ -122,3 +122,24 @@ def test_sample_pdf_full_size_properties():
     cnt = (z_f[:, :, None] == z[:, None, :]).any(1).all(-1)  # every coarse depth appears in the output
     assert cnt.all()
     assert (bins.min(-1).values <= z_f.max(-1).values).all()
+
+
+@pytest.mark.parametrize("B", [1, 37, 8192, 70001])
+def test_fused_mse_loss_matches_reference_formula(B):
+    """losses.py:9-14 + metrics.py:4-13 through hn_mse_loss: loss, gradient seeds and PSNR."""
+    from hypernerf_torch_b200 import losses, metrics
+    g = torch.Generator(device=DEV).manual_seed(B)
+    c = torch.rand(B, 3, device=DEV, generator=g, requires_grad=True)
+    f = torch.rand(B, 3, device=DEV, generator=g, requires_grad=True)
+    t = torch.rand(B, 3, device=DEV, generator=g)
+    loss, sums = losses.mse_coarse_fine({'coarse': {'rgb': c}, 'fine': {'rgb': f}}, t)
+    (3.0 * loss).backward()
+    c2, f2 = c.detach().clone().requires_grad_(True), f.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(c2, t) + torch.nn.functional.mse_loss(f2, t)
+    (3.0 * ref).backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert torch.allclose(c.grad, c2.grad, rtol=1e-5, atol=1e-9) and torch.allclose(f.grad, f2.grad, rtol=1e-5, atol=1e-9)
+    psnr = metrics.psnr_from_sum(sums[1], 3 * B)
+    assert abs(psnr.item() - metrics.psnr(f.detach(), t).item()) < 1e-3
+    only_coarse = losses.MSELoss()({'coarse': {'rgb': c.detach()}}, t)
+    assert abs(only_coarse.item() - torch.nn.functional.mse_loss(c.detach(), t).item()) < 1e-6
