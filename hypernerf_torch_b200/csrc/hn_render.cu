@@ -607,3 +607,50 @@ extern "C" int hn_mse_loss(const float* rgb_coarse, const float* rgb_fine, const
   hn::mse_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb_coarse, rgb_fine, targets, n, grad_scale, sums, g_coarse, g_fine);
   return hn::set_cuda_error(cudaGetLastError(), "hn_mse_loss");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// hn_make_ndc_rays — datasets/ray_utils.py:5-93 (get_ray_directions -> get_rays -> get_ndc_rays) + the ray-row layout
+// of datasets/llff.py:261-264 / 316-332 for one full frame, on the device: pixel (i = column, j = row) ->
+// camera direction ((i - W/2)/f, -(j - H/2)/f, -1) -> world (rotate by c2w[:, :3], normalise) -> NDC origin /
+// direction -> row [o(3), d(3), near = 0, far = 1, image id].  c2w: 12 floats, row-major (3,4), passed by value.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+struct C2W { float m[12]; };
+__global__ void __launch_bounds__(256) make_ndc_rays_kernel(int H, int W, float focal, C2W c, float near_plane, float image_id,
+                                                            int cols, float* __restrict__ rays) {
+  const int64_t n = (int64_t)H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const float i = (float)(p % W), j = (float)(p / W);
+    const float cx = (i - W / 2.f) / focal, cy = -(j - H / 2.f) / focal, cz = -1.f;
+    float dx = cx * c.m[0] + cy * c.m[1] + cz * c.m[2];
+    float dy = cx * c.m[4] + cy * c.m[5] + cz * c.m[6];
+    float dz = cx * c.m[8] + cy * c.m[9] + cz * c.m[10];
+    const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv; dy *= inv; dz *= inv;
+    float ox = c.m[3], oy = c.m[7], oz = c.m[11];
+    const float t = -(near_plane + oz) / dz;                 // shift the origin to the near plane
+    ox += t * dx; oy += t * dy; oz += t * dz;
+    const float ox_oz = ox / oz, oy_oz = oy / oz;
+    const float sx = -1.f / (W / (2.f * focal)), sy = -1.f / (H / (2.f * focal));
+    const float o2 = 1.f + 2.f * near_plane / oz;
+    float* r = rays + p * cols;
+    r[0] = sx * ox_oz; r[1] = sy * oy_oz; r[2] = o2;
+    r[3] = sx * (dx / dz - ox_oz); r[4] = sy * (dy / dz - oy_oz); r[5] = 1.f - o2;
+    r[6] = 0.f; r[7] = 1.f;
+    if (cols > 8) r[8] = image_id;
+  }
+}
+}  // namespace hn
+
+extern "C" int hn_make_ndc_rays(int H, int W, float focal, const float* c2w_host, float near_plane, float image_id, int cols,
+                                float* rays, void* stream) {
+  if (!c2w_host || !rays) return hn::set_error(-2, "hn_make_ndc_rays: null pointer");
+  if (H <= 0 || W <= 0 || focal <= 0.f || (cols != 8 && cols != 9)) return hn::set_error(-1, "hn_make_ndc_rays: bad H/W/focal/cols");
+  hn::C2W c;
+  for (int k = 0; k < 12; ++k) c.m[k] = c2w_host[k];
+  const int64_t n = (int64_t)H * W;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * (int64_t)hn::num_sms());
+  hn::make_ndc_rays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(H, W, focal, c, near_plane, image_id, cols, rays);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_make_ndc_rays");
+}

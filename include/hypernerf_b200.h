@@ -146,6 +146,12 @@ int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, 
 int hn_mse_loss(const float* rgb_coarse, const float* rgb_fine, const float* targets, int64_t B, float grad_scale, float* sums,
                 float* g_coarse, float* g_fine, void* stream);
 
+/* datasets/ray_utils.py:5-93 (get_ray_directions, get_rays, get_ndc_rays) + the ray-row layout of datasets/llff.py:316-332 for
+ * one H x W frame on the device: rays (H*W, cols) = [origin(3), direction(3), near = 0, far = 1 (, image id)], cols = 8
+ * or 9.  c2w_host: HOST pointer to the (3,4) row-major camera-to-world matrix. */
+int hn_make_ndc_rays(int H, int W, float focal, const float* c2w_host, float near_plane, float image_id, int cols,
+                     float* rays, void* stream);
+
 /* test hook: one UMMA tile D[128,N] = A * B^T through the shared-memory layouts the MLP kernels use.
  * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
 int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);

@@ -82,7 +82,40 @@ def make_static(name, n_rays, n_samples, n_importance, perturb, noise_std, seed)
     print(name, 'loss', float(loss), os.path.getsize(path) // 1024, 'KiB')
 
 
+def make_ndc_rays():
+    """tests/golden/ndc_rays.pt: datasets/ray_utils.py of the reference (kornia.create_meshgrid, absent here, stubbed with
+    the pixel-index grid it returns for normalized_coordinates=False, ray_utils.py:17-22) on two small frames."""
+    import types
+    k = types.ModuleType('kornia')
+
+    def create_meshgrid(H, W, normalized_coordinates=False):
+        ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing='ij')
+        return torch.stack([xs, ys], -1)[None]
+    k.create_meshgrid = create_meshgrid
+    sys.modules['kornia'] = k
+    sys.path.insert(0, ref_loader.reference_dir())
+    from datasets.ray_utils import get_ndc_rays, get_ray_directions, get_rays
+    torch.manual_seed(0)
+    cases = []
+    for (H, W, focal) in ((12, 16, 13.7), (756 // 9, 1008 // 9, 815.13 / 9)):
+        A = torch.linalg.qr(torch.randn(3, 3))[0]
+        if torch.det(A) < 0:
+            A[:, 0] = -A[:, 0]
+        R = torch.linalg.qr(torch.eye(3) * 0.9 + 0.1 * A)[0]
+        R = R * torch.sign(torch.diagonal(R))[None]      # mostly forward-facing camera
+        c2w = torch.cat([R, (torch.rand(3, 1) - 0.5) * 0.6], 1)
+        o, d = get_rays(get_ray_directions(H, W, focal), c2w)
+        o, d = get_ndc_rays(H, W, focal, 1.0, o, d)
+        rays = torch.cat([o, d, torch.zeros_like(o[:, :1]), torch.ones_like(o[:, :1])], 1)
+        cases.append(dict(H=H, W=W, focal=focal, c2w=c2w, rays=rays))
+    torch.save(cases, os.path.join(ROOT, 'tests', 'golden', 'ndc_rays.pt'))
+    print('ndc_rays', [tuple(c['rays'].shape) for c in cases])
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'rays':
+        make_ndc_rays()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'static':
         make_static('static_train_b32', 32, 64, 64, 1.0, 1.0, 20)       # training shape: perturbed, sigma noise
         make_static('static_eval_b16', 16, 64, 128, 0, 0.0, 30)         # eval shape: deterministic sampling, no noise

@@ -143,3 +143,18 @@ def test_fused_mse_loss_matches_reference_formula(B):
     assert abs(psnr.item() - metrics.psnr(f.detach(), t).item()) < 1e-3
     only_coarse = losses.MSELoss()({'coarse': {'rgb': c.detach()}}, t)
     assert abs(only_coarse.item() - torch.nn.functional.mse_loss(c.detach(), t).item()) < 1e-6
+
+
+def test_device_ray_generation_matches_reference_golden():
+    """datasets/ray_utils.py:5-93 on the device (hn_make_ndc_rays) against rows generated by the reference's functions."""
+    from conftest import load_golden
+    from hypernerf_torch_b200 import ray_utils
+    for case in load_golden("ndc_rays"):
+        rays = ray_utils.frame_rays_ndc(case['H'], case['W'], case['focal'], case['c2w'], near_plane=1.0)
+        ref = case['rays']
+        assert rays.shape == ref.shape
+        err = (rays.cpu() - ref).abs().max().item()
+        print(f"ndc rays {case['H']}x{case['W']} max_abs_err {err:.2e}")
+        assert err < 2e-5            # fp32, different association of the same formula
+        with_id = ray_utils.frame_rays_ndc(case['H'], case['W'], case['focal'], case['c2w'], near_plane=1.0, image_id=7)
+        assert with_id.shape[1] == 9 and torch.equal(with_id[:, :8], rays) and (with_id[:, 8] == 7).all()
