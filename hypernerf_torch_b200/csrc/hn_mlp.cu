@@ -14,6 +14,8 @@
 // and gives its registers away (setmaxnreg 40); warpgroups 1-2 are the epilogue (thread = sample row, one
 // warpgroup per sub-tile, setmaxnreg 216).  TMEM: 512 columns = 2 sub-tiles x 256 fp32 accumulator columns.
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
 #include <cudaTypedefs.h>
 #include "hn_api_internal.h"
@@ -69,9 +71,10 @@ struct Smem {
   static constexpr int INB = ACT + kSubTiles * ACT_BYTES;
   static constexpr int RING = INB + kSubTiles * INB_BYTES;        // kRingStages x kStageBytes
   static constexpr int BIAS = RING + kRingStages * kStageBytes;   // 2 x 256 fp32: this / next layer's bias
-  static constexpr int BARS = BIAS + 2 * 256 * 4;                 // full[], empty[], acc_full, act_ready
-    static constexpr int TMEMP = BARS + (2 * kRingStages + 2) * 8;
+  static constexpr int BARS = BIAS + 2 * 256 * 4;                 // full[], empty[], acc_full[2], act_ready[2], peer_full[]
+  static constexpr int TMEMP = BARS + (3 * kRingStages + 4) * 8;
   static constexpr int TOTAL = TMEMP + 16;
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 // pair mode: 3-D tensor maps over the packed blob viewed as [128-byte block][8 rows][8 bf16]; map i moves a contiguous
@@ -971,15 +974,40 @@ constexpr int kWgStageBytes = 2 * kWgStageA;          // + up to 256 X columns
 struct WgSmem {
   static constexpr int STAGES = 0;
   static constexpr int BARS = kWgStages * kWgStageBytes;  // full[3], empty[3], acc_full, acc_empty
-  static constexpr int TMEMP = BARS + 8 * 8;
+  static constexpr int TMEMP = BARS + (2 * kWgStages + 2) * 8;
   static constexpr int TOTAL = TMEMP + 16;
 };
+// Job groups: CTAs of group g run only the jobs with WgradJob::group == g, over 1/(CTAs per group) of the half tiles
+// each.  Jobs are spread over the groups by their operand bytes per half tile (the kernel is HBM-bound), largest first.
+static int wgrad_groups() {
+  static const int g = [] {
+    const char* e = getenv("HN_WGRAD_GROUPS");
+    int v = e ? atoi(e) : 4;
+    return std::max(1, std::min(v, 16));
+  }();
+  return g;
+}
+static void assign_wgrad_groups(WgradTable& t, int groups) {
+  int order[kMaxJobs];
+  int64_t load[16] = {};
+  auto cost = [&](int i) { return (int)t.jobs[i].dy_nchunks + t.jobs[i].x0_nchunks + t.jobs[i].x1_nchunks; };
+  for (int i = 0; i < t.njobs; ++i) order[i] = i;
+  std::stable_sort(order, order + t.njobs, [&](int a, int b) { return cost(a) > cost(b); });
+  for (int k = 0; k < t.njobs; ++k) {
+    int best = 0;
+    for (int g = 1; g < groups; ++g) if (load[g] < load[best]) best = g;
+    t.jobs[order[k]].group = (uint8_t)best;
+    load[best] += cost(order[k]);
+  }
+}
+
 struct WgradParams {
   WgradTable tab;
   const uint8_t* saved; const uint8_t* dsaved;
   float* flat_grad;
   int64_t n_half;
   int x_total, d_total;
+  int groups;   // job groups (WgradJob::group < groups); CTA b serves group b % groups
 };
 
 __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -1002,9 +1030,15 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // contiguous range of half tiles for this CTA
-  const int64_t per = (p.n_half + gridDim.x - 1) / gridDim.x;
-  const int64_t h0 = (int64_t)blockIdx.x * per;
+  // CTA b belongs to job group b % groups and owns a contiguous range of half tiles inside it.  Every CTA flushes its
+  // partial dW of the jobs it ran with fp32 atomics; with one group that is the whole 5.9 MB gradient per CTA (876 MB of
+  // atomic traffic and ~0.56 ms per launch, measured); with G groups each CTA runs 1/G of the jobs over G times more
+  // half tiles, the operand traffic is unchanged and the flush traffic drops G-fold.
+  const int groups = p.groups;
+  const int my_group = blockIdx.x % groups;
+  const int ctas_in_group = (gridDim.x - my_group + groups - 1) / groups;
+  const int64_t per = (p.n_half + ctas_in_group - 1) / ctas_in_group;
+  const int64_t h0 = (int64_t)(blockIdx.x / groups) * per;
   const int64_t h1 = min(h0 + per, p.n_half);
   const int njobs = p.tab.njobs;
 
@@ -1013,6 +1047,7 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
       int slot = 0; uint32_t phase = 0;
       for (int ji = 0; ji < njobs; ++ji) {
         const WgradJob& J = p.tab.jobs[ji];
+        if (J.group != my_group) continue;
         const uint32_t a_bytes = J.dy_nchunks * kHalfChunkBytes;
         const uint32_t b0_bytes = J.x0_nchunks * kHalfChunkBytes, b1_bytes = J.x1_nchunks * kHalfChunkBytes;
         for (int64_t h = h0; h < h1; ++h) {
@@ -1035,13 +1070,16 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
       // LBO = 8 rows (128 B), SBO = one chunk (kHalfChunkBytes)
       constexpr uint32_t kHi = (1u << 14) | (kHalfChunkBytes >> 4);
       const uint32_t st0 = smem_u32(smem);
+      bool first = true;
       for (int ji = 0; ji < njobs; ++ji) {
         const WgradJob& J = p.tab.jobs[ji];
+        if (J.group != my_group) continue;
         const uint32_t ncols = (J.x0_nchunks + J.x1_nchunks) * 8;  // UMMA N
         const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
         const bool two = J.mblocks == 2;
         const uint32_t d1 = tmem_base + ncols;
-        if (ji > 0) { mbar_wait(acc_empty, ph_empty); ph_empty ^= 1; tc_fence_after(); }
+        if (!first) { mbar_wait(acc_empty, ph_empty); ph_empty ^= 1; tc_fence_after(); }
+        first = false;
         for (int64_t h = h0; h < h1; ++h) {
           mbar_wait(&full[slot], phase);
           tc_fence_after();
@@ -1073,6 +1111,7 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
     int slot = 0; uint32_t phase = 0, ph_acc = 0;
     for (int ji = 0; ji < njobs; ++ji) {
       const WgradJob& J = p.tab.jobs[ji];
+      if (J.group != my_group) continue;
       const int ncols = (J.x0_nchunks + J.x1_nchunks) * 8;
       // chunks [c_lo, c_hi) of the dY part belong to this warp (<= 8 chunks)
       const int cpw = (J.dy_nchunks + 3) / 4;
@@ -1135,11 +1174,20 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
           for (int s = 0; s < J.nflush; ++s) {
             const FlushSeg& F = J.flush[s];
             if (drow >= F.row0 && drow < F.row0 + F.nrows) {
-              float* dst = p.flat_grad + F.dst + (int64_t)(drow - F.row0) * F.ld;
+              // this thread's 16 accumulator columns are 16 consecutive floats of one dW row: four 16-byte vector
+              // reductions when the row is 16-byte aligned (ld % 4 == 0, the wide layers), scalar ones otherwise
+              float* dst = p.flat_grad + F.dst + (int64_t)(drow - F.row0) * F.ld + (c0 - (int)F.col0);
+              const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                int col = c0 + j;
-                if (col >= F.col0 && col < F.col0 + F.ncols) atomicAdd(dst + (col - F.col0), __uint_as_float(r[j]));
+              for (int j = 0; j < 16; j += 4) {
+                const int col = c0 + j;
+                if (vec && col >= F.col0 && col + 4 <= F.col0 + F.ncols) {
+                  red_add_v4(dst + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
+                } else {
+#pragma unroll
+                  for (int jj = j; jj < j + 4; ++jj)
+                    if (c0 + jj >= F.col0 && c0 + jj < F.col0 + F.ncols) atomicAdd(dst + jj, __uint_as_float(r[jj]));
+                }
               }
             }
           }
@@ -1414,6 +1462,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.x_total = plan.info.x_total; wp.d_total = plan.info.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
     int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
+    wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? wgrad_groups() : 1;
+    assign_wgrad_groups(wp.tab, wp.groups);
     mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
     if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch")) return rc;
   }

@@ -48,8 +48,15 @@ constexpr int kCtaRows = kTileRows * kSubTiles;
 constexpr int kHalfRows = 64;    // granularity of the saved-activation layout and of the wgrad K step
 constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-row smem operand
 constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-row global slab
-constexpr int kRingStages = kSubTiles == 2 ? 3 : 2;   // two co-resident CTAs only have room for a 2-stage ring
-constexpr int kStageBytes = kSubTiles == 2 ? 16384 : 8192;
+// weight ring: 48 KB beside the resident activations (two co-resident CTAs only have room for 2 x 8 KB)
+#ifndef HN_RING_STAGES
+#define HN_RING_STAGES (HN_SUBTILES == 2 ? 3 : 2)
+#endif
+#ifndef HN_STAGE_BYTES
+#define HN_STAGE_BYTES (HN_SUBTILES == 2 ? 16384 : 8192)
+#endif
+constexpr int kRingStages = HN_RING_STAGES;
+constexpr int kStageBytes = HN_STAGE_BYTES;
 constexpr int kMaxOps = 40;
 constexpr int kMaxLayers = 24;
 constexpr int kMaxJobs = 40;
@@ -225,7 +232,7 @@ struct WgradJob {
   uint16_t x0_chunk, x0_nchunks;   // X columns (first range) copied as the B operand
   uint16_t x1_chunk, x1_nchunks;   // optional second range, placed right after the first
   uint8_t mblocks;                 // 1 or 2 blocks of 128 dY columns
-  uint8_t nflush, nbias, pad;
+  uint8_t nflush, nbias, group;    // group: which CTA group owns this job (hn_mlp.cu: kWgGroups)
   FlushSeg flush[3];
   BiasSeg bias[2];
 };
