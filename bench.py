@@ -154,7 +154,7 @@ def run_gpu_arm(args):
     model = model.to(dev)
     fg = hn_train.FlatGrads(model.parameters())
     model.attach_flat_grads(fg)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, eps=1e-8)   # utils/__init__.py:29-31, opt.py:53-56
+    opt = hn_train.FusedAdam(fg, lr=5e-4, eps=1e-8)   # Adam of utils/__init__.py:29-31 / opt.py:53-56, one launch
 
     # inputs: this rank's contiguous shard of the global batch, resident in HBM (value) and in pinned host memory (e2e)
     rays_all, rgbs_all = synthetic.train_rays(GLOBAL_RAYS, seed=0)

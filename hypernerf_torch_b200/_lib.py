@@ -21,7 +21,7 @@ HN_COMP_ACC_ALL = 2
 
 EXPORTS = [
     "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf",
-    "hn_composite_fwd", "hn_composite_bwd", "hn_mse_loss", "hn_make_ndc_rays", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
+    "hn_composite_fwd", "hn_composite_bwd", "hn_mse_loss", "hn_make_ndc_rays", "hn_adam_step", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
     "hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4", "hn_epi_rate", "hn_tmem_rate", "hn_debug_set_timing_buffer",
 ]
 
@@ -76,6 +76,7 @@ def lib():
     L.hn_composite_bwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]
     L.hn_mse_loss.argtypes = [vp, vp, vp, i64, f32, vp, vp, vp, vp]
     L.hn_make_ndc_rays.argtypes = [i32, i32, f32, C.POINTER(C.c_float), f32, f32, i32, vp, vp]
+    L.hn_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]
     L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]
     L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32,
                              C.POINTER(C.c_int64), vp, vp, vp]

@@ -654,3 +654,56 @@ extern "C" int hn_make_ndc_rays(int H, int W, float focal, const float* c2w_host
   hn::make_ndc_rays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(H, W, focal, c, near_plane, image_id, cols, rays);
   return hn::set_cuda_error(cudaGetLastError(), "hn_make_ndc_rays");
 }
+
+// ======================================================================================================
+// optimizer: torch.optim.Adam.step over the flat parameter / gradient buffers in one launch
+// ======================================================================================================
+namespace hn {
+struct AdamArgs { float beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale; };
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  g *= a.grad_scale;
+  if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);     // L2 form: grad + wd * param
+  m = m + (g - m) * (1.f - a.beta1);                              // lerp, as torch's exp_avg.lerp_(grad, 1 - beta1)
+  v = a.beta2 * v + (1.f - a.beta2) * g * g;
+  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+  p = p - a.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                                                   float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n,
+                                                   AdamArgs a) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = reinterpret_cast<float4*>(params)[i];
+    const float4 g = reinterpret_cast<const float4*>(grads)[i];
+    float4 m = reinterpret_cast<float4*>(exp_avg)[i];
+    float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
+    adam_one(p.x, g.x, m.x, v.x, a); adam_one(p.y, g.y, m.y, v.y, a);
+    adam_one(p.z, g.z, m.z, v.z, a); adam_one(p.w, g.w, m.w, v.w, a);
+    reinterpret_cast<float4*>(params)[i] = p;
+    reinterpret_cast<float4*>(exp_avg)[i] = m;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_one(params[i], grads[i], exp_avg[i], exp_avg_sq[i], a);
+}
+}  // namespace hn
+
+extern "C" int hn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                            void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return hn::set_error(-2, "hn_adam_step: null pointer");
+  if (n < 0 || step < 1) return hn::set_error(-1, "hn_adam_step: n < 0 or step < 1");
+  if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return hn::set_error(-3, "hn_adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  // bias corrections in double, as torch's Python scalars
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  hn::AdamArgs a{beta1, beta2, eps, weight_decay, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale};
+  const int blocks = (int)std::min<int64_t>(((n >> 2) + 255) / 256 + 1, 8 * (int64_t)hn::num_sms());
+  hn::adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, a);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_adam_step");
+}

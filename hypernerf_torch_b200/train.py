@@ -49,6 +49,59 @@ class FlatGrads:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
 
+class FusedAdam:
+    """torch.optim.Adam (utils/__init__.py:22-41: lr, eps=1e-8, weight_decay; betas (0.9, 0.999)) as ONE launch of
+    hn_adam_step over flat buffers.
+
+    The parameters of `flat_grads` are re-pointed into one flat fp32 buffer with the gradient buffer's offsets (the
+    nn.Parameter objects, their names and state_dict stay what they were), exp_avg / exp_avg_sq are flat too.
+    `param_groups[0]['lr']` is read every step, so torch.optim.lr_scheduler classes can drive it."""
+
+    def __init__(self, flat_grads, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        from . import _lib
+        self._lib = _lib
+        self.fg = flat_grads
+        if flat_grads.flat.device.type != 'cuda':
+            raise _lib.NativeLibraryError("FusedAdam needs CUDA parameters (no CPU path)")
+        self.flat = torch.zeros_like(flat_grads.flat)
+        with torch.no_grad():
+            for p, off in zip(flat_grads.params, flat_grads.offsets):
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = 0
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(params=flat_grads.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                  initial_lr=lr)]
+
+    def zero_grad(self, set_to_none=False):
+        self.fg.zero()
+
+    @torch.no_grad()
+    def step(self, grad_scale=1.0):
+        L, g = self._lib, self.param_groups[0]
+        self.step_count += 1
+        L.check(L.lib().hn_adam_step(L.ptr(self.flat), L.ptr(self.fg.flat), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                     self.flat.numel(), g['lr'], g['betas'][0], g['betas'][1], g['eps'],
+                                     g['weight_decay'], self.step_count, grad_scale, L.stream()), "hn_adam_step")
+        L.count(1)
+        # the parameters changed behind autograd's back: bump their version counters (the packed-weight cache of the
+        # models keys on them)
+        torch.autograd.graph.increment_version(self.fg.params)
+
+    def state_dict(self):
+        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
+                    param_groups=[{k: v for k, v in self.param_groups[0].items() if k != 'params'}])
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd['step'])
+        self.exp_avg.copy_(sd['exp_avg'])
+        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        self.param_groups[0].update(sd['param_groups'][0])
+
+
 def shard_bounds(n, rank, world):
     """Contiguous split of n rays over `world` ranks."""
     per = (n + world - 1) // world

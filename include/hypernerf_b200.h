@@ -152,6 +152,14 @@ int hn_mse_loss(const float* rgb_coarse, const float* rgb_fine, const float* tar
 int hn_make_ndc_rays(int H, int W, float focal, const float* c2w_host, float near_plane, float image_id, int cols,
                      float* rays, void* stream);
 
+/* utils/__init__.py:22-41 (get_optimizer: torch.optim.Adam(parameters, lr, eps=1e-8, weight_decay)) — one Adam.step over the
+ * flat fp32 buffers (parameters, gradient, exp_avg, exp_avg_sq; n floats each, 16-byte aligned) in a single launch:
+ *   g = grads * grad_scale + weight_decay * p;  m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)            (step counts from 1)
+ * grad_scale folds the 1/world_size of a summed all-reduce (or an AMP loss scale) into the same pass. */
+int hn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
 /* test hook: one UMMA tile D[128,N] = A * B^T through the shared-memory layouts the MLP kernels use.
  * a_mn / b_mn = 0: operand given row-major [rows][K]; 1: given as [K][rows] (MN-major). */
 int hn_umma_probe(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);

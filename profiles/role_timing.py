@@ -43,7 +43,7 @@ _lib.lib().hn_debug_set_timing_buffer(_lib.ptr(dbg))
 with torch.no_grad():
     for it in range(2):
         _lib.profile = []
-        _FusedMlp.apply(model, 1, pts, d, ids, None, 0.0, *params)
+        _FusedMlp.apply(model, 1, pts, d, ids, None, 0.0, *[q.detach() for q in params])
         report("fwd (inference, no stash)")
         for name, n, a, b in _lib.profile:
             print(f"   {name}: {a.elapsed_time(b):.3f} ms  {2 * 801536 * n / a.elapsed_time(b) / 1e9:.1f} TFLOP/s")

@@ -117,3 +117,27 @@ def test_gradient_is_linear_in_the_loss_scale():
         grads.append(fg.flat.clone())
     rel = (4.0 * grads[0] - grads[1]).norm() / grads[1].norm()
     assert rel < 2e-2, rel    # dY is rounded to bf16 before it enters the UMMAs, so scaling is linear up to bf16 rounding
+
+
+def test_training_with_fused_adam_tracks_torch_adam():
+    """Three train steps (train_step + FusedAdam on the flat buffers) against the same steps with torch.optim.Adam:
+    the loss trajectories agree, and the loss moves (the bf16 operand blobs are re-packed after every update)."""
+    B = 2048
+    rays, rgbs = synthetic.train_rays(B, seed=21, device=DEV)
+    traj = []
+    for fused in (True, False):
+        model = _model()
+        fg = hn_train.FlatGrads(model.parameters())
+        model.attach_flat_grads(fg)
+        opt = hn_train.FusedAdam(fg, lr=5e-4) if fused else torch.optim.Adam(model.parameters(), lr=5e-4, eps=1e-8)
+        losses = []
+        for it in range(3):
+            with ref_loader._DrawTape(_draws(B, 64, 64, seed=100 + it)):
+                losses.append(float(hn_train.train_step(model, rays, rgbs, fg, chunk=B, optimizer=opt)))
+        traj.append(losses)
+        assert set(model.state_dict().keys()) == set(synthetic.cfg1_state_dict_shapes().keys())
+    a, b = traj
+    assert a[0] == b[0]                                   # same weights, same draws: identical first loss
+    assert abs(a[1] - a[0]) > 1e-6 and abs(a[2] - a[1]) > 1e-6
+    for x, y in zip(a, b):
+        assert abs(x - y) <= 2e-3 * abs(y), (a, b)

@@ -158,3 +158,36 @@ def test_device_ray_generation_matches_reference_golden():
         assert err < 2e-5            # fp32, different association of the same formula
         with_id = ray_utils.frame_rays_ndc(case['H'], case['W'], case['focal'], case['c2w'], near_plane=1.0, image_id=7)
         assert with_id.shape[1] == 9 and torch.equal(with_id[:, :8], rays) and (with_id[:, 8] == 7).all()
+
+
+@pytest.mark.parametrize("weight_decay", [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam(weight_decay):
+    """hn_adam_step over the flat buffers == torch.optim.Adam(lr, eps=1e-8, weight_decay) (utils/__init__.py:22-41) on
+    the cfg-1 parameter shapes, 12 steps of random gradients, with an lr change in between (scheduler behaviour)."""
+    from hypernerf_torch_b200 import train as hn_train
+    shapes = synthetic.cfg1_state_dict_shapes()
+    sd = synthetic.make_state_dict(shapes, seed=0)
+    mine = [torch.nn.Parameter(v.clone().cuda()) for v in sd.values()]
+    ref = [torch.nn.Parameter(v.clone().cuda()) for v in sd.values()]
+    fg = hn_train.FlatGrads(mine)
+    opt = hn_train.FusedAdam(fg, lr=5e-4, eps=1e-8, weight_decay=weight_decay)
+    topt = torch.optim.Adam(ref, lr=5e-4, eps=1e-8, weight_decay=weight_decay)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for it in range(12):
+        if it == 6:
+            opt.param_groups[0]['lr'] = 5e-5
+            topt.param_groups[0]['lr'] = 5e-5
+        fg.zero()
+        for p, q in zip(mine, ref):
+            grad = torch.randn(p.shape, device="cuda", generator=g) * 10.0 ** float(it % 4 - 3)
+            p.grad.copy_(grad)          # view of the flat buffer
+            q.grad = grad.clone()
+        v0 = mine[0]._version
+        opt.step()
+        topt.step()
+        assert mine[0]._version > v0    # packed-weight caches key on the version counter
+    for name, p, q in zip(sd, mine, ref):
+        assert p.data_ptr() >= opt.flat.data_ptr() and p.data_ptr() < opt.flat.data_ptr() + 4 * opt.flat.numel()
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=2e-8, msg=name)
+    # padding between tensors stays untouched
+    assert torch.isfinite(opt.flat).all()
