@@ -648,11 +648,13 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
         float* bias = kPingPong ? sbias + chain * 256 : sbias + (li & 1) * 256;
+        const long long t_layer = HN_T0();
         if (kPingPong) epi_named_barrier(chain);   // single buffer per chain: everyone is done with the previous layer's bias
         for (int i = et; i < L.n_out; i += 128 * kSubsPerChain) bias[i] = __ldg(p.bias + L.bias_off + i);
         epi_named_barrier(chain);
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
+        const long long t_drain = HN_T0();
         if (L.epi == FE_RELU) {
           fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
         } else if (L.epi == FE_WSHEAD) {
@@ -715,6 +717,14 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tc_fence_before();
           { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
         }
+#if HN_ROLE_TIMING
+        // per-layer profile of CTA 0 (profiles/role_timing.py): [wait for the accumulator, drain] after the 8 role counters
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+          p.dbg[gridDim.x * 8 + li * 2] += t_drain - t_layer;
+          p.dbg[gridDim.x * 8 + li * 2 + 1] += HN_T0() - t_drain;
+        }
+#endif
+        (void)t_layer; (void)t_drain;
       }
     }
     if (p.dbg && threadIdx.x == 0) {

@@ -109,26 +109,77 @@ def shard_bounds(n, rank, world):
     return lo, min(lo + per, n)
 
 
-def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, optimizer=None):
+def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, optimizer=None, return_stats=False):
     """One data-parallel training step on this rank's ray rows (B,9) / target colours (B,3).
-    Returns the local contribution to the global-mean loss (sum over ranks = the reference's loss)."""
+    Returns the local contribution to the global-mean loss (sum over ranks = the reference's loss); with
+    return_stats, training_step's log entries {'train/loss', 'train/psnr'} (train.py:147-163; psnr of the fine level
+    over this rank's rays, metrics.py:4-13) as device tensors."""
     B = rays.shape[0]
     global_rays = B if global_rays is None else global_rays
     flat_grads.zero()
     total = torch.zeros((), device=rays.device, dtype=torch.float32)
+    fine_sq = None
     for i in range(0, B, chunk):
         rows = rays[i:i + chunk]
         tgt = rgbs[i:i + chunk]
         out = model(model_utils.prepare_ray_dict(rows), dict(EXTRA_PARAMS))
         # mean over the global batch: (sum_sq(coarse) + sum_sq(fine)) / (3 * global_rays), one fused kernel that also
         # seeds both levels' gradients (losses.py:9-14)
-        loss, _ = losses.mse_coarse_fine(out, tgt, global_count=3.0 * global_rays)
+        loss, sums = losses.mse_coarse_fine(out, tgt, global_count=3.0 * global_rays)
         loss.backward()
         total += loss.detach()
+        if return_stats:
+            fine_sq = sums[1] if fine_sq is None else fine_sq + sums[1]
     flat_grads.all_reduce()
     if optimizer is not None:
         optimizer.step()
+    if return_stats:
+        return {'train/loss': total, 'train/psnr': -10.0 * torch.log10(fine_sq / (3.0 * B))}
     return total
+
+
+def save_ckpt(model, path, epoch=0, global_step=0, optimizer=None, module_name='nerf'):
+    """Checkpoint in the layout Lightning's ModelCheckpoint writes for NeRFSystem (train.py:71: the model is the
+    attribute `nerf`, so its tensors are stored as `nerf.<name>` under 'state_dict'); readable by utils.load_ckpt
+    (utils/__init__.py:66-88) of this package and of the reference."""
+    blob = {'epoch': epoch, 'global_step': global_step,
+            'state_dict': {f'{module_name}.{k}': v.detach().cpu().clone() for k, v in model.state_dict().items()}}
+    if optimizer is not None:
+        osd = optimizer.state_dict()
+        blob['optimizer_states'] = [{k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in osd.items()}]
+    torch.save(blob, path)
+
+
+def fit(model, rays, rgbs, num_epochs=1, batch_size=1024, lr=5e-4, weight_decay=0.0, decay_step=(20,), decay_gamma=0.1,
+        chunk=8192, seed=0, ckpt_path=None, log_every=0):
+    """Minimal stand-in for `Trainer.fit(NeRFSystem)` (train.py:35-233) on a ray pool that is already on the device:
+    per epoch one shuffled pass over (rays (P,9), rgbs (P,3)) in batches of `batch_size` (train_dataloader,
+    train.py:133-138: shuffle=True; the last short batch is kept, as DataLoader's drop_last=False does), each batch
+    = train_step + Adam (get_optimizer, utils/__init__.py:22-41), MultiStepLR(decay_step, decay_gamma) stepped per epoch
+    (get_scheduler 'steplr', utils/__init__.py:43-47; opt.py:62-75 defaults).  Under torch.distributed every rank
+    passes its own shard of the pool; gradients are all-reduced inside train_step.
+    Returns a list of per-step dicts {'epoch', 'step', 'lr', 'train/loss', 'train/psnr'} (training_step's log)."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    fg = FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+    opt = FusedAdam(fg, lr=lr, eps=1e-8, weight_decay=weight_decay)
+    gen = torch.Generator(device=rays.device).manual_seed(seed)
+    P, step, log = rays.shape[0], 0, []
+    for epoch in range(num_epochs):
+        opt.param_groups[0]['lr'] = lr * decay_gamma ** sum(1 for m in decay_step if epoch >= m)
+        order = torch.randperm(P, device=rays.device, generator=gen)
+        for i in range(0, P, batch_size):
+            idx = order[i:i + batch_size]
+            r, t = rays[idx], rgbs[idx]
+            stats = train_step(model, r, t, fg, global_rays=world * r.shape[0], chunk=chunk, optimizer=opt,
+                               return_stats=True)
+            step += 1
+            log.append({'epoch': epoch, 'step': step, 'lr': opt.param_groups[0]['lr'], **stats})
+            if log_every and step % log_every == 0:
+                print({k: (float(v) if torch.is_tensor(v) else v) for k, v in log[-1].items()})
+        if ckpt_path is not None:
+            save_ckpt(model, ckpt_path.format(epoch=epoch), epoch=epoch, global_step=step, optimizer=opt)
+    return log
 
 
 @torch.no_grad()

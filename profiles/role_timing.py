@@ -23,19 +23,24 @@ o, d, ids = rays[:, :3].contiguous(), rays[:, 3:6].contiguous(), rays[:, 8].long
 z, _ = torch.sort(torch.rand(B, S, device=dev), -1)
 pts = (o[:, None] + z[..., None] * d[:, None]).contiguous()
 params = model._canonical_params()
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(148 * 8 + 64, dtype=torch.int64, device=dev)
 names = ["prod_wait_empty", "mma_wait_act_ready", "mma_wait_full", "mma_total", "epi_wait_acc", "epi_work", "epi_prologue",
          "epi_total"]
 
 
 def report(tag):
     torch.cuda.synchronize()
-    v = dbg.view(148, 8).double()
+    v = dbg[:148 * 8].view(148, 8).double()
     tot = v[:, 3].mean().item()
     if tot == 0:
         print(tag, '(library built without -DHN_ROLE_TIMING=1: no role counters)')
         return
     print(tag, " ".join(f"{n}={v[:, i].mean().item() / tot:.3f}" for i, n in enumerate(names)), f"cycles={tot:.3e}")
+    lay = dbg[148 * 8:].view(32, 2).double()
+    if lay.sum() > 0 and tag.startswith("fwd"):
+        tiles = 8192 * 128 / 256 / 148
+        print("   per layer of CTA 0, cycles per tile [wait acc | drain]:",
+              " ".join(f"{int(a / tiles)}|{int(b / tiles)}" for a, b in lay.tolist() if a + b > 0))
     dbg.zero_()
 
 
