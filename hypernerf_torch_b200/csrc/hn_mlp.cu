@@ -35,6 +35,11 @@ struct Shape {
   static constexpr int PE_X = 3 + 6 * XF, PE_H = H * (1 + 2 * HF), IN_T = PE_X + PE_H, KT = pad16(IN_T);
   static constexpr int PE_V = 3 + 6 * VF, KV = pad16(PE_V);
   static constexpr int IN_CHUNKS = (KW > KT ? (KW > KV ? KW : KV) : (KT > KV ? KT : KV)) / 8;
+  // bias folding (hn_mlp_program.h: HN_FOLD_BIAS): the last two columns of INB's last chunk pair hold 1.0; they sit in
+  // the zero padding of the widest input vector when every vector that reaches the last chunk has >= 2 pad columns
+  static constexpr bool ONES_IN_PAD = ones_fit_in_pad(IN_CHUNKS * 8, KW, IN_W) && ones_fit_in_pad(IN_CHUNKS * 8, KT, IN_T) &&
+                                      ones_fit_in_pad(IN_CHUNKS * 8, KV, PE_V);
+  static constexpr int INB_CHUNKS = (kFoldBias && !ONES_IN_PAD) ? IN_CHUNKS + 2 : IN_CHUNKS;
   static constexpr int N_RGB0A = pad16(kRgbW + 1);
 };
 using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
@@ -66,7 +71,7 @@ constexpr int kProducerWarp = kEpiWarps, kIssuerWarp = kEpiWarps + 1, kRelayWarp
 template <class C>
 struct Smem {
   static constexpr int ACT_BYTES = 32 * kChunkBytes;              // 128 x 256 bf16 per sub-tile
-  static constexpr int INB_BYTES = C::IN_CHUNKS * kChunkBytes;    // 128 x (IN_CHUNKS*8) bf16 per sub-tile
+  static constexpr int INB_BYTES = C::INB_CHUNKS * kChunkBytes;   // 128 x (INB_CHUNKS*8) bf16 per sub-tile
   static constexpr int ACT = 0;
   static constexpr int INB = ACT + kSubTiles * ACT_BYTES;
   static constexpr int RING = INB + kSubTiles * INB_BYTES;        // kRingStages x kStageBytes
@@ -362,6 +367,26 @@ __device__ __forceinline__ void posenc_bwd(const float* x, const float* g, float
   }
 }
 
+// zero padding of a K-wide input vector with IN real features; with folded biases a vector that reaches INB's last
+// chunk carries the two ones columns in its tail
+template <class C, int K, int IN>
+__device__ __forceinline__ void finish_features(float* f) {
+#pragma unroll
+  for (int i = IN; i < K; ++i) f[i] = 0.f;
+  if constexpr (kFoldBias && K / 8 == C::INB_CHUNKS) {
+    static_assert(IN <= K - 2, "no room for the ones columns");
+    f[K - 2] = 1.f; f[K - 1] = 1.f;
+  }
+}
+// the ones chunk pair of INB when the vector just stored (K columns) does not reach it
+template <class C, int K>
+__device__ __forceinline__ void store_ones_pair(uint8_t* inb_row) {
+  if constexpr (kFoldBias && K / 8 < C::INB_CHUNKS) {
+    if constexpr (K / 8 < C::INB_CHUNKS - 1) *reinterpret_cast<uint4*>(inb_row + (C::INB_CHUNKS - 2) * kChunkBytes) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(inb_row + (C::INB_CHUNKS - 1) * kChunkBytes) = make_uint4(0, 0, 0, 0x3F803F80u);   // bf16 1.0, 1.0
+  }
+}
+
 // write NCOL (multiple of 8) fp32 features of one row as bf16 packets into an smem operand (and the stash)
 template <int NCOL>
 __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row, uint4* save_row, int save_chunk) {
@@ -398,6 +423,10 @@ __device__ __forceinline__ void epi_named_barrier(int chain) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * kSubsPerChain) : "memory");
 }
 
+// bias of a head column: already inside the accumulator when the biases ride in the UMMAs
+template <bool FOLD>
+__device__ __forceinline__ float head_bias(const float* bias_s, int i) { return FOLD ? 0.f : bias_s[i]; }
+
 template <bool RELU, bool STASH>
 __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
                                             int chunk0, int save_chunk, uint32_t* gate_dst) {
@@ -405,12 +434,17 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
+    if constexpr (kFoldBias && !STASH) {   // inference: the accumulator already holds W x + b
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * q + j]);
+    } else {
     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * q);       // smem broadcast
     const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * q + 4);
     v[0] = __uint_as_float(r[8 * q + 0]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
     v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
     v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
     v[6] = __uint_as_float(r[8 * q + 6]) + b1.z; v[7] = __uint_as_float(r[8 * q + 7]) + b1.w;
+    }
     uint4 o;
     if (RELU) {
       o.x = pack_bf16_relu(v[0], v[1]); o.y = pack_bf16_relu(v[2], v[3]);
@@ -512,6 +546,7 @@ template <class C, bool STASH>
 __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
+  constexpr bool FOLD = kFoldBias && !STASH;   // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS)
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
   uint8_t* ring = smem + SM::RING;
@@ -633,9 +668,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
 #pragma unroll
           for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
         }
-#pragma unroll
-        for (int i = C::IN_W; i < C::KW; ++i) f[i] = 0.f;
+        finish_features<C, C::KW, C::IN_W>(f);
         store_features<C::KW>(f, inb_row, save_row, p.x_in_ws);
+        store_ones_pair<C, C::KW>(inb_row);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -649,9 +684,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
         float* bias = kPingPong ? sbias + chain * 256 : sbias + (li & 1) * 256;
         const long long t_layer = HN_T0();
-        if (kPingPong) epi_named_barrier(chain);   // single buffer per chain: everyone is done with the previous layer's bias
-        for (int i = et; i < L.n_out; i += 128 * kSubsPerChain) bias[i] = __ldg(p.bias + L.bias_off + i);
-        epi_named_barrier(chain);
+        if constexpr (!FOLD) {
+          if (kPingPong) epi_named_barrier(chain);   // single buffer per chain: everyone is done with the previous layer's bias
+          for (int i = et; i < L.n_out; i += 128 * kSubsPerChain) bias[i] = __ldg(p.bias + L.bias_off + i);
+          epi_named_barrier(chain);
+        }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         const long long t_drain = HN_T0();
@@ -663,9 +700,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tmem_ld16(tlane, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + bias[i]);
+          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
 #pragma unroll
-          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + bias[3 + i];
+          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + head_bias<FOLD>(bias, 3 + i);
           if (valid && p.warped != nullptr) {
 #pragma unroll
             for (int i = 0; i < 3 + C::H; ++i) p.warped[g * (3 + C::H) + i] = wp[i];
@@ -673,8 +710,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           float f[C::KT];
           posenc<3, C::XF>(wp, f);
           posenc<C::H, C::HF>(wp + 3, f + C::PE_X);
-#pragma unroll
-          for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
+          finish_features<C, C::KT, C::IN_T>(f);
           store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
           }
         } else if (L.epi == FE_SIGMA) {
@@ -682,7 +718,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
-          float a = __uint_as_float(r[0]) + bias[0];
+          float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, 0);
           if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;
           if (valid) p.sigma[g] = fmaxf(a, 0.f);
         } else if (L.epi == FE_BOTT) {
@@ -690,8 +726,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
           float f[C::KV];
           posenc<3, C::VF>(dir, f);
-#pragma unroll
-          for (int i = C::PE_V; i < C::KV; ++i) f[i] = 0.f;
+          finish_features<C, C::KV, C::PE_V>(f);
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
           if constexpr (!C::STATIC) {
@@ -699,7 +734,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
-          float a = __uint_as_float(r[0]) + bias[kRgbW];
+          float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, kRgbW);
           if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;  // noise_regularize, model_utils.py:312-316
           if (valid) p.sigma[g] = softplus_f(a);                          // models.py:491
           }
@@ -709,7 +744,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + bias[i]);
+            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
           }
         }
         if (li + 1 < prog.nlayers) {
@@ -1243,7 +1278,15 @@ __global__ void pack_kernel(const __grid_constant__ PackParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           int k = chunk * 8 + j;
-          if (k >= B.k0 && k < B.k0 + B.kk) v[j] = __ldg(p.flat + B.src + (int64_t)(n - B.n0) * B.sn + (int64_t)(k - B.k0) * B.sk);
+          if (k >= B.k0 && k < B.k0 + B.kk) {
+            if (B.sk == kBiasPairStride) {   // folded bias: bf16(b), bf16(b - bf16(b))
+              const float bv = __ldg(p.flat + B.src + (int64_t)(n - B.n0) * B.sn);
+              const float hi = __uint_as_float(pack_bf16(bv, 0.f) << 16);
+              v[j] = k == B.k0 ? hi : bv - hi;
+            } else {
+              v[j] = __ldg(p.flat + B.src + (int64_t)(n - B.n0) * B.sn + (int64_t)(k - B.k0) * B.sk);
+            }
+          }
         }
       }
       uint4 o;
@@ -1390,7 +1433,7 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
   static thread_local ModelPlan plan;
   build_plan(*desc, &plan);
   FwdParams fp;
-  fp.prog = plan.fwd;
+  fp.prog = saved != nullptr ? plan.fwd_train : plan.fwd;   // the stash-writing forward keeps its biases in the epilogue
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
   fp.w_row0 = (uint32_t)(plan.layout.fwd_off / 16);
   if (int rc = build_pair_maps(packed, plan.layout.total, &fp.maps)) return rc;

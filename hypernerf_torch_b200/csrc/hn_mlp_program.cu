@@ -29,6 +29,7 @@ struct Builder {
   Program* p;
   LogicalOps* lg;
   uint32_t w16 = 0;  // running weight offset (16-byte units)
+  int ones_col = -1; // forward programs with kFoldBias: INB column of the ones chunk pair (every op gets a bias K step)
   void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk, uint16_t gate_word = kNone) {
     Layer& L = p->layers[p->nlayers++];
     L.op0 = (uint8_t)p->nops; L.nops = 0; L.epi = epi; L.pad = 0;
@@ -50,12 +51,31 @@ struct Builder {
   }
   // One logical [n x (k0 + k1)] matrix; the K range is split over two source buffers when k1 > 0.
   void add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
+    const int kb = ones_col >= 0 ? 16 : 0;   // bias rows (hn_mlp_program.h: HN_FOLD_BIAS)
     LogicalOp& l = lg->ops[lg->n++];
-    l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k0 + k1);
-    emit(n, k0, s0, a0_col, tmem_col, acc_init, 0, (k0 + k1) / 8);
-    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1, k0 / 8, (k0 + k1) / 8);
+    l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k0 + k1 + kb);
+    emit(n, k0, s0, a0_col, tmem_col, acc_init, 0, (k0 + k1 + kb) / 8);
+    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1, k0 / 8, (k0 + k1 + kb) / 8);
+    if (kb > 0) {
+      emit(n, kb, SRC_INB, ones_col, tmem_col, 1, (k0 + k1) / 8, (k0 + k1 + kb) / 8);
+      p->ops[p->nops - 1].pad = 1;   // marks a bias step
+    }
   }
 };
+
+// copy of a program without its bias steps (weight offsets are absolute, so the same blob serves both)
+void without_bias_steps(const Program& src, Program* dst) {
+  memset(dst, 0, sizeof(*dst));
+  dst->nlayers = src.nlayers;
+  for (int li = 0; li < src.nlayers; ++li) {
+    Layer L = src.layers[li];
+    const int op0 = dst->nops;
+    for (int oi = L.op0; oi < L.op0 + L.nops; ++oi)
+      if (!src.ops[oi].pad) dst->ops[dst->nops++] = src.ops[oi];
+    L.op0 = (uint8_t)op0; L.nops = (uint8_t)(dst->nops - op0);
+    dst->layers[li] = L;
+  }
+}
 
 struct Packer {
   PackTable* t;
@@ -71,6 +91,12 @@ struct Packer {
     b.src = off[param] + src_extra; b.sn = sn; b.sk = sk;
     b.n0 = (uint16_t)n0; b.nn = (uint16_t)nn; b.k0 = (uint16_t)k0; b.kk = (uint16_t)kk;
     t->ops[cur].nblk++;
+  }
+  // bias of output rows [n0, n0 + nn) of the current op into its last two K rows (kFoldBias)
+  void bias_rows(int param, int n0, int nn) {
+    if (!kFoldBias) return;
+    const int k0 = t->ops[cur].k - 2;
+    block(param, 0, 1, kBiasPairStride, n0, nn, k0, 2);
   }
   void bias(int param, int dst, int cnt) {
     BiasBlock& b = t->bias[t->nbias++];
@@ -99,6 +125,7 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   // ------------------------------------------------------------------ forward program
   {
     Builder b{&plan->fwd, &plan->fwd_logical};
+    if (kFoldBias) b.ones_col = m.ones_col;
     int bias = 0;
     // warp + sheet, merged to one 192-wide net sharing the input buffer
     b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone, s.g_hws[0]);
@@ -140,6 +167,7 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     bias += 16;
     plan->layout.fwd_off = 0;
     plan->layout.bwd_off = (int64_t)b.w16 * 16;
+    without_bias_steps(plan->fwd, &plan->fwd_train);
   }
   // ------------------------------------------------------------------ backward-data program
   {
@@ -214,10 +242,13 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kWarpW, 0, m.in_w);
   pk.block(P_SHEET_W(0), 0, m.in_s, 1, kWarpW, kSheetW, 0, m.pe_s);
   pk.block(P_SHEET_W(0), m.pe_s, m.in_s, 1, kWarpW, kSheetW, m.pe_w, m.G);
+  pk.bias_rows(P_WARP_B(0), 0, kWarpW);
+  pk.bias_rows(P_SHEET_B(0), kWarpW, kSheetW);
   for (int l = 1; l < kWsDepth; ++l) {
     bool skip = (l == kSkip + 1);
     pk.op(F.ops[oi++]);
     pk.block(P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 1, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
+    pk.bias_rows(P_WARP_B(l), 0, kWarpW);
     pk.op(F.ops[oi++]);
     if (!skip) {
       pk.block(P_SHEET_W(l), 0, kSheetW, 1, 0, kSheetW, 0, kSheetW);
@@ -225,28 +256,38 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
       pk.block(P_SHEET_W(l), 0, lds5, 1, 0, kSheetW, 0, kSheetW + m.pe_s);
       pk.block(P_SHEET_W(l), kSheetW + m.pe_s, lds5, 1, 0, kSheetW, kSheetW + m.pe_w, m.G);
     }
+    pk.bias_rows(P_SHEET_B(l), 0, kSheetW);
   }
   pk.op(F.ops[oi++]);  // ws head: rows 0..2 warp logit, rows 3..3+H-1 sheet logit
   pk.block(P_WARP_W(kWsDepth), 0, kWarpW, 1, 0, 3, 0, kWarpW);
   pk.block(P_SHEET_W(kWsDepth), 0, kSheetW, 1, 3, m.H, kWarpW, kSheetW);
+  pk.bias_rows(P_WARP_B(kWsDepth), 0, 3);
+  pk.bias_rows(P_SHEET_B(kWsDepth), 3, m.H);
   pk.op(F.ops[oi++]);  // trunk 0
   pk.block(P_TRUNK_W(level, 0), 0, m.in_t, 1, 0, kTrunkW, 0, m.in_t);
+  pk.bias_rows(P_TRUNK_B(level, 0), 0, kTrunkW);
   for (int l = 1; l <= kTrunkDepth; ++l) {
     int ld = (l == kSkip + 1) ? kTrunkW + m.in_t : kTrunkW;
     pk.op(F.ops[oi++]);
     pk.block(P_TRUNK_W(level, l), 0, ld, 1, 0, kTrunkW, 0, ld);
+    pk.bias_rows(P_TRUNK_B(level, l), 0, kTrunkW);
   }
   pk.op(F.ops[oi++]);  // bottleneck
   pk.block(P_BOTT_W(level), 0, kTrunkW, 1, 0, kRgbW, 0, kTrunkW);
+  pk.bias_rows(P_BOTT_B(level), 0, kRgbW);
   pk.op(F.ops[oi++]);  // rgb0 | alpha
   pk.block(P_RGB_W(level, 0), 0, kRgbW + m.pe_v, 1, 0, kRgbW, 0, kRgbW + m.pe_v);
   pk.block(P_ALPHA_W(level), 0, kRgbW, 1, kRgbW, 1, 0, kRgbW);
+  pk.bias_rows(P_RGB_B(level, 0), 0, kRgbW);
+  pk.bias_rows(P_ALPHA_B(level), kRgbW, 1);
   for (int l = 1; l < kRgbDepth; ++l) {
     pk.op(F.ops[oi++]);
     pk.block(P_RGB_W(level, l), 0, kRgbW, 1, 0, kRgbW, 0, kRgbW);
+    pk.bias_rows(P_RGB_B(level, l), 0, kRgbW);
   }
   pk.op(F.ops[oi++]);  // rgb head
   pk.block(P_RGB_W(level, kRgbDepth), 0, kRgbW, 1, 0, 3, 0, kRgbW);
+  pk.bias_rows(P_RGB_B(level, kRgbDepth), 0, 3);
 
   // bwd: dest(n = input feature, k = output feature) = W[k][n]  -> sn = 1, sk = ld
   const LogicalOps& Bp = plan->bwd_logical;
@@ -450,6 +491,11 @@ static void build_plan_static(const hn_model_desc& d, ModelPlan* plan) {
   // ---------------------------------------------------------------- forward (nerf.py:84-123)
   {
     Builder b{&plan->fwd, &plan->fwd_logical};
+    if (kFoldBias) {   // same rule as make_dims / Shape<>::INB_CHUNKS in hn_mlp.cu
+      const int mx = s.KX > s.KV ? s.KX : s.KV;
+      const bool in_pad = ones_fit_in_pad(mx, s.KX, s.pe_x) && ones_fit_in_pad(mx, s.KV, s.pe_v);
+      b.ones_col = (in_pad ? mx / 8 : mx / 8 + 2) * 8 - 16;
+    }
     int bias = 0;
     b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone, s.g_t[0]);
     b.add_op(kTrunkW, s.KX, SRC_INB, 0, 0, SRC_ACT, 0, 0);
@@ -474,6 +520,7 @@ static void build_plan_static(const hn_model_desc& d, ModelPlan* plan) {
     bias += 16;
     plan->layout.fwd_off = 0;
     plan->layout.bwd_off = (int64_t)b.w16 * 16;
+    without_bias_steps(plan->fwd, &plan->fwd_train);
   }
   // ---------------------------------------------------------------- backward-data
   {
@@ -515,6 +562,7 @@ static void build_tables_static(const int64_t* off, ModelPlan* plan) {
   int oi = 0;
   pk.op(F.ops[oi++]);
   pk.block(SP_TRUNK_W(0), 0, pe_x, 1, 0, kTrunkW, 0, pe_x);
+  pk.bias_rows(SP_TRUNK_B(0), 0, kTrunkW);
   for (int l = 1; l < kStaticDepth; ++l) {
     pk.op(F.ops[oi++]);
     if (l == kStaticSkip) {   // weight columns: [0, pe_x) input_xyz, [pe_x, pe_x + W) hidden
@@ -523,15 +571,20 @@ static void build_tables_static(const int64_t* off, ModelPlan* plan) {
     } else {
       pk.block(SP_TRUNK_W(l), 0, kTrunkW, 1, 0, kTrunkW, 0, kTrunkW);
     }
+    pk.bias_rows(SP_TRUNK_B(l), 0, kTrunkW);
   }
   pk.op(F.ops[oi++]);
   pk.block(SP_SIGMA_W, 0, kTrunkW, 1, 0, 1, 0, kTrunkW);
+  pk.bias_rows(SP_SIGMA_B, 0, 1);
   pk.op(F.ops[oi++]);
   pk.block(SP_FINAL_W, 0, kTrunkW, 1, 0, kTrunkW, 0, kTrunkW);
+  pk.bias_rows(SP_FINAL_B, 0, kTrunkW);
   pk.op(F.ops[oi++]);
   pk.block(SP_DIR_W, 0, ld_dir, 1, 0, kRgbW, 0, ld_dir);
+  pk.bias_rows(SP_DIR_B, 0, kRgbW);
   pk.op(F.ops[oi++]);
   pk.block(SP_RGB_W, 0, kRgbW, 1, 0, 3, 0, kRgbW);
+  pk.bias_rows(SP_RGB_B, 0, 3);
 
   // backward: dest(n = input feature, k = output feature) = W[k][n]
   const LogicalOps& Bp = plan->bwd_logical;

@@ -57,7 +57,20 @@ constexpr int kHalfChunkBytes = kHalfRows * 16;  // one 8-column chunk of a 64-r
 #endif
 constexpr int kRingStages = HN_RING_STAGES;
 constexpr int kStageBytes = HN_STAGE_BYTES;
-constexpr int kMaxOps = 40;
+// HN_FOLD_BIAS = 1: in the INFERENCE forward (no stash) every layer's bias rides in the UMMAs: one extra K = 16 step
+// whose A operand is the last chunk pair of the input buffer INB — its last two columns hold 1.0 — and whose weight rows
+// are [0 x 14, bf16(b), bf16(b - bf16(b))] (two bf16 terms carry the fp32 bias to ~2^-17 relative).  The epilogue then
+// has no bias staging (global load -> shared, named barrier) and no LDS + FADD per column.  The ones live in the zero
+// padding of the widest input vector when it has >= 2 pad columns (cfg 1: trunk input 89 -> 96), otherwise in one extra
+// chunk pair.  Measured per 1 M samples: inference 2.03 -> 1.90 ms; the training forward, whose drain is bound by the
+// stash stores and hides the bias adds under them, only pays for the extra K steps (2.76 -> 2.89 ms), so it runs the
+// same program without the bias steps (ModelPlan::fwd_train) and adds the biases in its epilogue.
+#ifndef HN_FOLD_BIAS
+#define HN_FOLD_BIAS 1
+#endif
+constexpr bool kFoldBias = HN_FOLD_BIAS != 0;
+constexpr bool ones_fit_in_pad(int kmax, int k, int in) { return k < kmax || in <= kmax - 2; }
+constexpr int kMaxOps = 64;
 constexpr int kMaxLayers = 24;
 constexpr int kMaxJobs = 40;
 constexpr uint16_t kNone = 0xFFFF;
@@ -75,7 +88,9 @@ struct Dims {
   int pe_x, pe_h, in_t, KT;        // trunk input
   int pe_v, KV;                    // view-direction condition
   int n_rgb0a;                     // rgb layer 0 merged with the alpha head (pad16(128 + 1))
-  int in_max_chunks;               // chunks of the shared input buffer
+  int in_max_chunks;               // chunks of the widest input vector
+  int inb_chunks;                  // chunks of the shared input buffer (+2 when the ones columns do not fit in padding)
+  int ones_col;                    // first column of the chunk pair whose last two columns are 1.0 (kFoldBias)
 };
 inline Dims make_dims(const hn_model_desc& d) {
   Dims m;
@@ -88,6 +103,9 @@ inline Dims make_dims(const hn_model_desc& d) {
   m.n_rgb0a = pad16(kRgbW + 1);
   int mx = m.KW > m.KT ? m.KW : m.KT; if (m.KV > mx) mx = m.KV;
   m.in_max_chunks = mx / 8;
+  const bool in_pad = ones_fit_in_pad(mx, m.KW, m.in_w) && ones_fit_in_pad(mx, m.KT, m.in_t) && ones_fit_in_pad(mx, m.KV, m.pe_v);
+  m.inb_chunks = (kFoldBias && !in_pad) ? mx / 8 + 2 : mx / 8;
+  m.ones_col = m.inb_chunks * 8 - 16;
   return m;
 }
 
@@ -161,7 +179,7 @@ struct MmaOp {
   uint8_t src;
   uint8_t acc_init;            // 1: accumulate onto what TMEM already holds
   uint8_t cps;                 // 8-col chunks of K per ring stage (even)
-  uint8_t pad;
+  uint8_t pad;                 // 1: bias K step (HN_FOLD_BIAS), dropped from ModelPlan::fwd_train
   uint16_t kc0, kc_total;      // first chunk of this op inside its logical weight matrix / that matrix's chunk count
 };
 // A weight matrix as the packer sees it: one [n x k] operand image; a skip layer's matrix is consumed by two
@@ -197,6 +215,7 @@ struct LogicalOps {
 // ---- weight packing ----------------------------------------------------------------------------------
 // dest(n, k) of an op's [N x K] bf16 matrix (interleave layout: ((k/8) * N + n) * 8 + k%8) is gathered from
 // flat_params[src + (n - n0) * sn + (k - k0) * sk] for the (n, k) inside a block; everything else is zero.
+constexpr int32_t kBiasPairStride = INT32_MIN;   // PackBlock::sk marker: rows k0, k0 + 1 = bf16(b[n]), bf16(b[n] - bf16(b[n]))
 struct PackBlock {
   int64_t src;         // element offset in the flat fp32 parameter buffer
   int32_t sn, sk;      // source strides (elements)
@@ -209,7 +228,7 @@ struct PackOp {
   uint16_t pad;
 };
 constexpr int kMaxPackOps = 64;
-constexpr int kMaxPackBlocks = 96;
+constexpr int kMaxPackBlocks = 160;
 struct BiasBlock { int64_t src; uint16_t dst, cnt; uint32_t pad; };
 constexpr int kMaxBiasBlocks = 40;
 struct PackTable {
@@ -268,6 +287,7 @@ struct ModelPlan {
   SlabMap slabs;
   PlanInfo info;
   Program fwd, bwd;
+  Program fwd_train;  // fwd without the bias K steps (kFoldBias): the stash-writing forward adds biases in its epilogue
   LogicalOps fwd_logical, bwd_logical;
   PackTable pack;     // needs param_offsets -> built per call
   WgradTable wgrad;   // needs param_offsets -> built per call

@@ -2,7 +2,7 @@
 
 * chunk invariance: a ray's outputs and the accumulated gradient do not depend on how the batch is cut into chunks
   or which tile / CTA a ray lands in (8 192 rays in one call vs 5 uneven calls; same draws);
-* the inference and training instantiations of the forward kernel agree bit for bit;
+* the inference and training instantiations of the forward kernel agree (to bf16 rounding of the activations);
 * compositing invariants on the full 65 536-ray batch: weights in [0, 1], sum(weights) <= 1, acc / depth bounds,
   sorted fine samples, finite everything;
 * gradient linearity: grad of (a * loss) == a * grad of loss (the backward kernels accumulate into the flat buffer).
@@ -75,9 +75,16 @@ def test_inference_and_training_forward_agree():
     with torch.no_grad():
         a = _forward(model, rays, draws)            # inference instantiation (no stash)
     b = _forward(model, rays, draws)                # training instantiation (stash + gate words)
-    for lvl in ('coarse', 'fine'):
-        for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
-            assert torch.equal(a[lvl][k], b[lvl][k].detach()), (lvl, k)
+    # the inference instantiation adds the biases inside the UMMAs (extra K step against a ones column, bias as two
+    # bf16 terms), the training one in its epilogue: same math, different fp32 summation order, so activations can
+    # differ by one bf16 ulp here and there
+    for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
+        assert torch.equal(a['coarse'][k], b['coarse'][k].detach()) or \
+            (a['coarse'][k] - b['coarse'][k].detach()).abs().max() < 2e-3, ('coarse', k)
+    # the fine level resamples from the coarse weights: its depths move with them (continuously), so do its outputs
+    for k in ('rgb', 'depth', 'acc'):
+        d = (a['fine'][k] - b['fine'][k].detach()).abs().max()
+        assert d < 1e-2, ('fine', k, d)
 
 
 def test_full_batch_invariants():
