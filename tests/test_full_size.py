@@ -173,3 +173,42 @@ def test_fit_loop_learns_and_checkpoints_like_lightning(tmp_path):
     hn_utils.load_ckpt(fresh, str(tmp_path / "epoch=2.ckpt"), 'nerf')
     for (k, a), b in zip(model.state_dict().items(), fresh.state_dict().values()):
         assert torch.equal(a, b), k
+
+
+def test_full_frame_render_psnr_matches_oracle():
+    """BASELINE.json north_star / SURVEY.md §8(d) cfg3: one 1008 x 756 frame (762 048 rays, 64 + 128 samples, no_grad,
+    noise off, reference-initialised weights).  The fp32 oracle runs on the GPU in torch eager (timing is not the point
+    here); both sides get the same stratified / resampling draws.  PSNR against a fixed synthetic target image must
+    agree within 0.05 dB; rgb within the north-star 2e-3 max-abs."""
+    orc = H.orc
+    sd = synthetic.make_state_dict(synthetic.cfg1_state_dict_shapes(), seed=0, boosted=False)
+    model = H.make_model(n_fine=128, noise_std=None, sd=sd)
+    sd_dev = H.to_dev(sd)
+    cfg = orc.default_cfg(n_fine=128, noise_std=None)
+    rays = synthetic.frame_rays(image_id=3, seed=0, device=DEV)
+    N = rays.shape[0]
+    assert N == 1008 * 756
+    target = torch.rand(N, 3, generator=torch.Generator().manual_seed(5)).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(17)
+    sq_new = torch.zeros((), device=DEV, dtype=torch.float64)
+    sq_ref = torch.zeros((), device=DEV, dtype=torch.float64)
+    max_rgb = max_depth = 0.0
+    chunk = 16384
+    with torch.no_grad():
+        for i in range(0, N, chunk):
+            r = rays[i:i + chunk]
+            B = r.shape[0]
+            u_c = torch.rand(B, 64, device=DEV, generator=g)
+            u_f = torch.rand(B, 128, device=DEV, generator=g)
+            out = _forward(model, r, [u_c, u_f])['fine']
+            ref = orc.forward(sd_dev, r[:, :3], r[:, 3:6], r[:, 8].long(), {'u_coarse': u_c, 'u_fine': u_f}, cfg)['fine']
+            t = target[i:i + chunk]
+            sq_new += ((out['rgb'] - t).double() ** 2).sum()
+            sq_ref += ((ref['rgb'] - t).double() ** 2).sum()
+            max_rgb = max(max_rgb, (out['rgb'] - ref['rgb']).abs().max().item())
+            max_depth = max(max_depth, (out['depth'] - ref['depth']).abs().max().item())
+    psnr_new = -10.0 * torch.log10(sq_new / (3 * N)).item()
+    psnr_ref = -10.0 * torch.log10(sq_ref / (3 * N)).item()
+    print(f"frame PSNR new {psnr_new:.4f} dB, oracle {psnr_ref:.4f} dB; max |rgb| diff {max_rgb:.2e}, depth {max_depth:.2e}")
+    assert abs(psnr_new - psnr_ref) < 0.05
+    assert max_rgb < 2e-3 and max_depth < 2e-3
