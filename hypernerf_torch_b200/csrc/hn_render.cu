@@ -356,18 +356,70 @@ __device__ __forceinline__ void bitonic_sort_warp(float* a, int n2, int lane) {
   }
 }
 
+// The same network on registers: element e = r * 32 + lane lives in v[r] of its lane; partners closer than 32 are reached
+// with a shuffle, the others are another register of the same lane.  n = 32 R elements, ascending.
+template <int R>
+__device__ __forceinline__ void bitonic_sort_regs(float* a, int lane) {
+  float v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = a[r * 32 + lane];
+#pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int q = r ^ (j >> 5);
+          if (q > r) {
+            const bool up = (((r * 32) & k) == 0);   // lane bits do not reach k when k > 32
+            const float lo = fminf(v[r], v[q]), hi = fmaxf(v[r], v[q]);
+            v[r] = up ? lo : hi; v[q] = up ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          const float other = __shfl_xor_sync(kFull, v[r], j);
+          const bool up = (e & k) == 0;
+          const bool lower = (lane & j) == 0;        // this lane holds the smaller index of the pair
+          v[r] = (lower == up) ? fminf(v[r], other) : fmaxf(v[r], other);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r * 32 + lane] = v[r];
+  __syncwarp();
+}
+// n2 a power of two; below 32 or above 512 the shared-memory network
+__device__ __forceinline__ void sort_warp(float* a, int n2, int lane) {
+  switch (n2) {
+    case 32: bitonic_sort_regs<1>(a, lane); break;
+    case 64: bitonic_sort_regs<2>(a, lane); break;
+    case 128: bitonic_sort_regs<4>(a, lane); break;
+    case 256: bitonic_sort_regs<8>(a, lane); break;
+    default: bitonic_sort_warp(a, n2, lane); break;
+  }
+}
+
 __global__ void __launch_bounds__(4 * 32)
 sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_in, const float* __restrict__ wc,
                   int64_t w_stride, const float* __restrict__ u, const float* __restrict__ o,
-                  const float* __restrict__ d, int64_t B, int Nc, int nb, int Nf, int n2, float* __restrict__ zf,
+                  const float* __restrict__ d, int64_t B, int Nc, int nb, int Nf, int n2c, int n2, float* __restrict__ zf,
                   float* __restrict__ pts, int32_t* __restrict__ bin_idx) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * 4 + wid;
   if (ray >= B) return;
-  float* bins = sm + (size_t)wid * (2 * (nb + 1) + n2);
+  // per warp: bins[nb+1] | cdf[nb+1] | srt[n2c] coarse depths | smp[n2] new samples (both padded to powers of two)
+  //           | merged[Nc + Nf]
+  float* bins = sm + (size_t)wid * (2 * (nb + 1) + n2c + n2 + Nc + Nf);
   float* cdf = bins + nb + 1;
   float* srt = cdf + nb + 1;
+  float* smp = srt + n2c;
+  float* merged = smp + n2;
   const float* zr = zc + ray * Nc;
   const float* wr = wc + ray * w_stride - 1;  // wr[1 + i] = weight of bin i
   const float eps = 1e-5f;
@@ -423,13 +475,44 @@ sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_i
     float denom = __fsub_rn(c1, c0);
     if (denom < eps) denom = 1.f;
     float t = __fdiv_rn(__fsub_rn(uu, c0), denom);
-    float smp = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
-    srt[Nc + i] = smp;
+    smp[i] = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
     if (bin_idx != nullptr) bin_idx[ray * Nf + i] = inds;
   }
-  for (int i = Nc + Nf + lane; i < n2; i += 32) srt[i] = __int_as_float(0x7f800000);
   __syncwarp();
-  bitonic_sort_warp(srt, n2, lane);
+  // torch.sort(cat([z_vals, z_samples])) (model_utils.py:227) as sort(new samples) + merge with the sorted coarse depths:
+  // same multiset in ascending order, hence the same values.  The inverse CDF is monotone in u, so deterministic
+  // (linspace) draws arrive sorted and skip the sort.
+  bool ordered = true;
+  for (int i = lane; i < Nf; i += 32) ordered &= (i == 0) || (smp[i - 1] <= smp[i]);
+  if (!__all_sync(kFull, ordered)) {
+    for (int i = Nf + lane; i < n2; i += 32) smp[i] = __int_as_float(0x7f800000);
+    __syncwarp();
+    sort_warp(smp, n2, lane);
+  }
+  // the coarse depths of sample_along_rays are ascending; any other caller's are sorted here (the bins above were
+  // formed from the original order, as the reference does)
+  ordered = true;
+  for (int i = lane; i < Nc; i += 32) ordered &= (i == 0) || (srt[i - 1] <= srt[i]);
+  if (!__all_sync(kFull, ordered)) {
+    for (int i = Nc + lane; i < n2c; i += 32) srt[i] = __int_as_float(0x7f800000);
+    __syncwarp();
+    sort_warp(srt, n2c, lane);
+  }
+  // ranks: a coarse depth goes after the new samples strictly below it, a new sample after the coarse depths <= it
+  for (int i = lane; i < Nc; i += 32) {
+    const float v = srt[i];
+    int lo = 0, hi = Nf;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
+    merged[i + lo] = v;
+  }
+  for (int i = lane; i < Nf; i += 32) {
+    const float v = smp[i];
+    int lo = 0, hi = Nc;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (srt[mid] <= v) lo = mid + 1; else hi = mid; }
+    merged[i + lo] = v;
+  }
+  __syncwarp();
+  srt = merged;
   const int S = Nc + Nf;
   float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
   if (pts != nullptr) {
@@ -499,12 +582,13 @@ extern "C" int hn_sample_pdf(const float* z_coarse, const float* bins, const flo
   if (!z_coarse || !weights || !u || !z_fine) return set_error(-2, "hn_sample_pdf: null pointer");
   if (points && (!origins || !dirs)) return set_error(-2, "hn_sample_pdf: points need origins and dirs");
   if (B == 0) return 0;
-  int n2 = 1;
-  while (n2 < Nc + Nf) n2 <<= 1;
-  size_t smem = (size_t)4 * (2 * (nb + 1) + n2) * sizeof(float);
+  int n2 = 1, n2c = 1;   // new samples and coarse depths are sorted on their own (padded to powers of two), then merged
+  while (n2 < Nf) n2 <<= 1;
+  while (n2c < Nc) n2c <<= 1;
+  size_t smem = (size_t)4 * (2 * (nb + 1) + n2c + n2 + Nc + Nf) * sizeof(float);
   int64_t blocks = (B + 3) / 4;
   sample_pdf_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(z_coarse, bins, weights, w_stride, u, origins,
-                                                                          dirs, B, Nc, nb, Nf, n2, z_fine, points, bin_idx);
+                                                                          dirs, B, Nc, nb, Nf, n2c, n2, z_fine, points, bin_idx);
   return set_cuda_error(cudaGetLastError(), "hn_sample_pdf");
 }
 

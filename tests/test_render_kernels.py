@@ -108,6 +108,31 @@ def test_sample_pdf_bit_exact(B, Nc, Nf):
     assert torch.equal(z_g, z_ref2)
 
 
+@pytest.mark.parametrize("case", ["sorted_u", "unsorted_coarse", "ties"])
+def test_sample_pdf_merge_paths_bit_exact(case):
+    """The kernel sorts only the new samples and merges them with the coarse depths; deterministic (ascending) draws skip
+    the sort, non-ascending coarse depths are sorted first, ties between a coarse depth and a sample keep both."""
+    B, Nc, Nf = 33, 64, 128
+    o, d = _rays(B, seed=16)
+    g = torch.Generator(device=DEV).manual_seed(99)
+    z, _ = torch.sort(torch.rand(B, Nc, device=DEV, generator=g), -1)
+    w = torch.rand(B, Nc, device=DEV, generator=g)
+    u = torch.rand(B, Nf, device=DEV, generator=g)
+    if case == "sorted_u":     # eval path: u = linspace(0, 1 - eps, Nf) for every ray (model_utils.py:188-190)
+        u = torch.linspace(0., 1. - torch.finfo(torch.float32).eps, Nf, device=DEV).expand(B, Nf).contiguous()
+    elif case == "unsorted_coarse":
+        z = z[:, torch.randperm(Nc, device=DEV, generator=g)].contiguous()
+    else:                      # coarse depths on a coarse grid and zero-width bins make samples coincide with depths
+        z = (torch.round(z * 16) / 16).contiguous()
+        u[:, ::3] = u[:, 1::3][:, :u[:, ::3].shape[1]]
+    z_f, pts, inds = mu.sample_pdf_fused(z, w, o, d, Nf, u=u, want_inds=True)
+    bins = .5 * (z[..., 1:] + z[..., :-1])
+    z_ref, pts_ref, inds_ref = orc.sample_pdf(bins, w[..., 1:-1], o, d, z, u)
+    assert torch.equal(inds.long(), inds_ref)
+    assert torch.equal(z_f, z_ref)
+    assert torch.equal(pts, pts_ref)
+
+
 def test_sample_pdf_full_size_properties():
     """BASELINE cfg-2 size (65 536 rays): sortedness, coarse depths preserved, samples inside the bin range."""
     B, Nc, Nf = 65536, 64, 64
