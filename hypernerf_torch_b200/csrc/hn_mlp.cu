@@ -68,19 +68,30 @@ constexpr int kSubsPerChain = kSubTiles / kChains;
 constexpr int kEpiWarps = 4 * kSubTiles;
 constexpr int kProducerWarp = kEpiWarps, kIssuerWarp = kEpiWarps + 1, kRelayWarp = kEpiWarps + 2;
 
-template <class C>
-struct Smem {
+template <int INB_CHUNKS_, int STAGES_>
+struct SmemPlan {
+  static constexpr int STAGES = STAGES_;
   static constexpr int ACT_BYTES = 32 * kChunkBytes;              // 128 x 256 bf16 per sub-tile
-  static constexpr int INB_BYTES = C::INB_CHUNKS * kChunkBytes;   // 128 x (INB_CHUNKS*8) bf16 per sub-tile
+  static constexpr int INB_BYTES = INB_CHUNKS_ * kChunkBytes;     // 128 x (INB_CHUNKS*8) bf16 per sub-tile
   static constexpr int ACT = 0;
   static constexpr int INB = ACT + kSubTiles * ACT_BYTES;
-  static constexpr int RING = INB + kSubTiles * INB_BYTES;        // kRingStages x kStageBytes
-  static constexpr int BIAS = RING + kRingStages * kStageBytes;   // 2 x 256 fp32: this / next layer's bias
+  static constexpr int RING = INB + kSubTiles * INB_BYTES;        // STAGES x kStageBytes
+  static constexpr int BIAS = RING + STAGES * kStageBytes;        // 2 x 256 fp32: this / next layer's bias
   static constexpr int BARS = BIAS + 2 * 256 * 4;                 // full[], empty[], acc_full[2], act_ready[2], peer_full[]
-  static constexpr int TMEMP = BARS + (3 * kRingStages + 4) * 8;
+  static constexpr int TMEMP = BARS + (3 * STAGES + 4) * 8;
   static constexpr int TOTAL = TMEMP + 16;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
+// forward: INB holds the PE input vectors (UMMA operands of the first / skip / view layers)
+template <class C>
+using Smem = SmemPlan<C::INB_CHUNKS, kRingStages>;
+// backward-data: INB only holds the 16-column head gradient of the static model, so the weight ring gets the space.
+// With 3 stages of 512 cycles of UMMA work a refill (commit -> producer -> L2 -> complete_tx, ~1 100 cycles after the
+// stage's last UMMA retires) lands ~80 cycles after the issuer needs the slot again: 12 % of the issuer's time was
+// spent waiting for stages.
+constexpr int kBwdRingStages = kSubTiles == 2 && !kPair ? 5 : kRingStages;
+template <class C>
+using SmemBwd = SmemPlan<2, kBwdRingStages>;
 
 // pair mode: 3-D tensor maps over the packed blob viewed as [128-byte block][8 rows][8 bf16]; map i moves a contiguous
 // run of 2^i blocks (128 B .. 32 KB) in one request
@@ -141,10 +152,13 @@ struct BwdParams {
 #else
 #define HN_T0() (0ll)
 #endif
-struct RingState { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == kRingStages) { slot = 0; phase ^= 1; } } };
+template <int STAGES>
+struct RingStateT { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == STAGES) { slot = 0; phase ^= 1; } } };
+using RingState = RingStateT<kRingStages>;
 
+template <class RS>
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
-                                             uint64_t* full, uint64_t* empty, RingState& rs, long long& t_wait) {
+                                             uint64_t* full, uint64_t* empty, RS& rs, long long& t_wait) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
     for (int chain = 0; chain < kChains; ++chain) {   // ping-pong: every sub-tile makes its own pass over the layer
@@ -175,9 +189,10 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
 constexpr uint32_t kDescHi = (1u << 14) | (128u >> 4);   // descriptor version 1, SBO = 128 B, no swizzle
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
+template <class RS>
 __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, int sub0, uint32_t act_s, uint32_t inb_s,
                                             uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s,
-                                            uint32_t tmem_base, uint64_t* full, uint64_t* empty, RingState& rs,
+                                            uint32_t tmem_base, uint64_t* full, uint64_t* empty, RS& rs,
                                             long long& t_wait) {
   for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
@@ -223,9 +238,10 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
 #define HN_PAIR_DIRECT 1
 #endif
 // Producer of CTA `rank`: per stage, its half (rows [rank N/2, (rank+1) N/2) of every 8-column chunk) of the weights.
+template <class RS>
 __device__ __forceinline__ void produce_tile_pair(const Program& prog, const PairMaps& maps, uint32_t w_row0,
                                                   const uint8_t* __restrict__ weights, uint8_t* ring,
-                                                  uint64_t* full, uint64_t* empty, RingState& rs, uint32_t rank, long long& t_wait) {
+                                                  uint64_t* full, uint64_t* empty, RS& rs, uint32_t rank, long long& t_wait) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
     for (int chain = 0; chain < kChains; ++chain) {
@@ -263,7 +279,8 @@ __device__ __forceinline__ void produce_tile_pair(const Program& prog, const Pai
   }
 }
 // Relay of the non-leader CTA: tells the leader's issuer when this CTA's half of a stage has landed.
-__device__ __forceinline__ void relay_tile_pair(const Program& prog, uint64_t* full, uint32_t leader_peer_full, RingState& rs) {
+template <class RS>
+__device__ __forceinline__ void relay_tile_pair(const Program& prog, uint64_t* full, uint32_t leader_peer_full, RS& rs) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
     for (int chain = 0; chain < kChains; ++chain) {
@@ -280,9 +297,10 @@ __device__ __forceinline__ void relay_tile_pair(const Program& prog, uint64_t* f
   }
 }
 // Leader's issuer: one layer of one chain (= sub-tile `sub0` of both CTAs), cta_group::2, M = 256.
+template <class RS>
 __device__ __forceinline__ void issue_layer_pair(const Program& prog, const Layer& L, int sub0, uint32_t act_s, uint32_t inb_s,
                                                  uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s, uint32_t tmem_base,
-                                                 uint64_t* full, uint64_t* peer_full, uint64_t* empty, RingState& rs,
+                                                 uint64_t* full, uint64_t* peer_full, uint64_t* empty, RS& rs,
                                                  long long& t_wait, long long& t_peer) {
   for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
     const MmaOp& op = prog.ops[oi];
@@ -780,13 +798,14 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
 template <class C>
 __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  using SM = Smem<C>;
+  using SM = SmemBwd<C>;
+  using Ring = RingStateT<SM::STAGES>;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
   uint8_t* ring = smem + SM::RING;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BARS);
-  uint64_t* empty = full + kRingStages;
-  uint64_t* acc_full = empty + kRingStages;   // [2]: one per chain
+  uint64_t* empty = full + SM::STAGES;
+  uint64_t* acc_full = empty + SM::STAGES;    // [2]: one per chain
   uint64_t* act_ready = acc_full + 2;         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SM::TMEMP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -794,7 +813,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   uint64_t* peer_full = act_ready + 2;        // [kRingStages], pair mode: the other CTA's half of a stage has landed
   const uint32_t rank = kPair ? cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
+    for (int i = 0; i < SM::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     // one arrival per epilogue warp of the chain (pair mode: of both CTAs, the other CTA's arrive remotely)
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * kSubsPerChain * (kPair ? 2 : 1)); }
     fence_barrier_init();
@@ -813,7 +832,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   if (warp >= kEpiWarps) {
     setmaxnreg_dec<kSubTiles == 2 ? 56 : 40>();
     if (warp == kProducerWarp && lane == 0) {
-      RingState rs;
+      Ring rs;
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         if (kPair) produce_tile_pair(prog, p.maps, p.w_row0, p.weights, ring, full, empty, rs, rank, tw);
@@ -821,11 +840,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
     } else if (kPair && !HN_PAIR_DIRECT && warp == kRelayWarp && lane == 0 && rank == 1) {
-      RingState rs;
+      Ring rs;
       const uint32_t leader_peer_full = mapa_u32(peer_full, 0);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) relay_tile_pair(prog, full, leader_peer_full, rs);
     } else if (warp == kIssuerWarp && (!kPair || rank == 0)) {  // whole warp, converged: see elect_one_sync()
-      RingState rs;
+      Ring rs;
       uint32_t ph_ready = 0;
       long long t_ready = 0, t_full = 0, t_peer = 0;
       const long long t_begin = HN_T0();
@@ -908,6 +927,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
       t_pro += HN_T0() - t_tile;
 
+      float gx_skip[C::STATIC ? 1 : 3 + C::H] = {};   // skip-layer part of d(warped point, hyper coordinates)
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         if (L.epi == BE_MASK) {
@@ -934,10 +954,10 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           if (L.n_out == kTrunkW) bwd_cols<false, kTrunkW>(tlane, nullptr, act_row, save_row, L.save_chunk);
           else bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
         } else if constexpr (!C::STATIC) {   // (the static program only has BE_MASK / BE_LINEAR layers)
-        if (L.epi == BE_SKIPSTORE) {
-          bwd_cols<false, C::KT>(tlane, nullptr, inb_row, nullptr, 0);
-        } else if (L.epi == BE_TRUNKIN) {
-          // d(trunk input features) = layer-0 part (TMEM) + skip-layer part (INB, bf16)
+        if (L.epi == BE_SKIPSTORE || L.epi == BE_TRUNKIN) {
+          // d(trunk input features) arrives twice: from the skip layer and from layer 0.  The chain rule through the
+          // positional encoding is linear in it, so each part is pulled back to d(warped point, hyper coordinates)
+          // straight from the fp32 accumulator and the two 5-vectors are added: nothing is parked in shared memory.
           float gf[C::KT];
 #pragma unroll
           for (int c0 = 0; c0 < C::KT; c0 += 32) {
@@ -945,32 +965,29 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
             tmem_ld32(tlane + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 sk = *reinterpret_cast<const uint4*>(inb_row + ((c0 >> 3) + q) * kChunkBytes);
-              const uint32_t ss[4] = {sk.x, sk.y, sk.z, sk.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                gf[c0 + 8 * q + 2 * j] = __uint_as_float(r[8 * q + 2 * j]) + bf16_lo(ss[j]);
-                gf[c0 + 8 * q + 2 * j + 1] = __uint_as_float(r[8 * q + 2 * j + 1]) + bf16_hi(ss[j]);
-              }
-            }
+            for (int j = 0; j < 32; ++j) gf[c0 + j] = __uint_as_float(r[j]);
           }
           float wp[3 + C::H], gx[3 + C::H];
 #pragma unroll
           for (int i = 0; i < 3 + C::H; ++i) wp[i] = __ldg(p.warped + gc * (3 + C::H) + i);
           posenc_bwd<3, C::XF>(wp, gf, gx);
           posenc_bwd<C::H, C::HF>(wp + 3, gf + C::PE_X, gx + 3);
+          if (L.epi == BE_SKIPSTORE) {
+#pragma unroll
+            for (int i = 0; i < 3 + C::H; ++i) gx_skip[i] = gx[i];
+          } else {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 3 + C::H; ++i) {
-              f[i] = gx[i];
+              f[i] = gx[i] + gx_skip[i];
               if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + g * (3 + C::H) + i);
             }
           }
           store_features<16>(f, act_row, save_row, L.save_chunk);
+          }
         } else {  // BE_GLO: d(GLO embedding) of this sample -> per-ray reduction -> atomics on the table gradient
           uint32_t r[16];
           tmem_ld16(tlane + kWsW, r);
@@ -1499,11 +1516,11 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.dbg = g_dbg;
     int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
     if (stat) {
-      if (int rc = set_smem(mlp_dgrad_kernel<CfgStatic>, Smem<CfgStatic>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<CfgStatic>, grid, Smem<CfgStatic>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
+      if (int rc = set_smem(mlp_dgrad_kernel<CfgStatic>, SmemBwd<CfgStatic>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<CfgStatic>, grid, SmemBwd<CfgStatic>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
     } else {
-      if (int rc = set_smem(mlp_dgrad_kernel<Cfg1>, Smem<Cfg1>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<Cfg1>, grid, Smem<Cfg1>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
+      if (int rc = set_smem(mlp_dgrad_kernel<Cfg1>, SmemBwd<Cfg1>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
+      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<Cfg1>, grid, SmemBwd<Cfg1>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
     }
   }
   if (do_weights) {
