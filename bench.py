@@ -85,14 +85,52 @@ def run_reference_arm(args):
 # clocks
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (first sample at once, then every
+    20 ms, so even the 65 ms timed region of the 8-GPU run is covered); nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    MASKS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            gpu_index = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        except (ValueError, IndexError):
+            pass
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, threading.Event(), None
+
+    def _poll(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while True:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                if reasons_fn is not None:
+                    bits = int(reasons_fn(self.handle))
+                    for name, mask in self.MASKS:
+                        if bits & mask:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.02):
+                return
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
@@ -105,6 +143,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -122,7 +166,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------------------
