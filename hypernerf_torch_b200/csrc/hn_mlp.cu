@@ -58,6 +58,12 @@ using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (->
 #ifndef HN_PINGPONG
 #define HN_PINGPONG 0
 #endif
+// L2 cache policies on the bulk loads: bit 0 = evict_last for the weight stream of the forward / data-gradient kernels,
+// bit 1 = evict_first for the stash slabs the weight-gradient kernel streams through.  Measured with the streaming
+// stash stores in place: no effect on forward / data gradient, weight gradient 2.92 -> 2.97 ms; off.
+#ifndef HN_L2_HINTS
+#define HN_L2_HINTS 0
+#endif
 constexpr bool kPingPong = (HN_PINGPONG || kPair) && kSubTiles == 2;
 constexpr int kChains = kPingPong ? kSubTiles : 1;          // independently synchronised sub-tile groups
 constexpr int kSubsPerChain = kSubTiles / kChains;
@@ -159,6 +165,9 @@ using RingState = RingStateT<kRingStages>;
 template <class RS>
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
                                              uint64_t* full, uint64_t* empty, RS& rs, long long& t_wait) {
+#if HN_L2_HINTS & 1
+  const uint64_t keep = l2_policy_evict_last();   // the 1.6 MB of weights are re-read by every CTA for every tile
+#endif
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
     for (int chain = 0; chain < kChains; ++chain) {   // ping-pong: every sub-tile makes its own pass over the layer
@@ -173,7 +182,11 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
           mbar_wait(&empty[rs.slot], rs.phase ^ 1);
           t_wait += HN_T0() - t0;
           mbar_arrive_expect_tx(&full[rs.slot], bytes);
+#if HN_L2_HINTS & 1
+          bulk_g2s_hint(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot], keep);
+#else
           bulk_g2s(ring + rs.slot * kStageBytes, src + (size_t)c * op.n * 16, bytes, &full[rs.slot]);
+#endif
           rs.next();
         }
       }
@@ -405,6 +418,11 @@ __device__ __forceinline__ void store_ones_pair(uint8_t* inb_row) {
   }
 }
 
+// Stash stores are streaming (st.global.cs, evict-first): 9 GB per 1 M samples that nothing reads before the backward
+// pass would otherwise push the 1.6 MB of weights every SM keeps re-reading out of L2 (measured: forward 4.99 -> 4.69 M
+// cycles per CTA, the issuer's stage waits 13.8 -> 9.9 %).
+__device__ __forceinline__ void stash_store(uint4* dst, const uint4& v) { __stcs(dst, v); }
+
 // write NCOL (multiple of 8) fp32 features of one row as bf16 packets into an smem operand (and the stash)
 template <int NCOL>
 __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row, uint4* save_row, int save_chunk) {
@@ -416,7 +434,7 @@ __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row,
     v.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
     v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
     *reinterpret_cast<uint4*>(buf_row + q * kChunkBytes) = v;
-    if (save_row != nullptr) save_row[(save_chunk + q) * (kHalfChunkBytes / 16)] = v;
+    if (save_row != nullptr) stash_store(&save_row[(save_chunk + q) * (kHalfChunkBytes / 16)], v);
   }
 }
 
@@ -476,9 +494,9 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
       o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
     }
     *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
-    if (STASH) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = o;
+    if (STASH) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], o);
   }
-  if (RELU && STASH) gate_dst[(chunk0 >> 2) * kHalfRows] = gate_word_of(ge, go);
+  if (RELU && STASH) __stcs(&gate_dst[(chunk0 >> 2) * kHalfRows], gate_word_of(ge, go));
 }
 
 // ncols: multiple of 32
@@ -526,7 +544,7 @@ __device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t w, uint8
   for (int q = 0; q < 4; ++q) {
     const uint4 v = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = v;
-    if (save_row != nullptr) save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)] = v;
+    if (save_row != nullptr) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], v);
   }
 }
 // NCOLS: multiple of 32 (<= 256), compile time so that gw[] and both row buffers stay in registers
@@ -1106,6 +1124,12 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0 && h0 < h1) {
+#if HN_L2_HINTS & 2
+      const uint64_t once = l2_policy_evict_first();   // the stash streams through once; dW (atomics) should stay in L2
+#define HN_WG_LOAD(dst, src, bytes, bar) bulk_g2s_hint(dst, src, bytes, bar, once)
+#else
+#define HN_WG_LOAD(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#endif
       int slot = 0; uint32_t phase = 0;
       for (int ji = 0; ji < njobs; ++ji) {
         const WgradJob& J = p.tab.jobs[ji];
@@ -1116,11 +1140,11 @@ __global__ void __launch_bounds__(192, 1) mlp_wgrad_kernel(const __grid_constant
           uint8_t* st = smem + slot * kWgStageBytes;
           mbar_wait(&empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&full[slot], a_bytes + b0_bytes + b1_bytes);
-          bulk_g2s(st, p.dsaved + ((size_t)h * p.d_total + J.dy_chunk) * kHalfChunkBytes, a_bytes, &full[slot]);
-          bulk_g2s(st + kWgStageA, p.saved + ((size_t)h * p.x_total + J.x0_chunk) * kHalfChunkBytes, b0_bytes, &full[slot]);
+          HN_WG_LOAD(st, p.dsaved + ((size_t)h * p.d_total + J.dy_chunk) * kHalfChunkBytes, a_bytes, &full[slot]);
+          HN_WG_LOAD(st + kWgStageA, p.saved + ((size_t)h * p.x_total + J.x0_chunk) * kHalfChunkBytes, b0_bytes, &full[slot]);
           if (b1_bytes)
-            bulk_g2s(st + kWgStageA + b0_bytes, p.saved + ((size_t)h * p.x_total + J.x1_chunk) * kHalfChunkBytes, b1_bytes,
-                     &full[slot]);
+            HN_WG_LOAD(st + kWgStageA + b0_bytes, p.saved + ((size_t)h * p.x_total + J.x1_chunk) * kHalfChunkBytes, b1_bytes,
+                       &full[slot]);
           if (++slot == kWgStages) { slot = 0; phase ^= 1; }
         }
       }

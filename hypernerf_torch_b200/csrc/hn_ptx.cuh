@@ -74,6 +74,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same with an L2 cache policy (createpolicy): evict_last for data every SM keeps re-reading (weights), evict_first
+// for data that streams through once (stash slabs)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 // Tensor-map TMA load of a contiguous run of 128-byte blocks (3-D view [block][8 rows][8 bf16], box = 2^i blocks) into this CTA's shared memory whose completion (complete_tx) is signalled
 // on the LEADER CTA's mbarrier: the cta_group::2 form accepts the barrier of the pair's other CTA (bit 24 of the
 // shared::cluster address selects the CTA; cute/arch/copy_sm100_tma.hpp, SM100_TMA_2SM_LOAD_2D).  The plain
