@@ -48,15 +48,17 @@ using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (->
 // ------------------------------------------------------------------------------------------------------
 // shared memory plan of the fused kernels
 // ------------------------------------------------------------------------------------------------------
-// HN_PINGPONG = 1: the two sub-tiles of a CTA run half a step out of phase: each has its own accumulator /
+// Ping-pong schedule: the two sub-tiles of a CTA run half a step out of phase: each has its own accumulator /
 // activation barriers and makes its own pass over a layer's weight stages, so sub-tile 0's epilogue (TMEM drain,
 // stash stores) runs under sub-tile 1's UMMAs and vice versa.  Price: every weight stage is fetched from L2 once per
-// 128 instead of once per 256 samples.  HN_PINGPONG = 0: both sub-tiles consume each stage in lock step.
-// Measured: the 128-row passes need 64 B/clk of weights per SM while their UMMAs run; the 48 KB ring over the L2
-// latency sustains ~48, the issuer then waits 27 % of the time for stages and the gain from the overlap is lost
-// (fwd 2.79 vs 2.83 ms, dgrad 2.76 vs 2.78 ms per 1 M samples), so lock step stays the default.
+// 128 instead of once per 256 samples, i.e. the weight ring has to sustain twice the rate over the same ~1 100-cycle
+// refill latency.  Lock step: both sub-tiles consume each stage back to back.
+// HN_PINGPONG bits: 1 = training forward, 2 = data gradient, 4 = inference forward.  Measured per 1 M samples once
+// the stash stores stopped evicting the weights from L2 (streaming stores): data gradient (80 KB ring) 2.55 -> 2.31 ms,
+// training forward (48 KB ring) 2.50 -> 2.42 ms, inference forward (48 KB ring, short drains, bias K steps streamed
+// twice) 1.89 -> 2.34 ms.  Before the streaming stores none of the three gained anything.
 #ifndef HN_PINGPONG
-#define HN_PINGPONG 0
+#define HN_PINGPONG 3
 #endif
 // L2 cache policies on the bulk loads: bit 0 = evict_last for the weight stream of the forward / data-gradient kernels,
 // bit 1 = evict_first for the stash slabs the weight-gradient kernel streams through.  Measured with the streaming
@@ -64,9 +66,14 @@ using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (->
 #ifndef HN_L2_HINTS
 #define HN_L2_HINTS 0
 #endif
-constexpr bool kPingPong = (HN_PINGPONG || kPair) && kSubTiles == 2;
-constexpr int kChains = kPingPong ? kSubTiles : 1;          // independently synchronised sub-tile groups
-constexpr int kSubsPerChain = kSubTiles / kChains;
+constexpr bool kPingPongFwdTrain = ((HN_PINGPONG & 1) || kPair) && kSubTiles == 2;
+constexpr bool kPingPongBwd = ((HN_PINGPONG & 2) || kPair) && kSubTiles == 2;
+constexpr bool kPingPongFwdInfer = ((HN_PINGPONG & 4) || kPair) && kSubTiles == 2;
+template <bool PP>
+struct Sched {
+  static constexpr int CHAINS = PP ? kSubTiles : 1;          // independently synchronised sub-tile groups
+  static constexpr int SUBS = kSubTiles / CHAINS;            // sub-tiles per chain
+};
 // Warp roles.  The epilogue warpgroups come FIRST and the feeder warpgroup (weight producer, UMMA issuer, pair relay)
 // LAST: the SM's warp arbiter favours the highest warp id, and once a drain loop of one sub-tile runs concurrently with
 // the other sub-tile's UMMAs (ping-pong / pair schedules) low-numbered feeder warps were starved of issue slots
@@ -162,7 +169,7 @@ template <int STAGES>
 struct RingStateT { int slot = 0; uint32_t phase = 0; __device__ void next() { if (++slot == STAGES) { slot = 0; phase ^= 1; } } };
 using RingState = RingStateT<kRingStages>;
 
-template <class RS>
+template <bool PP, class RS>
 __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t* __restrict__ weights, uint8_t* ring,
                                              uint64_t* full, uint64_t* empty, RS& rs, long long& t_wait) {
 #if HN_L2_HINTS & 1
@@ -170,7 +177,7 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
 #endif
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
-    for (int chain = 0; chain < kChains; ++chain) {   // ping-pong: every sub-tile makes its own pass over the layer
+    for (int chain = 0; chain < Sched<PP>::CHAINS; ++chain) {   // ping-pong: every sub-tile makes its own pass over the layer
       for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
         const MmaOp& op = prog.ops[oi];
         const int nchunks = op.k >> 3;
@@ -202,7 +209,7 @@ __device__ __forceinline__ void produce_tile(const Program& prog, const uint8_t*
 constexpr uint32_t kDescHi = (1u << 14) | (128u >> 4);   // descriptor version 1, SBO = 128 B, no swizzle
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
-template <class RS>
+template <bool PP, class RS>
 __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L, int sub0, uint32_t act_s, uint32_t inb_s,
                                             uint32_t act_stride, uint32_t inb_stride, uint32_t ring_s,
                                             uint32_t tmem_base, uint64_t* full, uint64_t* empty, RS& rs,
@@ -230,7 +237,7 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
         for (uint32_t j = 0; j < cnt; j += 2) {
           const uint64_t bd = desc64(b_lo);
 #pragma unroll
-          for (int sub = 0; sub < kSubsPerChain; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
+          for (int sub = 0; sub < Sched<PP>::SUBS; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
           a_lo += 2 * (kChunkBytes >> 4);
           b_lo += 2 * n;
           acc = 1;
@@ -257,7 +264,7 @@ __device__ __forceinline__ void produce_tile_pair(const Program& prog, const Pai
                                                   uint64_t* full, uint64_t* empty, RS& rs, uint32_t rank, long long& t_wait) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
-    for (int chain = 0; chain < kChains; ++chain) {
+    for (int chain = 0; chain < kSubTiles; ++chain) {   // pair mode is always ping-pong
       for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
         const MmaOp& op = prog.ops[oi];
         const int nchunks = op.k >> 3;
@@ -296,7 +303,7 @@ template <class RS>
 __device__ __forceinline__ void relay_tile_pair(const Program& prog, uint64_t* full, uint32_t leader_peer_full, RS& rs) {
   for (int li = 0; li < prog.nlayers; ++li) {
     const Layer& L = prog.layers[li];
-    for (int chain = 0; chain < kChains; ++chain) {
+    for (int chain = 0; chain < kSubTiles; ++chain) {   // pair mode is always ping-pong
       for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) {
         const MmaOp& op = prog.ops[oi];
         const int nchunks = op.k >> 3;
@@ -455,8 +462,9 @@ __device__ __forceinline__ void warp_arrive_leader(uint32_t leader_bar) {
   if ((threadIdx.x & 31) == 0) mbar_arrive_remote(leader_bar);
 }
 // named barrier of one chain's epilogue threads (ids 1, 2; barrier 0 is __syncthreads)
+template <bool PP>
 __device__ __forceinline__ void epi_named_barrier(int chain) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * kSubsPerChain) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * Sched<PP>::SUBS) : "memory");
 }
 
 // bias of a head column: already inside the accumulator when the biases ride in the UMMAs
@@ -583,6 +591,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
   constexpr bool FOLD = kFoldBias && !STASH;   // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS)
+  constexpr bool PP = STASH ? kPingPongFwdTrain : kPingPongFwdInfer;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
   uint8_t* ring = smem + SM::RING;
@@ -599,7 +608,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     // one arrival per epilogue warp of the chain (pair mode: of both CTAs, the other CTA's arrive remotely)
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * kSubsPerChain * (kPair ? 2 : 1)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * (kPair ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == kIssuerWarp) {
@@ -620,7 +629,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         if (kPair) produce_tile_pair(prog, p.maps, p.w_row0, p.weights, ring, full, empty, rs, rank, tw);
-        else produce_tile(prog, p.weights, ring, full, empty, rs, tw);
+        else produce_tile<PP>(prog, p.weights, ring, full, empty, rs, tw);
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
     } else if (kPair && !HN_PAIR_DIRECT && warp == kRelayWarp && lane == 0 && rank == 1) {
@@ -635,17 +644,17 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
-          for (int chain = 0; chain < kChains; ++chain) {
+          for (int chain = 0; chain < Sched<PP>::CHAINS; ++chain) {
             long long t0 = HN_T0();
             if (kPair) mbar_wait_cluster(&act_ready[chain], ph_ready); else mbar_wait(&act_ready[chain], ph_ready);
             t_ready += HN_T0() - t0;
             tc_fence_after();
             if (kPair) {
-              issue_layer_pair(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s,
+              issue_layer_pair(prog, prog.layers[li], chain * Sched<PP>::SUBS, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s,
                                tmem_base, full, peer_full, empty, rs, t_full, t_peer);
               if (elect_one_sync()) umma2_commit_mc(&acc_full[chain], 3);   // accumulators of both CTAs are complete
             } else {
-              issue_layer(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
+              issue_layer<PP>(prog, prog.layers[li], chain * Sched<PP>::SUBS, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
                           full, empty, rs, t_full);
               if (elect_one_sync()) umma_commit(&acc_full[chain]);
             }
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
     }
   } else {
     setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
-    const int et = threadIdx.x & (128 * kSubsPerChain - 1);  // index inside this chain's epilogue threads
+    const int et = threadIdx.x & (128 * Sched<PP>::SUBS - 1);  // index inside this chain's epilogue threads
     // ---------------- epilogue warps: thread <-> sample row; warps 0..3 sub-tile 0, 4..7 sub-tile 1 ----------------
     const int sub = warp >> 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -669,7 +678,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
     uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
-    const int chain = kPingPong ? sub : 0;
+    const int chain = PP ? sub : 0;
     uint64_t* my_acc = &acc_full[chain];
     uint64_t* my_ready = &act_ready[chain];
     const uint32_t leader_ready = kPair ? mapa_u32(my_ready, 0) : 0;
@@ -718,12 +727,12 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         const Layer& L = prog.layers[li];
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
-        float* bias = kPingPong ? sbias + chain * 256 : sbias + (li & 1) * 256;
+        float* bias = PP ? sbias + chain * 256 : sbias + (li & 1) * 256;
         const long long t_layer = HN_T0();
         if constexpr (!FOLD) {
-          if (kPingPong) epi_named_barrier(chain);   // single buffer per chain: everyone is done with the previous layer's bias
-          for (int i = et; i < L.n_out; i += 128 * kSubsPerChain) bias[i] = __ldg(p.bias + L.bias_off + i);
-          epi_named_barrier(chain);
+          if (PP) epi_named_barrier<PP>(chain);   // single buffer per chain: everyone is done with the previous layer's bias
+          for (int i = et; i < L.n_out; i += 128 * Sched<PP>::SUBS) bias[i] = __ldg(p.bias + L.bias_off + i);
+          epi_named_barrier<PP>(chain);
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
@@ -818,6 +827,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = SmemBwd<C>;
   using Ring = RingStateT<SM::STAGES>;
+  constexpr bool PP = kPingPongBwd;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
   uint8_t* ring = smem + SM::RING;
@@ -833,7 +843,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < SM::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     // one arrival per epilogue warp of the chain (pair mode: of both CTAs, the other CTA's arrive remotely)
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * kSubsPerChain * (kPair ? 2 : 1)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * (kPair ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == kIssuerWarp) {
@@ -854,7 +864,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         if (kPair) produce_tile_pair(prog, p.maps, p.w_row0, p.weights, ring, full, empty, rs, rank, tw);
-        else produce_tile(prog, p.weights, ring, full, empty, rs, tw);
+        else produce_tile<PP>(prog, p.weights, ring, full, empty, rs, tw);
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = tw;
     } else if (kPair && !HN_PAIR_DIRECT && warp == kRelayWarp && lane == 0 && rank == 1) {
@@ -869,17 +879,17 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       const uint32_t act_s = smem_u32(act), inb_s = smem_u32(inb), ring_s = smem_u32(ring);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int li = 0; li < prog.nlayers; ++li) {
-          for (int chain = 0; chain < kChains; ++chain) {
+          for (int chain = 0; chain < Sched<PP>::CHAINS; ++chain) {
             long long t0 = HN_T0();
             if (kPair) mbar_wait_cluster(&act_ready[chain], ph_ready); else mbar_wait(&act_ready[chain], ph_ready);
             t_ready += HN_T0() - t0;
             tc_fence_after();
             if (kPair) {
-              issue_layer_pair(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s,
+              issue_layer_pair(prog, prog.layers[li], chain * Sched<PP>::SUBS, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s,
                                tmem_base, full, peer_full, empty, rs, t_full, t_peer);
               if (elect_one_sync()) umma2_commit_mc(&acc_full[chain], 3);   // accumulators of both CTAs are complete
             } else {
-              issue_layer(prog, prog.layers[li], chain * kSubsPerChain, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
+              issue_layer<PP>(prog, prog.layers[li], chain * Sched<PP>::SUBS, act_s, inb_s, SM::ACT_BYTES, SM::INB_BYTES, ring_s, tmem_base,
                           full, empty, rs, t_full);
               if (elect_one_sync()) umma_commit(&acc_full[chain]);
             }
@@ -901,7 +911,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
     uint8_t* inb_row = inb + sub * SM::INB_BYTES + row * 16;
-    const int chain = kPingPong ? sub : 0;
+    const int chain = PP ? sub : 0;
     uint64_t* my_acc = &acc_full[chain];
     uint64_t* my_ready = &act_ready[chain];
     const uint32_t leader_ready = kPair ? mapa_u32(my_ready, 0) : 0;
