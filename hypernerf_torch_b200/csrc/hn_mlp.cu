@@ -103,8 +103,9 @@ using Smem = SmemPlan<C::INB_CHUNKS, kRingStages>;
 // stage's last UMMA retires) lands ~80 cycles after the issuer needs the slot again: 12 % of the issuer's time was
 // spent waiting for stages.
 constexpr int kBwdRingStages = kSubTiles == 2 && !kPair ? 5 : kRingStages;
+// (the hyper model's data gradient keeps nothing in INB at all: 6 stages)
 template <class C>
-using SmemBwd = SmemPlan<2, kBwdRingStages>;
+using SmemBwd = SmemPlan<C::STATIC ? 2 : 0, (C::STATIC || kBwdRingStages != 5) ? kBwdRingStages : 6>;
 
 // pair mode: 3-D tensor maps over the packed blob viewed as [128-byte block][8 rows][8 bf16]; map i moves a contiguous
 // run of 2^i blocks (128 B .. 32 KB) in one request
