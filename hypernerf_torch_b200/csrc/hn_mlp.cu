@@ -8,11 +8,13 @@
 //   mlp_wgrad_kernel  dW = dY^T X and db = sum dY over all samples, accumulated into the flat gradient.
 //   pack_kernel       fp32 (out,in) nn.Linear weights -> bf16 operand images (forward and transposed).
 //
-// One CTA (one per SM) owns 256 samples as two 128-row sub-tiles (128 = UMMA M = TMEM lanes); both sub-tiles
-// consume every weight stage, so each byte fetched from L2 feeds two UMMAs.  384 threads = 3 warpgroups:
-// warpgroup 0 holds the weight producer (warp 0 lane 0, 6-deep bulk-copy ring) and the UMMA issuer (warp 1 lane 0)
-// and gives its registers away (setmaxnreg 40); warpgroups 1-2 are the epilogue (thread = sample row, one
-// warpgroup per sub-tile, setmaxnreg 216).  TMEM: 512 columns = 2 sub-tiles x 256 fp32 accumulator columns.
+// One CTA (one per SM) owns 256 samples as two 128-row sub-tiles (128 = UMMA M = TMEM lanes).  Inference forward: both
+// sub-tiles consume every weight stage in lock step, so each byte fetched from L2 feeds two UMMAs.  Training forward and
+// data gradient: the sub-tiles run out of phase (Sched<PP>), one draining its accumulator and writing its stash while
+// the other's UMMAs run.  384 threads = 3 warpgroups: warpgroups 0-1 are the epilogue (thread = sample row, one
+// warpgroup per sub-tile, setmaxnreg 216); the last warpgroup holds the weight producer (one thread, 3 x 16 KB bulk-copy
+// ring; 5-6 stages in the data gradient) and the UMMA issuer (one elected thread) and gives its registers away.
+// TMEM: 512 columns = 2 sub-tiles x 256 fp32 accumulator columns.  Stash stores are streaming (st.global.cs).
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
