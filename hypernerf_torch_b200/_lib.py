@@ -20,8 +20,8 @@ HN_COMP_WHITE_BKGD = 1
 HN_COMP_ACC_ALL = 2
 
 EXPORTS = [
-    "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf",
-    "hn_composite_fwd", "hn_composite_bwd", "hn_mse_loss", "hn_make_ndc_rays", "hn_adam_step", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
+    "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf", "hn_sample_pdf_ranks",
+    "hn_composite_fwd", "hn_composite_bwd", "hn_mse_loss", "hn_make_ndc_rays", "hn_adam_step", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_mlp_fwd_trunk", "hn_mlp_bwd_trunk", "hn_mlp_bwd_trunk_data", "hn_mlp_bwd_trunk_weights",
     "hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4", "hn_epi_rate", "hn_tmem_rate", "hn_debug_set_timing_buffer",
 ]
 
@@ -72,6 +72,7 @@ def lib():
     L.hn_pack_weights.argtypes = [C.POINTER(ModelDesc), vp, C.POINTER(C.c_int64), i32, vp, vp]
     L.hn_sample_coarse.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]
     L.hn_sample_pdf.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    L.hn_sample_pdf_ranks.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.hn_composite_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]
     L.hn_composite_bwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]
     L.hn_mse_loss.argtypes = [vp, vp, vp, i64, f32, vp, vp, vp, vp]
@@ -82,6 +83,11 @@ def lib():
                              C.POINTER(C.c_int64), vp, vp, vp]
     L.hn_mlp_bwd_data.argtypes = L.hn_mlp_bwd.argtypes
     L.hn_mlp_bwd_weights.argtypes = [C.POINTER(ModelDesc), vp, i64, i32, i32, C.POINTER(C.c_int64), vp, vp, vp]
+    L.hn_mlp_fwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp]
+    L.hn_mlp_bwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, C.POINTER(C.c_int64),
+                                   vp, vp, vp, vp]
+    L.hn_mlp_bwd_trunk_data.argtypes = L.hn_mlp_bwd_trunk.argtypes
+    L.hn_mlp_bwd_trunk_weights.argtypes = L.hn_mlp_bwd_weights.argtypes
     L.hn_debug_set_timing_buffer.argtypes = [vp]
     L.hn_tmem_rate.argtypes = [i32, i32, i32, i32, vp, vp]
     L.hn_umma_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp]

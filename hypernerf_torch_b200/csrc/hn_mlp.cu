@@ -121,6 +121,7 @@ struct FwdParams {
   const float* bias;        // packed blob base + bias_off
   const float* glo;         // (E, G) fp32 copy of the GLO table
   const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
+  const float* warped_in;   // trunk-only program (hn_mlp_fwd_trunk): (n, 3 + H) warped points + hyper coordinates, else NULL
   float noise_std;
   int64_t n;                // samples = B * S
   int S;
@@ -142,6 +143,7 @@ struct BwdParams {
   const int64_t* ids;
   const float* sigma; const float* rgb; const float* warped;
   const float* g_sigma; const float* g_rgb; const float* g_warped;
+  float* g_warped_out;      // trunk-only program: (n, 3 + H) gradient w.r.t. warped_in, written by the last layer; else NULL
   const uint8_t* saved;     // forward stash (X slabs; only its gate-word region is read here)
   const uint32_t* gates;    // ReLU gate words written by the forward: [half tile][g_total][64 rows]
   int g_total;
@@ -702,11 +704,27 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
       }
       float pt[3], dir[3];
+      const bool trunk_only = !C::STATIC && p.warped_in != nullptr;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         dir[i] = __ldg(p.viewdirs + ray * 3 + i);
-        pt[i] = __ldg(p.points + gc * 3 + i);
+        pt[i] = trunk_only ? 0.f : __ldg(p.points + gc * 3 + i);
       }
+      if (trunk_only) {
+        // trunk-only program: the warped point / hyper coordinates of this row were computed by another launch (the
+        // coarse level's, for the depths the fine level inherits); the prologue does what FE_WSHEAD's epilogue does
+        if constexpr (!C::STATIC) {
+          float w[3 + C::H];
+#pragma unroll
+          for (int i = 0; i < 3 + C::H; ++i) w[i] = __ldg(p.warped_in + gc * (3 + C::H) + i);
+          float f[C::KT];
+          posenc<3, C::XF>(w, f);
+          posenc<C::H, C::HF>(w + 3, f + C::PE_X);
+          finish_features<C, C::KT, C::IN_T>(f);
+          store_features<C::KT>(f, inb_row, save_row, p.x_in_t);
+          store_ones_pair<C, C::KT>(inb_row);
+        }
+      } else
       // prologue: [posenc(points, WF) | GLO | 0] -> INB   (static baseline: [Embedding(xyz) | 0], nerf.py:21-38)
       {
         float f[C::KW];
@@ -1006,6 +1024,12 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           if (L.epi == BE_SKIPSTORE) {
 #pragma unroll
             for (int i = 0; i < 3 + C::H; ++i) gx_skip[i] = gx[i];
+          } else if (p.g_warped_out != nullptr) {
+            // trunk-only program: this is the last layer; the gradient goes back to whoever produced warped_in
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 3 + C::H; ++i) p.g_warped_out[g * (3 + C::H) + i] = gx[i] + gx_skip[i];
+            }
           } else {
           float f[16];
 #pragma unroll
@@ -1475,19 +1499,24 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
 }
 
-extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
-                          const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
-                          float* rgb, float* warped, void* saved, void* stream) {
-  if (!desc || !packed || !points || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
+// warped_in != NULL: trunk-only program (hn_mlp_fwd_trunk)
+static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const float* points, const float* warped_in,
+                        const float* viewdirs, const int64_t* ids, const float* noise, float noise_std, int64_t B, int S,
+                        float* sigma, float* rgb, float* warped, void* saved, void* stream) {
+  const bool trunk = warped_in != nullptr;
+  if (!desc || !packed || (!points && !trunk) || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
   if (int rc = validate_desc(*desc)) return rc;
   const bool stat = is_static(*desc);
-  if (!stat && !ids) return set_error(-2, "hn_mlp_fwd: null ids");
+  if (trunk && stat) return set_error(-13, "hn_mlp_fwd_trunk: the static model has no warp / sheet stage to skip");
+  if (!stat && !trunk && !ids) return set_error(-2, "hn_mlp_fwd: null ids");
   if (B == 0) return 0;
   static thread_local ModelPlan plan;
   build_plan(*desc, &plan);
   FwdParams fp;
-  fp.prog = saved != nullptr ? plan.fwd_train : plan.fwd;   // the stash-writing forward keeps its biases in the epilogue
+  // the stash-writing forward keeps its biases in the epilogue
+  fp.prog = trunk ? (saved != nullptr ? plan.fwd_trunk_train : plan.fwd_trunk) : (saved != nullptr ? plan.fwd_train : plan.fwd);
+  fp.warped_in = warped_in;
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
   fp.w_row0 = (uint32_t)(plan.layout.fwd_off / 16);
   if (int rc = build_pair_maps(packed, plan.layout.total, &fp.maps)) return rc;
@@ -1516,13 +1545,31 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
 #undef HN_LAUNCH_FWD
 }
 
+extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
+                          const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
+                          float* rgb, float* warped, void* saved, void* stream) {
+  if (!points) return set_error(-2, "hn_mlp_fwd: null pointer");
+  return mlp_fwd_impl(desc, packed, points, nullptr, viewdirs, ids, noise, noise_std, B, S, sigma, rgb, warped, saved, stream);
+}
+
+extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
+                                const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb, void* saved,
+                                void* stream) {
+  if (!warped_in) return set_error(-2, "hn_mlp_fwd_trunk: null pointer");
+  return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, nullptr, noise, noise_std, B, S, sigma, rgb, nullptr, saved,
+                      stream);
+}
+
 static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                         const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
                         const float* g_warped, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
-                        void* workspace, void* stream, bool do_data, bool do_weights) {
+                        void* workspace, void* stream, bool do_data, bool do_weights, bool trunk = false,
+                        float* g_warped_out = nullptr) {   // trunk: trunk-only programs (hn_mlp_bwd_trunk*)
   if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
   const bool stat = desc && is_static(*desc);
-  if (do_data && (!packed || !sigma || !rgb || !g_sigma || !g_rgb || (!stat && (!ids || !warped))))
+  if (trunk && do_data && !g_warped_out) return set_error(-2, "hn_mlp_bwd_trunk: null pointer");
+  if (trunk && stat) return set_error(-13, "hn_mlp_bwd_trunk: the static model has no warp / sheet stage to skip");
+  if (do_data && (!packed || !sigma || !rgb || !g_sigma || !g_rgb || (!stat && ((!ids && !trunk) || !warped))))
     return set_error(-2, "hn_mlp_bwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_bwd: bad B/S");
   if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
@@ -1536,7 +1583,8 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_bwd: too many samples");
   if (do_data) {
     BwdParams bp;
-    bp.prog = plan.bwd;
+    bp.prog = trunk ? plan.bwd_trunk : plan.bwd;
+    bp.g_warped_out = g_warped_out;
     bp.weights = (const uint8_t*)packed + plan.layout.bwd_off;
     bp.w_row0 = (uint32_t)(plan.layout.bwd_off / 16);
     if (int rc = build_pair_maps(packed, plan.layout.total, &bp.maps)) return rc;
@@ -1562,7 +1610,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
   }
   if (do_weights) {
     WgradParams wp;
-    wp.tab = plan.wgrad;
+    wp.tab = trunk ? plan.wgrad_trunk : plan.wgrad;
     wp.saved = (const uint8_t*)saved; wp.dsaved = (const uint8_t*)workspace;
     wp.flat_grad = flat_grad;
     wp.n_half = 2 * kSubTiles * nt;
@@ -1597,6 +1645,28 @@ extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, 
                                   const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
   return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
                       param_offsets, flat_grad, (void*)workspace, stream, false, true);
+}
+
+extern "C" int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
+                                const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B,
+                                int S, int level, const int64_t* param_offsets, float* flat_grad, float* g_warped_in,
+                                void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, nullptr, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
+                      flat_grad, workspace, stream, true, true, true, g_warped_in);
+}
+
+extern "C" int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
+                                     const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb,
+                                     int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
+                                     float* g_warped_in, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, nullptr, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
+                      flat_grad, workspace, stream, true, false, true, g_warped_in);
+}
+
+extern "C" int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
+                                        const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
+                      param_offsets, flat_grad, (void*)workspace, stream, false, true, true, nullptr);
 }
 
 // debug hook (not part of the drop-in surface): device buffer of 8 x uint64 per CTA that the fused kernels fill with

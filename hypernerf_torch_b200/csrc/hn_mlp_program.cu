@@ -77,6 +77,18 @@ void without_bias_steps(const Program& src, Program* dst) {
   }
 }
 
+// layers [l0, l1) of a program as a program of their own (weight offsets are absolute: same blob)
+void slice_program(const Program& src, int l0, int l1, Program* dst) {
+  memset(dst, 0, sizeof(*dst));
+  for (int li = l0; li < l1; ++li) {
+    Layer L = src.layers[li];
+    const int op0 = dst->nops;
+    for (int oi = L.op0; oi < L.op0 + L.nops; ++oi) dst->ops[dst->nops++] = src.ops[oi];
+    L.op0 = (uint8_t)op0;
+    dst->layers[dst->nlayers++] = L;
+  }
+}
+
 struct Packer {
   PackTable* t;
   const int64_t* off;
@@ -168,6 +180,9 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     plan->layout.fwd_off = 0;
     plan->layout.bwd_off = (int64_t)b.w16 * 16;
     without_bias_steps(plan->fwd, &plan->fwd_train);
+    // trunk-only: everything after the warp / sheet head (kWsDepth hidden layers + the head layer)
+    slice_program(plan->fwd, kWsDepth + 1, plan->fwd.nlayers, &plan->fwd_trunk);
+    slice_program(plan->fwd_train, kWsDepth + 1, plan->fwd_train.nlayers, &plan->fwd_trunk_train);
   }
   // ------------------------------------------------------------------ backward-data program
   {
@@ -214,6 +229,10 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     b.begin_layer(BE_GLO, 16, 0, kNone, kNone);
     b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW, /*acc_init=*/1);
     plan->layout.bias_off = plan->layout.bwd_off + (int64_t)b.w16 * 16;
+    // trunk-only: up to and including the trunk-input layer (BE_TRUNKIN), whose epilogue then emits d(warped point)
+    int n_trunk = 0;
+    while (n_trunk < plan->bwd.nlayers && plan->bwd.layers[n_trunk].epi != BE_TRUNKIN) ++n_trunk;
+    slice_program(plan->bwd, 0, n_trunk + 1, &plan->bwd_trunk);
   }
   plan->layout.glo_off = plan->layout.bias_off + (int64_t)fwd_bias_floats(m) * 4;
   plan->layout.glo_off = (plan->layout.glo_off + 15) / 16 * 16;
@@ -445,6 +464,11 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
     flush(j, P_RGB_W(level, kRgbDepth), 0, kRgbW, 0, 3, 0, kRgbW);
     bseg(j, P_RGB_B(level, kRgbDepth), 0, 3);
   }
+  // trunk-only job table: everything whose dY slab is not one of the warp / sheet slabs (those come first in the map)
+  WgradTable& wt = plan->wgrad_trunk;
+  memset(&wt, 0, sizeof(wt));
+  for (int i = 0; i < w.njobs; ++i)
+    if (w.jobs[i].dy_chunk >= s.d_t[0]) wt.jobs[wt.njobs++] = w.jobs[i];
   (void)d;
 }
 

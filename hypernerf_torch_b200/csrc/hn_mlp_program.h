@@ -288,6 +288,11 @@ struct ModelPlan {
   PlanInfo info;
   Program fwd, bwd;
   Program fwd_train;  // fwd without the bias K steps (kFoldBias): the stash-writing forward adds biases in its epilogue
+  // Trunk-only programs (hyper model): the template NeRF (trunk, bottleneck, rgb / alpha heads) for rows whose warped
+  // point and hyper coordinates are already known — the fine level inherits the coarse depths, and the warp / sheet nets
+  // are shared between the levels, so those rows' warp / sheet evaluations are the coarse pass's (hn_mlp_fwd_trunk).
+  Program fwd_trunk, fwd_trunk_train, bwd_trunk;
+  WgradTable wgrad_trunk;   // built per call next to `wgrad`
   LogicalOps fwd_logical, bwd_logical;
   PackTable pack;     // needs param_offsets -> built per call
   WgradTable wgrad;   // needs param_offsets -> built per call

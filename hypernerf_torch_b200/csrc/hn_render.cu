@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(4 * 32)
 sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_in, const float* __restrict__ wc,
                   int64_t w_stride, const float* __restrict__ u, const float* __restrict__ o,
                   const float* __restrict__ d, int64_t B, int Nc, int nb, int Nf, int n2c, int n2, float* __restrict__ zf,
-                  float* __restrict__ pts, int32_t* __restrict__ bin_idx) {
+                  float* __restrict__ pts, int32_t* __restrict__ bin_idx, int32_t* __restrict__ pos_c,
+                  int32_t* __restrict__ pos_n) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * 4 + wid;
@@ -504,12 +505,14 @@ sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_i
     int lo = 0, hi = Nf;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
     merged[i + lo] = v;
+    if (pos_c != nullptr) pos_c[ray * Nc + i] = i + lo;
   }
   for (int i = lane; i < Nf; i += 32) {
     const float v = smp[i];
     int lo = 0, hi = Nc;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (srt[mid] <= v) lo = mid + 1; else hi = mid; }
     merged[i + lo] = v;
+    if (pos_n != nullptr) pos_n[ray * Nf + i] = i + lo;
   }
   __syncwarp();
   srt = merged;
@@ -573,9 +576,10 @@ extern "C" int hn_sample_coarse(const float* origins, const float* dirs, const f
   return set_cuda_error(cudaGetLastError(), "hn_sample_coarse");
 }
 
-extern "C" int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
-                             const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
-                             float* z_fine, float* points, int32_t* bin_idx, void* stream) {
+static int sample_pdf_impl(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
+                           const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
+                           float* z_fine, float* points, int32_t* bin_idx, int32_t* pos_coarse, int32_t* pos_new,
+                           void* stream) {
   if (B < 0 || Nc < 1 || nb < 1 || Nf <= 0) return set_error(-1, "hn_sample_pdf: need Nc >= 1, nb >= 1, Nf >= 1");
   if (bins == nullptr && nb != Nc - 2) return set_error(-1, "hn_sample_pdf: in-kernel bins need nb == Nc - 2");
   if (Nc + Nf > kPdfMaxN || nb + 1 > kPdfMaxN) return set_error(-1, "hn_sample_pdf: Nc + Nf > 512 unsupported");
@@ -588,8 +592,25 @@ extern "C" int hn_sample_pdf(const float* z_coarse, const float* bins, const flo
   size_t smem = (size_t)4 * (2 * (nb + 1) + n2c + n2 + Nc + Nf) * sizeof(float);
   int64_t blocks = (B + 3) / 4;
   sample_pdf_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(z_coarse, bins, weights, w_stride, u, origins,
-                                                                          dirs, B, Nc, nb, Nf, n2c, n2, z_fine, points, bin_idx);
+                                                                          dirs, B, Nc, nb, Nf, n2c, n2, z_fine, points, bin_idx, pos_coarse,
+                                                                          pos_new);
   return set_cuda_error(cudaGetLastError(), "hn_sample_pdf");
+}
+
+extern "C" int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
+                             const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
+                             float* z_fine, float* points, int32_t* bin_idx, void* stream) {
+  return sample_pdf_impl(z_coarse, bins, weights, w_stride, u, origins, dirs, B, Nc, nb, Nf, z_fine, points, bin_idx, nullptr,
+                         nullptr, stream);
+}
+
+extern "C" int hn_sample_pdf_ranks(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
+                                   const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
+                                   float* z_fine, float* points, int32_t* bin_idx, int32_t* pos_coarse, int32_t* pos_new,
+                                   void* stream) {
+  if (!pos_coarse || !pos_new) return set_error(-2, "hn_sample_pdf_ranks: null pointer");
+  return sample_pdf_impl(z_coarse, bins, weights, w_stride, u, origins, dirs, B, Nc, nb, Nf, z_fine, points, bin_idx,
+                         pos_coarse, pos_new, stream);
 }
 
 #define HN_DISPATCH_C(FN, ...)                                              \

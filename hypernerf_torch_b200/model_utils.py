@@ -90,8 +90,10 @@ def sample_pdf(bins, weights, origins, directions, z_vals, num_coarse_samples, u
     return z_fine, pts
 
 
-def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None, want_inds=False):
-    """models.py:752-755 in one launch: bins = .5*(z[1:]+z[:-1]) and weights[...,1:-1] are formed in-kernel."""
+def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None, want_inds=False, want_ranks=False):
+    """models.py:752-755 in one launch: bins = .5*(z[1:]+z[:-1]) and weights[...,1:-1] are formed in-kernel.
+    want_ranks: also return (pos_coarse (B,Nc), pos_new (B,n_new)) int64 — where the merge put every coarse depth and
+    the i-th smallest new sample in the sorted row (a permutation of 0..Nc+n_new-1 per ray)."""
     B, Nc = z_vals.shape
     dev = z_vals.device
     if u is None:
@@ -104,6 +106,14 @@ def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None,
     pts = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
     inds = torch.empty(B, n_new, device=dev, dtype=torch.int32) if want_inds else None
     wptr = C.c_void_p(w.data_ptr() + 4)  # weights[..., 1:-1]
+    if want_ranks:
+        pos_c = torch.empty(B, Nc, device=dev, dtype=torch.int32)
+        pos_n = torch.empty(B, n_new, device=dev, dtype=torch.int32)
+        check(lib().hn_sample_pdf_ranks(ptr(zc), None, wptr, Nc, ptr(u), ptr(o), ptr(d), B, Nc, Nc - 2, n_new, ptr(z_fine),
+                                        ptr(pts), ptr(inds), ptr(pos_c), ptr(pos_n), stream()), "hn_sample_pdf_ranks")
+        _lib.count(1)
+        ranks = (pos_c.long(), pos_n.long())
+        return (z_fine, pts, inds, ranks) if want_inds else (z_fine, pts, ranks)
     check(lib().hn_sample_pdf(ptr(zc), None, wptr, Nc, ptr(u), ptr(o), ptr(d), B, Nc, Nc - 2, n_new, ptr(z_fine),
                               ptr(pts), ptr(inds), stream()), "hn_sample_pdf")
     _lib.count(1)

@@ -14,6 +14,7 @@ Random draws use the same torch generator calls, in the same order and shapes as
 (SURVEY.md App. A.5), and are handed to the kernels as tensors.
 """
 import ctypes as C
+import os
 from typing import Any, Dict, Optional
 
 import torch
@@ -114,8 +115,82 @@ class _FusedMlp(torch.autograd.Function):
         return (None,) * 7 + tuple(grads)
 
 
+class _FusedTrunk(torch.autograd.Function):
+    """hn_mlp_fwd_trunk / hn_mlp_bwd_trunk: the template NeRF of one level on rows whose warped point / hyper coordinates
+    are given (differentiable input).  Used for the coarse depths the fine level inherits: the warp / sheet nets are
+    shared between the levels, so their outputs at those depths are the coarse pass's."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, level, warped_in, viewdirs, noise, noise_std, *params):
+        B, S = warped_in.shape[0], warped_in.shape[1]
+        dev = warped_in.device
+        desc = model._desc
+        packed = model._packed_weights(level)
+        wi = warped_in.detach().to(torch.float32).contiguous()
+        vd = viewdirs.detach().to(torch.float32).contiguous()
+        sigma = torch.empty(B, S, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[2] or any(ctx.needs_input_grad[6:])
+        saved = None
+        if need_grad:
+            saved = torch.empty(model._sizes(B * S).saved_bytes, device=dev, dtype=torch.uint8)
+        with _lib.timed("mlp_fwd_trunk", B * S):
+            check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(wi), ptr(vd), ptr(noise), float(noise_std), B, S,
+                                         ptr(sigma), ptr(rgb), ptr(saved), stream()), "hn_mlp_fwd_trunk")
+        _lib.count(1)
+        ctx.model, ctx.level, ctx.shape = model, level, (B, S)
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        ctx.save_for_backward(sigma, rgb, wi, saved, packed)
+        ctx.set_materialize_grads(False)
+        return sigma, rgb
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g_sigma, g_rgb):
+        sigma, rgb, wi, saved, packed = ctx.saved_tensors
+        model, level = ctx.model, ctx.level
+        B, S = ctx.shape
+        if saved is None:
+            raise RuntimeError("hn_mlp_bwd_trunk needs the activation stash; forward ran without grad enabled")
+        dev = sigma.device
+        g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.to(torch.float32).contiguous()
+        g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
+        direct = model._flat_grads is not None and model._flat_grads.flat.device == dev
+        if direct:
+            fg = model._flat_grads
+            offs, flat_grad = fg.c_offsets(), fg.flat
+        else:
+            offs, total = model._grad_offsets()
+            flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        work = torch.empty(model._sizes(B * S).workspace_bytes, device=dev, dtype=torch.uint8)
+        g_wi = torch.empty_like(wi)
+        with _lib.timed("mlp_dgrad_trunk", B * S):
+            check(lib().hn_mlp_bwd_trunk_data(C.byref(model._desc), ptr(packed), ptr(sigma), ptr(rgb), ptr(wi), ptr(saved),
+                                              ptr(g_sigma), ptr(g_rgb), B, S, level, offs, ptr(flat_grad), ptr(g_wi),
+                                              ptr(work), stream()), "hn_mlp_bwd_trunk_data")
+        with _lib.timed("mlp_wgrad_trunk", B * S):
+            check(lib().hn_mlp_bwd_trunk_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad),
+                                                 ptr(work), stream()), "hn_mlp_bwd_trunk_weights")
+        _lib.count(2)
+        head = (None, None, g_wi if ctx.needs_input_grad[2] else None, None, None, None)
+        if direct:
+            return head + (None,) * len(ctx.param_meta)
+        mine = range(*model._level_param_range(level))
+        grads = [flat_grad[offs[i]:offs[i] + n].view(shape) if (i in mine and ctx.needs_input_grad[6 + i]) else None
+                 for i, (shape, n) in enumerate(ctx.param_meta)]
+        return head + tuple(grads)
+
+
 class NerfModel(nn.Module):
     """Nerf NN Model with both coarse and fine MLPs (reference: hypernerf/models.py:67-780)."""
+
+    # The fine level's sorted depths contain the coarse depths (models.py:752-755), and the warp field / hyper sheet are
+    # shared between the levels (models.py:143-182), so the reference evaluates them twice at those points.  With this on,
+    # the fine level runs the full network only on its new depths and the template NeRF alone (hn_mlp_fwd_trunk) on the
+    # inherited ones, fed with the coarse pass's warped points; outputs are bit-identical, the warp / sheet parameters
+    # receive the sum of both levels' gradients through one backward pass.
+    reuse_coarse_warp = os.environ.get("HN_REUSE_COARSE_WARP", "1") != "0"
 
     def __init__(self, embeddings_dict,
                  near: float = 0.0, far: float = 1.0,
@@ -300,8 +375,9 @@ class NerfModel(nn.Module):
 
     def render_samples(self, level, points, z_vals, directions, viewdirs, metadata, extra_params, use_warp=True,
                        metadata_encoded=False, return_warp_jacobian=False, use_sample_at_infinity=False,
-                       render_opts=None):
-        """models.py:587-671."""
+                       render_opts=None, _inherited=None):
+        """models.py:587-671.  _inherited = (warped points of the inherited depths (B,Ni,3+H), their positions (B,Ni) and
+        the positions (B,S-Ni) of the remaining depths in the sorted row): see `reuse_coarse_warp`."""
         if metadata_encoded:
             raise NotImplementedError("metadata_encoded=True is not built (callers pass ids; train.py:102, eval.py:86)")
         if return_warp_jacobian:
@@ -323,8 +399,24 @@ class NerfModel(nn.Module):
             # autograd.Function reports needs_input_grad for parameters even under no_grad; detached parameters make
             # the eval path (eval.py:77 @torch.no_grad) take the inference kernel, which writes no activation stash
             params = [q.detach() for q in params]
-        sigma, rgb, warped_points = _FusedMlp.apply(self, 1 if level == 'fine' else 0, points, viewdirs, ids, noise,
-                                                    noise_std, *params)
+        lvl = 1 if level == 'fine' else 0
+        if _inherited is None:
+            sigma, rgb, warped_points = _FusedMlp.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
+        else:
+            known_warped, pos_known, pos_new = _inherited
+            pts_new = torch.gather(points, 1, pos_new[..., None].expand(-1, -1, 3))
+            noise_new = noise_known = None
+            if noise is not None:
+                noise_new = torch.gather(noise, 1, pos_new[..., None])
+                noise_known = torch.gather(noise, 1, pos_known[..., None])
+            s_new, c_new, w_new = _FusedMlp.apply(self, lvl, pts_new, viewdirs, ids, noise_new, noise_std, *params)
+            s_known, c_known = _FusedTrunk.apply(self, lvl, known_warped, viewdirs, noise_known, noise_std, *params)
+            pos = torch.cat([pos_new, pos_known], 1)                               # a permutation of 0..S-1 per ray
+            sigma = torch.empty_like(z_vals).scatter(1, pos, torch.cat([s_new, s_known], 1))
+            rgb = points.new_empty(B, S, 3).scatter(1, pos[..., None].expand(-1, -1, 3), torch.cat([c_new, c_known], 1))
+            wcat = torch.cat([w_new, known_warped], 1)
+            warped_points = wcat.new_empty(B, S, wcat.shape[-1]).scatter(
+                1, pos[..., None].expand(-1, -1, wcat.shape[-1]), wcat)
         sigma = filter_sigma(points, sigma, render_opts)
         out['warped_points'] = warped_points
         comp = model_utils.volumetric_rendering(rgb, sigma, z_vals, directions,
@@ -361,7 +453,12 @@ class NerfModel(nn.Module):
                                          use_sample_at_infinity=self.use_sample_at_infinity)
         out = {'coarse': coarse_ret}
         if self.num_fine_samples > 0:
-            if self.use_stratified_sampling:
+            inherited = None
+            if self.use_stratified_sampling and self.reuse_coarse_warp:
+                z_vals, points, (pos_c, pos_n) = model_utils.sample_pdf_fused(
+                    z_vals, coarse_ret['weights'], origins, directions, self.num_fine_samples, want_ranks=True)
+                inherited = (coarse_ret['warped_points'], pos_c, pos_n)
+            elif self.use_stratified_sampling:
                 z_vals, points = model_utils.sample_pdf_fused(z_vals, coarse_ret['weights'], origins, directions,
                                                               self.num_fine_samples)
             else:
@@ -371,5 +468,6 @@ class NerfModel(nn.Module):
             out['fine'] = self.render_samples('fine', points, z_vals, directions, viewdirs, metadata, extra_params,
                                               use_warp=use_warp, metadata_encoded=metadata_encoded,
                                               return_warp_jacobian=return_warp_jacobian,
-                                              use_sample_at_infinity=use_sample_at_infinity, render_opts=render_opts)
+                                              use_sample_at_infinity=use_sample_at_infinity, render_opts=render_opts,
+                                              _inherited=inherited)
         return out

@@ -95,6 +95,12 @@ int hn_sample_coarse(const float* origins, const float* dirs, const float* u, co
 int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride, const float* u,
                   const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf, float* z_fine,
                   float* points, int32_t* bin_idx, void* stream);
+/* The same, additionally reporting where the merge put every input: pos_coarse (B,Nc) / pos_new (B,Nf) int32 = index in
+ * the sorted output row of coarse depth i / of the i-th smallest new sample (a permutation of 0..Nc+Nf-1 per ray).  The
+ * drop-in model uses it to evaluate inherited and new depths in separate launches (hn_mlp_fwd_trunk). */
+int hn_sample_pdf_ranks(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride, const float* u,
+                        const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf, float* z_fine,
+                        float* points, int32_t* bin_idx, int32_t* pos_coarse, int32_t* pos_new, void* stream);
 
 /* model_utils.volumetric_rendering + compute_depth_index (model_utils.py:43-107, 319-362).
  * flags: HN_COMP_*.  eps = 1e-5 and last_delta = 1e7 reproduce the HyperNeRF path; the static
@@ -138,6 +144,30 @@ int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t
                     float* flat_grad, void* workspace, void* stream);
 int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                        const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
+
+/* Trunk-only evaluation of one level (hyper model only): the template NeRF — positional encoding of the warped point and
+ * the hyper coordinates, trunk, bottleneck, rgb / alpha heads (NerfMLP modules.py:172-298, query_template models.py:447-493)
+ * — for rows whose (3 + H) warped point / hyper coordinates are given.  NerfModel.forward (models.py:745-767) re-evaluates
+ * the shared TranslationField / HyperSheetMLP at the coarse depths the fine level inherits (`sort(cat[z_coarse, z_new])`);
+ * the drop-in model takes those rows' warp-field outputs from the coarse pass instead and runs them through this entry
+ * point.  Same stash / workspace sizes as hn_mlp_fwd / hn_mlp_bwd (the warp / sheet slabs stay unused).
+ *   hn_mlp_fwd_trunk  warped_in (B,S,3+H) -> sigma (B,S), rgb (B,S,3)
+ *   hn_mlp_bwd_trunk  data + weight gradients of the trunk / heads into flat_grad, and g_warped_in (B,S,3+H) =
+ *                     d loss / d warped_in (to be added to the upstream gradient of whoever produced warped_in). */
+int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
+                     const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb, void* saved,
+                     void* stream);
+int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
+                     const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B, int S,
+                     int level, const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in, void* workspace,
+                     void* stream);
+/* hn_mlp_bwd_trunk split like hn_mlp_bwd_data / hn_mlp_bwd_weights (same workspace hand-off). */
+int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
+                          const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B,
+                          int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in,
+                          void* workspace, void* stream);
+int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
+                             const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
 
 /* losses.py:9-14 (MSELoss: mean-MSE of coarse.rgb + fine.rgb against the target colours) fused with its gradient seed and
  * with the fine-level MSE of metrics.py:4-13 (psnr = -10 log10(mse)).  sums[0] += sum (coarse - t)^2, sums[1] += sum

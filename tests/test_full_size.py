@@ -212,3 +212,41 @@ def test_full_frame_render_psnr_matches_oracle():
     print(f"frame PSNR new {psnr_new:.4f} dB, oracle {psnr_ref:.4f} dB; max |rgb| diff {max_rgb:.2e}, depth {max_depth:.2e}")
     assert abs(psnr_new - psnr_ref) < 0.05
     assert max_rgb < 2e-3 and max_depth < 2e-3
+
+
+@pytest.mark.parametrize("n_fine,noise_std", [(64, 1.0), (128, None)])
+def test_reusing_the_coarse_warp_outputs_changes_nothing(n_fine, noise_std):
+    """NerfModel.reuse_coarse_warp: the fine level runs the full network on its new depths only and the template NeRF
+    alone (hn_mlp_fwd_trunk) on the depths it inherits from the coarse level, fed with the coarse pass's warped points.
+    Every output is bit-identical to evaluating all depths through the full network (what the reference does); the
+    gradient differs only by where the bf16 rounding of the summed warp / sheet upstream gradient happens."""
+    B = 3000
+    rays, rgbs = synthetic.train_rays(B, seed=13, device=DEV)
+    d4 = _draws(B, 64, n_fine, seed=23)
+    draws = d4 if noise_std is not None else [d4[0], d4[2]]
+    res = []
+    for reuse in (False, True):
+        model = _model(noise_std=noise_std, n_fine=n_fine)
+        model.reuse_coarse_warp = reuse
+        fg = hn_train.FlatGrads(model.parameters())
+        model.attach_flat_grads(fg)
+        fg.zero()
+        out = _forward(model, rays, draws)
+        loss = torch.nn.functional.mse_loss(out['coarse']['rgb'], rgbs) + torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs) \
+            + 0.1 * out['fine']['warped_points'].square().mean()       # also exercises the gradient into warped_points
+        loss.backward()
+        res.append((out, fg.flat.clone(), [p.numel() for p in fg.params], fg.offsets))
+        with torch.no_grad():
+            res[-1] = res[-1] + (_forward(model, rays, draws),)      # inference instantiation of both paths
+    (a, ga, numels, offs, ia), (b, gb, _, _, ib) = res
+    for lvl in ('coarse', 'fine'):
+        assert set(a[lvl]) == set(b[lvl])
+        for k in a[lvl]:
+            assert torch.equal(a[lvl][k], b[lvl][k]), (lvl, k)
+            assert torch.equal(ia[lvl][k], ib[lvl][k]), ('inference', lvl, k)
+    rel = (ga - gb).norm() / ga.norm()
+    assert rel < 5e-3, rel
+    names = [n for n, _ in _model().named_parameters()]
+    for name, off, n in zip(names, offs, numels):
+        x, y = ga[off:off + n], gb[off:off + n]
+        assert (x - y).norm() <= 2e-2 * x.norm() + 1e-9, (name, ((x - y).norm() / x.norm()).item())
