@@ -38,13 +38,20 @@ def short(name):
 
 lines = [f"# ncu summary `{tag}`", ""]
 traffic = {}
+per_kernel = {}
+# samples per MLP launch of profiles/prof_chunk.py 8192: until r1g the fine level was one 8192 x 128 launch; since r1h
+# (NerfModel.reuse_coarse_warp) every launch has 8192 x 64 samples: coarse (full program), fine new depths (full program),
+# fine inherited depths (trunk-only program)
+SPLIT = tag >= "r1h"
 rep = os.path.join(OUT, f"prof_{tag}.ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
-    lines += [f"`ncu --set full --clock-control none --import-source on` of `profiles/prof_chunk.py 8192` "
-              "(one 8 192-ray chunk: coarse level = 0.5 M samples, fine level = 1 M samples per launch). "
+    what = ("(one 8 192-ray chunk, 0.5 M samples per launch: coarse level, fine level new depths, fine level inherited "
+            "depths = trunk-only program, the launch with the smaller numbers). " if SPLIT else
+            "(one 8 192-ray chunk: coarse level = 0.5 M samples, fine level = 1 M samples per launch). ")
+    lines += ["`ncu --set full --clock-control none --import-source on` of `profiles/prof_chunk.py 8192` " + what +
               "dram % is of ncu's nominal 8 TB/s peak, not of the measured 6.54 TB/s.", "",
               "| kernel | " + " | ".join(k for _, k in KEYS) + " |", "|---|" + "---|" * len(KEYS)]
     for r in rows[2:]:
@@ -61,12 +68,18 @@ if os.path.exists(rep):
         try:
             t = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * 1e9
             key = {"mlp_fwd_kernel": "mlp_fwd", "mlp_dgrad_kernel": "mlp_dgrad", "mlp_wgrad_kernel": "mlp_wgrad"}.get(short(d["Kernel Name"]))
-            if key and t > traffic.get(key, {}).get("dram_bytes_per_launch", 0):   # the 1 M-sample (fine-level) launch
-                traffic[key] = {"dram_bytes_per_launch": t, "samples_in_launch": 8192 * 128,
-                                "dram_bytes_per_sample": t / (8192 * 128), "source": f"profiles/{tag}_ncu_summary.md"}
+            if key:
+                per_kernel.setdefault(key, []).append(t)
         except (KeyError, ValueError):
             pass
     lines.append("")
+    for key, ts in per_kernel.items():
+        n = 8192 * 64 if SPLIT else 8192 * 128
+        traffic[key] = {"dram_bytes_per_launch": max(ts), "samples_in_launch": n, "dram_bytes_per_sample": max(ts) / n,
+                        "source": f"profiles/{tag}_ncu_summary.md"}
+        if SPLIT:   # the launch with the least traffic is the trunk-only one
+            traffic[key + "_trunk"] = {"dram_bytes_per_launch": min(ts), "samples_in_launch": n,
+                                       "dram_bytes_per_sample": min(ts) / n, "source": f"profiles/{tag}_ncu_summary.md"}
 
 lc = os.path.join(OUT, f"launches_{tag}.csv")
 if os.path.exists(lc):
