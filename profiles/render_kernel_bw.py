@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hypernerf_torch_b200 import model_utils as mu  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+ITERS = int(sys.argv[2]) if len(sys.argv) > 2 else 20     # 1 for an ncu capture (one warm-up, one launch per kernel)
 dev = torch.device("cuda", 0)
 peak = 6540.5
 try:
@@ -20,8 +21,9 @@ except Exception:
     pass
 
 
-def timed(fn, iters=20):
-    for _ in range(3):
+def timed(fn, iters=None):
+    iters = ITERS if iters is None else iters
+    for _ in range(3 if iters > 1 else 1):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
