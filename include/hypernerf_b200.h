@@ -97,7 +97,9 @@ int hn_sample_pdf(const float* z_coarse, const float* bins, const float* weights
                   float* points, int32_t* bin_idx, void* stream);
 /* The same, additionally reporting where the merge put every input: pos_coarse (B,Nc) / pos_new (B,Nf) int32 = index in
  * the sorted output row of coarse depth i / of the i-th smallest new sample (a permutation of 0..Nc+Nf-1 per ray).  The
- * drop-in model uses it to evaluate inherited and new depths in separate launches (hn_mlp_fwd_trunk). */
+ * drop-in model uses it to evaluate inherited and new depths in separate launches (hn_mlp_fwd_trunk).  pos_coarse[i]
+ * refers to input element i only for ascending z_coarse rows — what sample_along_rays produces; a non-ascending row is
+ * sorted first and i then counts in ascending order. */
 int hn_sample_pdf_ranks(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride, const float* u,
                         const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf, float* z_fine,
                         float* points, int32_t* bin_idx, int32_t* pos_coarse, int32_t* pos_new, void* stream);
