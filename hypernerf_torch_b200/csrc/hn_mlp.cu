@@ -68,6 +68,12 @@ using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (->
 #ifndef HN_L2_HINTS
 #define HN_L2_HINTS 0
 #endif
+// HN_FOLD_BIAS_TRAIN = 1: the stash-writing forward also carries its biases in the UMMAs (one extra K = 16 step per op)
+// instead of 8 LDS + 32 FADD per 32 accumulator columns in the drain.
+#ifndef HN_FOLD_BIAS_TRAIN
+#define HN_FOLD_BIAS_TRAIN 0
+#endif
+constexpr bool kFoldBiasTrain = kFoldBias && HN_FOLD_BIAS_TRAIN != 0;
 constexpr bool kPingPongFwdTrain = ((HN_PINGPONG & 1) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongBwd = ((HN_PINGPONG & 2) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongFwdInfer = ((HN_PINGPONG & 4) || kPair) && kSubTiles == 2;
@@ -483,7 +489,7 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
-    if constexpr (kFoldBias && !STASH) {   // inference: the accumulator already holds W x + b
+    if constexpr (kFoldBias && (!STASH || kFoldBiasTrain)) {   // the accumulator already holds W x + b
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * q + j]);
     } else {
@@ -595,7 +601,7 @@ template <class C, bool STASH>
 __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
-  constexpr bool FOLD = kFoldBias && !STASH;   // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS)
+  constexpr bool FOLD = kFoldBias && (!STASH || kFoldBiasTrain);   // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS)
   constexpr bool PP = STASH ? kPingPongFwdTrain : kPingPongFwdInfer;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
@@ -1515,7 +1521,8 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   build_plan(*desc, &plan);
   FwdParams fp;
   // the stash-writing forward keeps its biases in the epilogue
-  fp.prog = trunk ? (saved != nullptr ? plan.fwd_trunk_train : plan.fwd_trunk) : (saved != nullptr ? plan.fwd_train : plan.fwd);
+  const bool nobias_prog = saved != nullptr && !kFoldBiasTrain;
+  fp.prog = trunk ? (nobias_prog ? plan.fwd_trunk_train : plan.fwd_trunk) : (nobias_prog ? plan.fwd_train : plan.fwd);
   fp.warped_in = warped_in;
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
   fp.w_row0 = (uint32_t)(plan.layout.fwd_off / 16);
