@@ -22,8 +22,11 @@ HN_COMP_ACC_ALL = 2
 EXPORTS = [
     "hn_abi_version", "hn_last_error", "hn_query", "hn_pack_weights", "hn_sample_coarse", "hn_sample_pdf", "hn_sample_pdf_ranks",
     "hn_composite_fwd", "hn_composite_bwd", "hn_mse_loss", "hn_make_ndc_rays", "hn_adam_step", "hn_mlp_fwd", "hn_mlp_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_mlp_fwd_trunk", "hn_mlp_bwd_trunk", "hn_mlp_bwd_trunk_data", "hn_mlp_bwd_trunk_weights",
-    "hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4", "hn_epi_rate", "hn_tmem_rate", "hn_debug_set_timing_buffer",
 ]
+# microbenchmarks / descriptor probes: their own library and header (include/hypernerf_b200_probe.h), not the product ABI
+PROBE_LIB_PATH = os.path.join(_HERE, "libhypernerf_b200_probe.so")
+PROBE_EXPORTS = ["hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4",
+                 "hn_epi_rate", "hn_tmem_rate"]
 
 
 class ModelDesc(C.Structure):
@@ -88,7 +91,30 @@ def lib():
                                    vp, vp, vp, vp]
     L.hn_mlp_bwd_trunk_data.argtypes = L.hn_mlp_bwd_trunk.argtypes
     L.hn_mlp_bwd_trunk_weights.argtypes = L.hn_mlp_bwd_weights.argtypes
-    L.hn_debug_set_timing_buffer.argtypes = [vp]
+    if hasattr(L, "hn_debug_set_timing_buffer"):   # role-timing builds only (make timing; HN_LIB selects them)
+        L.hn_debug_set_timing_buffer.argtypes = [vp]
+        L.hn_debug_set_timing_buffer.restype = C.c_int
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("hn_last_error",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+_probe = None
+
+
+def probe_lib():
+    """libhypernerf_b200_probe.so (include/hypernerf_b200_probe.h): test / measurement hooks, not the product ABI."""
+    global _probe
+    if _probe is not None:
+        return _probe
+    if not os.path.exists(PROBE_LIB_PATH):
+        raise NativeLibraryError(f"{PROBE_LIB_PATH} not found: build it with __graft_entry__.build()")
+    L = C.CDLL(PROBE_LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int
+    L.hn_last_error.restype = C.c_char_p
     L.hn_tmem_rate.argtypes = [i32, i32, i32, i32, vp, vp]
     L.hn_umma_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.hn_umma_rate2.argtypes = [i32] * 9 + [vp, vp]
@@ -97,11 +123,9 @@ def lib():
     L.hn_umma_probe2.argtypes = [vp, vp, vp, i32, i32, vp]
     L.hn_umma_rate4.argtypes = [i32] * 5 + [vp, vp]
     L.hn_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
-    for name in EXPORTS:
-        fn = getattr(L, name)
-        if name not in ("hn_last_error",):
-            fn.restype = C.c_int
-    _lib = L
+    for name in PROBE_EXPORTS:
+        getattr(L, name).restype = C.c_int
+    _probe = L
     return L
 
 
@@ -135,9 +159,9 @@ class timed:
             profile.append((self.name, self.n, self.e0, self.e1))
 
 
-def check(rc: int, what: str):
+def check(rc: int, what: str, library=None):
     if rc != 0:
-        msg = lib().hn_last_error().decode("utf-8", "replace")
+        msg = (library or lib()).hn_last_error().decode("utf-8", "replace")
         raise NativeLibraryError(f"{what} failed (rc={rc}): {msg}")
 
 
@@ -149,8 +173,18 @@ def ptr(t):
         raise NativeLibraryError("hypernerf_b200 kernels take CUDA tensors only (no CPU path)")
     if not t.is_contiguous():
         raise NativeLibraryError("hypernerf_b200 kernels take contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        # the C entry points launch on the CURRENT device and stream(): a tensor of another GPU would be dereferenced by
+        # the wrong device.  Callers on multi-GPU hosts wrap their calls in torch.cuda.device(t.device).
+        raise NativeLibraryError(f"tensor lives on cuda:{t.device.index} but the current device is "
+                                 f"cuda:{torch.cuda.current_device()}; use torch.cuda.set_device / torch.cuda.device()")
     return C.c_void_p(t.data_ptr())
 
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+MIN_TORCH = (2, 4)   # torch.autograd.graph.increment_version(iterable), torch.amp.custom_fwd(device_type=...)
+if tuple(int(x) for x in torch.__version__.split("+")[0].split(".")[:2]) < MIN_TORCH:
+    raise ImportError(f"hypernerf_torch_b200 needs torch >= {MIN_TORCH[0]}.{MIN_TORCH[1]}, found {torch.__version__}")

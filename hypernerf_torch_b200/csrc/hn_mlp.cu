@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <string.h>
+#include <unordered_map>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
 #include <cudaTypedefs.h>
 #include "hn_api_internal.h"
@@ -129,6 +131,7 @@ struct FwdParams {
   const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
   const float* warped_in;   // trunk-only program (hn_mlp_fwd_trunk): (n, 3 + H) warped points + hyper coordinates, else NULL
   float noise_std;
+  int n_embed;              // rows of the GLO table: an id outside [0, n_embed) traps (nn.Embedding raises, modules.py:155-167)
   int64_t n;                // samples = B * S
   int S;
   int n_tiles;
@@ -155,6 +158,7 @@ struct BwdParams {
   int g_total;
   uint8_t* dsaved;          // pre-activation gradients for the wgrad kernel
   float* glo_grad;          // flat_grad + offset of the GLO table
+  int n_embed;
   int64_t n;
   int S;
   int n_tiles;
@@ -736,7 +740,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         float f[C::KW];
         posenc<3, C::WF>(pt, f);
         if constexpr (!C::STATIC) {
-          const float* e = p.glo + __ldg(p.ids + ray) * C::G;
+          const int64_t id = __ldg(p.ids + ray);
+          if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();   // out-of-range metadata id
+          const float* e = p.glo + id * C::G;
 #pragma unroll
           for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
         }
@@ -1054,6 +1060,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           tmem_ld16(tlane + kWsW, r);
           tmem_ld_wait();
           const int64_t id = __ldg(p.ids + ray);
+          if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
           const bool uniform = __all_sync(0xffffffffu, id == __shfl_sync(0xffffffffu, id, 0));
 #pragma unroll
           for (int i = 0; i < C::G; ++i) {
@@ -1446,10 +1453,43 @@ static cudaError_t launch_mlp(K kernel, int grid, int smem, cudaStream_t stream,
   return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is set once per (kernel, device) instead of before every launch
 template <class K>
 static int set_smem(K kernel, int bytes, const char* what) {
+  static thread_local std::unordered_map<const void*, int> done;   // kernel -> device it was set on
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return set_cuda_error(e, what);
+  auto it = done.find((const void*)kernel);
+  if (it != done.end() && it->second == dev) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[(const void*)kernel] = dev;
   return set_cuda_error(e, what);
+}
+
+// The layer programs / slab maps depend on the descriptor only, the pack and weight-gradient tables additionally on
+// (level, parameter offsets): both are cached per thread, so a launch does not rebuild several KB of tables.
+struct PlanCache {
+  bool have_plan = false, have_tables = false;
+  hn_model_desc desc;
+  int level = -1;
+  int64_t offs[HN_NUM_PARAM_TENSORS];
+  ModelPlan plan;
+};
+static ModelPlan& cached_plan(const hn_model_desc& d, int level = -1, const int64_t* offsets = nullptr) {
+  static thread_local PlanCache c;
+  if (!c.have_plan || memcmp(&c.desc, &d, sizeof(d)) != 0) {
+    build_plan(d, &c.plan);
+    c.desc = d; c.have_plan = true; c.have_tables = false;
+  }
+  if (offsets != nullptr) {
+    const size_t nb = sizeof(int64_t) * c.plan.info.n_params;
+    if (!c.have_tables || c.level != level || memcmp(c.offs, offsets, nb) != 0) {
+      build_tables(d, level, offsets, &c.plan);
+      memcpy(c.offs, offsets, nb);
+      c.level = level; c.have_tables = true;
+    }
+  }
+  return c.plan;
 }
 
 }  // namespace hn
@@ -1460,8 +1500,7 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
   if (!desc || !out) return set_error(-2, "hn_query: null pointer");
   if (int rc = validate_desc(*desc)) return rc;
   if (n_samples < 0) return set_error(-1, "hn_query: negative n_samples");
-  static thread_local ModelPlan plan;
-  build_plan(*desc, &plan);
+  const ModelPlan& plan = cached_plan(*desc);
   memset(out, 0, sizeof(*out));
   const int64_t halves = 2 * kSubTiles * tiles_of(n_samples);
   out->packed_bytes = plan.layout.total;
@@ -1489,9 +1528,7 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   if (!desc || !flat_params || !param_offsets || !packed) return set_error(-2, "hn_pack_weights: null pointer");
   if (level < 0 || level > 1) return set_error(-1, "hn_pack_weights: level must be 0 or 1");
   if (int rc = validate_desc(*desc)) return rc;
-  static thread_local ModelPlan plan;
-  build_plan(*desc, &plan);
-  build_tables(*desc, level, param_offsets, &plan);
+  const ModelPlan& plan = cached_plan(*desc, level, param_offsets);
   PackParams pp;
   pp.tab = plan.pack;
   pp.flat = flat_params;
@@ -1517,8 +1554,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   if (trunk && stat) return set_error(-13, "hn_mlp_fwd_trunk: the static model has no warp / sheet stage to skip");
   if (!stat && !trunk && !ids) return set_error(-2, "hn_mlp_fwd: null ids");
   if (B == 0) return 0;
-  static thread_local ModelPlan plan;
-  build_plan(*desc, &plan);
+  const ModelPlan& plan = cached_plan(*desc);
   FwdParams fp;
   // the stash-writing forward keeps its biases in the epilogue
   const bool nobias_prog = saved != nullptr && !kFoldBiasTrain;
@@ -1530,7 +1566,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.bias = (const float*)((const uint8_t*)packed + plan.layout.bias_off);
   fp.glo = (const float*)((const uint8_t*)packed + plan.layout.glo_off);
   fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
-  fp.n = B * S; fp.S = S;
+  fp.n = B * S; fp.S = S; fp.n_embed = desc->num_embeddings;
   int64_t nt = tiles_of(fp.n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_fwd: too many samples");
   fp.n_tiles = (int)nt;
@@ -1582,9 +1618,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
   if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
   if (int rc = validate_desc(*desc)) return rc;
   if (B == 0) return 0;
-  static thread_local ModelPlan plan;
-  build_plan(*desc, &plan);
-  build_tables(*desc, level, param_offsets, &plan);
+  const ModelPlan& plan = cached_plan(*desc, level, param_offsets);
   const int64_t n = B * S;
   const int64_t nt = tiles_of(n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_bwd: too many samples");
@@ -1601,7 +1635,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.g_total = plan.info.g_total;
     bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes);
     bp.glo_grad = stat ? nullptr : flat_grad + param_offsets[P_GLO];
-    bp.n = n; bp.S = S;
+    bp.n = n; bp.S = S; bp.n_embed = desc->num_embeddings;
     bp.n_tiles = (int)nt;
     bp.x_total = plan.info.x_total; bp.d_total = plan.info.d_total;
     bp.d_rgbhead = plan.info.d_rgbhead; bp.d_sigma = plan.info.d_sigma;
@@ -1676,9 +1710,11 @@ extern "C" int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* s
                       param_offsets, flat_grad, (void*)workspace, stream, false, true, true, nullptr);
 }
 
-// debug hook (not part of the drop-in surface): device buffer of 8 x uint64 per CTA that the fused kernels fill with
-// per-role cycle counters; NULL switches it off.
+#if HN_ROLE_TIMING
+// profiling hook of the role-timing builds (include/hypernerf_b200_probe.h; not part of the drop-in surface): device buffer
+// of 8 x uint64 per CTA that the fused kernels fill with per-role cycle counters; NULL switches it off.
 extern "C" int hn_debug_set_timing_buffer(void* dev_buffer) {
   g_dbg = (unsigned long long*)dev_buffer;
   return 0;
 }
+#endif

@@ -4,6 +4,7 @@
 // exactly these layouts.
 #include "hn_ptx.cuh"
 #include "hn_api_internal.h"
+#include "../../include/hypernerf_b200_probe.h"
 
 namespace hn {
 

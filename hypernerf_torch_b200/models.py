@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, model_utils, modules
+from ._packing import PackedWeights
 from ._lib import check, lib, ptr, stream
 
 
@@ -182,7 +183,7 @@ class _FusedTrunk(torch.autograd.Function):
         return head + tuple(grads)
 
 
-class NerfModel(nn.Module):
+class NerfModel(PackedWeights, nn.Module):
     """Nerf NN Model with both coarse and fine MLPs (reference: hypernerf/models.py:67-780)."""
 
     # The fine level's sorted depths contain the coarse depths (models.py:752-755), and the warp field / hyper sheet are
@@ -282,7 +283,8 @@ class NerfModel(nn.Module):
         if n_params != sizes.flat_param_floats or len(self._canonical_params()) != _lib.HN_NUM_PARAM_TENSORS:
             raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} parameters, "
                                           f"library expects {sizes.flat_param_floats}")
-        self._pack_cache = {}
+        self._pack_levels = 2
+        self._init_packing()
         self._flat_grads = None
         self._grad_off_cache = None
         self._size_cache = {}
@@ -331,28 +333,6 @@ class NerfModel(nn.Module):
             check(lib().hn_query(C.byref(self._desc), n_samples, C.byref(s)), "hn_query")
             self._size_cache[n_samples] = s
         return s
-
-    def _packed_weights(self, level):
-        """bf16 kernel-layout weights of one level; re-packed (hn_pack_weights) whenever a parameter changed."""
-        params = self._canonical_params()
-        dev = params[0].device
-        if dev.type != 'cuda':
-            raise _lib.NativeLibraryError("NerfModel parameters must live on a CUDA device (no CPU path)")
-        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
-        hit = self._pack_cache.get(level)
-        if hit is not None and hit[0] == key:
-            return hit[1]
-        for p in params:
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise _lib.NativeLibraryError("parameters must be contiguous fp32 tensors")
-        base = min(p.data_ptr() for p in params)
-        offs = (C.c_int64 * len(params))(*[(p.data_ptr() - base) // 4 for p in params])
-        packed = torch.empty(self._packed_bytes, device=dev, dtype=torch.uint8)
-        check(lib().hn_pack_weights(C.byref(self._desc), C.c_void_p(base), offs, level, ptr(packed), stream()),
-              "hn_pack_weights")
-        _lib.count(1)
-        self._pack_cache[level] = (key, packed)
-        return packed
 
     # ------------------------------------------------------------------------------------------------------
     # reference API
@@ -432,6 +412,12 @@ class NerfModel(nn.Module):
                 return_points=False, return_weights=False, return_warp_jacobian=False, near=None, far=None,
                 use_sample_at_infinity=None, render_opts=None, deterministic=False):
         """models.py:673-780.  Returns {'coarse': {...}, 'fine': {...}} with the reference's keys."""
+        with self.packed_frozen():   # re-packs the bf16 weight blobs unless an enclosing block froze them (_packing.py)
+            return self._forward(rays_dict, extra_params, metadata_encoded, use_warp, return_points, return_weights,
+                                 return_warp_jacobian, near, far, use_sample_at_infinity, render_opts, deterministic)
+
+    def _forward(self, rays_dict, extra_params, metadata_encoded, use_warp, return_points, return_weights,
+                 return_warp_jacobian, near, far, use_sample_at_infinity, render_opts, deterministic):
         use_warp = self.use_warp and use_warp
         origins = rays_dict['origins']
         directions = rays_dict['directions']

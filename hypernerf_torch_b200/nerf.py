@@ -13,6 +13,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import check, lib, ptr, stream
+from ._packing import PackedWeights
 
 
 class Embedding(nn.Module):
@@ -92,7 +93,7 @@ class _FusedStatic(torch.autograd.Function):
         return (None,) * 5 + tuple(grads)
 
 
-class NeRF(nn.Module):
+class NeRF(PackedWeights, nn.Module):
     """models/nerf.py:41-123: D=8 x W=256 ReLU layers with the input concatenated in front of layer `skips`, sigma head,
     feature layer, view-direction layer and rgb head.  Only the default topology is built into the kernels."""
 
@@ -116,8 +117,10 @@ class NeRF(nn.Module):
         self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
         self._desc = _lib.ModelDesc(glo_dim=0, hyper_dim=0, xyz_freqs=10, hyper_freqs=0, view_freqs=4, warp_freqs=0,
                                     sheet_freqs=0, num_embeddings=0, flags=_lib.HN_FLAG_STATIC_NERF)
-        self._pack_cache = None
+        self._pack_levels = 1
+        self._init_packing()
         self._size_cache = {}
+        self._packed_bytes = self._sizes(0).packed_bytes
         self._grad_off_cache = None
 
     # -- native plumbing ---------------------------------------------------------------------------------------------
@@ -148,33 +151,14 @@ class NeRF(nn.Module):
             self._grad_off_cache = ((C.c_int64 * len(offs))(*offs), total)
         return self._grad_off_cache
 
-    def _packed_weights(self):
-        params = self._canonical_params()
-        dev = params[0].device
-        if dev.type != 'cuda':
-            raise _lib.NativeLibraryError("NeRF parameters must live on a CUDA device (no CPU path)")
-        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
-        if self._pack_cache is not None and self._pack_cache[0] == key:
-            return self._pack_cache[1]
-        for p in params:
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise _lib.NativeLibraryError("parameters must be contiguous fp32 tensors")
-        base = min(p.data_ptr() for p in params)
-        offs = (C.c_int64 * len(params))(*[(p.data_ptr() - base) // 4 for p in params])
-        packed = torch.empty(self._sizes(0).packed_bytes, device=dev, dtype=torch.uint8)
-        check(lib().hn_pack_weights(C.byref(self._desc), C.c_void_p(base), offs, 0, ptr(packed), stream()),
-              "hn_pack_weights")
-        _lib.count(1)
-        self._pack_cache = (key, packed)
-        return packed
-
     def query(self, points, dirs, noise=None, noise_std=0.0):
         """Fused evaluation on raw sample points (B,S,3) and ray directions (B,3):
         returns (relu(sigma_raw + noise * noise_std) (B,S), rgb (B,S,3))."""
         params = self._canonical_params()
         if not torch.is_grad_enabled():
             params = [q.detach() for q in params]
-        return _FusedStatic.apply(self, points, dirs, noise, noise_std, *params)
+        with self.packed_frozen():   # re-packs unless an enclosing block froze the blobs (_packing.py)
+            return _FusedStatic.apply(self, points, dirs, noise, noise_std, *params)
 
     def forward(self, x, sigma_only=False):
         """models/nerf.py:84-123 on EMBEDDED inputs (B, 63 [+ 27]).  The first three channels of each embedding are the

@@ -119,17 +119,18 @@ def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, opti
     flat_grads.zero()
     total = torch.zeros((), device=rays.device, dtype=torch.float32)
     fine_sq = None
-    for i in range(0, B, chunk):
-        rows = rays[i:i + chunk]
-        tgt = rgbs[i:i + chunk]
-        out = model(model_utils.prepare_ray_dict(rows), dict(EXTRA_PARAMS))
-        # mean over the global batch: (sum_sq(coarse) + sum_sq(fine)) / (3 * global_rays), one fused kernel that also
-        # seeds both levels' gradients (losses.py:9-14)
-        loss, sums = losses.mse_coarse_fine(out, tgt, global_count=3.0 * global_rays)
-        loss.backward()
-        total += loss.detach()
-        if return_stats:
-            fine_sq = sums[1] if fine_sq is None else fine_sq + sums[1]
+    with model.packed_frozen():   # the weights do not change between the chunks of one step: pack the bf16 blobs once
+        for i in range(0, B, chunk):
+            rows = rays[i:i + chunk]
+            tgt = rgbs[i:i + chunk]
+            out = model(model_utils.prepare_ray_dict(rows), dict(EXTRA_PARAMS))
+            # mean over the global batch: (sum_sq(coarse) + sum_sq(fine)) / (3 * global_rays), one fused kernel that
+            # also seeds both levels' gradients (losses.py:9-14)
+            loss, sums = losses.mse_coarse_fine(out, tgt, global_count=3.0 * global_rays)
+            loss.backward()
+            total += loss.detach()
+            if return_stats:
+                fine_sq = sums[1] if fine_sq is None else fine_sq + sums[1]
     flat_grads.all_reduce()
     if optimizer is not None:
         optimizer.step()
@@ -159,18 +160,30 @@ def fit(model, rays, rgbs, num_epochs=1, batch_size=1024, lr=5e-4, weight_decay=
     (get_scheduler 'steplr', utils/__init__.py:43-47; opt.py:62-75 defaults).  Under torch.distributed every rank
     passes its own shard of the pool; gradients are all-reduced inside train_step.
     Returns a list of per-step dicts {'epoch', 'step', 'lr', 'train/loss', 'train/psnr'} (training_step's log)."""
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     fg = FlatGrads(model.parameters())
     model.attach_flat_grads(fg)
     opt = FusedAdam(fg, lr=lr, eps=1e-8, weight_decay=weight_decay)
+    P = rays.shape[0]
+    if distributed:
+        # what DDP guarantees (train.py:224-229): every rank starts from rank 0's parameters, and every rank runs the
+        # same number of steps — with unequal shards the ranks are cut to the shortest one, as DistributedSampler's
+        # drop_last does, otherwise the all-reduce of the extra steps would never be matched
+        dist.broadcast(opt.flat, src=0)
+        model.invalidate_packed()
+        n = torch.tensor([P], device=rays.device, dtype=torch.int64)
+        dist.all_reduce(n, op=dist.ReduceOp.MIN)
+        P = int(n.item())
     gen = torch.Generator(device=rays.device).manual_seed(seed)
-    P, step, log = rays.shape[0], 0, []
+    step, log = 0, []
     for epoch in range(num_epochs):
         opt.param_groups[0]['lr'] = lr * decay_gamma ** sum(1 for m in decay_step if epoch >= m)
-        order = torch.randperm(P, device=rays.device, generator=gen)
+        order = torch.randperm(rays.shape[0], device=rays.device, generator=gen)[:P]
         for i in range(0, P, batch_size):
             idx = order[i:i + batch_size]
             r, t = rays[idx], rgbs[idx]
+            # every rank holds P rows and the same batch boundaries, so the global batch is world * local
+            world = dist.get_world_size() if distributed else 1
             stats = train_step(model, r, t, fg, global_rays=world * r.shape[0], chunk=chunk, optimizer=opt,
                                return_stats=True)
             step += 1
@@ -187,8 +200,9 @@ def render_rays(model, rays, chunk=32768, keys=('rgb', 'depth')):
     """Chunked inference (eval.py:77-103 `batched_inference`), keeping only the per-ray outputs in `keys` of the
     fine level instead of concatenating every per-sample tensor."""
     outs = {k: [] for k in keys}
-    for i in range(0, rays.shape[0], chunk):
-        out = model(model_utils.prepare_ray_dict(rays[i:i + chunk]), dict(EXTRA_PARAMS))
-        for k in keys:
-            outs[k].append(out['fine'][k])
+    with model.packed_frozen():
+        for i in range(0, rays.shape[0], chunk):
+            out = model(model_utils.prepare_ray_dict(rays[i:i + chunk]), dict(EXTRA_PARAMS))
+            for k in keys:
+                outs[k].append(out['fine'][k])
     return {k: torch.cat(v, 0) for k, v in outs.items()}

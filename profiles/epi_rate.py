@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hypernerf_torch_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
+L = _lib.probe_lib()
 grid = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 out = torch.zeros(grid * 2, dtype=torch.int64, device="cuda")
 gout = torch.empty(grid * 256 * 512, dtype=torch.uint8, device="cuda")

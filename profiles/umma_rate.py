@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hypernerf_torch_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
+L = _lib.probe_lib()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 
 

@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE.  Per-tensor gradient parity of the fused train step against autograd of the fp32 oracle at a
+training-size batch (north star: "gradients within 1e-2 relative" of the reference PyTorch path).
+
+For one batch (default 8 192 rays, 64+64 samples, noise_std 1) the flat gradient of `train.train_step` is compared,
+tensor by tensor, with autograd of `oracle.hypernerf_oracle.forward` run in torch eager on the same device with the same
+weights, rays and random draws (the draws of the product's forward are recorded and replayed), in three precisions:
+
+    f32    the reference arithmetic (the parity oracle)
+    amp16  the same under torch.autocast(float16) with the loss scaled by 2^16 before backward and the gradients unscaled
+           after (what Lightning's native AMP + GradScaler do) — how the reference actually trains (train.py:217-218)
+    bf16   the oracle's emulation of the kernels' rounding points (bf16 operands, fp32 accumulate)
+
+Per tensor: rel = ||g - g_f32|| / ||g_f32||.  `python tests/grad_parity.py` writes profiles/grad_parity.md.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import hypernerf_oracle as orc  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+
+def oracle_grads(sd, rays, rgbs, draws, cfg, mode, z_fine=None, chunk=1024):
+    """Gradients of the global-mean MSE (losses.py:9-14) through the oracle, accumulated over ray chunks."""
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    B = rays.shape[0]
+    cfg = dict(cfg, emulate_bf16=(mode == 'bf16'))
+    total = 0.0
+    scale = 65536.0 if mode == 'amp16' else 1.0   # GradScaler's initial scale
+    for i in range(0, B, chunk):
+        sl = slice(i, i + chunk)
+        dr = {k: (None if v is None else v[sl]) for k, v in draws.items()}
+        with torch.autocast('cuda', dtype=torch.float16, enabled=(mode == 'amp16')):
+            out = orc.forward(sd, rays[sl, :3], rays[sl, 3:6], rays[sl, 8].long(), dr, cfg,
+                              fine_z=None if z_fine is None else z_fine[sl])
+            loss = ((out['coarse']['rgb'].float() - rgbs[sl]) ** 2).sum() / (3.0 * B) + \
+                   ((out['fine']['rgb'].float() - rgbs[sl]) ** 2).sum() / (3.0 * B)
+        (loss * scale).backward()
+        total += float(loss.detach())
+    return {k: v.grad.detach() / scale for k, v in sd.items()}, total
+
+
+def product_grads(model, fg, rays, rgbs, chunk):
+    """Flat gradient of train.train_step + the recorded draws + the fine depths the product resampled."""
+    from hypernerf_torch_b200 import model_utils as mu
+    from hypernerf_torch_b200 import train as hn_train
+    taps = {}
+    orig = mu.sample_pdf_fused
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        taps.setdefault('z_fine', []).append(r[0].detach().clone())
+        return r
+
+    mu.sample_pdf_fused = spy
+    try:
+        with ref_loader._DrawTape() as tape:
+            loss = hn_train.train_step(model, rays, rgbs, fg, global_rays=rays.shape[0], chunk=chunk)
+    finally:
+        mu.sample_pdf_fused = orig
+    torch.cuda.synchronize()
+    t = tape.tape
+    per = 4 if len(t) % 4 == 0 and t[1].dim() == 3 else 2
+    chunks = [t[i:i + per] for i in range(0, len(t), per)]
+    noise = per == 4
+    draws = dict(u_coarse=torch.cat([c[0] for c in chunks]),
+                 noise_coarse=torch.cat([c[1] for c in chunks]) if noise else None,
+                 u_fine=torch.cat([c[2 if noise else 1] for c in chunks]),
+                 noise_fine=torch.cat([c[3] for c in chunks]) if noise else None)
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    return grads, float(loss), draws, torch.cat(taps['z_fine'])
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+def compare(model, rays, rgbs, chunk=8192, noise_std=1.0, n_fine=64):
+    from hypernerf_torch_b200 import train as hn_train
+    fg = hn_train.FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+    try:
+        g_k, loss_k, draws, z_fine = product_grads(model, fg, rays, rgbs, chunk)
+    finally:
+        model.attach_flat_grads(None)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cfg = orc.default_cfg(n_fine=n_fine, noise_std=noise_std)
+    rows, losses = {}, {'kernel': loss_k}
+    g32, losses['f32'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'f32')
+    g32_iso, _ = oracle_grads(sd, rays, rgbs, draws, cfg, 'f32', z_fine=z_fine)
+    g16, losses['amp16'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'amp16')
+    gbf, losses['bf16'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'bf16')
+    for k in g_k:
+        rows[k] = dict(norm=float(g32[k].double().norm()), numel=g32[k].numel(), kernel=rel(g_k[k], g32[k]),
+                       kernel_iso=rel(g_k[k], g32_iso[k]), amp16=rel(g16[k], g32[k]), bf16=rel(gbf[k], g32[k]),
+                       kernel_vs_bf16=rel(g_k[k], gbf[k]))
+    flat = lambda g: torch.cat([g[k].flatten().double() for k in g_k])   # noqa: E731
+    whole = dict(kernel=float((flat(g_k) - flat(g32)).norm() / flat(g32).norm()),
+                 kernel_iso=float((flat(g_k) - flat(g32_iso)).norm() / flat(g32_iso).norm()),
+                 amp16=float((flat(g16) - flat(g32)).norm() / flat(g32).norm()),
+                 bf16=float((flat(gbf) - flat(g32)).norm() / flat(g32).norm()),
+                 kernel_vs_bf16=float((flat(g_k) - flat(gbf)).norm() / flat(gbf).norm()))
+    return rows, whole, losses
+
+
+def setup(n_rays=8192, adam_steps=0, seed=0, device="cuda"):
+    from hypernerf_torch_b200 import synthetic
+    from hypernerf_torch_b200 import train as hn_train
+    from hypernerf_torch_b200.models import NerfModel
+    model = NerfModel(ref_loader.EMBEDDINGS, **ref_loader.cfg1_kwargs(n_fine=64, noise_std=1.0))
+    model.load_state_dict(synthetic.make_state_dict(model, seed=seed, boosted=False))
+    model = model.to(device)
+    rays, rgbs = synthetic.train_rays(n_rays, seed=seed + 3, device=device)
+    if adam_steps:
+        fg = hn_train.FlatGrads(model.parameters())
+        model.attach_flat_grads(fg)
+        opt = hn_train.FusedAdam(fg, lr=5e-4)
+        torch.manual_seed(77)
+        for i in range(adam_steps):
+            r, t = synthetic.train_rays(n_rays, seed=1000 + i, device=device)
+            hn_train.train_step(model, r, t, fg, global_rays=n_rays, chunk=8192, optimizer=opt)
+        model.attach_flat_grads(None)
+    return model, rays, rgbs
+
+
+def table(title, rows, whole, losses):
+    out = [f"## {title}", "",
+           f"loss: kernel {losses['kernel']:.6f}, oracle f32 {losses['f32']:.6f}, amp16 {losses['amp16']:.6f}, "
+           f"bf16-emulation {losses['bf16']:.6f}", "",
+           f"whole flat gradient, relative L2 vs the fp32 oracle: **kernel {whole['kernel']:.2e}** "
+           f"(fine level at the kernel's own resampled depths: {whole['kernel_iso']:.2e}), reference-style fp16 autocast "
+           f"{whole['amp16']:.2e}, bf16-emulating oracle {whole['bf16']:.2e}; kernel vs the bf16-emulating oracle "
+           f"{whole['kernel_vs_bf16']:.2e}", "",
+           "| tensor | numel | ‖g‖ fp32 oracle | kernel | kernel (fine depths shared) | fp16 autocast oracle | bf16-emulating oracle | kernel vs bf16-emulating oracle |",
+           "|---|---|---|---|---|---|---|---|"]
+    for k, r in rows.items():
+        out.append(f"| `{k}` | {r['numel']} | {r['norm']:.3e} | {r['kernel']:.2e} | {r['kernel_iso']:.2e} | {r['amp16']:.2e} | {r['bf16']:.2e} | {r['kernel_vs_bf16']:.2e} |")
+    return out
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+    md = ["# Gradient parity at a training-size batch", "",
+          f"`python tests/grad_parity.py {n}` on a B200: {n} rays, 64+64 samples, noise_std 1, loss = MSE(coarse) + MSE(fine)",
+          "(losses.py:9-14).  Every column is `‖g − g_f32‖ / ‖g_f32‖` per parameter tensor, `g_f32` = autograd of the fp32 oracle",
+          "(torch eager on the GPU, same weights / rays / random draws).  `fp16 autocast oracle` is the same oracle under",
+          "`torch.autocast(float16)`, i.e. the precision the reference trains in (train.py:217-218); `bf16-emulating oracle`",
+          "rounds where the kernels hold bf16 operands.  `kernel (fine depths shared)` evaluates the oracle's fine level at the",
+          "depths the product resampled (stage isolation: removes the effect of coarse-weight differences on `sample_pdf`).", ""]
+    for title, steps in (("reference-init weights", 0), ("after 50 FusedAdam steps (lr 5e-4)", 50)):
+        model, rays, rgbs = setup(n_rays=n, adam_steps=steps)
+        rows, whole, losses = compare(model, rays, rgbs)
+        md += table(title, rows, whole, losses) + [""]
+        print(title, whole, losses)
+        worst = sorted(rows.items(), key=lambda kv: -kv[1]['kernel'])[:8]
+        for k, r in worst:
+            print(f"  {k:55s} kernel {r['kernel']:.2e} iso {r['kernel_iso']:.2e} amp16 {r['amp16']:.2e} bf16 {r['bf16']:.2e} k_vs_bf16 {r['kernel_vs_bf16']:.2e} |g| {r['norm']:.2e}")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    open(os.path.join(ROOT, "gpurun_out", "grad_parity.md"), "w").write("\n".join(md) + "\n")

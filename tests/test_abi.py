@@ -26,6 +26,16 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert _lib.lib().hn_abi_version() == 1
+    # the product ABI carries no test / microbenchmark hooks: those live in libhypernerf_b200_probe.so with their own header
+    assert not any(n.startswith(("hn_umma", "hn_epi", "hn_tmem", "hn_debug")) for n in declared)
+    for n in ("hn_umma_probe", "hn_epi_rate", "hn_debug_set_timing_buffer"):
+        assert not hasattr(L, n), n
+    probe_h = open(os.path.join(ROOT, "include", "hypernerf_b200_probe.h")).read()
+    probe_decl = set(re.findall(r"^\s*int\s+(hn_\w+)\s*\(", probe_h, flags=re.M)) - {"hn_debug_set_timing_buffer"}
+    assert probe_decl == set(_lib.PROBE_EXPORTS), probe_decl ^ set(_lib.PROBE_EXPORTS)
+    P = C.CDLL(_lib.PROBE_LIB_PATH)
+    for name in probe_decl:
+        assert hasattr(P, name), name
 
 
 def test_query_matches_reference_parameter_count():

@@ -20,8 +20,8 @@ def test_umma_probe(N, K, a_mn, b_mn):
     Ain = A.t().contiguous() if a_mn else A.contiguous()
     Bin = B.t().contiguous() if b_mn else B.contiguous()
     D = torch.full((128, N), float("nan"), device="cuda")
-    _lib.check(_lib.lib().hn_umma_probe(_lib.ptr(Ain), _lib.ptr(Bin), _lib.ptr(D), N, K, a_mn, b_mn, _lib.stream()),
-               "hn_umma_probe")
+    _lib.check(_lib.probe_lib().hn_umma_probe(_lib.ptr(Ain), _lib.ptr(Bin), _lib.ptr(D), N, K, a_mn, b_mn, _lib.stream()),
+               "hn_umma_probe", _lib.probe_lib())
     torch.cuda.synchronize()
     err = (D - ref).abs().max().item()
     print(f"probe N={N} K={K} a_mn={a_mn} b_mn={b_mn} max_err={err:.3e}")
@@ -36,8 +36,8 @@ def test_umma_pair_probe(N, K):
     B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
     ref = A.float() @ B.float().t()
     D = torch.full((256, N), float("nan"), device="cuda")
-    _lib.check(_lib.lib().hn_umma_probe2(_lib.ptr(A.contiguous()), _lib.ptr(B.contiguous()), _lib.ptr(D), N, K, _lib.stream()),
-               "hn_umma_probe2")
+    _lib.check(_lib.probe_lib().hn_umma_probe2(_lib.ptr(A.contiguous()), _lib.ptr(B.contiguous()), _lib.ptr(D), N, K, _lib.stream()),
+               "hn_umma_probe2", _lib.probe_lib())
     torch.cuda.synchronize()
     err = (D - ref).abs().max().item()
     print(f"pair probe N={N} K={K} max_err={err:.3e}")
