@@ -43,7 +43,10 @@ class PackedWeights:
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.NativeLibraryError("parameters must be contiguous fp32 tensors")
         base = min(p.data_ptr() for p in params)
-        offs = (C.c_int64 * len(params))(*[(p.data_ptr() - base) // 4 for p in params])
+        if hasattr(self, "_param_offsets"):      # slot table with gaps (NerfModel): -1 for absent slots
+            offs = self._param_offsets(base)
+        else:
+            offs = (C.c_int64 * len(params))(*[(p.data_ptr() - base) // 4 for p in params])
         key = self._pack_key(params)
         for level in range(self._pack_levels):
             hit = self._pack_cache.get(level)

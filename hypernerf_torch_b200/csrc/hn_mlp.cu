@@ -34,19 +34,23 @@ namespace hn {
 template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_, bool STATIC_ = false>
 struct Shape {
   static constexpr bool STATIC = STATIC_;   // static baseline models/nerf.py: no GLO / warp / sheet / hyper coordinates
-  static constexpr int G = G_, H = H_, WF = WF_, SF = SF_, XF = XF_, HF = HF_, VF = VF_;
-  static constexpr int PE_W = 3 + 6 * WF, IN_W = PE_W + G, KW = pad16(IN_W);
+  static constexpr bool NOWARP = !STATIC_ && H_ == 0;   // NerfModel(use_warp=False): the template alone on the raw points
+  static constexpr int G = G_, H = H_, WF = WF_, SF = SF_, XF = XF_, HF = HF_;
+  static constexpr int VF = VF_;            // hyper model: the MAXIMUM view frequency count (run time: FwdParams::view_freqs)
+  static constexpr int PE_W = 3 + 6 * WF, IN_W = PE_W + G, KW = NOWARP ? 0 : pad16(IN_W);
   static constexpr int PE_X = 3 + 6 * XF, PE_H = H * (1 + 2 * HF), IN_T = PE_X + PE_H, KT = pad16(IN_T);
-  static constexpr int PE_V = 3 + 6 * VF, KV = pad16(PE_V);
-  static constexpr int IN_CHUNKS = (KW > KT ? (KW > KV ? KW : KV) : (KT > KV ? KT : KV)) / 8;
+  static constexpr int PE_V = 3 + 6 * VF, KV = STATIC ? pad16(PE_V) : kKV;
+  static constexpr bool TIN_ACT = !STATIC && trunk_in_act(KT);   // trunk input vector in ACT (hn_mlp_program.h: kMaxTrunkInInb)
   // bias folding (hn_mlp_program.h: HN_FOLD_BIAS): the last two columns of INB's last chunk pair hold 1.0; they sit in
   // the zero padding of the widest input vector when every vector that reaches the last chunk has >= 2 pad columns
-  static constexpr bool ONES_IN_PAD = ones_fit_in_pad(IN_CHUNKS * 8, KW, IN_W) && ones_fit_in_pad(IN_CHUNKS * 8, KT, IN_T) &&
-                                      ones_fit_in_pad(IN_CHUNKS * 8, KV, PE_V);
-  static constexpr int INB_CHUNKS = (kFoldBias && !ONES_IN_PAD) ? IN_CHUNKS + 2 : IN_CHUNKS;
+  static constexpr int INB_CHUNKS = STATIC ? inb_chunks_of(KW, IN_W, 0, 0, KV, PE_V) : inb_chunks_of(KW, IN_W, KT, IN_T, KV, PE_V);
   static constexpr int N_RGB0A = pad16(kRgbW + 1);
+  static constexpr int NWARPED = 3 + H;     // columns of a warped point + hyper coordinates
 };
 using Cfg1 = Shape<8, 2, 10, 7, 10, 6, 6>;
+using CfgH4 = Shape<8, 4, 10, 7, 10, 6, 6>;   // opt.py default hyper_slice_out_dim (opt.py:92)
+using CfgH8 = Shape<8, 8, 10, 7, 10, 6, 6>;   // bendy sheet with 8 outputs, or axis-aligned slicing (hyper point = GLO vector)
+using CfgT = Shape<8, 0, 10, 7, 10, 6, 6>;    // no warp: template NeRF on the raw points
 using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (-> K 64), dir PE 27 (-> K 32)
 
 // ------------------------------------------------------------------------------------------------------
@@ -121,6 +125,9 @@ using SmemBwd = SmemPlan<C::STATIC ? 2 : 0, (C::STATIC || kBwdRingStages != 5) ?
 // run of 2^i blocks (128 B .. 32 KB) in one request
 struct PairMaps { CUtensorMap m[kPair ? 9 : 1]; };
 
+// run-time model flags of the fused kernels (from hn_model_desc::flags)
+enum ModelFlags : int { MF_AXIS = 1, MF_COND = 2 };   // hyper point = GLO vector; GLO condition columns in the view vector
+
 struct FwdParams {
   Program prog;
   PairMaps maps;
@@ -131,6 +138,8 @@ struct FwdParams {
   const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
   const float* warped_in;   // trunk-only program (hn_mlp_fwd_trunk): (n, 3 + H) warped points + hyper coordinates, else NULL
   float noise_std;
+  int view_freqs;           // hyper model: posenc_orig frequencies of the view direction (<= kMaxViewFreqs), run time
+  int mflags;               // MF_*
   int n_embed;              // rows of the GLO table: an id outside [0, n_embed) traps (nn.Embedding raises, modules.py:155-167)
   int64_t n;                // samples = B * S
   int S;
@@ -158,6 +167,7 @@ struct BwdParams {
   int g_total;
   uint8_t* dsaved;          // pre-activation gradients for the wgrad kernel
   float* glo_grad;          // flat_grad + offset of the GLO table
+  int mflags;               // MF_*
   int n_embed;
   int64_t n;
   int S;
@@ -420,6 +430,26 @@ __device__ __forceinline__ void posenc_bwd(const float* x, const float* g, float
   }
 }
 
+// posenc_orig with a run-time frequency count nf <= NFMAX: the columns of the frequencies >= nf are zero
+template <int NC, int NFMAX>
+__device__ __forceinline__ void posenc_rt(const float* x, float* out, int nf) {
+  float s[NC], c[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { out[i] = x[i]; sincosf(x[i], &s[i], &c[i]); }
+#pragma unroll
+  for (int k = 0; k < NFMAX; ++k) {
+    const bool on = k < nf;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      out[NC + 2 * NC * k + i] = on ? s[i] : 0.f;
+      out[NC + 2 * NC * k + NC + i] = on ? c[i] : 0.f;
+      float s2 = 2.f * s[i] * c[i];
+      float c2 = 1.f - 2.f * s[i] * s[i];
+      s[i] = s2; c[i] = c2;
+    }
+  }
+}
+
 // zero padding of a K-wide input vector with IN real features; with folded biases a vector that reaches INB's last
 // chunk carries the two ones columns in its tail
 template <class C, int K, int IN>
@@ -457,6 +487,49 @@ __device__ __forceinline__ void store_features(const float* f, uint8_t* buf_row,
     v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
     *reinterpret_cast<uint4*>(buf_row + q * kChunkBytes) = v;
     if (save_row != nullptr) stash_store(&save_row[(save_chunk + q) * (kHalfChunkBytes / 16)], v);
+  }
+}
+
+// the ones chunk pair of INB on its own (trunk-only rows of a model whose trunk input lives in ACT)
+template <class C>
+__device__ __forceinline__ void store_ones_only(uint8_t* inb_row) {
+  if constexpr (kFoldBias) {
+    *reinterpret_cast<uint4*>(inb_row + (C::INB_CHUNKS - 2) * kChunkBytes) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(inb_row + (C::INB_CHUNKS - 1) * kChunkBytes) = make_uint4(0, 0, 0, 0x3F803F80u);   // bf16 1.0, 1.0
+  }
+}
+
+// Trunk input vector of the template (models.py:458-478): [posenc_orig(xyz, XF) | posenc_orig(hyper, HF) | 0], written as
+// bf16 into INB, or into ACT[0, KT) for the wide vectors (hn_mlp_program.h: kMaxTrunkInInb), and into the stash.
+template <class C>
+__device__ __forceinline__ void store_trunk_input(const float* wp, uint8_t* act_row, uint8_t* inb_row, uint4* save_row, int save_chunk) {
+  float f[C::KT];
+  posenc<3, C::XF>(wp, f);
+  if constexpr (C::H > 0) posenc<C::H, C::HF>(wp + 3, f + C::PE_X);
+  if constexpr (C::TIN_ACT) {
+#pragma unroll
+    for (int i = C::IN_T; i < C::KT; ++i) f[i] = 0.f;
+    store_features<C::KT>(f, act_row, save_row, save_chunk);
+  } else {
+    finish_features<C, C::KT, C::IN_T>(f);
+    store_features<C::KT>(f, inb_row, save_row, save_chunk);
+  }
+}
+
+// d(GLO embedding) of one sample (G values in r[0..G)) -> per-ray reduction -> atomics on the table gradient
+template <int G>
+__device__ __forceinline__ void glo_grad_add(const float* v_in, bool valid, int64_t id, float* __restrict__ glo_grad, int lane) {
+  const bool uniform = __all_sync(0xffffffffu, id == __shfl_sync(0xffffffffu, id, 0));
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    float v = valid ? v_in[i] : 0.f;
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(glo_grad + id * G + i, v);
+    } else {
+      atomicAdd(glo_grad + id * G + i, v);
+    }
   }
 }
 
@@ -714,6 +787,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
       }
       float pt[3], dir[3];
+      float wp[C::NWARPED + (C::STATIC ? 1 : 0)];  // warped point + hyper coordinates
       const bool trunk_only = !C::STATIC && p.warped_in != nullptr;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -722,21 +796,16 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       }
       if (trunk_only) {
         // trunk-only program: the warped point / hyper coordinates of this row were computed by another launch (the
-        // coarse level's, for the depths the fine level inherits); the prologue does what FE_WSHEAD's epilogue does
+        // coarse level's, for the depths the fine level inherits) or are the raw sample point (model without warp); the
+        // prologue does what FE_WSHEAD's epilogue does
         if constexpr (!C::STATIC) {
-          float w[3 + C::H];
 #pragma unroll
-          for (int i = 0; i < 3 + C::H; ++i) w[i] = __ldg(p.warped_in + gc * (3 + C::H) + i);
-          float f[C::KT];
-          posenc<3, C::XF>(w, f);
-          posenc<C::H, C::HF>(w + 3, f + C::PE_X);
-          finish_features<C, C::KT, C::IN_T>(f);
-          store_features<C::KT>(f, inb_row, save_row, p.x_in_t);
-          store_ones_pair<C, C::KT>(inb_row);
+          for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped_in + gc * C::NWARPED + i);
+          store_trunk_input<C>(wp, act_row, inb_row, save_row, p.x_in_t);
+          if constexpr (C::TIN_ACT) store_ones_only<C>(inb_row); else store_ones_pair<C, C::KT>(inb_row);
         }
-      } else
+      } else if constexpr (!C::NOWARP) {
       // prologue: [posenc(points, WF) | GLO | 0] -> INB   (static baseline: [Embedding(xyz) | 0], nerf.py:21-38)
-      {
         float f[C::KW];
         posenc<3, C::WF>(pt, f);
         if constexpr (!C::STATIC) {
@@ -755,7 +824,6 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
       t_pro += HN_T0() - t_tile;
 
-      float wp[3 + C::H + (C::STATIC ? 1 : 0)];  // warped point + hyper coordinates
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         // stage this layer's bias in shared memory while the MMAs run (L1 is ~0 KB at this smem carve-out,
@@ -773,7 +841,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         if (L.epi == FE_RELU) {
           fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
         } else if (L.epi == FE_WSHEAD) {
-          if constexpr (!C::STATIC) {
+          if constexpr (!C::STATIC && !C::NOWARP) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
@@ -781,16 +849,23 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
 #pragma unroll
           for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + head_bias<FOLD>(bias, 3 + i);
+          if constexpr (C::H == C::G) {
+            if (p.mflags & MF_AXIS) {   // axis-aligned slicing: the hyper point is the GLO vector (models.py:533-534)
+              const float* e = p.glo + __ldg(p.ids + ray) * C::G;
+#pragma unroll
+              for (int i = 0; i < C::G; ++i) wp[3 + i] = __ldg(e + i);
+            }
+          }
           if (valid && p.warped != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 3 + C::H; ++i) p.warped[g * (3 + C::H) + i] = wp[i];
+            for (int i = 0; i < C::NWARPED; ++i) p.warped[g * C::NWARPED + i] = wp[i];
           }
-          float f[C::KT];
-          posenc<3, C::XF>(wp, f);
-          posenc<C::H, C::HF>(wp + 3, f + C::PE_X);
-          finish_features<C, C::KT, C::IN_T>(f);
-          store_features<C::KT>(f, inb_row, save_row, L.save_chunk);
+          store_trunk_input<C>(wp, act_row, inb_row, save_row, L.save_chunk);
           }
+        } else if (L.epi == FE_SKIPFEED) {
+          // hidden part of the skip layer is in the accumulator and stays there; ACT[0, KT) <- the trunk input vector,
+          // recomputed from the warped point this thread still holds, for the input part that accumulates on top
+          if constexpr (C::TIN_ACT) store_trunk_input<C>(wp, act_row, inb_row, nullptr, 0);
         } else if (L.epi == FE_SIGMA) {
           // static baseline: raw sigma = Linear(W, 1)(h8) (nerf.py:109); rendering.py:150 uses relu(sigma + noise)
           uint32_t r[16];
@@ -803,8 +878,22 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, nullptr);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
           float f[C::KV];
-          posenc<3, C::VF>(dir, f);
-          finish_features<C, C::KV, C::PE_V>(f);
+          if constexpr (C::STATIC) {
+            posenc<3, C::VF>(dir, f);
+            finish_features<C, C::KV, C::PE_V>(f);
+          } else {
+            // [posenc_orig(viewdirs, view_freqs) | 0 .. | GLO condition] (hn_mlp_program.h: kViewCondCol)
+            posenc_rt<3, kMaxViewFreqs>(dir, f, p.view_freqs);
+#pragma unroll
+            for (int i = 3 + 6 * kMaxViewFreqs; i < C::KV; ++i) f[i] = 0.f;
+            if (p.mflags & MF_COND) {   // get_condition_inputs, models.py:421-434
+              const int64_t id = __ldg(p.ids + ray);
+              if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
+              const float* e = p.glo + id * C::G;
+#pragma unroll
+              for (int i = 0; i < C::G; ++i) f[kViewCondCol + i] = __ldg(e + i);
+            }
+          }
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
         } else if (L.epi == FE_RGB0A) {
           if constexpr (!C::STATIC) {
@@ -850,6 +939,52 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   __syncthreads();
   if (kPair) cluster_sync_all();   // the leader's UMMAs read this CTA's shared memory and TMEM until the very end
   if (warp == kIssuerWarp) { if (kPair) tmem_dealloc2(tmem_base, 256 * kSubTiles); else tmem_dealloc(tmem_base, 256 * kSubTiles); }
+}
+
+// d(trunk input features) in this row's accumulator columns [0, KT) -> d(warped point, hyper coordinates) through the
+// chain rule of posenc_orig.  The wide vectors (hyper_dim 4 / 8) are consumed in two phases so that no more than ~120
+// accumulator values are live at a time: columns [0, 64) = the xyz block and the first hyper column, then the rest.
+template <class C>
+__device__ __forceinline__ void trunk_in_bwd(uint32_t tlane, const float* wp, float* gx) {
+  if constexpr (C::KT <= 96) {
+    float gf[C::KT];
+#pragma unroll
+    for (int c0 = 0; c0 < C::KT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tlane + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) gf[c0 + j] = __uint_as_float(r[j]);
+    }
+    posenc_bwd<3, C::XF>(wp, gf, gx);
+    if constexpr (C::H > 0) posenc_bwd<C::H, C::HF>(wp + 3, gf + C::PE_X, gx + 3);
+  } else {
+    static_assert(C::PE_X == 63, "the two-phase pull-back assumes the hyper block starts at column 63");
+    float gh[C::PE_H + 8];
+    {
+      float ga[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tlane + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ga[c0 + j] = __uint_as_float(r[j]);
+      }
+      posenc_bwd<3, C::XF>(wp, ga, gx);
+      gh[0] = ga[63];
+    }
+#pragma unroll
+    for (int c0 = 64; c0 < C::KT; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tlane + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 - 63 + j < C::PE_H) gh[c0 - 63 + j] = __uint_as_float(r[j]);
+    }
+    posenc_bwd<C::H, C::HF>(wp + 3, gh, gx + 3);
+  }
 }
 
 // ======================================================================================================
@@ -988,7 +1123,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
       t_pro += HN_T0() - t_tile;
 
-      float gx_skip[C::STATIC ? 1 : 3 + C::H] = {};   // skip-layer part of d(warped point, hyper coordinates)
+      float gx_skip[C::STATIC ? 1 : C::NWARPED] = {};   // skip-layer part of d(warped point, hyper coordinates)
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         if (L.epi == BE_MASK) {
@@ -1011,68 +1146,75 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
-        if (L.epi == BE_LINEAR) {
+        if (L.epi == BE_LINEAR || L.epi == BE_LINCOND) {
           if (L.n_out == kTrunkW) bwd_cols<false, kTrunkW>(tlane, nullptr, act_row, save_row, L.save_chunk);
           else bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
+          if constexpr (!C::STATIC) {
+            if (L.epi == BE_LINCOND) {
+              // gradient of the GLO condition columns of the view vector (alpha / rgb conditioning, modules.py:283,292),
+              // parked in accumulator columns [128, 144) -> gradient of the condition table
+              uint32_t r[16];
+              tmem_ld16(tlane + kRgbW, r);
+              tmem_ld_wait();
+              float v[C::G];
+#pragma unroll
+              for (int i = 0; i < C::G; ++i) v[i] = __uint_as_float(r[i]);
+              const int64_t id = __ldg(p.ids + ray);
+              if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
+              glo_grad_add<C::G>(v, valid, id, p.glo_grad, lane);
+            }
+          }
         } else if constexpr (!C::STATIC) {   // (the static program only has BE_MASK / BE_LINEAR layers)
         if (L.epi == BE_SKIPSTORE || L.epi == BE_TRUNKIN) {
           // d(trunk input features) arrives twice: from the skip layer and from layer 0.  The chain rule through the
           // positional encoding is linear in it, so each part is pulled back to d(warped point, hyper coordinates)
-          // straight from the fp32 accumulator and the two 5-vectors are added: nothing is parked in shared memory.
-          float gf[C::KT];
+          // straight from the fp32 accumulator and the two vectors are added: nothing is parked in shared memory.
+          float wp[C::NWARPED], gx[C::NWARPED];
 #pragma unroll
-          for (int c0 = 0; c0 < C::KT; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tlane + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) gf[c0 + j] = __uint_as_float(r[j]);
-          }
-          float wp[3 + C::H], gx[3 + C::H];
-#pragma unroll
-          for (int i = 0; i < 3 + C::H; ++i) wp[i] = __ldg(p.warped + gc * (3 + C::H) + i);
-          posenc_bwd<3, C::XF>(wp, gf, gx);
-          posenc_bwd<C::H, C::HF>(wp + 3, gf + C::PE_X, gx + 3);
+          for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped + gc * C::NWARPED + i);
+          trunk_in_bwd<C>(tlane, wp, gx);
           if (L.epi == BE_SKIPSTORE) {
 #pragma unroll
-            for (int i = 0; i < 3 + C::H; ++i) gx_skip[i] = gx[i];
+            for (int i = 0; i < C::NWARPED; ++i) gx_skip[i] = gx[i];
           } else if (p.g_warped_out != nullptr) {
             // trunk-only program: this is the last layer; the gradient goes back to whoever produced warped_in
             if (valid) {
 #pragma unroll
-              for (int i = 0; i < 3 + C::H; ++i) p.g_warped_out[g * (3 + C::H) + i] = gx[i] + gx_skip[i];
+              for (int i = 0; i < C::NWARPED; ++i) p.g_warped_out[g * C::NWARPED + i] = gx[i] + gx_skip[i];
             }
-          } else {
+          } else if constexpr (!C::NOWARP) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 3 + C::H; ++i) {
+            for (int i = 0; i < C::NWARPED; ++i) {
               f[i] = gx[i] + gx_skip[i];
-              if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + g * (3 + C::H) + i);
+              if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + g * C::NWARPED + i);
+            }
+          }
+          if constexpr (C::H == C::G) {
+            if (p.mflags & MF_AXIS) {
+              // axis-aligned slicing: the hyper coordinates ARE the GLO vector (models.py:533-534), their gradient
+              // goes to the table; the (absent) sheet head receives nothing
+              const int64_t id = __ldg(p.ids + ray);
+              glo_grad_add<C::G>(f + 3, valid, id, p.glo_grad, lane);
+#pragma unroll
+              for (int i = 0; i < C::G; ++i) f[3 + i] = 0.f;
             }
           }
           store_features<16>(f, act_row, save_row, L.save_chunk);
           }
-        } else {  // BE_GLO: d(GLO embedding) of this sample -> per-ray reduction -> atomics on the table gradient
+        } else if constexpr (!C::NOWARP) {  // BE_GLO: d(GLO embedding) of this sample -> per-ray reduction -> atomics on the table gradient
           uint32_t r[16];
           tmem_ld16(tlane + kWsW, r);
           tmem_ld_wait();
+          float v[C::G];
+#pragma unroll
+          for (int i = 0; i < C::G; ++i) v[i] = __uint_as_float(r[i]);
           const int64_t id = __ldg(p.ids + ray);
           if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
-          const bool uniform = __all_sync(0xffffffffu, id == __shfl_sync(0xffffffffu, id, 0));
-#pragma unroll
-          for (int i = 0; i < C::G; ++i) {
-            float v = valid ? __uint_as_float(r[i]) : 0.f;
-            if (uniform) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              if (lane == 0) atomicAdd(p.glo_grad + id * C::G + i, v);
-            } else {
-              atomicAdd(p.glo_grad + id * C::G + i, v);
-            }
-          }
+          glo_grad_add<C::G>(v, valid, id, p.glo_grad, lane);
         }
         }
         if (li + 1 < prog.nlayers) {
@@ -1514,11 +1656,15 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
                              lin(kTrunkW, kTrunkW) + lin(kRgbW, kTrunkW + m.pe_v) + lin(3, kRgbW);
     return 0;
   }
-  int64_t cnt = (int64_t)desc->num_embeddings * m.G;
-  cnt += lin(kSheetW, m.in_s) + 4 * lin(kSheetW, kSheetW) + lin(kSheetW, kSheetW + m.in_s) + lin(m.H, kSheetW);
-  cnt += lin(kWarpW, m.in_w) + 4 * lin(kWarpW, kWarpW) + lin(kWarpW, kWarpW + m.in_w) + lin(3, kWarpW);
+  // parameters of the canonical slots this configuration has (include/hypernerf_b200.h)
+  int64_t cnt = plan.info.glo_floats;
+  if (!m.nowarp) {
+    if (!m.axis) cnt += lin(kSheetW, m.in_s) + 4 * lin(kSheetW, kSheetW) + lin(kSheetW, kSheetW + m.in_s) + lin(m.H, kSheetW);
+    cnt += lin(kWarpW, m.in_w) + 4 * lin(kWarpW, kWarpW) + lin(kWarpW, kWarpW + m.in_w) + lin(3, kWarpW);
+  }
   int64_t lvl = lin(kTrunkW, m.in_t) + 7 * lin(kTrunkW, kTrunkW) + lin(kTrunkW, kTrunkW + m.in_t) + lin(kRgbW, kTrunkW) +
-                lin(kRgbW, kRgbW + m.pe_v) + 3 * lin(kRgbW, kRgbW) + lin(3, kRgbW) + lin(1, kRgbW);
+                lin(kRgbW, kRgbW + m.pe_v + (m.cond_r ? m.G : 0)) + 3 * lin(kRgbW, kRgbW) + lin(3, kRgbW) +
+                lin(1, kRgbW + (m.cond_a ? m.G : 0));
   out->flat_param_floats = cnt + 2 * lvl;
   return 0;
 }
@@ -1535,24 +1681,49 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   pp.blob = (uint8_t*)packed;
   pp.bias_off = plan.layout.bias_off;
   pp.glo_off = plan.layout.glo_off;
-  pp.glo_src = is_static(*desc) ? 0 : param_offsets[P_GLO];
+  pp.glo_src = plan.info.glo_param >= 0 ? param_offsets[plan.info.glo_param] : 0;
+  if (plan.info.glo_param >= 0 && pp.glo_src < 0) return set_error(-2, "hn_pack_weights: the GLO table of this configuration has no offset");
   pp.glo_floats = plan.info.glo_floats;
   dim3 grid(16, plan.pack.nops + 1);
   pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp);
   return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
 }
 
-// warped_in != NULL: trunk-only program (hn_mlp_fwd_trunk)
+// run-time model flags of the fused kernels
+static int model_flags(const hn_model_desc& d) {
+  int f = 0;
+  if (d.flags & HN_FLAG_SLICE_AXIS) f |= MF_AXIS;
+  if (d.flags & (HN_FLAG_ALPHA_COND | HN_FLAG_RGB_COND)) f |= MF_COND;
+  return f;
+}
+// which compile-time shape serves a descriptor: 0 static, 1 hyper_dim 2, 2 hyper_dim 4, 3 hyper_dim 8, 4 no warp
+static int shape_of(const hn_model_desc& d) {
+  if (is_static(d)) return 0;
+  if (!(d.flags & HN_FLAG_WARP_TRANSLATION)) return 4;
+  return d.hyper_dim == 2 ? 1 : d.hyper_dim == 4 ? 2 : 3;
+}
+#define HN_DISPATCH_SHAPE(shape, MACRO) \
+  switch (shape) {                      \
+    case 0: MACRO(CfgStatic); break;    \
+    case 1: MACRO(Cfg1); break;         \
+    case 2: MACRO(CfgH4); break;        \
+    case 3: MACRO(CfgH8); break;        \
+    default: MACRO(CfgT); break;        \
+  }
+
+// warped_in != NULL: trunk-only program (hn_mlp_fwd_trunk; always the case for a model without warp: warped_in = points)
 static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const float* points, const float* warped_in,
                         const float* viewdirs, const int64_t* ids, const float* noise, float noise_std, int64_t B, int S,
                         float* sigma, float* rgb, float* warped, void* saved, void* stream) {
-  const bool trunk = warped_in != nullptr;
-  if (!desc || !packed || (!points && !trunk) || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
+  if (!desc || !packed || (!points && !warped_in) || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
   if (int rc = validate_desc(*desc)) return rc;
   const bool stat = is_static(*desc);
+  const int mflags = stat ? 0 : model_flags(*desc);
+  if (!stat && !(desc->flags & HN_FLAG_WARP_TRANSLATION) && !warped_in) { warped_in = points; warped = nullptr; }
+  const bool trunk = warped_in != nullptr;
   if (trunk && stat) return set_error(-13, "hn_mlp_fwd_trunk: the static model has no warp / sheet stage to skip");
-  if (!stat && !trunk && !ids) return set_error(-2, "hn_mlp_fwd: null ids");
+  if (!stat && !ids && (!trunk || (mflags & MF_COND))) return set_error(-2, "hn_mlp_fwd: null ids");
   if (B == 0) return 0;
   const ModelPlan& plan = cached_plan(*desc);
   FwdParams fp;
@@ -1567,6 +1738,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.glo = (const float*)((const uint8_t*)packed + plan.layout.glo_off);
   fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
   fp.n = B * S; fp.S = S; fp.n_embed = desc->num_embeddings;
+  fp.view_freqs = desc->view_freqs; fp.mflags = mflags;
   int64_t nt = tiles_of(fp.n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_fwd: too many samples");
   fp.n_tiles = (int)nt;
@@ -1577,15 +1749,18 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
   int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
-#define HN_LAUNCH_FWD(CFG, ST)                                                                                              \
-  do {                                                                                                                      \
-    if (int rc = set_smem(mlp_fwd_kernel<CFG, ST>, Smem<CFG>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;                   \
-    return set_cuda_error(launch_mlp(mlp_fwd_kernel<CFG, ST>, grid, Smem<CFG>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd"); \
+#define HN_LAUNCH_FWD(CFG)                                                                                                   \
+  do {                                                                                                                       \
+    if (saved != nullptr) {                                                                                                  \
+      if (int rc = set_smem(mlp_fwd_kernel<CFG, true>, Smem<CFG>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;                \
+      return set_cuda_error(launch_mlp(mlp_fwd_kernel<CFG, true>, grid, Smem<CFG>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd"); \
+    }                                                                                                                        \
+    if (int rc = set_smem(mlp_fwd_kernel<CFG, false>, Smem<CFG>::TOTAL, "hn_mlp_fwd: smem attr")) return rc;                 \
+    return set_cuda_error(launch_mlp(mlp_fwd_kernel<CFG, false>, grid, Smem<CFG>::TOTAL, (cudaStream_t)stream, fp), "hn_mlp_fwd"); \
   } while (0)
-  if (stat) { if (saved != nullptr) HN_LAUNCH_FWD(CfgStatic, true); else HN_LAUNCH_FWD(CfgStatic, false); }
-  if (saved != nullptr) HN_LAUNCH_FWD(Cfg1, true);
-  HN_LAUNCH_FWD(Cfg1, false);
+  HN_DISPATCH_SHAPE(shape_of(*desc), HN_LAUNCH_FWD)
 #undef HN_LAUNCH_FWD
+  return set_error(-1, "hn_mlp_fwd: unreachable");
 }
 
 extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
@@ -1596,10 +1771,10 @@ extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const f
 }
 
 extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
-                                const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb, void* saved,
-                                void* stream) {
+                                const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
+                                float* rgb, void* saved, void* stream) {
   if (!warped_in) return set_error(-2, "hn_mlp_fwd_trunk: null pointer");
-  return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, nullptr, noise, noise_std, B, S, sigma, rgb, nullptr, saved,
+  return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, ids, noise, noise_std, B, S, sigma, rgb, nullptr, saved,
                       stream);
 }
 
@@ -1610,9 +1785,13 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
                         float* g_warped_out = nullptr) {   // trunk: trunk-only programs (hn_mlp_bwd_trunk*)
   if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
   const bool stat = desc && is_static(*desc);
-  if (trunk && do_data && !g_warped_out) return set_error(-2, "hn_mlp_bwd_trunk: null pointer");
+  const bool nowarp = !stat && !(desc->flags & HN_FLAG_WARP_TRANSLATION);
+  const int mflags = stat ? 0 : model_flags(*desc);
+  if (nowarp) trunk = true;   // a model without warp only has the template: `warped` are the raw sample points
+  if (trunk && do_data && !g_warped_out && !nowarp) return set_error(-2, "hn_mlp_bwd_trunk: null pointer");
   if (trunk && stat) return set_error(-13, "hn_mlp_bwd_trunk: the static model has no warp / sheet stage to skip");
-  if (do_data && (!packed || !sigma || !rgb || !g_sigma || !g_rgb || (!stat && ((!ids && !trunk) || !warped))))
+  if (do_data && (!packed || !sigma || !rgb || !g_sigma || !g_rgb ||
+                  (!stat && ((!ids && (!trunk || (mflags & MF_COND))) || !warped))))
     return set_error(-2, "hn_mlp_bwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_bwd: bad B/S");
   if (level < 0 || level > 1) return set_error(-1, "hn_mlp_bwd: level must be 0 or 1");
@@ -1634,20 +1813,26 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
     bp.g_total = plan.info.g_total;
     bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes);
-    bp.glo_grad = stat ? nullptr : flat_grad + param_offsets[P_GLO];
+    bp.glo_grad = nullptr;
+    if (plan.info.glo_param >= 0) {
+      if (param_offsets[plan.info.glo_param] < 0) return set_error(-2, "hn_mlp_bwd: the GLO table of this configuration has no gradient offset");
+      bp.glo_grad = flat_grad + param_offsets[plan.info.glo_param];
+    }
+    bp.mflags = mflags;
     bp.n = n; bp.S = S; bp.n_embed = desc->num_embeddings;
     bp.n_tiles = (int)nt;
     bp.x_total = plan.info.x_total; bp.d_total = plan.info.d_total;
     bp.d_rgbhead = plan.info.d_rgbhead; bp.d_sigma = plan.info.d_sigma;
     bp.dbg = g_dbg;
     int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
-    if (stat) {
-      if (int rc = set_smem(mlp_dgrad_kernel<CfgStatic>, SmemBwd<CfgStatic>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<CfgStatic>, grid, SmemBwd<CfgStatic>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
-    } else {
-      if (int rc = set_smem(mlp_dgrad_kernel<Cfg1>, SmemBwd<Cfg1>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;
-      if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<Cfg1>, grid, SmemBwd<Cfg1>::TOTAL, (cudaStream_t)stream, bp), "hn_mlp_bwd: dgrad launch")) return rc;
-    }
+#define HN_LAUNCH_BWD(CFG)                                                                                                  \
+  do {                                                                                                                      \
+    if (int rc = set_smem(mlp_dgrad_kernel<CFG>, SmemBwd<CFG>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;            \
+    if (int rc = set_cuda_error(launch_mlp(mlp_dgrad_kernel<CFG>, grid, SmemBwd<CFG>::TOTAL, (cudaStream_t)stream, bp),     \
+                                "hn_mlp_bwd: dgrad launch")) return rc;                                                     \
+  } while (0)
+    HN_DISPATCH_SHAPE(shape_of(*desc), HN_LAUNCH_BWD)
+#undef HN_LAUNCH_BWD
   }
   if (do_weights) {
     WgradParams wp;
@@ -1688,19 +1873,19 @@ extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, 
                       param_offsets, flat_grad, (void*)workspace, stream, false, true);
 }
 
-extern "C" int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
-                                const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B,
-                                int S, int level, const int64_t* param_offsets, float* flat_grad, float* g_warped_in,
-                                void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, nullptr, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
+extern "C" int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                                const float* rgb, const float* warped_in, const void* saved, const float* g_sigma,
+                                const float* g_rgb, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
+                                float* g_warped_in, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
                       flat_grad, workspace, stream, true, true, true, g_warped_in);
 }
 
-extern "C" int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
-                                     const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb,
-                                     int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
-                                     float* g_warped_in, void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, nullptr, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
+extern "C" int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                                     const float* rgb, const float* warped_in, const void* saved, const float* g_sigma,
+                                     const float* g_rgb, int64_t B, int S, int level, const int64_t* param_offsets,
+                                     float* flat_grad, float* g_warped_in, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
                       flat_grad, workspace, stream, true, false, true, g_warped_in);
 }
 

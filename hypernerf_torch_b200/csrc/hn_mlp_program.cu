@@ -12,14 +12,29 @@ int validate_desc(const hn_model_desc& d) {
       return set_error(-11, "hn_model_desc: the static NeRF kernels are instantiated for xyz / dir freqs 10 / 4 (models/nerf.py defaults)");
     return 0;
   }
-  if ((d.flags & (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY)) != (HN_FLAG_WARP_TRANSLATION | HN_FLAG_SLICE_BENDY))
-    return set_error(-10, "hn_model_desc: this build implements TranslationField warp + bendy_sheet slicing only");
-  if (d.glo_dim != 8 || d.hyper_dim != 2 || d.xyz_freqs != 10 || d.hyper_freqs != 6 || d.view_freqs != 6 ||
-      d.warp_freqs != 10 || d.sheet_freqs != 7)
-    return set_error(-11,
-                     "hn_model_desc: kernels are instantiated for G=8, H=2, xyz/hyper/view freqs 10/6/6 "
-                     "(warp 10, sheet 7); add an instantiation in hn_mlp.cu for other shapes");
-  if (d.num_embeddings <= 0) return set_error(-12, "hn_model_desc: num_embeddings must be positive");
+  const bool warp = (d.flags & HN_FLAG_WARP_TRANSLATION) != 0;
+  const bool bendy = (d.flags & HN_FLAG_SLICE_BENDY) != 0, axis = (d.flags & HN_FLAG_SLICE_AXIS) != 0;
+  const bool cond = (d.flags & (HN_FLAG_ALPHA_COND | HN_FLAG_RGB_COND)) != 0;
+  if (warp && (bendy == axis))
+    return set_error(-10, "hn_model_desc: a warped model needs exactly one of bendy_sheet / axis_aligned_plane slicing "
+                          "(slice 'none' with warp is broken in the reference, models.py:269-270)");
+  if (!warp && (bendy || axis))
+    return set_error(-10, "hn_model_desc: without warp map_points returns the raw points (models.py:568-569): pass no slicing flag");
+  if (d.xyz_freqs != 10 || d.view_freqs < 0 || d.view_freqs > kMaxViewFreqs)
+    return set_error(-11, "hn_model_desc: kernels are instantiated for xyz freqs 10 and view freqs <= 6");
+  if (warp) {
+    if (d.glo_dim != 8 || d.hyper_freqs != 6 || d.warp_freqs != 10 || d.sheet_freqs != 7)
+      return set_error(-11, "hn_model_desc: kernels are instantiated for G=8, hyper freqs 6 (warp 10, sheet 7); add an "
+                            "instantiation in hn_mlp.cu for other shapes");
+    if (d.hyper_dim != 2 && d.hyper_dim != 4 && d.hyper_dim != 8)
+      return set_error(-11, "hn_model_desc: kernels are instantiated for hyper_dim 2, 4 and 8");
+    if (axis && d.hyper_dim != d.glo_dim)
+      return set_error(-11, "hn_model_desc: axis_aligned_plane needs hyper_dim == glo_dim (the hyper point is the GLO vector, "
+                            "models.py:533-534)");
+  } else if (cond && d.glo_dim != 8) {
+    return set_error(-11, "hn_model_desc: kernels are instantiated for G=8");
+  }
+  if ((warp || cond) && d.num_embeddings <= 0) return set_error(-12, "hn_model_desc: num_embeddings must be positive");
   return 0;
 }
 
@@ -30,6 +45,7 @@ struct Builder {
   LogicalOps* lg;
   uint32_t w16 = 0;  // running weight offset (16-byte units)
   int ones_col = -1; // forward programs with kFoldBias: INB column of the ones chunk pair (every op gets a bias K step)
+  int lg_chunks = 0, lg_total = 0;   // chunk cursor inside / chunk count of the logical matrix being emitted
   void begin_layer(uint8_t epi, int n_out, int bias_off, uint16_t save_chunk, uint16_t mask_chunk, uint16_t gate_word = kNone) {
     Layer& L = p->layers[p->nlayers++];
     L.op0 = (uint8_t)p->nops; L.nops = 0; L.epi = epi; L.pad = 0;
@@ -49,24 +65,37 @@ struct Builder {
     w16 += (uint32_t)n * (uint32_t)k / 8;  // n * K * 2 bytes / 16
     p->layers[p->nlayers - 1].nops++;
   }
-  // One logical [n x (k0 + k1)] matrix; the K range is split over two source buffers when k1 > 0.
-  void add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
+  // One logical [n x k_total] weight matrix (+ 16 bias rows in the folded-bias forward programs), consumed by one or
+  // more parts; the parts may sit in consecutive layers (split skip layer, see kMaxTrunkInInb).
+  void begin_logical(int n, int k_total) {
     const int kb = ones_col >= 0 ? 16 : 0;   // bias rows (hn_mlp_program.h: HN_FOLD_BIAS)
     LogicalOp& l = lg->ops[lg->n++];
-    l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k0 + k1 + kb);
-    emit(n, k0, s0, a0_col, tmem_col, acc_init, 0, (k0 + k1 + kb) / 8);
-    if (k1 > 0) emit(n, k1, s1, a1_col, tmem_col, 1, k0 / 8, (k0 + k1 + kb) / 8);
-    if (kb > 0) {
-      emit(n, kb, SRC_INB, ones_col, tmem_col, 1, (k0 + k1) / 8, (k0 + k1 + kb) / 8);
-      p->ops[p->nops - 1].pad = 1;   // marks a bias step
-    }
+    l.w_off16 = w16; l.n = (uint16_t)n; l.k = (uint16_t)(k_total + kb);
+    lg_chunks = 0; lg_total = (k_total + kb) / 8;
+  }
+  void part(int n, int k, Src s, int a_col, int tmem_col, int acc_init) {
+    emit(n, k, s, a_col, tmem_col, acc_init, lg_chunks, lg_total);
+    lg_chunks += k / 8;
+  }
+  void bias_part(int n, int tmem_col) {
+    if (ones_col < 0) return;
+    emit(n, 16, SRC_INB, ones_col, tmem_col, 1, lg_chunks, lg_total);
+    p->ops[p->nops - 1].pad = 1;   // marks a bias step
+    lg_chunks += 2;
+  }
+  // the common case: the K range is split over at most two source buffers inside one layer
+  void add_op(int n, int k0, Src s0, int a0_col, int k1, Src s1, int a1_col, int tmem_col, int acc_init = 0) {
+    begin_logical(n, k0 + k1);
+    part(n, k0, s0, a0_col, tmem_col, acc_init);
+    if (k1 > 0) part(n, k1, s1, a1_col, tmem_col, 1);
+    bias_part(n, tmem_col);
   }
 };
 
 // copy of a program without its bias steps (weight offsets are absolute, so the same blob serves both)
 void without_bias_steps(const Program& src, Program* dst) {
   memset(dst, 0, sizeof(*dst));
-  dst->nlayers = src.nlayers;
+  dst->nlayers = src.nlayers; dst->flags = src.flags;
   for (int li = 0; li < src.nlayers; ++li) {
     Layer L = src.layers[li];
     const int op0 = dst->nops;
@@ -80,6 +109,7 @@ void without_bias_steps(const Program& src, Program* dst) {
 // layers [l0, l1) of a program as a program of their own (weight offsets are absolute: same blob)
 void slice_program(const Program& src, int l0, int l1, Program* dst) {
   memset(dst, 0, sizeof(*dst));
+  dst->flags = src.flags;
   for (int li = l0; li < l1; ++li) {
     Layer L = src.layers[li];
     const int op0 = dst->nops;
@@ -89,6 +119,8 @@ void slice_program(const Program& src, int l0, int l1, Program* dst) {
   }
 }
 
+// A tensor the configuration does not have carries a negative offset (include/hypernerf_b200.h): its pack blocks are left
+// out (the operand image stays zero), its gradient segments are dropped.
 struct Packer {
   PackTable* t;
   const int64_t* off;
@@ -99,6 +131,7 @@ struct Packer {
     po.w_off16 = o.w_off16; po.n = o.n; po.k = o.k; po.blk0 = (uint8_t)t->nblocks; po.nblk = 0; po.pad = 0;
   }
   void block(int param, int64_t src_extra, int sn, int sk, int n0, int nn, int k0, int kk) {
+    if (off[param] < 0 || nn <= 0 || kk <= 0) return;
     PackBlock& b = t->blocks[t->nblocks++];
     b.src = off[param] + src_extra; b.sn = sn; b.sk = sk;
     b.n0 = (uint16_t)n0; b.nn = (uint16_t)nn; b.k0 = (uint16_t)k0; b.kk = (uint16_t)kk;
@@ -111,17 +144,13 @@ struct Packer {
     block(param, 0, 1, kBiasPairStride, n0, nn, k0, 2);
   }
   void bias(int param, int dst, int cnt) {
+    if (off[param] < 0) return;
     BiasBlock& b = t->bias[t->nbias++];
     b.src = off[param]; b.dst = (uint16_t)dst; b.cnt = (uint16_t)cnt; b.pad = 0;
   }
 };
 
 }  // namespace
-
-// Forward bias array layout (floats): one run of n_out per layer, in layer order.
-static int fwd_bias_floats(const Dims& m) {
-  return kWsDepth * kWsW + 16 + (kTrunkDepth + 1) * kTrunkW + kRgbW + m.n_rgb0a + (kRgbDepth - 1) * kRgbW + 16;
-}
 
 static void build_plan_static(const hn_model_desc& d, ModelPlan* plan);
 static void build_tables_static(const int64_t* off, ModelPlan* plan);
@@ -131,36 +160,54 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
   if (is_static(d)) { build_plan_static(d, plan); return; }
   const Dims m = make_dims(d);
   const SlabMap s = make_slabs(m);
+  const bool cond = m.cond_a || m.cond_r;
   plan->dims = m;
   plan->slabs = s;
+  int bias_floats = 0;
 
   // ------------------------------------------------------------------ forward program
   {
     Builder b{&plan->fwd, &plan->fwd_logical};
     if (kFoldBias) b.ones_col = m.ones_col;
+    plan->fwd.flags = m.t_in_act ? PF_TIN_ACT : 0;
     int bias = 0;
-    // warp + sheet, merged to one 192-wide net sharing the input buffer
-    b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone, s.g_hws[0]);
-    b.add_op(kWsW, m.KW, SRC_INB, 0, 0, SRC_ACT, 0, 0);
-    bias += kWsW;
-    for (int l = 1; l < kWsDepth; ++l) {
-      b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[l], kNone, s.g_hws[l]);
-      bool skip = (l == kSkip + 1);
-      b.add_op(kWarpW, kWarpW, SRC_ACT, 0, skip ? m.KW : 0, SRC_INB, 0, 0);
-      b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, skip ? m.KW : 0, SRC_INB, 0, kWarpW);
+    if (!m.nowarp) {
+      // warp + sheet, merged to one 192-wide net sharing the input buffer (axis-aligned slicing has no sheet MLP: its
+      // part of the operand images stays zero)
+      b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone, s.g_hws[0]);
+      b.add_op(kWsW, m.KW, SRC_INB, 0, 0, SRC_ACT, 0, 0);
       bias += kWsW;
+      for (int l = 1; l < kWsDepth; ++l) {
+        b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[l], kNone, s.g_hws[l]);
+        bool skip = (l == kSkip + 1);
+        b.add_op(kWarpW, kWarpW, SRC_ACT, 0, skip ? m.KW : 0, SRC_INB, 0, 0);
+        b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, skip ? m.KW : 0, SRC_INB, 0, kWarpW);
+        bias += kWsW;
+      }
+      b.begin_layer(FE_WSHEAD, 16, bias, s.x_in_t, kNone);
+      b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      bias += 16;
     }
-    b.begin_layer(FE_WSHEAD, 16, bias, s.x_in_t, kNone);
-    b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
-    bias += 16;
+    const int n_ws_layers = plan->fwd.nlayers;
     // trunk
+    const Src tsrc = m.t_in_act ? SRC_ACT : SRC_INB;
     b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[0], kNone, s.g_t[0]);
-    b.add_op(kTrunkW, m.KT, SRC_INB, 0, 0, SRC_ACT, 0, 0);
+    b.add_op(kTrunkW, m.KT, tsrc, 0, 0, SRC_ACT, 0, 0);
     bias += kTrunkW;
     for (int l = 1; l <= kTrunkDepth; ++l) {  // l == kTrunkDepth is the logit layer (ReLU output, modules.py:230)
-      b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone, s.g_t[l]);
-      bool skip = (l == kSkip + 1);
-      b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, skip ? m.KT : 0, SRC_INB, 0, 0);
+      const bool skip = (l == kSkip + 1);
+      if (skip && m.t_in_act) {
+        // hidden part; its epilogue re-fills ACT[0, KT) with the trunk input vector; then the input part on top
+        b.begin_layer(FE_SKIPFEED, kTrunkW, bias, kNone, kNone);
+        b.begin_logical(kTrunkW, kTrunkW + m.KT);
+        b.part(kTrunkW, kTrunkW, SRC_ACT, 0, 0, 0);
+        b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone, s.g_t[l]);
+        b.part(kTrunkW, m.KT, SRC_ACT, 0, 0, 1);
+        b.bias_part(kTrunkW, 0);
+      } else {
+        b.begin_layer(FE_RELU, kTrunkW, bias, s.x_t[l], kNone, s.g_t[l]);
+        b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, skip ? m.KT : 0, SRC_INB, 0, 0);
+      }
       bias += kTrunkW;
     }
     b.begin_layer(FE_BOTT, kRgbW, bias, s.x_bott, kNone);
@@ -177,12 +224,13 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     b.begin_layer(FE_RGBHEAD, 16, bias, kNone, kNone);
     b.add_op(16, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     bias += 16;
+    bias_floats = bias;
     plan->layout.fwd_off = 0;
     plan->layout.bwd_off = (int64_t)b.w16 * 16;
     without_bias_steps(plan->fwd, &plan->fwd_train);
-    // trunk-only: everything after the warp / sheet head (kWsDepth hidden layers + the head layer)
-    slice_program(plan->fwd, kWsDepth + 1, plan->fwd.nlayers, &plan->fwd_trunk);
-    slice_program(plan->fwd_train, kWsDepth + 1, plan->fwd_train.nlayers, &plan->fwd_trunk_train);
+    // trunk-only: everything after the warp / sheet head (without warp that is the whole program)
+    slice_program(plan->fwd, n_ws_layers, plan->fwd.nlayers, &plan->fwd_trunk);
+    slice_program(plan->fwd_train, n_ws_layers, plan->fwd_train.nlayers, &plan->fwd_trunk_train);
   }
   // ------------------------------------------------------------------ backward-data program
   {
@@ -196,16 +244,18 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
       b.begin_layer(last ? BE_RGB1 : BE_MASK, kRgbW, 0, last ? s.d_rgb0a : s.d_r[l - 1], s.x_r[l - 1], s.g_r[l - 1]);
       b.add_op(kRgbW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     }
-    // D4: (rgb0 | alpha)^T -> bottleneck gradient (no activation on the bottleneck, modules.py:232,277)
-    b.begin_layer(BE_LINEAR, kRgbW, 0, s.d_bott, kNone);
+    // D4: (rgb0 | alpha)^T -> bottleneck gradient (no activation on the bottleneck, modules.py:232,277); with template
+    // conditioning also the gradient of the GLO columns of the view vector, parked in TMEM cols [128, 144)
+    b.begin_layer(cond ? BE_LINCOND : BE_LINEAR, kRgbW, 0, s.d_bott, kNone);
     b.add_op(kRgbW, m.n_rgb0a, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+    if (cond) b.add_op(16, m.n_rgb0a, SRC_ACT, 0, 0, SRC_ACT, 0, kRgbW);
     // D5: bottleneck^T, gated by the trunk output ReLU
     b.begin_layer(BE_MASK, kTrunkW, 0, s.d_t[kTrunkDepth], s.x_t[kTrunkDepth], s.g_t[kTrunkDepth]);
     b.add_op(kTrunkW, kRgbW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     // trunk layers l = 8 (logit) .. 1: gradient w.r.t. h_{l-1}
     for (int l = kTrunkDepth; l >= 1; --l) {
       if (l == kSkip + 1) {
-        // input part of the skip layer first (result parked in INB as bf16), then the hidden part
+        // input part of the skip layer first (pulled back through the posenc chain rule by the epilogue), then the hidden part
         b.begin_layer(BE_SKIPSTORE, m.KT, 0, kNone, kNone);
         b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
       }
@@ -213,42 +263,46 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
       b.add_op(kTrunkW, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     }
     // trunk layer 0^T -> gradient of the trunk input features -> chain rule through posenc
-    b.begin_layer(BE_TRUNKIN, m.KT, 0, s.d_wshead, kNone);
+    b.begin_layer(BE_TRUNKIN, m.KT, 0, m.nowarp ? kNone : s.d_wshead, kNone);
     b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
-    // warp/sheet head^T
-    b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1], s.g_hws[kWsDepth - 1]);
-    b.add_op(kWsW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
-    for (int l = kWsDepth - 1; l >= 1; --l) {
-      b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[l - 1], s.x_hws[l - 1], s.g_hws[l - 1]);
-      if (l == kSkip + 1)  // GLO columns of the skip input, parked in TMEM cols [192,208)
-        b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW);
-      b.add_op(kWarpW, kWarpW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
-      b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, 0, SRC_ACT, 0, kWarpW);
+    const int n_trunk_layers = plan->bwd.nlayers;
+    if (!m.nowarp) {
+      // warp/sheet head^T
+      b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1], s.g_hws[kWsDepth - 1]);
+      b.add_op(kWsW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      for (int l = kWsDepth - 1; l >= 1; --l) {
+        b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[l - 1], s.x_hws[l - 1], s.g_hws[l - 1]);
+        if (l == kSkip + 1)  // GLO columns of the skip input, parked in TMEM cols [192,208)
+          b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW);
+        b.add_op(kWarpW, kWarpW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+        b.add_op(kSheetW, kSheetW, SRC_ACT, kWarpW, 0, SRC_ACT, 0, kWarpW);
+      }
+      // GLO columns of layer 0, accumulated on top
+      b.begin_layer(BE_GLO, 16, 0, kNone, kNone);
+      b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW, /*acc_init=*/1);
     }
-    // GLO columns of layer 0, accumulated on top
-    b.begin_layer(BE_GLO, 16, 0, kNone, kNone);
-    b.add_op(16, kWsW, SRC_ACT, 0, 0, SRC_ACT, 0, kWsW, /*acc_init=*/1);
     plan->layout.bias_off = plan->layout.bwd_off + (int64_t)b.w16 * 16;
     // trunk-only: up to and including the trunk-input layer (BE_TRUNKIN), whose epilogue then emits d(warped point)
-    int n_trunk = 0;
-    while (n_trunk < plan->bwd.nlayers && plan->bwd.layers[n_trunk].epi != BE_TRUNKIN) ++n_trunk;
-    slice_program(plan->bwd, 0, n_trunk + 1, &plan->bwd_trunk);
+    slice_program(plan->bwd, 0, n_trunk_layers, &plan->bwd_trunk);
   }
-  plan->layout.glo_off = plan->layout.bias_off + (int64_t)fwd_bias_floats(m) * 4;
-  plan->layout.glo_off = (plan->layout.glo_off + 15) / 16 * 16;
-  plan->layout.total = plan->layout.glo_off + (int64_t)d.num_embeddings * m.G * 4;
-  plan->layout.total = (plan->layout.total + 255) / 256 * 256;
   PlanInfo& I = plan->info;
+  I.glo_param = m.nowarp ? (cond ? P_COND_GLO : -1) : P_GLO;
+  I.glo_floats = I.glo_param >= 0 ? d.num_embeddings * m.G : 0;
+  plan->layout.glo_off = plan->layout.bias_off + (int64_t)bias_floats * 4;
+  plan->layout.glo_off = (plan->layout.glo_off + 15) / 16 * 16;
+  plan->layout.total = plan->layout.glo_off + (int64_t)I.glo_floats * 4;
+  plan->layout.total = (plan->layout.total + 255) / 256 * 256;
   I.x_total = s.x_total; I.d_total = s.d_total; I.g_total = s.g_total;
   I.x_in0 = s.x_in_ws; I.x_in_t = s.x_in_t; I.x_in_v = s.x_in_v;
   I.d_rgbhead = s.d_rgbhead; I.d_sigma = kNone;
-  I.n_params = HN_NUM_PARAM_TENSORS; I.glo_floats = d.num_embeddings * m.G;
+  I.n_params = HN_NUM_PARAM_TENSORS;
 }
 
 void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPlan* plan) {
   if (is_static(d)) { build_tables_static(off, plan); return; }
   const Dims& m = plan->dims;
   const SlabMap& s = plan->slabs;
+  const bool cond = m.cond_a || m.cond_r;
   // ------------------------------------------------------------------ pack table
   PackTable& t = plan->pack;
   memset(&t, 0, sizeof(t));
@@ -256,32 +310,38 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   const LogicalOps& F = plan->fwd_logical;
   int oi = 0;
   const int ldw5 = kWarpW + m.in_w, lds5 = kSheetW + m.in_s;
-  // fwd ws0
-  pk.op(F.ops[oi++]);
-  pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kWarpW, 0, m.in_w);
-  pk.block(P_SHEET_W(0), 0, m.in_s, 1, kWarpW, kSheetW, 0, m.pe_s);
-  pk.block(P_SHEET_W(0), m.pe_s, m.in_s, 1, kWarpW, kSheetW, m.pe_w, m.G);
-  pk.bias_rows(P_WARP_B(0), 0, kWarpW);
-  pk.bias_rows(P_SHEET_B(0), kWarpW, kSheetW);
-  for (int l = 1; l < kWsDepth; ++l) {
-    bool skip = (l == kSkip + 1);
+  // rgb layer 0 reads [bottleneck | view PE (pe_v) | GLO (rgb condition)], the alpha head [bottleneck | GLO (alpha condition)]
+  // (modules.py:283,292); inside the operand the view vector is [PE padded to 40 | GLO] (hn_mlp_program.h: kViewCondCol)
+  const int ld_rgb0 = kRgbW + m.pe_v + (m.cond_r ? m.G : 0), ld_alpha = kRgbW + (m.cond_a ? m.G : 0);
+  const int k_cond = kRgbW + kViewCondCol;
+  if (!m.nowarp) {
+    // fwd ws0
     pk.op(F.ops[oi++]);
-    pk.block(P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 1, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
-    pk.bias_rows(P_WARP_B(l), 0, kWarpW);
-    pk.op(F.ops[oi++]);
-    if (!skip) {
-      pk.block(P_SHEET_W(l), 0, kSheetW, 1, 0, kSheetW, 0, kSheetW);
-    } else {
-      pk.block(P_SHEET_W(l), 0, lds5, 1, 0, kSheetW, 0, kSheetW + m.pe_s);
-      pk.block(P_SHEET_W(l), kSheetW + m.pe_s, lds5, 1, 0, kSheetW, kSheetW + m.pe_w, m.G);
+    pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kWarpW, 0, m.in_w);
+    pk.block(P_SHEET_W(0), 0, m.in_s, 1, kWarpW, kSheetW, 0, m.pe_s);
+    pk.block(P_SHEET_W(0), m.pe_s, m.in_s, 1, kWarpW, kSheetW, m.pe_w, m.G);
+    pk.bias_rows(P_WARP_B(0), 0, kWarpW);
+    pk.bias_rows(P_SHEET_B(0), kWarpW, kSheetW);
+    for (int l = 1; l < kWsDepth; ++l) {
+      bool skip = (l == kSkip + 1);
+      pk.op(F.ops[oi++]);
+      pk.block(P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 1, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
+      pk.bias_rows(P_WARP_B(l), 0, kWarpW);
+      pk.op(F.ops[oi++]);
+      if (!skip) {
+        pk.block(P_SHEET_W(l), 0, kSheetW, 1, 0, kSheetW, 0, kSheetW);
+      } else {
+        pk.block(P_SHEET_W(l), 0, lds5, 1, 0, kSheetW, 0, kSheetW + m.pe_s);
+        pk.block(P_SHEET_W(l), kSheetW + m.pe_s, lds5, 1, 0, kSheetW, kSheetW + m.pe_w, m.G);
+      }
+      pk.bias_rows(P_SHEET_B(l), 0, kSheetW);
     }
-    pk.bias_rows(P_SHEET_B(l), 0, kSheetW);
+    pk.op(F.ops[oi++]);  // ws head: rows 0..2 warp logit, rows 3..3+H-1 sheet logit
+    pk.block(P_WARP_W(kWsDepth), 0, kWarpW, 1, 0, 3, 0, kWarpW);
+    pk.block(P_SHEET_W(kWsDepth), 0, kSheetW, 1, 3, m.H, kWarpW, kSheetW);
+    pk.bias_rows(P_WARP_B(kWsDepth), 0, 3);
+    pk.bias_rows(P_SHEET_B(kWsDepth), 3, m.H);
   }
-  pk.op(F.ops[oi++]);  // ws head: rows 0..2 warp logit, rows 3..3+H-1 sheet logit
-  pk.block(P_WARP_W(kWsDepth), 0, kWarpW, 1, 0, 3, 0, kWarpW);
-  pk.block(P_SHEET_W(kWsDepth), 0, kSheetW, 1, 3, m.H, kWarpW, kSheetW);
-  pk.bias_rows(P_WARP_B(kWsDepth), 0, 3);
-  pk.bias_rows(P_SHEET_B(kWsDepth), 3, m.H);
   pk.op(F.ops[oi++]);  // trunk 0
   pk.block(P_TRUNK_W(level, 0), 0, m.in_t, 1, 0, kTrunkW, 0, m.in_t);
   pk.bias_rows(P_TRUNK_B(level, 0), 0, kTrunkW);
@@ -295,8 +355,10 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   pk.block(P_BOTT_W(level), 0, kTrunkW, 1, 0, kRgbW, 0, kTrunkW);
   pk.bias_rows(P_BOTT_B(level), 0, kRgbW);
   pk.op(F.ops[oi++]);  // rgb0 | alpha
-  pk.block(P_RGB_W(level, 0), 0, kRgbW + m.pe_v, 1, 0, kRgbW, 0, kRgbW + m.pe_v);
-  pk.block(P_ALPHA_W(level), 0, kRgbW, 1, kRgbW, 1, 0, kRgbW);
+  pk.block(P_RGB_W(level, 0), 0, ld_rgb0, 1, 0, kRgbW, 0, kRgbW + m.pe_v);
+  if (m.cond_r) pk.block(P_RGB_W(level, 0), kRgbW + m.pe_v, ld_rgb0, 1, 0, kRgbW, k_cond, m.G);
+  pk.block(P_ALPHA_W(level), 0, ld_alpha, 1, kRgbW, 1, 0, kRgbW);
+  if (m.cond_a) pk.block(P_ALPHA_W(level), kRgbW, ld_alpha, 1, kRgbW, 1, k_cond, m.G);
   pk.bias_rows(P_RGB_B(level, 0), 0, kRgbW);
   pk.bias_rows(P_ALPHA_B(level), kRgbW, 1);
   for (int l = 1; l < kRgbDepth; ++l) {
@@ -320,8 +382,13 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
     pk.block(P_RGB_W(level, l), 0, 1, kRgbW, 0, kRgbW, 0, kRgbW);
   }
   bop();  // D4
-  pk.block(P_RGB_W(level, 0), 0, 1, kRgbW + m.pe_v, 0, kRgbW, 0, kRgbW);
-  pk.block(P_ALPHA_W(level), 0, 1, kRgbW, 0, kRgbW, kRgbW, 1);
+  pk.block(P_RGB_W(level, 0), 0, 1, ld_rgb0, 0, kRgbW, 0, kRgbW);
+  pk.block(P_ALPHA_W(level), 0, 1, ld_alpha, 0, kRgbW, kRgbW, 1);
+  if (cond) {  // GLO condition columns: dest(g, k < 128) = Wrgb0[k][128 + pe_v + g], dest(g, 128) = Walpha[0][128 + g]
+    bop();
+    if (m.cond_r) pk.block(P_RGB_W(level, 0), kRgbW + m.pe_v, 1, ld_rgb0, 0, m.G, 0, kRgbW);
+    if (m.cond_a) pk.block(P_ALPHA_W(level), kRgbW, 1, ld_alpha, 0, m.G, kRgbW, 1);
+  }
   bop();  // D5 bottleneck^T: n < 256, k < 128
   pk.block(P_BOTT_W(level), 0, 1, kTrunkW, 0, kTrunkW, 0, kRgbW);
   for (int l = kTrunkDepth; l >= 1; --l) {
@@ -335,35 +402,39 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   }
   bop();  // trunk 0^T
   pk.block(P_TRUNK_W(level, 0), 0, 1, m.in_t, 0, m.in_t, 0, kTrunkW);
-  bop();  // ws head^T: n < 128 <- warp logit (k < 3); n = 128 + j <- sheet logit (k = 3 + h)
-  pk.block(P_WARP_W(kWsDepth), 0, 1, kWarpW, 0, kWarpW, 0, 3);
-  pk.block(P_SHEET_W(kWsDepth), 0, 1, kSheetW, kWarpW, kSheetW, 3, m.H);
-  for (int l = kWsDepth - 1; l >= 1; --l) {
-    bool skip = (l == kSkip + 1);
-    if (skip) {  // GLO columns: dest(g, k<128) = warpW5[k][128 + pe_w + g]; dest(g, 128 + j) = sheetW5[j][64 + pe_s + g]
+  if (!m.nowarp) {
+    bop();  // ws head^T: n < 128 <- warp logit (k < 3); n = 128 + j <- sheet logit (k = 3 + h)
+    pk.block(P_WARP_W(kWsDepth), 0, 1, kWarpW, 0, kWarpW, 0, 3);
+    pk.block(P_SHEET_W(kWsDepth), 0, 1, kSheetW, kWarpW, kSheetW, 3, m.H);
+    for (int l = kWsDepth - 1; l >= 1; --l) {
+      bool skip = (l == kSkip + 1);
+      if (skip) {  // GLO columns: dest(g, k<128) = warpW5[k][128 + pe_w + g]; dest(g, 128 + j) = sheetW5[j][64 + pe_s + g]
+        bop();
+        pk.block(P_WARP_W(l), kWarpW + m.pe_w, 1, ldw5, 0, m.G, 0, kWarpW);
+        pk.block(P_SHEET_W(l), kSheetW + m.pe_s, 1, lds5, 0, m.G, kWarpW, kSheetW);
+      }
       bop();
-      pk.block(P_WARP_W(l), kWarpW + m.pe_w, 1, ldw5, 0, m.G, 0, kWarpW);
-      pk.block(P_SHEET_W(l), kSheetW + m.pe_s, 1, lds5, 0, m.G, kWarpW, kSheetW);
+      pk.block(P_WARP_W(l), 0, 1, skip ? ldw5 : kWarpW, 0, kWarpW, 0, kWarpW);
+      bop();
+      pk.block(P_SHEET_W(l), 0, 1, skip ? lds5 : kSheetW, 0, kSheetW, 0, kSheetW);
     }
-    bop();
-    pk.block(P_WARP_W(l), 0, 1, skip ? ldw5 : kWarpW, 0, kWarpW, 0, kWarpW);
-    bop();
-    pk.block(P_SHEET_W(l), 0, 1, skip ? lds5 : kSheetW, 0, kSheetW, 0, kSheetW);
+    bop();  // GLO columns of layer 0
+    pk.block(P_WARP_W(0), m.pe_w, 1, m.in_w, 0, m.G, 0, kWarpW);
+    pk.block(P_SHEET_W(0), m.pe_s, 1, m.in_s, 0, m.G, kWarpW, kSheetW);
   }
-  bop();  // GLO columns of layer 0
-  pk.block(P_WARP_W(0), m.pe_w, 1, m.in_w, 0, m.G, 0, kWarpW);
-  pk.block(P_SHEET_W(0), m.pe_s, 1, m.in_s, 0, m.G, kWarpW, kSheetW);
 
   // biases, in forward layer order
   int bo = 0;
-  for (int l = 0; l < kWsDepth; ++l) {
-    pk.bias(P_WARP_B(l), bo, kWarpW);
-    pk.bias(P_SHEET_B(l), bo + kWarpW, kSheetW);
-    bo += kWsW;
+  if (!m.nowarp) {
+    for (int l = 0; l < kWsDepth; ++l) {
+      pk.bias(P_WARP_B(l), bo, kWarpW);
+      pk.bias(P_SHEET_B(l), bo + kWarpW, kSheetW);
+      bo += kWsW;
+    }
+    pk.bias(P_WARP_B(kWsDepth), bo, 3);
+    pk.bias(P_SHEET_B(kWsDepth), bo + 3, m.H);
+    bo += 16;
   }
-  pk.bias(P_WARP_B(kWsDepth), bo, 3);
-  pk.bias(P_SHEET_B(kWsDepth), bo + 3, m.H);
-  bo += 16;
   for (int l = 0; l <= kTrunkDepth; ++l) { pk.bias(P_TRUNK_B(level, l), bo, kTrunkW); bo += kTrunkW; }
   pk.bias(P_BOTT_B(level), bo, kRgbW); bo += kRgbW;
   pk.bias(P_RGB_B(level, 0), bo, kRgbW);
@@ -386,45 +457,57 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
     return j;
   };
   auto flush = [&](WgradJob& j, int param, int64_t extra, int ld, int row0, int nrows, int col0, int ncols) {
+    if (off[param] < 0 || nrows <= 0 || ncols <= 0) return;
     FlushSeg& f = j.flush[j.nflush++];
     f.dst = off[param] + extra; f.ld = ld; f.row0 = (uint16_t)row0; f.nrows = (uint16_t)nrows;
     f.col0 = (uint16_t)col0; f.ncols = (uint16_t)ncols;
   };
   auto bseg = [&](WgradJob& j, int param, int col0, int ncols) {
+    if (off[param] < 0 || ncols <= 0) return;
     BiasSeg& b = j.bias[j.nbias++];
     b.dst = off[param]; b.col0 = (uint16_t)col0; b.ncols = (uint16_t)ncols; b.pad = 0;
   };
-  // warp / sheet layer 0
-  {
-    WgradJob& j = job(s.d_ws[0], kWarpW, s.x_in_ws, m.KW, 0, 0);
-    flush(j, P_WARP_W(0), 0, m.in_w, 0, kWarpW, 0, m.in_w);
-    bseg(j, P_WARP_B(0), 0, kWarpW);
-    WgradJob& k = job(s.d_ws[0] + kWarpW / 8, kSheetW, s.x_in_ws, m.KW, 0, 0);
-    flush(k, P_SHEET_W(0), 0, m.in_s, 0, kSheetW, 0, m.pe_s);
-    flush(k, P_SHEET_W(0), m.pe_s, m.in_s, 0, kSheetW, m.pe_w, m.G);
-    bseg(k, P_SHEET_B(0), 0, kSheetW);
-  }
-  for (int l = 1; l < kWsDepth; ++l) {
-    bool skip = (l == kSkip + 1);
-    WgradJob& j = job(s.d_ws[l], kWarpW, s.x_hws[l - 1], kWarpW, s.x_in_ws, skip ? m.KW : 0);
-    flush(j, P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
-    bseg(j, P_WARP_B(l), 0, kWarpW);
-    WgradJob& k = job(s.d_ws[l] + kWarpW / 8, kSheetW, s.x_hws[l - 1] + kWarpW / 8, kSheetW, s.x_in_ws, skip ? m.KW : 0);
-    if (!skip) {
-      flush(k, P_SHEET_W(l), 0, kSheetW, 0, kSheetW, 0, kSheetW);
-    } else {
-      flush(k, P_SHEET_W(l), 0, lds5, 0, kSheetW, 0, kSheetW + m.pe_s);
-      flush(k, P_SHEET_W(l), kSheetW + m.pe_s, lds5, 0, kSheetW, kSheetW + m.pe_w, m.G);
+  // a job none of whose outputs exists (the sheet MLP with axis-aligned slicing) is dropped again
+  auto keep = [&](WgradJob& j) { if (j.nflush == 0 && j.nbias == 0) { memset(&j, 0, sizeof(j)); --w.njobs; } };
+  if (!m.nowarp) {
+    // warp / sheet layer 0
+    {
+      WgradJob& j = job(s.d_ws[0], kWarpW, s.x_in_ws, m.KW, 0, 0);
+      flush(j, P_WARP_W(0), 0, m.in_w, 0, kWarpW, 0, m.in_w);
+      bseg(j, P_WARP_B(0), 0, kWarpW);
+      keep(j);
+      WgradJob& k = job(s.d_ws[0] + kWarpW / 8, kSheetW, s.x_in_ws, m.KW, 0, 0);
+      flush(k, P_SHEET_W(0), 0, m.in_s, 0, kSheetW, 0, m.pe_s);
+      flush(k, P_SHEET_W(0), m.pe_s, m.in_s, 0, kSheetW, m.pe_w, m.G);
+      bseg(k, P_SHEET_B(0), 0, kSheetW);
+      keep(k);
     }
-    bseg(k, P_SHEET_B(l), 0, kSheetW);
+    for (int l = 1; l < kWsDepth; ++l) {
+      bool skip = (l == kSkip + 1);
+      WgradJob& j = job(s.d_ws[l], kWarpW, s.x_hws[l - 1], kWarpW, s.x_in_ws, skip ? m.KW : 0);
+      flush(j, P_WARP_W(l), 0, skip ? ldw5 : kWarpW, 0, kWarpW, 0, skip ? ldw5 : kWarpW);
+      bseg(j, P_WARP_B(l), 0, kWarpW);
+      keep(j);
+      WgradJob& k = job(s.d_ws[l] + kWarpW / 8, kSheetW, s.x_hws[l - 1] + kWarpW / 8, kSheetW, s.x_in_ws, skip ? m.KW : 0);
+      if (!skip) {
+        flush(k, P_SHEET_W(l), 0, kSheetW, 0, kSheetW, 0, kSheetW);
+      } else {
+        flush(k, P_SHEET_W(l), 0, lds5, 0, kSheetW, 0, kSheetW + m.pe_s);
+        flush(k, P_SHEET_W(l), kSheetW + m.pe_s, lds5, 0, kSheetW, kSheetW + m.pe_w, m.G);
+      }
+      bseg(k, P_SHEET_B(l), 0, kSheetW);
+      keep(k);
+    }
+    {
+      WgradJob& j = job(s.d_wshead, 16, s.x_hws[kWsDepth - 1], kWsW, 0, 0);
+      flush(j, P_WARP_W(kWsDepth), 0, kWarpW, 0, 3, 0, kWarpW);
+      flush(j, P_SHEET_W(kWsDepth), 0, kSheetW, 3, m.H, kWarpW, kSheetW);
+      bseg(j, P_WARP_B(kWsDepth), 0, 3);
+      bseg(j, P_SHEET_B(kWsDepth), 3, m.H);
+      keep(j);
+    }
   }
-  {
-    WgradJob& j = job(s.d_wshead, 16, s.x_hws[kWsDepth - 1], kWsW, 0, 0);
-    flush(j, P_WARP_W(kWsDepth), 0, kWarpW, 0, 3, 0, kWarpW);
-    flush(j, P_SHEET_W(kWsDepth), 0, kSheetW, 3, m.H, kWarpW, kSheetW);
-    bseg(j, P_WARP_B(kWsDepth), 0, 3);
-    bseg(j, P_SHEET_B(kWsDepth), 3, m.H);
-  }
+  const int first_trunk_job = w.njobs;
   // trunk
   {
     WgradJob& j = job(s.d_t[0], kTrunkW, s.x_in_t, m.KT, 0, 0);
@@ -449,8 +532,10 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   }
   {
     WgradJob& j = job(s.d_rgb0a, m.n_rgb0a, s.x_bott, kRgbW, s.x_in_v, m.KV);
-    flush(j, P_RGB_W(level, 0), 0, kRgbW + m.pe_v, 0, kRgbW, 0, kRgbW + m.pe_v);
-    flush(j, P_ALPHA_W(level), 0, kRgbW, kRgbW, 1, 0, kRgbW);
+    flush(j, P_RGB_W(level, 0), 0, ld_rgb0, 0, kRgbW, 0, kRgbW + m.pe_v);
+    if (m.cond_r) flush(j, P_RGB_W(level, 0), kRgbW + m.pe_v, ld_rgb0, 0, kRgbW, k_cond, m.G);
+    flush(j, P_ALPHA_W(level), 0, ld_alpha, kRgbW, 1, 0, kRgbW);
+    if (m.cond_a) flush(j, P_ALPHA_W(level), kRgbW, ld_alpha, kRgbW, 1, k_cond, m.G);
     bseg(j, P_RGB_B(level, 0), 0, kRgbW);
     bseg(j, P_ALPHA_B(level), kRgbW, 1);
   }
@@ -464,11 +549,10 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
     flush(j, P_RGB_W(level, kRgbDepth), 0, kRgbW, 0, 3, 0, kRgbW);
     bseg(j, P_RGB_B(level, kRgbDepth), 0, 3);
   }
-  // trunk-only job table: everything whose dY slab is not one of the warp / sheet slabs (those come first in the map)
+  // trunk-only job table: everything after the warp / sheet jobs
   WgradTable& wt = plan->wgrad_trunk;
   memset(&wt, 0, sizeof(wt));
-  for (int i = 0; i < w.njobs; ++i)
-    if (w.jobs[i].dy_chunk >= s.d_t[0]) wt.jobs[wt.njobs++] = w.jobs[i];
+  for (int i = first_trunk_job; i < w.njobs; ++i) wt.jobs[wt.njobs++] = w.jobs[i];
   (void)d;
 }
 
@@ -568,7 +652,7 @@ static void build_plan_static(const hn_model_desc& d, ModelPlan* plan) {
   I.x_total = s.x_total; I.d_total = s.d_total; I.g_total = s.g_total;
   I.x_in0 = s.x_in_x; I.x_in_t = kNone; I.x_in_v = s.x_in_v;
   I.d_rgbhead = s.d_rgbhead; I.d_sigma = s.d_sigma;
-  I.n_params = HN_NUM_STATIC_PARAM_TENSORS; I.glo_floats = 0;
+  I.n_params = HN_NUM_STATIC_PARAM_TENSORS; I.glo_floats = 0; I.glo_param = -1;
   // the descriptor is needed again by build_tables_static: keep the derived sizes in dims (unused otherwise)
   plan->dims.KW = s.KX; plan->dims.KV = s.KV; plan->dims.pe_x = s.pe_x; plan->dims.pe_v = s.pe_v;
 }

@@ -81,30 +81,57 @@ constexpr int pad16(int x) { return (x + 15) / 16 * 16; }
 constexpr int kTrunkW = 256, kTrunkDepth = 8, kRgbW = 128, kRgbDepth = 4;
 constexpr int kWarpW = 128, kSheetW = 64, kWsDepth = 6, kWsW = kWarpW + kSheetW, kSkip = 4;
 
+// View-direction condition vector of the template (hyper model): [posenc_orig(viewdirs, view_freqs <= 6) zero-padded to 40
+// columns | GLO condition (8 columns, zero without template conditioning)] = 48 columns, whatever view_freqs is, so that
+// the view frequency count and the conditioning flags are run-time values of one kernel instantiation.
+constexpr int kViewPeCols = 40, kViewCondCol = 40, kKV = 48, kMaxViewFreqs = 6;
+// The trunk input vector (posenc of the warped point + hyper coordinates) lives in the input buffer INB when it is at
+// most this wide (hyper_dim <= 2: 89 -> 96 columns); wider ones (hyper_dim 4: 128, 8: 176 columns) would not leave room
+// for the weight ring, so they are written into the activation buffer ACT instead — free at that point — and the skip
+// layer, which needs the vector a second time, becomes two layers: the hidden part, then (ACT re-filled with the
+// recomputed vector by the FE_SKIPFEED epilogue) the input part accumulating on top.
+constexpr int kMaxTrunkInInb = 96;
+constexpr int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+// Shared-input-buffer geometry from the padded vector widths (KW = 0: no warp / sheet stage); used by the compile-time
+// Shape<> of hn_mlp.cu and by make_dims, which must agree.
+constexpr bool trunk_in_act(int KT) { return KT > kMaxTrunkInInb; }
+constexpr int inb_max_cols(int KW, int KT, int KV) { return max3(KW, trunk_in_act(KT) ? 0 : KT, KV); }
+constexpr bool inb_ones_in_pad(int KW, int in_w, int KT, int in_t, int KV, int in_v) {
+  const int mx = inb_max_cols(KW, KT, KV);
+  return (KW == 0 || ones_fit_in_pad(mx, KW, in_w)) && (trunk_in_act(KT) || ones_fit_in_pad(mx, KT, in_t)) &&
+         ones_fit_in_pad(mx, KV, in_v);
+}
+constexpr int inb_chunks_of(int KW, int in_w, int KT, int in_t, int KV, int in_v) {
+  const int mx = inb_max_cols(KW, KT, KV);
+  return (kFoldBias && !inb_ones_in_pad(KW, in_w, KT, in_t, KV, in_v)) ? mx / 8 + 2 : mx / 8;
+}
+
 // Derived channel counts for a model descriptor.
 struct Dims {
   int G, H;
-  int pe_w, pe_s, in_w, in_s, KW;  // warp / sheet inputs, shared padded input width
+  bool nowarp, axis, cond_a, cond_r;   // no warp / sheet stage; hyper point = GLO vector; template GLO conditioning
+  int pe_w, pe_s, in_w, in_s, KW;  // warp / sheet inputs, shared padded input width (KW = 0 without warp)
   int pe_x, pe_h, in_t, KT;        // trunk input
-  int pe_v, KV;                    // view-direction condition
+  int pe_v, KV;                    // view-direction condition: pe_v real posenc columns inside the kKV-wide vector
   int n_rgb0a;                     // rgb layer 0 merged with the alpha head (pad16(128 + 1))
-  int in_max_chunks;               // chunks of the widest input vector
+  bool t_in_act;                   // trunk input vector lives in ACT (see kMaxTrunkInInb)
   int inb_chunks;                  // chunks of the shared input buffer (+2 when the ones columns do not fit in padding)
   int ones_col;                    // first column of the chunk pair whose last two columns are 1.0 (kFoldBias)
 };
 inline Dims make_dims(const hn_model_desc& d) {
-  Dims m;
-  m.G = d.glo_dim; m.H = d.hyper_dim;
+  Dims m{};
+  m.nowarp = (d.flags & HN_FLAG_WARP_TRANSLATION) == 0;
+  m.axis = (d.flags & HN_FLAG_SLICE_AXIS) != 0;
+  m.cond_a = (d.flags & HN_FLAG_ALPHA_COND) != 0; m.cond_r = (d.flags & HN_FLAG_RGB_COND) != 0;
+  m.G = d.glo_dim; m.H = m.nowarp ? 0 : d.hyper_dim;
   m.pe_w = 3 + 6 * d.warp_freqs; m.pe_s = 3 + 6 * d.sheet_freqs;
-  m.in_w = m.pe_w + m.G; m.in_s = m.pe_s + m.G; m.KW = pad16(m.in_w);
+  m.in_w = m.pe_w + m.G; m.in_s = m.pe_s + m.G; m.KW = m.nowarp ? 0 : pad16(m.in_w);
   m.pe_x = 3 + 6 * d.xyz_freqs; m.pe_h = m.H * (1 + 2 * d.hyper_freqs);
   m.in_t = m.pe_x + m.pe_h; m.KT = pad16(m.in_t);
-  m.pe_v = 3 + 6 * d.view_freqs; m.KV = pad16(m.pe_v);
+  m.pe_v = 3 + 6 * d.view_freqs; m.KV = kKV;
   m.n_rgb0a = pad16(kRgbW + 1);
-  int mx = m.KW > m.KT ? m.KW : m.KT; if (m.KV > mx) mx = m.KV;
-  m.in_max_chunks = mx / 8;
-  const bool in_pad = ones_fit_in_pad(mx, m.KW, m.in_w) && ones_fit_in_pad(mx, m.KT, m.in_t) && ones_fit_in_pad(mx, m.KV, m.pe_v);
-  m.inb_chunks = (kFoldBias && !in_pad) ? mx / 8 + 2 : mx / 8;
+  m.t_in_act = trunk_in_act(m.KT);
+  m.inb_chunks = inb_chunks_of(m.KW, m.in_w, m.KT, m.in_t, m.KV, m.pe_v);
   m.ones_col = m.inb_chunks * 8 - 16;
   return m;
 }
@@ -124,6 +151,7 @@ inline int P_RGB_W(int level, int l) { return P_LEVEL(level) + 20 + 2 * l; }  //
 inline int P_RGB_B(int level, int l) { return P_LEVEL(level) + 21 + 2 * l; }
 inline int P_ALPHA_W(int level) { return P_LEVEL(level) + 30; }
 inline int P_ALPHA_B(int level) { return P_LEVEL(level) + 31; }
+constexpr int P_COND_GLO = 93;   // nerf_embed.embed.weight: the condition table without warp
 
 // ---- saved-activation (forward) and pre-activation-gradient (backward) slab offsets, in 8-col chunks ---
 struct SlabMap {
@@ -142,7 +170,7 @@ inline SlabMap make_slabs(const Dims& m) {
   SlabMap s{};
   uint16_t c = 0;
   s.x_in_ws = c; c += m.KW / 8;
-  for (int l = 0; l < kWsDepth; ++l) { s.x_hws[l] = c; c += kWsW / 8; }
+  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.x_hws[l] = c; c += kWsW / 8; }
   s.x_in_t = c; c += m.KT / 8;
   for (int l = 0; l <= kTrunkDepth; ++l) { s.x_t[l] = c; c += kTrunkW / 8; }
   s.x_bott = c; c += kRgbW / 8;
@@ -150,8 +178,10 @@ inline SlabMap make_slabs(const Dims& m) {
   for (int l = 0; l < kRgbDepth; ++l) { s.x_r[l] = c; c += kRgbW / 8; }
   s.x_total = c;
   c = 0;
-  for (int l = 0; l < kWsDepth; ++l) { s.d_ws[l] = c; c += kWsW / 8; }
-  s.d_wshead = c; c += 2;
+  if (!m.nowarp) {
+    for (int l = 0; l < kWsDepth; ++l) { s.d_ws[l] = c; c += kWsW / 8; }
+    s.d_wshead = c; c += 2;
+  }
   for (int l = 0; l <= kTrunkDepth; ++l) { s.d_t[l] = c; c += kTrunkW / 8; }
   s.d_bott = c; c += kRgbW / 8;
   s.d_rgb0a = c; c += m.n_rgb0a / 8;
@@ -160,7 +190,7 @@ inline SlabMap make_slabs(const Dims& m) {
   s.d_rgbhead = c; c += 2;
   s.d_total = c;
   c = 0;
-  for (int l = 0; l < kWsDepth; ++l) { s.g_hws[l] = c; c += kWsW / 32; }
+  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.g_hws[l] = c; c += kWsW / 32; }
   for (int l = 0; l <= kTrunkDepth; ++l) { s.g_t[l] = c; c += kTrunkW / 32; }
   for (int l = 0; l < kRgbDepth; ++l) { s.g_r[l] = c; c += kRgbW / 32; }
   s.g_total = c;
@@ -189,8 +219,11 @@ struct LogicalOp {
   uint16_t n, k;
 };
 
-enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD, FE_SIGMA };
-enum BwdEpi : uint8_t { BE_MASK = 0, BE_LINEAR, BE_RGB1, BE_SKIPSTORE, BE_TRUNKIN, BE_GLO };
+// FE_SKIPFEED: no drain — the accumulator keeps the hidden part of the skip layer; the epilogue re-fills ACT with the trunk
+// input vector for the input part (see kMaxTrunkInInb).  BE_LINCOND: BE_LINEAR + the GLO-condition columns (-> table gradient).
+enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD, FE_SIGMA, FE_SKIPFEED };
+enum BwdEpi : uint8_t { BE_MASK = 0, BE_LINEAR, BE_RGB1, BE_SKIPSTORE, BE_TRUNKIN, BE_GLO, BE_LINCOND };
+enum ProgFlags : int32_t { PF_TIN_ACT = 1 };   // Program::flags
 
 struct Layer {
   uint8_t op0, nops, epi, pad;
@@ -204,6 +237,7 @@ struct Layer {
 
 struct Program {
   int32_t nlayers, nops;
+  int32_t flags, pad;
   Layer layers[kMaxLayers];
   MmaOp ops[kMaxOps];
 };
@@ -252,7 +286,7 @@ struct WgradJob {
   uint16_t x1_chunk, x1_nchunks;   // optional second range, placed right after the first
   uint8_t mblocks;                 // 1 or 2 blocks of 128 dY columns
   uint8_t nflush, nbias, group;    // group: which CTA group owns this job (hn_mlp.cu: kWgGroups)
-  FlushSeg flush[3];
+  FlushSeg flush[4];
   BiasSeg bias[2];
 };
 struct WgradTable {
@@ -273,6 +307,7 @@ struct PlanInfo {
   uint16_t d_rgbhead, d_sigma;          // dY slabs written by the data-gradient prologue
   int32_t n_params;                     // canonical parameter tensors
   int32_t glo_floats;
+  int32_t glo_param;                    // canonical index of the GLO table the kernels read (copied into the blob); -1: none
 };
 
 // static baseline (models/nerf.py): canonical parameter indices = state_dict order

@@ -39,9 +39,23 @@ def filter_sigma(points, sigma, render_opts):
     return sigma
 
 
+def _param_grads(ctx, model, level, flat_grad, offs, first):
+    """Gradients of the autograd inputs `*params` (the model's slot parameters, model._slot_params()) as views of the
+    flat buffer; the other level's tensors and anything that needs no gradient get None."""
+    other = range(*model._level_param_range(1 - level))
+    grads = []
+    for i, (slot, shape, n) in enumerate(ctx.param_meta):
+        if slot in other or not ctx.needs_input_grad[first + i]:
+            grads.append(None)
+        else:
+            grads.append(flat_grad[offs[slot]:offs[slot] + n].view(shape))
+    return grads
+
+
 class _FusedMlp(torch.autograd.Function):
-    """hn_mlp_fwd / hn_mlp_bwd as one autograd node per level.  Inputs after the fixed arguments are the 93
-    parameter tensors in canonical (state_dict) order; gradients come back as views of one flat fp32 buffer."""
+    """hn_mlp_fwd / hn_mlp_bwd as one autograd node per level.  Inputs after the fixed arguments are the parameter
+    tensors of the canonical slots this configuration has (include/hypernerf_b200.h); gradients come back as views of
+    one flat fp32 buffer."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -69,7 +83,7 @@ class _FusedMlp(torch.autograd.Function):
                   "hn_mlp_fwd")
         _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
-        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
         ctx.save_for_backward(ids, sigma, rgb, warped, saved, packed)
         ctx.set_materialize_grads(False)
         return sigma, rgb, warped
@@ -89,8 +103,7 @@ class _FusedMlp(torch.autograd.Function):
         direct = model._flat_grads is not None and model._flat_grads.flat.device == dev
         if direct:
             # accumulate straight into the bound flat gradient buffer (train.FlatGrads): no per-tensor adds
-            fg = model._flat_grads
-            offs, flat_grad = fg.c_offsets(), fg.flat
+            offs, flat_grad = model._flat_offsets(), model._flat_grads.flat
         else:
             offs, total = model._grad_offsets()
             flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -106,14 +119,7 @@ class _FusedMlp(torch.autograd.Function):
         _lib.count(2)
         if direct:
             return (None,) * (7 + len(ctx.param_meta))
-        grads = []
-        other = range(*model._level_param_range(1 - level))
-        for i, (shape, n) in enumerate(ctx.param_meta):
-            if i in other or not ctx.needs_input_grad[7 + i]:
-                grads.append(None)
-            else:
-                grads.append(flat_grad[offs[i]:offs[i] + n].view(shape))
-        return (None,) * 7 + tuple(grads)
+        return (None,) * 7 + tuple(_param_grads(ctx, model, level, flat_grad, offs, 7))
 
 
 class _FusedTrunk(torch.autograd.Function):
@@ -123,7 +129,7 @@ class _FusedTrunk(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, model, level, warped_in, viewdirs, noise, noise_std, *params):
+    def forward(ctx, model, level, warped_in, viewdirs, ids, noise, noise_std, *params):
         B, S = warped_in.shape[0], warped_in.shape[1]
         dev = warped_in.device
         desc = model._desc
@@ -132,24 +138,28 @@ class _FusedTrunk(torch.autograd.Function):
         vd = viewdirs.detach().to(torch.float32).contiguous()
         sigma = torch.empty(B, S, device=dev, dtype=torch.float32)
         rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
-        need_grad = ctx.needs_input_grad[2] or any(ctx.needs_input_grad[6:])
+        if ids is not None:
+            ids = ids.reshape(-1).to(torch.int64).contiguous()
+            if ids.numel() != B:
+                raise ValueError(f"metadata ids must have one entry per ray, got {tuple(ids.shape)} for {B} rays")
+        need_grad = ctx.needs_input_grad[2] or any(ctx.needs_input_grad[7:])
         saved = None
         if need_grad:
             saved = torch.empty(model._sizes(B * S).saved_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_fwd_trunk", B * S):
-            check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(wi), ptr(vd), ptr(noise), float(noise_std), B, S,
-                                         ptr(sigma), ptr(rgb), ptr(saved), stream()), "hn_mlp_fwd_trunk")
+            check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(wi), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
+                                         B, S, ptr(sigma), ptr(rgb), ptr(saved), stream()), "hn_mlp_fwd_trunk")
         _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
-        ctx.param_meta = [(p.shape, p.numel()) for p in params]
-        ctx.save_for_backward(sigma, rgb, wi, saved, packed)
+        ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
+        ctx.save_for_backward(sigma, rgb, wi, saved, packed, ids)
         ctx.set_materialize_grads(False)
         return sigma, rgb
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_sigma, g_rgb):
-        sigma, rgb, wi, saved, packed = ctx.saved_tensors
+        sigma, rgb, wi, saved, packed, ids = ctx.saved_tensors
         model, level = ctx.model, ctx.level
         B, S = ctx.shape
         if saved is None:
@@ -159,32 +169,38 @@ class _FusedTrunk(torch.autograd.Function):
         g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
         direct = model._flat_grads is not None and model._flat_grads.flat.device == dev
         if direct:
-            fg = model._flat_grads
-            offs, flat_grad = fg.c_offsets(), fg.flat
+            offs, flat_grad = model._flat_offsets(), model._flat_grads.flat
         else:
             offs, total = model._grad_offsets()
             flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         work = torch.empty(model._sizes(B * S).workspace_bytes, device=dev, dtype=torch.uint8)
-        g_wi = torch.empty_like(wi)
+        # a model without warp feeds the raw sample points: nothing upstream wants their gradient
+        g_wi = torch.empty_like(wi) if (ctx.needs_input_grad[2] or model.use_warp) else None
         with _lib.timed("mlp_dgrad_trunk", B * S):
-            check(lib().hn_mlp_bwd_trunk_data(C.byref(model._desc), ptr(packed), ptr(sigma), ptr(rgb), ptr(wi), ptr(saved),
-                                              ptr(g_sigma), ptr(g_rgb), B, S, level, offs, ptr(flat_grad), ptr(g_wi),
-                                              ptr(work), stream()), "hn_mlp_bwd_trunk_data")
+            check(lib().hn_mlp_bwd_trunk_data(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(wi),
+                                              ptr(saved), ptr(g_sigma), ptr(g_rgb), B, S, level, offs, ptr(flat_grad),
+                                              ptr(g_wi), ptr(work), stream()), "hn_mlp_bwd_trunk_data")
         with _lib.timed("mlp_wgrad_trunk", B * S):
             check(lib().hn_mlp_bwd_trunk_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad),
                                                  ptr(work), stream()), "hn_mlp_bwd_trunk_weights")
         _lib.count(2)
-        head = (None, None, g_wi if ctx.needs_input_grad[2] else None, None, None, None)
+        head = (None, None, g_wi if ctx.needs_input_grad[2] else None, None, None, None, None)
         if direct:
             return head + (None,) * len(ctx.param_meta)
-        mine = range(*model._level_param_range(level))
-        grads = [flat_grad[offs[i]:offs[i] + n].view(shape) if (i in mine and ctx.needs_input_grad[6 + i]) else None
-                 for i, (shape, n) in enumerate(ctx.param_meta)]
-        return head + tuple(grads)
+        return head + tuple(_param_grads(ctx, model, level, flat_grad, offs, 7))
 
 
 class NerfModel(PackedWeights, nn.Module):
-    """Nerf NN Model with both coarse and fine MLPs (reference: hypernerf/models.py:67-780)."""
+    """Nerf NN Model with both coarse and fine MLPs (reference: hypernerf/models.py:67-780).
+
+    Configurations (the combinations that run in the reference):
+      use_warp + hyper_slice_method='bendy_sheet'          TranslationField + HyperSheetMLP, hyper_slice_out_dim in {2, 4, 8}
+      use_warp + 'axis_aligned_plane'                      hyper point = the GLO vector, hyper_slice_out_dim == GLO_dim == 8
+      use_warp=False (any slicing argument)                the template NeRF on the raw points (models.py:568-569)
+    each with or without template GLO conditioning (use_nerf_embed + use_alpha_cond [+ use_rgb_cond], models.py:404-445),
+    view_fourier_dim <= 6, xyz / hyper fourier dims 10 / 6, GLO_dim 8.  Combinations that fail inside the reference's
+    forward (use_warp with slicing 'none'; use_nerf_embed without use_alpha_cond; use_rgb_cond without use_nerf_embed:
+    matmul shape errors) construct, like there, and raise RuntimeError when called."""
 
     # The fine level's sorted depths contain the coarse depths (models.py:752-755), and the warp field / hyper sheet are
     # shared between the levels (models.py:143-182), so the reference evaluates them twice at those points.  With this on,
@@ -242,30 +258,39 @@ class NerfModel(PackedWeights, nn.Module):
         if self.use_nerf_embed and not (self.use_rgb_condition or self.use_alpha_condition):
             raise ValueError('Template metadata is enabled but none of the condition'
                              'branches are.')
-        # ---- what the sm_100a kernels of this build implement (cfg 1/2/3 family) -------------
-        if not (use_warp and self.hyper_slice_method == 'bendy_sheet'):
-            raise NotImplementedError(
-                "libhypernerf_b200 implements the TranslationField warp + bendy_sheet path "
-                f"(got use_warp={use_warp}, hyper_slice_method={self.hyper_slice_method!r}); there is no fallback")
-        if use_nerf_embed or use_rgb_cond:
-            raise NotImplementedError("template GLO conditioning (use_nerf_embed / use_rgb_cond) is not built yet")
 
-        n_embed = max(self.embeddings_dict[self.warp_embed_key]) + 1
-        self.warp_embed = modules.GLOEmbed(num_embeddings=n_embed, embedding_dim=GLO_dim)
-        self.hyper_sheet_mlp = modules.HyperSheetMLP(out_ch=self.hyper_sheet_out_dim, in_ch_embed=GLO_dim)
-        self.warp_field = modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
+        # ---- module tree in the reference's registration order (models.py:215-309): state_dict names / order ---------
+        def n_embed(key):
+            return max(self.embeddings_dict[key]) + 1
+
+        if self.use_nerf_embed:
+            self.nerf_embed = modules.GLOEmbed(num_embeddings=n_embed(self.nerf_embed_key), embedding_dim=GLO_dim)
+        if self.use_warp:
+            self.warp_embed = modules.GLOEmbed(num_embeddings=n_embed(self.warp_embed_key), embedding_dim=GLO_dim)
+        if self.hyper_slice_method == 'axis_aligned_plane':
+            self.hyper_embed = modules.GLOEmbed(num_embeddings=n_embed(self.hyper_embed_key), embedding_dim=GLO_dim)
+        elif self.hyper_slice_method == 'bendy_sheet':
+            if not self.hyper_use_warp_embed:
+                self.hyper_embed = modules.GLOEmbed(num_embeddings=n_embed(self.hyper_embed_key), embedding_dim=GLO_dim)
+            self.hyper_sheet_mlp = modules.HyperSheetMLP(out_ch=self.hyper_sheet_out_dim, in_ch_embed=GLO_dim)
+        if self.use_warp:
+            self.warp_field = modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
         self.alpha_default = 0.0
         self.nerf_in_ch_pos = modules.posenc_channels(3, self.xyz_freq)
         self.nerf_cond_ch_rgb = modules.posenc_channels(3, self.dir_freq)
         self.hyper_feat_ch = modules.posenc_channels(self.hyper_sheet_out_dim, self.hyper_freq)
-        self.nerf_in_ch_pos += self.hyper_feat_ch
+        if self.use_warp:
+            self.nerf_in_ch_pos += self.hyper_feat_ch
+        if self.use_rgb_condition:
+            self.nerf_cond_ch_rgb += GLO_dim
 
         def make_nerf_mlp():
             return modules.NerfMLP(in_ch=self.nerf_in_ch_pos, trunk_depth=self.nerf_trunk_depth,
                                    trunk_width=self.nerf_trunk_width, rgb_branch_depth=self.nerf_rgb_branch_depth,
                                    rgb_branch_width=self.nerf_rgb_branch_width, skips=self.nerf_skips,
                                    alpha_channels=self.alpha_channels, rgb_channels=self.rgb_channels,
-                                   alpha_condition_dim=0, rgb_condition_dim=self.nerf_cond_ch_rgb)
+                                   alpha_condition_dim=GLO_dim if self.use_nerf_embed else 0,
+                                   rgb_condition_dim=self.nerf_cond_ch_rgb)
 
         self.nerf_mlps_coarse = make_nerf_mlp()
         if self.num_fine_samples > 0:
@@ -273,58 +298,122 @@ class NerfModel(PackedWeights, nn.Module):
         else:
             raise NotImplementedError("n_samples_fine == 0: the reference itself fails here (models.py:292-309)")
 
-        self._desc = _lib.ModelDesc(GLO_dim, hyper_slice_out_dim, xyz_fourier_dim, hyper_fourier_dim, view_fourier_dim,
-                                    modules.TranslationField.n_freq, modules.HyperSheetMLP.n_freq, n_embed,
-                                    _lib.HN_FLAG_WARP_TRANSLATION | _lib.HN_FLAG_SLICE_BENDY)
-        sizes = _lib.Sizes()
-        check(lib().hn_query(C.byref(self._desc), 0, C.byref(sizes)), "hn_query")
-        self._packed_bytes = sizes.packed_bytes
-        n_params = sum(p.numel() for p in self.parameters())
-        if n_params != sizes.flat_param_floats or len(self._canonical_params()) != _lib.HN_NUM_PARAM_TENSORS:
-            raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} parameters, "
-                                          f"library expects {sizes.flat_param_floats}")
+        # ---- what the reference's own forward cannot run: same exception type, raised at call time -------------------
+        self._forward_error = None
+        if self.use_warp and self.hyper_slice_method == 'none':
+            self._forward_error = ("use_warp with hyper_slice_method 'none': the trunk is built for posenc(xyz) + posenc(hyper) "
+                                   "channels but map_points yields no hyper point (models.py:269-270, 575-579)")
+        elif self.use_warp and self.hyper_slice_method == 'axis_aligned_plane' and hyper_slice_out_dim != GLO_dim:
+            self._forward_error = ("axis_aligned_plane: the hyper point is the GLO vector (models.py:533-534), so "
+                                   "hyper_slice_out_dim must equal GLO_dim")
+        elif self.use_nerf_embed and not self.use_alpha_condition:
+            self._forward_error = "use_nerf_embed without use_alpha_cond: alpha_mlp expects 128 + GLO_dim inputs (modules.py:283)"
+        elif self.use_rgb_condition and not self.use_nerf_embed:
+            self._forward_error = "use_rgb_cond without use_nerf_embed: rgb_mlp expects the GLO columns (models.py:269-272)"
+        elif self.hyper_slice_method not in ('none', 'bendy_sheet', 'axis_aligned_plane'):
+            self._forward_error = f'Unknown hyper slice method {self.hyper_slice_method}.'   # models.py:394-396
+
+        # ---- the kernels' view of the model ---------------------------------------------------------------------------
+        cond_a = self.use_nerf_embed and self.use_alpha_condition
+        cond_r = self.use_nerf_embed and self.use_rgb_condition
+        flags = (_lib.HN_FLAG_ALPHA_COND if cond_a else 0) | (_lib.HN_FLAG_RGB_COND if cond_r else 0)
+        self._ids_key, n_rows = None, 0
+        if self.use_warp:
+            flags |= _lib.HN_FLAG_WARP_TRANSLATION
+            flags |= _lib.HN_FLAG_SLICE_AXIS if self.hyper_slice_method == 'axis_aligned_plane' else _lib.HN_FLAG_SLICE_BENDY
+            self._ids_key, n_rows = self.warp_embed_key, n_embed(self.warp_embed_key)
+        elif cond_a or cond_r:
+            # without warp the condition comes from nerf_embed[metadata['warp']] (models.py:425-430)
+            self._ids_key, n_rows = self.nerf_embed_key, n_embed(self.nerf_embed_key)
+        self._desc = _lib.ModelDesc(GLO_dim, hyper_slice_out_dim if self.use_warp else 0, xyz_fourier_dim, hyper_fourier_dim,
+                                    view_fourier_dim, modules.TranslationField.n_freq, modules.HyperSheetMLP.n_freq, n_rows,
+                                    flags)
+        self._slot_cache = None
         self._pack_levels = 2
         self._init_packing()
         self._flat_grads = None
+        self._flat_off_cache = None
         self._grad_off_cache = None
         self._size_cache = {}
+        if self._forward_error is None:
+            sizes = _lib.Sizes()
+            check(lib().hn_query(C.byref(self._desc), 0, C.byref(sizes)), "hn_query")   # rejects shapes that are not built
+            self._packed_bytes = sizes.packed_bytes
+            n_params = sum(p.numel() for p in self._slot_params() if p is not None)
+            if n_params != sizes.flat_param_floats:
+                raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} kernel-visible parameters, "
+                                              f"library expects {sizes.flat_param_floats}")
 
     # ------------------------------------------------------------------------------------------------------
     # native plumbing
     # ------------------------------------------------------------------------------------------------------
-    def _canonical_params(self):
-        """The 93 parameter tensors in the order include/hypernerf_b200.h documents (= state_dict order)."""
-        out = [self.warp_embed.embed.weight]
-        for mlp in (self.hyper_sheet_mlp.mlp, self.warp_field.mlp):
-            for lin in list(mlp.linears) + [mlp.logit_layer]:
-                out += [lin.weight, lin.bias]
-        for nm in (self.nerf_mlps_coarse, self.nerf_mlps_fine):
-            for lin in list(nm.trunk_mlp.linears) + [nm.trunk_mlp.logit_layer, nm.bottleneck_mlp] + \
-                    list(nm.rgb_mlp.linears) + [nm.rgb_mlp.logit_layer, nm.alpha_mlp]:
-                out += [lin.weight, lin.bias]
+    def _slot_params(self):
+        """The parameter tensors by canonical slot (include/hypernerf_b200.h, HN_NUM_PARAM_TENSORS entries); None for a
+        slot this configuration does not have."""
+        if self._slot_cache is not None:
+            return self._slot_cache
+        out = [None] * _lib.HN_NUM_PARAM_TENSORS
+
+        def put(first, lins):
+            for i, lin in enumerate(lins):
+                out[first + 2 * i], out[first + 2 * i + 1] = lin.weight, lin.bias
+
+        bendy = self.hyper_slice_method == 'bendy_sheet'
+        if self.use_warp:
+            out[0] = self.warp_embed.embed.weight
+            if bendy:
+                put(1, list(self.hyper_sheet_mlp.mlp.linears) + [self.hyper_sheet_mlp.mlp.logit_layer])
+            put(15, list(self.warp_field.mlp.linears) + [self.warp_field.mlp.logit_layer])
+        elif self.use_nerf_embed:
+            out[93] = self.nerf_embed.embed.weight
+        for level, nm in enumerate((self.nerf_mlps_coarse, self.nerf_mlps_fine)):
+            put(29 + 32 * level, list(nm.trunk_mlp.linears) + [nm.trunk_mlp.logit_layer, nm.bottleneck_mlp] +
+                list(nm.rgb_mlp.linears) + [nm.rgb_mlp.logit_layer, nm.alpha_mlp])
+        self._slot_cache = out
         return out
+
+    def _slots_present(self):
+        return [i for i, p in enumerate(self._slot_params()) if p is not None]
+
+    def _canonical_params(self):
+        """The kernel-visible parameter tensors in slot order (the `*params` of the autograd functions)."""
+        return [p for p in self._slot_params() if p is not None]
 
     @staticmethod
     def _level_param_range(level):
         return 29 + 32 * level, 29 + 32 * (level + 1)
 
+    def _c_offsets(self, offset_of):
+        return (C.c_int64 * _lib.HN_NUM_PARAM_TENSORS)(*[-1 if p is None else offset_of(p) for p in self._slot_params()])
+
+    def _param_offsets(self, base):
+        """Element offsets of the slot parameters relative to `base` (hn_pack_weights); -1 for absent slots."""
+        return self._c_offsets(lambda p: (p.data_ptr() - base) // 4)
+
     def _grad_offsets(self):
+        """Private flat gradient layout (autograd path without train.FlatGrads): (offsets by slot, total floats)."""
         if self._grad_off_cache is None:
-            offs, total = [], 0
+            offs, total = {}, 0
             for p in self._canonical_params():
-                offs.append(total)
+                offs[id(p)] = total
                 total += (p.numel() + 3) // 4 * 4  # 16-byte aligned slices
-            self._grad_off_cache = ((C.c_int64 * len(offs))(*offs), total)
+            self._grad_off_cache = (self._c_offsets(lambda p: offs[id(p)]), total)
         return self._grad_off_cache
+
+    def _flat_offsets(self):
+        """Offsets by slot into the attached train.FlatGrads buffer."""
+        if self._flat_off_cache is None:
+            self._flat_off_cache = self._c_offsets(self._flat_grads.offset_of)
+        return self._flat_off_cache
 
     def attach_flat_grads(self, flat_grads):
         """Opt-in: hn_mlp_bwd accumulates directly into `flat_grads.flat` (train.FlatGrads built over
         `self.parameters()`), bypassing autograd's per-tensor accumulation.  Pass None to detach."""
         if flat_grads is not None:
-            ps = self._canonical_params()
-            if len(flat_grads.params) != len(ps) or any(a is not b for a, b in zip(flat_grads.params, ps)):
-                raise ValueError("FlatGrads must be built over this model's parameters() in order")
+            for q in self._canonical_params():
+                flat_grads.offset_of(q)    # raises if a kernel-visible parameter is not part of the buffer
         self._flat_grads = flat_grads
+        self._flat_off_cache = None
 
     def _sizes(self, n_samples):
         s = self._size_cache.get(n_samples)
@@ -338,8 +427,16 @@ class NerfModel(PackedWeights, nn.Module):
     # reference API
     # ------------------------------------------------------------------------------------------------------
     @property
+    def num_nerf_embeds(self):
+        return max(self.embeddings_dict[self.nerf_embed_key]) + 1
+
+    @property
     def num_warp_embeds(self):
         return max(self.embeddings_dict[self.warp_embed_key]) + 1
+
+    @property
+    def num_hyper_embeds(self):
+        return max(self.embeddings_dict[self.hyper_embed_key]) + 1
 
     @property
     def has_hyper(self):
@@ -358,16 +455,20 @@ class NerfModel(PackedWeights, nn.Module):
                        render_opts=None, _inherited=None):
         """models.py:587-671.  _inherited = (warped points of the inherited depths (B,Ni,3+H), their positions (B,Ni) and
         the positions (B,S-Ni) of the remaining depths in the sorted row): see `reuse_coarse_warp`."""
+        if self._forward_error is not None:
+            raise RuntimeError(self._forward_error)
         if metadata_encoded:
             raise NotImplementedError("metadata_encoded=True is not built (callers pass ids; train.py:102, eval.py:86)")
         if return_warp_jacobian:
             raise NotImplementedError  # warping.py:121-122
-        if not use_warp:
-            raise NotImplementedError("use_warp=False at call time is not built in this round")
+        if self.use_warp and not use_warp:
+            # the reference hands the raw 3-channel points to a trunk built for posenc(xyz) + posenc(hyper) channels
+            raise RuntimeError("use_warp=False at call time on a model built with use_warp=True: the template expects the "
+                               "hyper channels (models.py:568-569, 269-270)")
         if metadata.get('hyper_point') is not None:
             raise NotImplementedError('hyper_point_override is not implemented.')  # models.py:528-529
         out = {'points': points}
-        ids = metadata[self.warp_embed_key]
+        ids = metadata[self._ids_key] if self._ids_key is not None else None
         B, S = points.shape[0], points.shape[1]
         noise, noise_std = None, 0.0
         if (self.noise_std is not None) and self.noise_std > 0.0 and self.use_stratified_sampling:
@@ -380,7 +481,11 @@ class NerfModel(PackedWeights, nn.Module):
             # the eval path (eval.py:77 @torch.no_grad) take the inference kernel, which writes no activation stash
             params = [q.detach() for q in params]
         lvl = 1 if level == 'fine' else 0
-        if _inherited is None:
+        if not self.use_warp:
+            # map_points returns the raw points (models.py:568-569): the template alone
+            sigma, rgb = _FusedTrunk.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
+            warped_points = points
+        elif _inherited is None:
             sigma, rgb, warped_points = _FusedMlp.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
         else:
             known_warped, pos_known, pos_new = _inherited
@@ -390,7 +495,7 @@ class NerfModel(PackedWeights, nn.Module):
                 noise_new = torch.gather(noise, 1, pos_new[..., None])
                 noise_known = torch.gather(noise, 1, pos_known[..., None])
             s_new, c_new, w_new = _FusedMlp.apply(self, lvl, pts_new, viewdirs, ids, noise_new, noise_std, *params)
-            s_known, c_known = _FusedTrunk.apply(self, lvl, known_warped, viewdirs, noise_known, noise_std, *params)
+            s_known, c_known = _FusedTrunk.apply(self, lvl, known_warped, viewdirs, ids, noise_known, noise_std, *params)
             pos = torch.cat([pos_new, pos_known], 1)                               # a permutation of 0..S-1 per ray
             sigma = torch.empty_like(z_vals).scatter(1, pos, torch.cat([s_new, s_known], 1))
             rgb = points.new_empty(B, S, 3).scatter(1, pos[..., None].expand(-1, -1, 3), torch.cat([c_new, c_known], 1))
@@ -440,7 +545,7 @@ class NerfModel(PackedWeights, nn.Module):
         out = {'coarse': coarse_ret}
         if self.num_fine_samples > 0:
             inherited = None
-            if self.use_stratified_sampling and self.reuse_coarse_warp:
+            if self.use_stratified_sampling and self.reuse_coarse_warp and self.use_warp:
                 z_vals, points, (pos_c, pos_n) = model_utils.sample_pdf_fused(
                     z_vals, coarse_ret['weights'], origins, directions, self.num_fine_samples, want_ranks=True)
                 inherited = (coarse_ret['warped_points'], pos_c, pos_n)

@@ -65,23 +65,24 @@ def make_state_dict(module_or_shapes, seed=0, boosted=False):
     boosted=False follows the reference initialisers' scales (xavier-uniform hidden layers, warp output U(0,1e-4),
     sheet output N(0,1e-5), GLO N(0, 0.1/G), biases U(+-1/sqrt(fan_in))); boosted=True scales the warp / sheet output
     layers to trained-model magnitudes (warp offsets ~0.05, hyper coordinates ~0.3) and uses a 0.5-std GLO table so
-    the warp and hyper-sheet branches carry signal in tests."""
+    the warp and hyper-sheet branches carry signal in tests; boosted='glo' keeps the reference scales everywhere except the
+    GLO tables (0.5 std), so that template conditioning and axis-aligned hyper points carry signal."""
     shapes = module_or_shapes if isinstance(module_or_shapes, dict) else \
         {k: tuple(v.shape) for k, v in module_or_shapes.state_dict().items()}
     g = torch.Generator().manual_seed(seed)
     out = {}
     for name, shape in shapes.items():
         if name.endswith("embed.weight"):
-            std = 0.5 if boosted else 0.1 / shape[1]
+            std = 0.5 if boosted else 0.1 / shape[1]   # (boosted == 'glo' is truthy)
             out[name] = torch.randn(shape, generator=g) * std
         elif name.endswith(".weight"):
             fan_out, fan_in = shape
             bound = math.sqrt(6.0 / (fan_in + fan_out))
             wt = (torch.rand(shape, generator=g) * 2 - 1) * bound
             if name == "warp_field.mlp.logit_layer.weight":
-                wt = wt * 0.05 if boosted else torch.rand(shape, generator=g) * 1e-4
+                wt = wt * 0.05 if boosted is True else torch.rand(shape, generator=g) * 1e-4
             if name == "hyper_sheet_mlp.mlp.logit_layer.weight":
-                wt = wt * 0.3 if boosted else torch.randn(shape, generator=g) * 1e-5
+                wt = wt * 0.3 if boosted is True else torch.randn(shape, generator=g) * 1e-5
             out[name] = wt
         else:  # bias: nn.Linear default U(-1/sqrt(fan_in), 1/sqrt(fan_in))
             fan_in = shapes[name[:-4] + "weight"][1]

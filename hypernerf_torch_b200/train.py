@@ -27,6 +27,12 @@ class FlatGrads:
         self.flat = torch.zeros(total, device=p0.device, dtype=p0.dtype)
         self.bind()
 
+    def offset_of(self, param):
+        """Element offset of `param`'s gradient inside `flat` (KeyError if it is not one of this buffer's parameters)."""
+        if getattr(self, "_by_id", None) is None:
+            self._by_id = {id(p): off for p, off in zip(self.params, self.offsets)}
+        return self._by_id[id(param)]
+
     def c_offsets(self):
         import ctypes
         if getattr(self, "_c_offs", None) is None:

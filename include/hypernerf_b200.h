@@ -20,11 +20,16 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 1
+#define HN_ABI_VERSION 2
 
-/* Topology of one NerfModel (reference: hypernerf/models.py:111-309).  Round 1 supports the cfg-1 family:
- * TranslationField warp (warping.py:28-125) + bendy_sheet HyperSheetMLP (modules.py:302-337) + NerfMLP
- * (modules.py:172-298) with trunk 8x256 skip@4, rgb branch 4x128, warp 6x128 skip@4, sheet 6x64 skip@4. */
+/* Topology of one NerfModel (reference: hypernerf/models.py:111-309): NerfMLP (modules.py:172-298) with trunk 8x256
+ * skip@4 and rgb branch 4x128, optionally conditioned on a GLO embedding, behind one of the working combinations of
+ * SURVEY.md App. B.2:
+ *   warp + bendy_sheet     TranslationField 6x128 skip@4 (warping.py:28-125) + HyperSheetMLP 6x64 skip@4 (modules.py:302-337)
+ *   warp + axis_aligned    TranslationField + hyper point = the GLO vector itself (models.py:533-534; hyper_dim == glo_dim)
+ *   no warp + no slicing   the template alone on the raw sample points (models.py:545-581 with use_warp=False)
+ * Instantiated shapes: glo_dim 8, hyper_dim 1..8 (0 without warp), xyz / hyper freqs 10 / 6, view freqs <= 6,
+ * warp / sheet freqs 10 / 7.  Anything else is rejected by hn_query with a message (there is no fallback). */
 typedef struct hn_model_desc {
   int32_t glo_dim;        /* G: GLO embedding width (opt.py:99)                                  */
   int32_t hyper_dim;      /* H: hyper_slice_out_dim (opt.py:92)                                  */
@@ -40,6 +45,9 @@ typedef struct hn_model_desc {
 
 #define HN_FLAG_WARP_TRANSLATION 1  /* use_warp with TranslationField                            */
 #define HN_FLAG_SLICE_BENDY 2       /* hyper_slice_method == 'bendy_sheet'                       */
+#define HN_FLAG_SLICE_AXIS 8        /* hyper_slice_method == 'axis_aligned_plane': hyper point = GLO vector (models.py:533-534) */
+#define HN_FLAG_ALPHA_COND 16       /* use_nerf_embed + use_alpha_cond: alpha head input [bottleneck | GLO] (modules.py:283)   */
+#define HN_FLAG_RGB_COND 32         /* use_nerf_embed + use_rgb_cond: rgb branch input [bottleneck | view PE | GLO] (:292)     */
 #define HN_FLAG_STATIC_NERF 4       /* static baseline models/nerf.py:41-123 (one NeRF per blob; xyz_freqs 10,
                                        view_freqs 4; glo/hyper/warp/sheet fields ignored).  hn_mlp_fwd then returns
                                        sigma = relu(raw + noise * noise_std) (rendering.py:150) and rgb; ids / warped
@@ -54,9 +62,12 @@ typedef struct hn_model_desc {
  *   15..28                 warp_field.mlp.linears.{0..5}.{weight,bias}, logit_layer.{weight,bias}
  *   29 + 32*level + ...    nerf_mlps_{coarse,fine}: trunk linears 0..7 + logit (18), bottleneck (2),
  *                          rgb linears 0..3 + logit (10), alpha (2)
+ *   93                     nerf_embed.embed.weight (E,G): the condition table when there is no warp (models.py:425-430;
+ *                          with a warp the condition is warp_embed, slot 0, models.py:421-423)
  * Offsets tables give the element offset of tensor i relative to a base pointer; the tensors need not be
- * contiguous with each other (the Python shim passes base = lowest parameter address). */
-#define HN_NUM_PARAM_TENSORS 93
+ * contiguous with each other (the Python shim passes base = lowest parameter address).  A tensor the configuration
+ * does not have (sheet MLP with axis-aligned slicing, warp MLP without warp, ...) has a NEGATIVE offset. */
+#define HN_NUM_PARAM_TENSORS 94
 
 typedef struct hn_sizes {
   int64_t packed_bytes;       /* one level's packed bf16 weights (forward + transposed) + fp32 biases */
@@ -157,17 +168,17 @@ int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, 
  *   hn_mlp_bwd_trunk  data + weight gradients of the trunk / heads into flat_grad, and g_warped_in (B,S,3+H) =
  *                     d loss / d warped_in (to be added to the upstream gradient of whoever produced warped_in). */
 int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
-                     const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb, void* saved,
-                     void* stream);
-int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
+                     const int64_t* ids /* NULL unless the template is GLO-conditioned */, const float* noise, float noise_std,
+                     int64_t B, int S, float* sigma, float* rgb, void* saved, void* stream);
+int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma, const float* rgb,
                      const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B, int S,
                      int level, const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in, void* workspace,
                      void* stream);
 /* hn_mlp_bwd_trunk split like hn_mlp_bwd_data / hn_mlp_bwd_weights (same workspace hand-off). */
-int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const float* sigma, const float* rgb,
-                          const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B,
-                          int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in,
-                          void* workspace, void* stream);
+int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
+                          const float* rgb, const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb,
+                          int64_t B, int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad,
+                          float* g_warped_in, void* workspace, void* stream);
 int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                              const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
 

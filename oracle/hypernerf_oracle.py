@@ -57,13 +57,17 @@ def mlp(sd, prefix, x, depth, skips=(4,), out_act=None, q=_ident, gates=None):
     return out_act(x) if out_act is not None else x
 
 
-def nerf_mlp(sd, prefix, feat, rgb_cond, q=_ident, gates=None):
-    """hypernerf/modules.py:266-298 without GLO conditioning: trunk (ReLU on the logit layer, :230), bottleneck
-    (no activation), alpha Linear, rgb MLP depth 4 (skip never fires) + Sigmoid (models.py:164)."""
+def nerf_mlp(sd, prefix, feat, rgb_cond, q=_ident, gates=None, alpha_cond=None):
+    """hypernerf/modules.py:266-298: trunk (ReLU on the logit layer, :230), bottleneck (no activation), alpha Linear on
+    [bottleneck | alpha condition] (:280-286), rgb MLP depth 4 (skip never fires) on [bottleneck | rgb condition] (:290-296)
+    + Sigmoid (models.py:164)."""
     g = gates or {}
     x = q(mlp(sd, f"{prefix}.trunk_mlp", q(feat), 8, out_act=F.relu, q=q, gates=g.get('trunk')))
     bott = q(F.linear(x, q(sd[f"{prefix}.bottleneck_mlp.weight"]), sd[f"{prefix}.bottleneck_mlp.bias"]))
-    alpha = F.linear(bott, q(sd[f"{prefix}.alpha_mlp.weight"]), sd[f"{prefix}.alpha_mlp.bias"])
+    alpha_in = bott
+    if alpha_cond is not None:
+        alpha_in = torch.cat([bott, q(alpha_cond)[:, None, :].expand(-1, bott.shape[1], -1)], -1)
+    alpha = F.linear(alpha_in, q(sd[f"{prefix}.alpha_mlp.weight"]), sd[f"{prefix}.alpha_mlp.bias"])
     cond = q(rgb_cond)[:, None, :].expand(-1, bott.shape[1], -1)  # broadcast_condition, modules.py:254-264
     rgb = mlp(sd, f"{prefix}.rgb_mlp", torch.cat([bott, cond], -1), 4, out_act=torch.sigmoid, q=q, gates=g.get('rgb'))
     return rgb, alpha
@@ -136,25 +140,46 @@ def sample_pdf(bins, weights, origins, directions, z, u):
 # model
 # ------------------------------------------------------------------------------------------------------------
 def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None, gates=None):
-    """map_points + query_template (hypernerf/models.py:545-581, 447-493) for TranslationField + bendy_sheet.
-    Returns (rgb (B,S,3), sigma (B,S), warped_points (B,S,3+H), raw alpha)."""
+    """map_points + query_template (hypernerf/models.py:545-581, 447-493).  cfg['slice'] in {'bendy_sheet' (default),
+    'axis_aligned_plane', 'none'}, cfg['use_warp'] (default True), cfg['cond_alpha'] / cfg['cond_rgb'] (template GLO
+    conditioning, models.py:404-445).  ids: dict of metadata id rows {'time', 'warp'} or a single row used for both.
+    Returns (rgb (B,S,3), sigma (B,S), warped_points (B,S,3[+H]), raw alpha)."""
     B, S, _ = points.shape
     q = bf16_ste if cfg.get('emulate_bf16') else _ident
-    embed = sd["warp_embed.embed.weight"][ids.reshape(-1)]            # GLOEmbed, modules.py:155-167
-    embed = embed[:, None, :].expand(B, S, embed.shape[-1])           # models.py:627-632
-    # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
-    warp_in = q(torch.cat([posenc_orig(points, 10), embed], -1))
+    use_warp = cfg.get('use_warp', True)
+    slice_method = cfg.get('slice', 'bendy_sheet')
+    if not isinstance(ids, dict):
+        ids = {'time': ids, 'warp': ids}
     g = gates or {}
-    warped = points + mlp(sd, "warp_field.mlp", warp_in, 6, q=q, gates=g.get('warp'))
-    # HyperSheetMLP on the UNWARPED points, modules.py:331-337 (n_freq 7), models.py:571-572
-    sheet_in = q(torch.cat([posenc_orig(points, 7), embed], -1))
-    hyper = mlp(sd, "hyper_sheet_mlp.mlp", sheet_in, 6, q=q, gates=g.get('sheet'))
-    warped_points = torch.cat([warped, hyper], -1)
-    feat = torch.cat([posenc_orig(warped_points[..., :3], cfg['xyz_freq']),
-                      posenc_orig(warped_points[..., 3:], cfg['hyper_freq'])], -1)   # models.py:458-478
+    if use_warp:
+        embed_b = sd["warp_embed.embed.weight"][ids['time'].reshape(-1)]   # GLOEmbed, modules.py:155-167; key 'time'
+        embed = embed_b[:, None, :].expand(B, S, embed_b.shape[-1])        # models.py:627-632
+        # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
+        warp_in = q(torch.cat([posenc_orig(points, 10), embed], -1))
+        warped = points + mlp(sd, "warp_field.mlp", warp_in, 6, q=q, gates=g.get('warp'))
+        if slice_method == 'bendy_sheet':
+            # HyperSheetMLP on the UNWARPED points, modules.py:331-337 (n_freq 7), models.py:571-572
+            sheet_in = q(torch.cat([posenc_orig(points, 7), embed], -1))
+            hyper = mlp(sd, "hyper_sheet_mlp.mlp", sheet_in, 6, q=q, gates=g.get('sheet'))
+        else:
+            hyper = embed            # axis_aligned_plane: hyper_points = hyper_embed = warp_embed (models.py:533-534, 618-619)
+        warped_points = torch.cat([warped, hyper], -1)
+        feat = torch.cat([posenc_orig(warped_points[..., :3], cfg['xyz_freq']),
+                          posenc_orig(warped_points[..., 3:], cfg['hyper_freq'])], -1)   # models.py:458-478
+    else:
+        warped_points = points       # map_points, models.py:568-569
+        feat = posenc_orig(points, cfg['xyz_freq'])
     rgb_cond = posenc_orig(viewdirs, cfg['view_freq'])                                # models.py:410-419
+    alpha_cond = None
+    if cfg.get('cond_alpha') or cfg.get('cond_rgb'):
+        # get_condition_inputs, models.py:421-434: warp_embed[metadata['time']] with a warp, nerf_embed[metadata['warp']] without
+        nerf_embed = embed_b if use_warp else sd["nerf_embed.embed.weight"][ids['warp'].reshape(-1)]
+        if cfg.get('cond_alpha'):
+            alpha_cond = nerf_embed
+        if cfg.get('cond_rgb'):
+            rgb_cond = torch.cat([rgb_cond, nerf_embed], -1)
     prefix = "nerf_mlps_fine" if level == 'fine' else "nerf_mlps_coarse"
-    rgb, alpha = nerf_mlp(sd, prefix, feat, rgb_cond, q=q, gates=gates)
+    rgb, alpha = nerf_mlp(sd, prefix, feat, rgb_cond, q=q, gates=gates, alpha_cond=alpha_cond)
     if noise is not None:
         alpha = alpha + noise * cfg['noise_std']                                      # model_utils.py:312-316
     sigma = F.softplus(alpha.squeeze(-1))                                             # models.py:491
@@ -190,9 +215,23 @@ def forward(sd, origins, directions, ids, draws, cfg, fine_z=None):
     return {'coarse': coarse, 'fine': fine}
 
 
-def default_cfg(n_fine=64, noise_std=1.0, emulate_bf16=False):
-    return dict(near=0., far=1., n_coarse=64, n_fine=n_fine, noise_std=noise_std, xyz_freq=10, hyper_freq=6,
-                view_freq=6, emulate_bf16=emulate_bf16)
+def default_cfg(n_fine=64, noise_std=1.0, emulate_bf16=False, **over):
+    cfg = dict(near=0., far=1., n_coarse=64, n_fine=n_fine, noise_std=noise_std, xyz_freq=10, hyper_freq=6,
+               view_freq=6, emulate_bf16=emulate_bf16, use_warp=True, slice='bendy_sheet', cond_alpha=False, cond_rgb=False)
+    cfg.update(over)
+    return cfg
+
+
+def cfg_from_kwargs(kw, emulate_bf16=False):
+    """Oracle configuration for a NerfModel constructor-argument dict (reference signature, models.py:111-127)."""
+    nerf_embed = kw.get('use_nerf_embed', True)
+    return default_cfg(n_fine=kw.get('n_samples_fine', 128), noise_std=kw.get('noise_std') or 0.0, emulate_bf16=emulate_bf16,
+                       near=kw.get('near', 0.), far=kw.get('far', 1.), n_coarse=kw.get('n_samples_coarse', 64),
+                       xyz_freq=kw.get('xyz_fourier_dim', 10), hyper_freq=kw.get('hyper_fourier_dim', 6),
+                       view_freq=kw.get('view_fourier_dim', 4), use_warp=kw.get('use_warp', True),
+                       slice=kw.get('hyper_slice_method') or 'none',
+                       cond_alpha=nerf_embed and kw.get('use_alpha_cond', True),
+                       cond_rgb=nerf_embed and kw.get('use_rgb_cond', False))
 
 
 def mse_loss(out, target):

@@ -48,6 +48,63 @@ def make(name, n_rays, n_fine, noise_std, boosted, seed):
     print(name, 'loss', float(loss), os.path.getsize(path) // 1024, 'KiB')
 
 
+# Configurations beyond cfg 1-3: constructor arguments exactly as the reference takes them.
+CONFIGS = {
+    # NeRFSystem's call (train.py:48-67) with the opt.py defaults: hyper_slice_out_dim 4, no template conditioning, 64+128
+    'optdefault_b16': dict(kw=dict(near=0., far=1., n_samples_coarse=64, n_samples_fine=128, noise_std=1.0, use_warp=True,
+                                   use_nerf_embed=False, use_alpha_cond=False, use_rgb_cond=False,
+                                   hyper_slice_method='bendy_sheet', hyper_slice_out_dim=4, GLO_dim=8, share_GLO=True,
+                                   xyz_fourier_dim=10, hyper_fourier_dim=6, view_fourier_dim=6), boosted=True, seed=40),
+    # the constructor's own defaults where they run (models.py:111-127: nerf embed + alpha condition, view freqs 4, H 4) + rgb condition
+    'cond_h4_vf4_b16': dict(kw=dict(n_samples_fine=64, noise_std=1.0, use_rgb_cond=True, hyper_slice_method='bendy_sheet'),
+                            boosted='glo', seed=41),
+    'alphacond_h8_b16': dict(kw=dict(n_samples_fine=64, noise_std=None, hyper_slice_method='bendy_sheet',
+                                     hyper_slice_out_dim=8, view_fourier_dim=6), boosted=True, seed=42),
+    # axis-aligned slicing: hyper point = GLO vector (models.py:533-534), hyper_slice_out_dim == GLO_dim
+    'axis_h8_b16': dict(kw=dict(n_samples_fine=64, noise_std=1.0, use_nerf_embed=False, use_alpha_cond=False,
+                                hyper_slice_method='axis_aligned_plane', hyper_slice_out_dim=8, view_fourier_dim=6),
+                        boosted='glo', seed=43),
+    # no warp: the template alone on the raw points (models.py:568-569)
+    'nowarp_b16': dict(kw=dict(n_samples_fine=64, noise_std=1.0, use_warp=False, use_nerf_embed=False, use_alpha_cond=False),
+                       boosted=False, seed=44),
+    'nowarp_cond_b16': dict(kw=dict(n_samples_fine=128, noise_std=None, use_warp=False, use_rgb_cond=True, view_fourier_dim=6),
+                            boosted='glo', seed=45),
+}
+
+
+def make_config(name, n_rays=16):
+    """Fixture for one entry of CONFIGS: like make(), with the constructor arguments stored and every gradient tensor of
+    at most 4 096 elements kept in full (norms for all)."""
+    torch.set_num_threads(8)
+    ref_models, _ = ref_loader.load_reference()
+    c = CONFIGS[name]
+    torch.manual_seed(0)
+    model = ref_models.NerfModel(ref_loader.EMBEDDINGS, **c['kw'])
+    sd = synthetic.make_state_dict(model, seed=c['seed'], boosted=c['boosted'])
+    model.load_state_dict(sd)
+    rays, rgbs = synthetic.train_rays(n_rays, seed=c['seed'] + 10)
+    torch.manual_seed(1234)
+    taps = {}
+    out, tape = ref_loader.run_reference(model, rays, taps=taps)
+    loss = torch.nn.functional.mse_loss(out['coarse']['rgb'], rgbs) + torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs)
+    loss.backward()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    fix = {
+        'name': name, 'kw': c['kw'], 'boosted': c['boosted'], 'weight_seed': c['seed'],
+        'n_fine': c['kw'].get('n_samples_fine', 128), 'noise_std': c['kw'].get('noise_std'),
+        'weight_checksum': float(sum(v.double().abs().sum() for v in sd.values())),
+        'shapes': {k: tuple(v.shape) for k, v in sd.items()},
+        'rays': rays, 'rgbs': rgbs, 'draws': tape, 'loss': float(loss.detach()), 'taps': taps,
+        'out': {lvl: {k: v.detach().clone() for k, v in out[lvl].items()} for lvl in out},
+        'grad_norms': {k: (float(g.double().norm()) if g is not None else None) for k, g in grads.items()},
+        'grad_small': {k: g for k, g in grads.items() if g is not None and g.numel() <= 4096},
+    }
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.pt')
+    torch.save(fix, path)
+    print(name, 'loss', float(loss), os.path.getsize(path) // 1024, 'KiB',
+          'no-grad params:', [k for k, g in grads.items() if g is None])
+
+
 STATIC_SMALL_GRADS = ["sigma.weight", "sigma.bias", "rgb.0.weight", "rgb.0.bias", "xyz_encoding_1.0.bias",
                       "xyz_encoding_5.0.bias", "dir_encoding.0.bias", "xyz_encoding_final.bias"]
 
@@ -113,6 +170,10 @@ def make_ndc_rays():
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'configs':
+        for name in (sys.argv[2:] or CONFIGS):
+            make_config(name)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'rays':
         make_ndc_rays()
         sys.exit(0)

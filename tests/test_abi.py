@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().hn_abi_version() == 1
+    assert _lib.lib().hn_abi_version() == 2
     # the product ABI carries no test / microbenchmark hooks: those live in libhypernerf_b200_probe.so with their own header
     assert not any(n.startswith(("hn_umma", "hn_epi", "hn_tmem", "hn_debug")) for n in declared)
     for n in ("hn_umma_probe", "hn_epi_rate", "hn_debug_set_timing_buffer"):
@@ -57,8 +57,12 @@ def test_errors_are_reported_not_crashed():
     s = _lib.Sizes()
     assert L.hn_query(C.byref(_desc(flags=1)), 64, C.byref(s)) < 0
     assert b"bendy_sheet" in L.hn_last_error()
-    assert L.hn_query(C.byref(_desc(hyper_dim=4)), 64, C.byref(s)) < 0
+    assert L.hn_query(C.byref(_desc(hyper_dim=3)), 64, C.byref(s)) < 0
     assert b"instantiated" in L.hn_last_error()
+    for h in (4, 8):                                  # opt.py default hyper_slice_out_dim and the axis-aligned shape
+        assert L.hn_query(C.byref(_desc(hyper_dim=h)), 64, C.byref(s)) == 0
+    assert L.hn_query(C.byref(_desc(hyper_dim=8, flags=1 | 8 | 16)), 64, C.byref(s)) == 0   # axis-aligned + alpha condition
+    assert L.hn_query(C.byref(_desc(hyper_dim=0, flags=0)), 64, C.byref(s)) == 0            # no warp
     assert L.hn_query(None, 64, C.byref(s)) < 0
     # shape / null checks happen before any launch, so they are testable without a GPU
     assert L.hn_sample_pdf(None, None, None, 0, None, None, None, 4, 64, 62, 64, None, None, None, None) < 0

@@ -64,6 +64,40 @@ def test_oracle_matches_golden_grads(name):
         torch.testing.assert_close(sd[k].grad, ref, rtol=1e-3, atol=1e-9, msg=k)
 
 
+CONFIG_FIXTURES = ["optdefault_b16", "cond_h4_vf4_b16", "alphacond_h8_b16", "axis_h8_b16", "nowarp_b16", "nowarp_cond_b16"]
+
+
+@pytest.mark.parametrize("name", CONFIG_FIXTURES)
+def test_oracle_matches_config_goldens(name):
+    """The configurations beyond cfg 1-3 (opt.py defaults with hyper_slice_out_dim 4, template GLO conditioning,
+    axis-aligned slicing, no warp): oracle outputs and gradients against the unmodified reference's (make_golden.py configs)."""
+    from hypernerf_torch_b200 import synthetic
+    fix = load_golden(name)
+    sd = synthetic.make_state_dict(fix['shapes'], seed=fix['weight_seed'], boosted=fix['boosted'])
+    chk = float(sum(v.double().abs().sum() for v in sd.values()))
+    assert abs(chk - fix['weight_checksum']) <= 1e-6 * abs(chk)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rays = fix['rays']
+    cfg = orc.cfg_from_kwargs(fix['kw'])
+    draws = ref_loader.draws_to_dict(fix['draws'], noise=bool(fix['noise_std']))
+    out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), draws, cfg, fine_z=fix['taps']['z_fine'])
+    for lvl in ("coarse", "fine"):
+        for k in KEYS:
+            ref = fix['out'][lvl][k]
+            assert out[lvl][k].shape == ref.shape, (lvl, k)
+            torch.testing.assert_close(out[lvl][k], ref, rtol=2e-5, atol=2e-6, msg=f"{name} {lvl} {k}")
+    loss = orc.mse_loss(out, fix['rgbs'])
+    assert abs(float(loss.detach()) - fix['loss']) < 1e-6
+    loss.backward()
+    for k, n in fix['grad_norms'].items():
+        if n is None:     # parameters the reference itself leaves without a gradient (unused embedding tables)
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+            continue
+        assert abs(float(sd[k].grad.double().norm()) - n) <= 1e-4 * n + 1e-12, k
+    for k, ref in fix['grad_small'].items():
+        torch.testing.assert_close(sd[k].grad, ref, rtol=1e-3, atol=1e-9, msg=k)
+
+
 @pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
 def test_oracle_matches_live_reference():
     from hypernerf_torch_b200 import synthetic
