@@ -517,6 +517,8 @@ class NerfModel(PackedWeights, nn.Module):
                 return_points=False, return_weights=False, return_warp_jacobian=False, near=None, far=None,
                 use_sample_at_infinity=None, render_opts=None, deterministic=False):
         """models.py:673-780.  Returns {'coarse': {...}, 'fine': {...}} with the reference's keys."""
+        if self._forward_error is not None:
+            raise RuntimeError(self._forward_error)
         with self.packed_frozen():   # re-packs the bf16 weight blobs unless an enclosing block froze them (_packing.py)
             return self._forward(rays_dict, extra_params, metadata_encoded, use_warp, return_points, return_weights,
                                  return_warp_jacobian, near, far, use_sample_at_infinity, render_opts, deterministic)
