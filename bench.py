@@ -8,7 +8,7 @@ per step), plus the Adam update.  Metric: train rays/s.
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference        # the reference algorithm (oracle port, fp32 torch) on the host CPU cores
+    python bench.py --impl reference        # the reference's CPU path on the host cores (live reference if reachable, else the pinned port)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -35,33 +35,105 @@ WORKLOAD = "cfg2: HyperNeRF translation warp + bendy_sheet (hyper_dim 2), 65536-
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU baseline: the reference algorithm (oracle restatement, fp32 torch) on the host cores, bounded sample
+# CPU baseline: the reference's own per-ray path on the host cores, on a bounded sample of each workload.
+# The live, unmodified reference is used when its tree is reachable (oracle/ref_loader.py: $HN_REFERENCE_DIR, /root/reference,
+# baseline/_ref) -> kind "reference"; on the GPU box, where a Python reference cannot travel, the pinned restatement
+# (oracle/, checked against the live reference and its goldens by tests/test_oracle.py) -> kind "port".
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(n_rays=1024, repeats=2, warmup=1):
-    from hypernerf_torch_b200 import synthetic
-    from oracle import hypernerf_oracle as orc
+def _cpu_setup():
+    from oracle import ref_loader
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synthetic.make_state_dict(synthetic.cfg1_state_dict_shapes(), seed=0, boosted=False)
-    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    return cores, ref_loader.reference_available()
+
+
+def _draws(n_rays, n_fine, it, noise=True):
+    g = torch.Generator().manual_seed(it)
+    d = dict(u_coarse=torch.rand(n_rays, N_COARSE, generator=g),
+             noise_coarse=torch.randn(n_rays, N_COARSE, 1, generator=g) if noise else None,
+             u_fine=torch.rand(n_rays, n_fine, generator=g),
+             noise_fine=torch.randn(n_rays, N_COARSE + n_fine, 1, generator=g) if noise else None)
+    return d
+
+
+def cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="train"):
+    """rays/s of the reference path on the host CPU.  workload: 'train' (cfg2 shape: 64+64, fwd + loss + bwd), 'render'
+    (cfg3: 64+128, no_grad forward), 'static' (cfg4: models/nerf.py x2 + render_rays, 128+128, fwd + bwd)."""
+    from hypernerf_torch_b200 import synthetic
+    from oracle import hypernerf_oracle as orc
+    from oracle import ref_loader, static_oracle
+    cores, live = _cpu_setup()
+    kind = "reference" if live else "port"
     rays, rgbs = synthetic.train_rays(n_rays, seed=0)
-    cfg = orc.default_cfg(n_fine=N_FINE, noise_std=1.0)
+    n_fine = {"train": N_FINE, "render": 128, "static": 128}[workload]
+    if workload == "static":
+        sds = [synthetic.make_state_dict(synthetic.static_state_dict_shapes(), seed=i) for i in range(2)]
+        if live:
+            ref_loader.load_reference()
+            from models.nerf import Embedding, NeRF            # the reference's own modules (sys.path set by the loader)
+            from models.rendering import render_rays as ref_render_rays
+            models = [NeRF(), NeRF()]
+            for m, sd in zip(models, sds):
+                m.load_state_dict(sd)
+            emb = [Embedding(3, 10), Embedding(3, 4)]
+
+            def step(it):
+                for m in models:
+                    m.zero_grad(set_to_none=True)
+                torch.manual_seed(it)
+                out = ref_render_rays(models, emb, rays[:, :8].contiguous(), N_samples=128, perturb=1.0, noise_std=1.0,
+                                      N_importance=128, chunk=1 << 15)
+                (torch.nn.functional.mse_loss(out['rgb_coarse'], rgbs) + torch.nn.functional.mse_loss(out['rgb_fine'], rgbs)).backward()
+        else:
+            sds = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in sds]
+
+            def step(it):
+                g = torch.Generator().manual_seed(it)
+                draws = dict(u_perturb=torch.rand(n_rays, 128, generator=g), noise_coarse=torch.randn(n_rays, 128, generator=g),
+                             u_pdf=torch.rand(n_rays, 128, generator=g), noise_fine=torch.randn(n_rays, 256, generator=g))
+                for sd in sds:
+                    for v in sd.values():
+                        v.grad = None
+                out = static_oracle.render_rays(sds, rays[:, :8], draws, n_samples=128, n_importance=128)
+                (torch.nn.functional.mse_loss(out['rgb_coarse'], rgbs) + torch.nn.functional.mse_loss(out['rgb_fine'], rgbs)).backward()
+        what = "cfg4 static NeRF (128+128 samples, fwd+bwd)"
+    else:
+        train = workload == "train"
+        sd = synthetic.make_state_dict(synthetic.cfg1_state_dict_shapes(), seed=0, boosted=False)
+        if live:
+            model = ref_loader.build_reference_model(seed=0, n_samples_fine=n_fine, noise_std=1.0 if train else None)
+            model.load_state_dict(sd)
+
+            def step(it):
+                model.zero_grad(set_to_none=True)
+                torch.manual_seed(it)
+                with torch.set_grad_enabled(train):
+                    out, _ = ref_loader.run_reference(model, rays)
+                    if train:
+                        (torch.nn.functional.mse_loss(out['coarse']['rgb'], rgbs) +
+                         torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs)).backward()
+        else:
+            sd = {k: v.clone().requires_grad_(train) for k, v in sd.items()}
+            cfg = orc.default_cfg(n_fine=n_fine, noise_std=1.0 if train else 0.0)
+
+            def step(it):
+                for v in sd.values():
+                    v.grad = None
+                with torch.set_grad_enabled(train):
+                    out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), _draws(n_rays, n_fine, it, noise=train), cfg)
+                    if train:
+                        orc.mse_loss(out, rgbs).backward()
+        what = "cfg2 train step (64+64 samples, fwd+loss+bwd)" if train else "cfg3 render (64+128 samples, no_grad forward)"
     best = float("inf")
     for it in range(warmup + repeats):
-        g = torch.Generator().manual_seed(it)
-        draws = dict(u_coarse=torch.rand(n_rays, N_COARSE, generator=g),
-                     noise_coarse=torch.randn(n_rays, N_COARSE, 1, generator=g),
-                     u_fine=torch.rand(n_rays, N_FINE, generator=g),
-                     noise_fine=torch.randn(n_rays, N_COARSE + N_FINE, 1, generator=g))
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
-        out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), draws, cfg)
-        orc.mse_loss(out, rgbs).backward()
+        step(it)
         dt = time.perf_counter() - t0
         if it >= warmup:
             best = min(best, dt)
-    return n_rays / best, cores, f"{n_rays} rays of the cfg2 workload (64+64 samples, fwd+bwd, fp32 torch on CPU), best of {repeats}"
+    impl = "the unmodified reference imported in place" if live else "oracle port of the reference (a Python reference cannot travel to the GPU box)"
+    return {"value": n_rays / best, "unit": "rays/s", "cores": cores, "kind": kind,
+            "sample": f"{n_rays} rays of {what}, fp32 torch on {cores} CPU threads, {impl}, best of {repeats}"}
 
 
 def run_reference_arm(args):
@@ -69,13 +141,14 @@ def run_reference_arm(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 5))
-    rate, cores, sample = cpu_reference_rate(n_rays=1024, repeats=steps, warmup=min(args.warmup, 1))
+    cpu = cpu_reference_rate(n_rays=1024, repeats=steps, warmup=min(args.warmup, 1), workload="train")
+    rate = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * 1024 / rate, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a 1024-ray sample of the workload"},
-        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,9 +246,66 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
+# Algorithmic work per sample evaluation (unpadded MACs x 2): which figure a profiled kernel launch counts
+STATIC_FLOP_PER_EVAL = 2 * 593408         # models/nerf.py NeRF(D=8, W=256): 593 408 MAC per sample
+# stash bytes the weight-gradient kernel streams per sample (design traffic): X slabs + dY slabs, read once
+WGRAD_STASH_BYTES = {"mlp_wgrad": 8640 + 8288, "mlp_wgrad_trunk": 6176 + 5952}
+
+
+def kernel_table(prof, secs, flop_full, flop_trunk):
+    """Per-kernel totals of the CUDA-event pairs recorded around every MLP launch of a timed region (_lib.timed)."""
+    per = {}
+    for name, n, a, b in prof or []:
+        d = per.setdefault(name, [0.0, 0, 0])
+        d[0] += a.elapsed_time(b) / 1e3; d[1] += 1; d[2] += n
+    kernels, executed = {}, 0.0
+    for name, (t, cnt, nsamp) in per.items():
+        # fwd, dgrad and wgrad each count 1x the forward FLOPs of the samples they process (bwd = 2x fwd)
+        flops = (flop_trunk if name.endswith("_trunk") else flop_full) * nsamp
+        executed += flops
+        kernels[name] = {"launches": cnt, "seconds": t, "samples": nsamp, "tflops": flops / t / 1e12 if t > 0 else None,
+                         "share_of_region": t / (secs if secs > 0 else 1)}
+        if name in WGRAD_STASH_BYTES and t > 0:
+            kernels[name]["stash_gbs"] = WGRAD_STASH_BYTES[name] * nsamp / t / 1e9
+    return kernels, executed
+
+
+def roofline_of(kernels, executed, secs, peaks, traffic_json, ms_key="avg_launch_ms"):
+    """`roofline` object of one leg: the dominant MLP kernel (by summed CUDA-event time inside the timed region) against
+    the roofline SURVEY.md §8(d) names for the MLP stack — dense bf16 tensor throughput on UNPADDED algorithmic FLOPs.
+    The HBM view of the weight-gradient kernel (which streams this design's activation stashes) is kept next to it as
+    `hbm_view`, and the whole region's executed-FLOP rate as `step_tensor_frac` (the north-star utilisation figure)."""
+    if not kernels:
+        return None
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_hbm = peaks.get("hbm_gbs", 6650.0)
+    src = ("MEASURED_PEAKS.json: bf16_tflops_sustained (kernels timed inside a long step), hbm_gbs" if peaks else
+           "fallback 1.4 PFLOP/s sustained, 6.65 TB/s (B200_PROFILING.md)")
+    dom = max(kernels, key=lambda k: kernels[k]["seconds"])
+    k = kernels[dom]
+    traffic = None
+    tr = traffic_json.get(dom)
+    if tr:
+        traffic = tr["dram_bytes_per_sample"] * k["samples"] / k["launches"]     # ncu dram bytes per launch
+    roof = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": k["tflops"] / peak_tf, "traffic": traffic, "peak_source": src,
+            ms_key: 1e3 * k["seconds"] / k["launches"],
+            "algorithmic_flop_per_launch": k["tflops"] * 1e12 * k["seconds"] / k["launches"],
+            "step_tensor_frac": (executed / secs / 1e12) / peak_tf, "executed_tflops_per_gpu": executed / secs / 1e12,
+            "kernels": kernels}
+    wg = [n for n in kernels if n in WGRAD_STASH_BYTES]
+    if wg:
+        n = max(wg, key=lambda x: kernels[x]["seconds"])
+        roof["hbm_view"] = {"kernel": n, "bound": "hbm", "achieved": kernels[n]["stash_gbs"], "peak": peak_hbm, "unit": "GB/s",
+                            "frac": kernels[n]["stash_gbs"] / peak_hbm,
+                            "note": "bytes are this design's stash traffic (X + dY slabs read once), not algorithmic bytes of "
+                                    "the reference path: explains the tensor fraction, does not replace it"}
+    return roof
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
-    from hypernerf_torch_b200 import _lib, synthetic
+    from hypernerf_torch_b200 import _lib, ray_utils, synthetic
     from hypernerf_torch_b200 import train as hn_train
     from hypernerf_torch_b200.models import NerfModel
 
@@ -190,6 +320,16 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the native library is missing
 
+    peaks, traffic_json = {}, {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    try:
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
+
     emb = {'warp': list(range(100)), 'camera': [0], 'appearance': list(range(100)), 'time': list(range(100))}
     model = NerfModel(emb, near=0., far=1., n_samples_coarse=N_COARSE, n_samples_fine=N_FINE, noise_std=1.0,
                       hyper_slice_method='bendy_sheet', hyper_slice_out_dim=2, use_warp=True, use_nerf_embed=False,
@@ -199,10 +339,17 @@ def run_gpu_arm(args):
     model = model.to(dev)
     fg = hn_train.FlatGrads(model.parameters())
     model.attach_flat_grads(fg)
+
+    rays_all, rgbs_all = synthetic.train_rays(GLOBAL_RAYS, seed=0)
+    # one-shot check before anything is timed: the N-GPU step (ray shards, rank-sliced global draws, one flat all-reduce)
+    # reproduces the 1-GPU step on the same 4 096 rays; raises if it does not
+    dp_parity = None
+    if world > 1:
+        dp_parity = {"rays": 4096, "tol": 1e-4,
+                     "rel_l2": hn_train.dp_parity_check(model, fg, rays_all[:4096].to(dev), rgbs_all[:4096].to(dev), tol=1e-4)}
     opt = hn_train.FusedAdam(fg, lr=5e-4, eps=1e-8)   # Adam of utils/__init__.py:29-31 / opt.py:53-56, one launch
 
     # inputs: this rank's contiguous shard of the global batch, resident in HBM (value) and in pinned host memory (e2e)
-    rays_all, rgbs_all = synthetic.train_rays(GLOBAL_RAYS, seed=0)
     lo, hi = hn_train.shard_bounds(GLOBAL_RAYS, rank, world)
     rays_h = rays_all[lo:hi].contiguous().pin_memory()
     rgbs_h = rgbs_all[lo:hi].contiguous().pin_memory()
@@ -226,7 +373,7 @@ def run_gpu_arm(args):
 
     def timed_loop(fn, steps, profile=False):
         """EXACTLY `steps` steps; device time by CUDA events on the launching stream, L2 flushed between steps
-        (outside the events); returns (seconds summed over steps, launches)."""
+        (outside the events); returns (seconds summed over steps, max over ranks; launches; per-kernel events)."""
         evs = []
         launches0 = _lib.launches
         if profile:
@@ -265,9 +412,18 @@ def run_gpu_arm(args):
 
     e2e_step()
     secs_e2e, _, _ = timed_loop(e2e_step, args.steps)
+    kernels, executed = kernel_table(prof, secs, FWD_FLOP_PER_EVAL, TRUNK_FLOP_PER_EVAL)
+    roof = roofline_of(kernels, executed, secs, peaks, traffic_json)
+    if roof:
+        roof["executed_mflop_per_ray"] = executed / (args.steps * GLOBAL_RAYS / world) / 1e6
 
-    # secondary metric of BASELINE.json ("render Mrays/s", configs[2]): one 1008x756 frame, 64+128 samples, no_grad,
-    # random-init weights, rows of the frame sharded over the ranks (no collective); device time, max over ranks
+    # ---------------------------------------------------------------------------------------------------------------
+    # secondary metric of BASELINE.json ("render Mrays/s", configs[2]): 1008x756 frames, 64+128 samples, no_grad,
+    # random-init weights, rows of the frame sharded over the ranks (no collective); device time, max over ranks.
+    #   value: the frame's ray rows resident in HBM;
+    #   e2e:   per frame a camera pose comes from the host (48 bytes), the rays are generated on the device
+    #          (hn_make_ndc_rays), rendered, and the rgb image goes back to pinned host memory.
+    # ---------------------------------------------------------------------------------------------------------------
     render = None
     if not args.no_render:
         rmodel = NerfModel(emb, near=0., far=1., n_samples_coarse=64, n_samples_fine=128, noise_std=None,
@@ -276,18 +432,40 @@ def run_gpu_arm(args):
                            hyper_fourier_dim=6, view_fourier_dim=6)
         rmodel.load_state_dict(model.state_dict())
         rmodel = rmodel.to(dev).eval()
-        frame = synthetic.frame_rays(image_id=3, seed=0)
-        flo, fhi = hn_train.shard_bounds(frame.shape[0], rank, world)
-        frame_d = frame[flo:fhi].contiguous().to(dev)
-        hn_train.render_rays(rmodel, frame_d[:32768], chunk=32768)       # warm-up (packs the weights)
-        secs_r, launches_r, _ = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=32768), 2)
-        render = {"value": frame.shape[0] * 2 / secs_r / 1e6, "unit": "Mrays/s", "rays_per_frame": int(frame.shape[0]),
-                  "samples": "64+128", "ms_per_frame": 1e3 * secs_r / 2, "frames_timed": 2,
+        Hh, Ww = synthetic.H, synthetic.W
+        n_frame = Hh * Ww
+        flo, fhi = hn_train.shard_bounds(n_frame, rank, world)
+        frame_d = synthetic.frame_rays(image_id=3, seed=0)[flo:fhi].contiguous().to(dev)
+        frames = max(5, args.render_frames)
+        hn_train.render_rays(rmodel, frame_d[:32768], chunk=32768)       # warm-up
+        secs_r, launches_r, prof_r = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=32768), frames, profile=True)
+        img_h = torch.empty(fhi - flo, 3, dtype=torch.float32).pin_memory()
+        poses = [torch.tensor([[1., 0., 0., 0.02 * i], [0., 1., 0., -0.01 * i], [0., 0., 1., 0.0]]) for i in range(frames)]
+        it = iter(range(10 ** 9))
+
+        def render_e2e():
+            c2w = poses[next(it) % frames]
+            rows = ray_utils.frame_rays_ndc(Hh, Ww, synthetic.FOCAL, c2w, image_id=3, device=dev)[flo:fhi]
+            out = hn_train.render_rays(rmodel, rows, chunk=32768, keys=('rgb',))
+            img_h.copy_(out['rgb'], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        render_e2e()
+        secs_re, _, _ = timed_loop(render_e2e, frames)
+        rk, rexec = kernel_table(prof_r, secs_r, FWD_FLOP_PER_EVAL, TRUNK_FLOP_PER_EVAL)
+        render = {"value": n_frame * frames / secs_r / 1e6, "unit": "Mrays/s", "rays_per_frame": int(n_frame),
+                  "samples": "64+128", "ms_per_frame": 1e3 * secs_r / frames, "frames_timed": frames,
+                  "e2e": {"value": n_frame * frames / secs_re / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 48,
+                          "d2h_bytes_per_step": int(img_h.numel() * 4), "ms_per_frame": 1e3 * secs_re / frames,
+                          "note": "pose in (host), rays generated on the device, rgb image out (pinned host)"},
+                  "gpu_launches": launches_r, "roofline": roofline_of(rk, rexec, secs_r, peaks, traffic_json),
                   "workload": "cfg3: full-frame eval render 1008x756, random-init weights, no_grad"}
         del rmodel, frame_d
 
+    # ---------------------------------------------------------------------------------------------------------------
     # secondary workload (BASELINE.json configs[3]): static NeRF baseline (models/nerf.py x2 + render_rays), 262 144-ray
     # batch sharded over the ranks, 128+128 samples, perturb=1, noise_std=1, forward + backward (no optimizer)
+    # ---------------------------------------------------------------------------------------------------------------
     static = None
     if not args.no_static:
         from hypernerf_torch_b200.nerf import Embedding, NeRF
@@ -296,91 +474,54 @@ def run_gpu_arm(args):
         semb = [Embedding(3, 10), Embedding(3, 4)]
         n_static = 262144
         slo, shi = hn_train.shard_bounds(n_static, rank, world)
-        srays9, srgbs = synthetic.train_rays(shi - slo, seed=7 + rank, device=dev)
-        srays = srays9[:, :8].contiguous()
+        srays9, srgbs_c = synthetic.train_rays(shi - slo, seed=7 + rank)
+        srays_h, srgbs_h = srays9[:, :8].contiguous().pin_memory(), srgbs_c.contiguous().pin_memory()
+        srays, srgbs = srays_h.to(dev), srgbs_h.to(dev)
 
-        def static_step():
+        def static_step(rays_in=None, rgbs_in=None):
+            r_in = srays if rays_in is None else rays_in
+            t_in = srgbs if rgbs_in is None else rgbs_in
             for m in smodels:
                 m.zero_grad(set_to_none=True)
-            for i in range(0, srays.shape[0], 32768):
-                out = static_render_rays(smodels, semb, srays[i:i + 32768], N_samples=128, perturb=1.0, noise_std=1.0,
+            total = torch.zeros((), device=dev)
+            for i in range(0, r_in.shape[0], 32768):
+                out = static_render_rays(smodels, semb, r_in[i:i + 32768], N_samples=128, perturb=1.0, noise_std=1.0,
                                          N_importance=128)
-                tgt = srgbs[i:i + 32768]
+                tgt = t_in[i:i + 32768]
                 loss = (torch.nn.functional.mse_loss(out['rgb_coarse'], tgt, reduction='sum') +
                         torch.nn.functional.mse_loss(out['rgb_fine'], tgt, reduction='sum')) / (3.0 * n_static)
                 loss.backward()
+                total += loss.detach()
+            return total
+
+        def static_e2e():
+            loss = static_step(srays_h.to(dev, non_blocking=True), srgbs_h.to(dev, non_blocking=True))
+            loss_h.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
         static_step()
-        secs_s, _, _ = timed_loop(static_step, 2)
-        static = {"value": n_static * 2 / secs_s, "unit": "rays/s", "rays_per_step": n_static, "samples": "128+128",
-                  "ms_per_step": 1e3 * secs_s / 2, "steps_timed": 2,
+        ssteps = max(3, args.static_steps)
+        secs_s, launches_s, prof_s = timed_loop(static_step, ssteps, profile=True)
+        static_e2e()
+        secs_se, _, _ = timed_loop(static_e2e, ssteps)
+        sk, sexec = kernel_table(prof_s, secs_s, STATIC_FLOP_PER_EVAL, STATIC_FLOP_PER_EVAL)
+        static = {"value": n_static * ssteps / secs_s, "unit": "rays/s", "rays_per_step": n_static, "samples": "128+128",
+                  "ms_per_step": 1e3 * secs_s / ssteps, "steps_timed": ssteps,
+                  "e2e": {"value": n_static * ssteps / secs_se, "unit": "rays/s",
+                          "h2d_bytes_per_step": int(srays_h.numel() * 4 + srgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
+                  "gpu_launches": launches_s, "roofline": roofline_of(sk, sexec, secs_s, peaks, {}),
                   "workload": "cfg4: static NeRF baseline, 262144-ray batch, perturb=1, noise_std=1, fwd+bwd"}
         del smodels, srays, srgbs
-
-    # roofline of the dominant kernel from the per-kernel events recorded inside the timed region
-    per = {}
-    for name, n, a, b in prof or []:
-        d = per.setdefault(name, [0.0, 0, 0])
-        d[0] += a.elapsed_time(b) / 1e3; d[1] += 1; d[2] += n
-    roof, kernels = None, {}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_hbm = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "MEASURED_PEAKS.json (bf16_tflops_sustained / hbm_gbs: kernels timed inside a long step)" if peaks else \
-        "fallback 1.4 PFLOP/s sustained, 6.65 TB/s (B200_PROFILING.md)"
-    # Which roofline bounds each kernel: the fused forward and data-gradient kernels are dense
-    # contractions (tensor pipe); the weight-gradient kernel streams both activation stashes once and is HBM bound.
-    # Algorithmic HBM bytes per sample: X stash 8640 B + dY stash 8288 B read once by wgrad.
-    # The fine level evaluates the depths it inherits from the coarse level with the trunk-only program (the shared warp /
-    # sheet nets were already evaluated there by the coarse pass): 673 664 MAC per sample, and the stashes without the
-    # warp / sheet slabs (X 6 176 B + dY 5 952 B).
-    ALG_BYTES = {"mlp_wgrad": 8640 + 8288, "mlp_wgrad_trunk": 6176 + 5952}
-    executed_flop = 0.0
-    for name, (t, cnt, nsamp) in per.items():
-        # fwd, dgrad and wgrad each count 1x forward FLOPs (bwd = 2x fwd)
-        flops = (TRUNK_FLOP_PER_EVAL if name.endswith("_trunk") else FWD_FLOP_PER_EVAL) * nsamp
-        executed_flop += flops
-        kernels[name] = {"launches": cnt, "seconds": t, "tflops": flops / t / 1e12 if t > 0 else None,
-                         "share_of_step": t / (secs if secs > 0 else 1)}
-        if name in ALG_BYTES and t > 0:
-            kernels[name]["hbm_gbs"] = ALG_BYTES[name] * nsamp / t / 1e9
-    if kernels:
-        dom = max(kernels, key=lambda k: kernels[k]["seconds"])
-        k = kernels[dom]
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
-            # ncu dram bytes per sample of this kernel x the average samples per launch of the timed region
-            traffic = tr["dram_bytes_per_sample"] * per[dom][2] / per[dom][1]
-        except Exception:
-            pass
-        if dom in ALG_BYTES:
-            roof = {"kernel": dom, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
-                    "frac": k["hbm_gbs"] / peak_hbm, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ALG_BYTES[dom] * per[dom][2] / per[dom][1],
-                    "avg_launch_ms": 1e3 * k["seconds"] / k["launches"], "kernels": kernels}
-        else:
-            roof = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": k["tflops"] / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_ms": 1e3 * k["seconds"] / k["launches"], "kernels": kernels}
-        # the whole step against the tensor roofline, for the north-star utilisation target
-        # (executed FLOPs of this rank's launches: the redundant warp / sheet evaluations the reference makes at the
-        # inherited depths are not counted)
-        roof["step_tensor_frac"] = (executed_flop / secs / 1e12) / peak_tf
-        roof["executed_mflop_per_ray"] = executed_flop / (args.steps * GLOBAL_RAYS / world) / 1e6
-        roof["executed_tflops_per_gpu"] = executed_flop / secs / 1e12
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, sample = cpu_reference_rate(n_rays=1024, repeats=2, warmup=1)
-            cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+            cpu = cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="train")
+            if render is not None:
+                render["cpu_baseline"] = cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="render")
+            if static is not None:
+                static["cpu_baseline"] = cpu_reference_rate(n_rays=512, repeats=1, warmup=1, workload="static")
         rays_per_s = GLOBAL_RAYS * args.steps / secs
-        total_flop = GLOBAL_RAYS * EVALS_PER_RAY * FWD_FLOP_PER_EVAL * 3
         line = {
             "metric": METRIC, "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
@@ -389,10 +530,9 @@ def run_gpu_arm(args):
                        "samples": f"{N_COARSE}+{N_FINE}", "parallelism": f"dp{world} (ray shards, 1 flat NCCL all-reduce/step)",
                        "optimizer": "Adam step inside the timed region", "timing": "CUDA events per step, max over ranks",
                        "l2": "256 MB buffer written between timed steps; per-step working set (>10 GB) exceeds L2",
-                       "flop_accounting": "model_tflops counts the reference's 923.4 MFLOP per ray (192 full-network "
-                                          "evaluations); roofline.* count executed FLOPs (the fine level's 64 inherited "
-                                          "depths skip the shared warp / sheet nets)"},
-            "model_tflops": total_flop * args.steps / secs / 1e12,
+                       "flop_accounting": "roofline.* count EXECUTED unpadded FLOPs (the fine level's 64 inherited depths skip "
+                                          "the shared warp / sheet nets: 874.3 MFLOP per ray instead of the reference's 923.4)",
+                       "dp_parity": dp_parity},
             "e2e": {"value": GLOBAL_RAYS * args.steps / secs_e2e, "unit": "rays/s",
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render, "static_nerf": static,
@@ -429,6 +569,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary full-frame render measurement")
     ap.add_argument("--no-static", action="store_true", help="skip the secondary static-NeRF (cfg4) measurement")
+    ap.add_argument("--render-frames", type=int, default=5, help="timed frames of the render leg (>= 5)")
+    ap.add_argument("--static-steps", type=int, default=3, help="timed steps of the static-NeRF leg (>= 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -715,6 +715,44 @@ extern "C" int hn_mse_loss(const float* rgb_coarse, const float* rgb_fine, const
 
 
 // ------------------------------------------------------------------------------------------------------
+// hn_filter_sigma — filter_sigma (models.py:35-63): out = mask * values with mask = (sigma >= dust_threshold) and
+// (point inside the bounding box), either test optional.  Forward: values = sigma; backward: values = upstream gradient
+// (the reference multiplies by the boolean masks, so the gradient passes where the mask is set).
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+struct BBox { float v[6]; };
+__global__ void __launch_bounds__(256) filter_sigma_kernel(const float* __restrict__ points, const float* __restrict__ sigma,
+                                                           const float* __restrict__ values, int64_t n, float dust, int use_dust,
+                                                           BBox b, int use_bbox, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bool keep = true;
+    // the two tests compose as in the reference: the bounding-box product sees the dust-filtered value, which changes
+    // nothing for the mask itself
+    if (use_dust) keep = __ldg(sigma + i) >= dust;
+    if (use_bbox) {
+      const float x = __ldg(points + 3 * i), y = __ldg(points + 3 * i + 1), z = __ldg(points + 3 * i + 2);
+      keep = keep && x >= b.v[0] && x <= b.v[1] && y >= b.v[2] && y <= b.v[3] && z >= b.v[4] && z <= b.v[5];
+    }
+    out[i] = keep ? __ldg(values + i) : 0.f;
+  }
+}
+}  // namespace hn
+
+extern "C" int hn_filter_sigma(const float* points, const float* sigma, const float* values, int64_t n, float dust_threshold,
+                               int use_dust, const float* bbox_host, float* out, void* stream) {
+  if (!sigma || !values || !out || (bbox_host && !points)) return hn::set_error(-2, "hn_filter_sigma: null pointer");
+  if (n < 0) return hn::set_error(-1, "hn_filter_sigma: negative n");
+  if (n == 0) return 0;
+  hn::BBox b{};
+  if (bbox_host) for (int k = 0; k < 6; ++k) b.v[k] = bbox_host[k];
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * (int64_t)hn::num_sms());
+  hn::filter_sigma_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(points, sigma, values, n, dust_threshold, use_dust, b,
+                                                                    bbox_host != nullptr, out);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_filter_sigma");
+}
+
+
+// ------------------------------------------------------------------------------------------------------
 // hn_make_ndc_rays — datasets/ray_utils.py:5-93 (get_ray_directions -> get_rays -> get_ndc_rays) + the ray-row layout
 // of datasets/llff.py:261-264 / 316-332 for one full frame, on the device: pixel (i = column, j = row) ->
 // camera direction ((i - W/2)/f, -(j - H/2)/f, -1) -> world (rotate by c2w[:, :3], normalise) -> NDC origin /

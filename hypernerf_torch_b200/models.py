@@ -25,18 +25,45 @@ from ._packing import PackedWeights
 from ._lib import check, lib, ptr, stream
 
 
+class _FilterSigma(torch.autograd.Function):
+    """hn_filter_sigma with the mask re-applied to the upstream gradient."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, points, sigma, dust, use_dust, bbox):
+        pts = points.detach().to(torch.float32).contiguous()
+        sig = sigma.detach().contiguous()
+        out = torch.empty_like(sig)
+        box = None if bbox is None else (C.c_float * 6)(*[float(v) for v in bbox])
+        check(lib().hn_filter_sigma(ptr(pts), ptr(sig), ptr(sig), sig.numel(), float(dust), int(use_dust), box, ptr(out),
+                                    stream()), "hn_filter_sigma")
+        _lib.count(1)
+        ctx.save_for_backward(pts, sig)
+        ctx.cfg = (float(dust), int(use_dust), box)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        pts, sig = ctx.saved_tensors
+        dust, use_dust, box = ctx.cfg
+        g = g.to(torch.float32).contiguous()
+        out = torch.empty_like(g)
+        check(lib().hn_filter_sigma(ptr(pts), ptr(sig), ptr(g), g.numel(), dust, use_dust, box, ptr(out), stream()),
+              "hn_filter_sigma")
+        _lib.count(1)
+        return None, out, None, None, None
+
+
 def filter_sigma(points, sigma, render_opts):
     """models.py:35-63 (dust threshold / bounding box); a no-op unless render_opts is given."""
     if render_opts is None:
         return sigma
-    if 'dust_threshold' in render_opts:
-        sigma = (sigma >= render_opts.get('dust_threshold', 0.0)) * sigma
-    if 'bounding_box' in render_opts:
-        xmin, xmax, ymin, ymax, zmin, zmax = render_opts['bounding_box']
-        mask = ((points[..., 0] >= xmin) & (points[..., 0] <= xmax) & (points[..., 1] >= ymin) &
-                (points[..., 1] <= ymax) & (points[..., 2] >= zmin) & (points[..., 2] <= zmax))
-        sigma = mask * sigma
-    return sigma
+    use_dust = 'dust_threshold' in render_opts
+    bbox = render_opts.get('bounding_box') if 'bounding_box' in render_opts else None
+    if not use_dust and bbox is None:
+        return sigma
+    return _FilterSigma.apply(points, sigma, render_opts.get('dust_threshold', 0.0) if use_dust else 0.0, use_dust, bbox)
 
 
 def _param_grads(ctx, model, level, flat_grad, offs, first):

@@ -145,6 +145,73 @@ def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, opti
     return total
 
 
+class _Replay:
+    """Replays a fixed list of tensors for the torch.rand / torch.randn calls of one forward (the
+    draws are made with the reference's own generator calls; data-parallel parity needs every rank to consume its slice of
+    the SAME global draws)."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+
+    def __enter__(self):
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def take(*a, **k):
+            return self.tensors.pop(0)
+
+        torch.rand = torch.randn = take
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._rand, self._randn
+
+
+def global_draws(model, n_rays, device, seed):
+    """The four draws of one forward over a batch of n_rays (rand[B,Nc], randn(B,Nc,1), rand(B,Nf), randn(B,Nc+Nf,1); the
+    randn's only with noise) from one seeded generator."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    Nc, Nf = model.num_coarse_samples, model.num_fine_samples
+    noise = model.noise_std is not None and model.noise_std > 0
+    out = [torch.rand(n_rays, Nc, device=device, generator=g)]
+    if noise:
+        out.append(torch.randn(n_rays, Nc, 1, device=device, generator=g))
+    out.append(torch.rand(n_rays, Nf, device=device, generator=g))
+    if noise:
+        out.append(torch.randn(n_rays, Nc + Nf, 1, device=device, generator=g))
+    return out
+
+
+def dp_parity_check(model, flat_grads, rays, rgbs, seed=4321, tol=1e-4):
+    """N-GPU step == 1-GPU step: every rank runs train_step on its contiguous shard of (rays, rgbs)
+    with its slice of globally drawn randoms and all-reduces; rank 0 also runs the whole batch alone; the all-reduced flat
+    gradient must equal the single-rank one to `tol` (relative L2).  Returns the relative difference (same on all ranks).
+    Leaves flat_grads zeroed."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    n, dev = rays.shape[0], rays.device
+    draws = global_draws(model, n, dev, seed)
+    lo, hi = shard_bounds(n, rank, world)
+    with _Replay([d[lo:hi] for d in draws]):
+        train_step(model, rays[lo:hi], rgbs[lo:hi], flat_grads, global_rays=n, chunk=max(hi - lo, 1))
+    sharded = flat_grads.flat.clone()
+    rel = torch.zeros((), device=dev)
+    if rank == 0:
+        flat_grads.zero()
+        with model.packed_frozen():
+            with _Replay(list(draws)):
+                out = model(model_utils.prepare_ray_dict(rays), dict(EXTRA_PARAMS))
+            loss, _ = losses.mse_coarse_fine(out, rgbs, global_count=3.0 * n)
+            loss.backward()
+        rel = (sharded - flat_grads.flat).norm() / flat_grads.flat.norm()
+    if world > 1:
+        dist.broadcast(rel, src=0)
+    flat_grads.zero()
+    rel = float(rel)
+    if not rel <= tol:
+        raise AssertionError(f"data-parallel gradient differs from the single-GPU gradient: relative L2 {rel:.3e} > {tol}")
+    return rel
+
+
 def save_ckpt(model, path, epoch=0, global_step=0, optimizer=None, module_name='nerf'):
     """Checkpoint in the layout Lightning's ModelCheckpoint writes for NeRFSystem (train.py:71: the model is the
     attribute `nerf`, so its tensors are stored as `nerf.<name>` under 'state_dict'); readable by utils.load_ckpt

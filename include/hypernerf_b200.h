@@ -129,6 +129,12 @@ int hn_composite_bwd(const float* sigma, const float* rgb, const float* z, const
                      int flags, float eps, float last_delta, const float* g_out_rgb, const float* g_depth,
                      const float* g_acc, const float* g_weights, float* g_sigma, float* g_rgb, void* stream);
 
+/* filter_sigma (models.py:35-63; applied to the fine level only, models.py:768): out[i] = values[i] where sigma[i] >=
+ * dust_threshold (if use_dust) and points[i] lies inside bbox = {xmin, xmax, ymin, ymax, zmin, zmax} (HOST pointer, NULL =
+ * no box test), else 0.  Forward: values = sigma.  Backward: values = the upstream gradient (same mask).  n = B * S. */
+int hn_filter_sigma(const float* points, const float* sigma, const float* values, int64_t n, float dust_threshold, int use_dust,
+                    const float* bbox_host, float* out, void* stream);
+
 /* render_samples up to and including query_template (models.py:587-650 -> :447-493): GLO lookup, posenc_orig,
  * TranslationField, HyperSheetMLP, NerfMLP, noise_regularize, Softplus — one fused tcgen05 kernel.
  * points (B,S,3); viewdirs (B,3) (the reference passes the raw ray directions, models.py:717-720);

@@ -186,16 +186,31 @@ def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None, gates=None):
     return rgb, sigma, warped_points, alpha.squeeze(-1)
 
 
-def render_samples(sd, level, points, z, directions, viewdirs, ids, cfg, noise=None):
+def filter_sigma(points, sigma, render_opts):
+    """hypernerf/models.py:35-63."""
+    if render_opts is None:
+        return sigma
+    if 'dust_threshold' in render_opts:
+        sigma = (sigma >= render_opts.get('dust_threshold', 0.0)) * sigma
+    if 'bounding_box' in render_opts:
+        xmin, xmax, ymin, ymax, zmin, zmax = render_opts['bounding_box']
+        mask = ((points[..., 0] >= xmin) & (points[..., 0] <= xmax) & (points[..., 1] >= ymin) & (points[..., 1] <= ymax)
+                & (points[..., 2] >= zmin) & (points[..., 2] <= zmax))
+        sigma = mask * sigma
+    return sigma
+
+
+def render_samples(sd, level, points, z, directions, viewdirs, ids, cfg, noise=None, render_opts=None):
     """hypernerf/models.py:587-671."""
     rgb, sigma, warped_points, alpha = query_fields(sd, level, points, viewdirs, ids, cfg, noise)
+    sigma = filter_sigma(points, sigma, render_opts)                                  # models.py:650
     out = {'points': points, 'warped_points': warped_points, 'sigma': sigma, 'rgb_samples': rgb}
     out.update(volumetric_rendering(rgb, sigma, z, directions))
     out['med_points'] = torch.gather(warped_points, -2, out['med_idx'][..., None, None])   # models.py:664-669
     return out
 
 
-def forward(sd, origins, directions, ids, draws, cfg, fine_z=None):
+def forward(sd, origins, directions, ids, draws, cfg, fine_z=None, render_opts=None):
     """hypernerf/models.py:673-780.  draws: dict(u_coarse (B,Nc), noise_coarse (B,Nc,1)|None, u_fine (B,Nf),
     noise_fine (B,Nc+Nf,1)|None) in the reference's RNG order.
     cfg: dict(near, far, n_coarse, n_fine, noise_std, xyz_freq, hyper_freq, view_freq).
@@ -209,7 +224,8 @@ def forward(sd, origins, directions, ids, draws, cfg, fine_z=None):
     if fine_z is not None:
         z_f = fine_z
         points_f = origins[:, None, :] + z_f[..., None] * directions[:, None, :]
-    fine = render_samples(sd, 'fine', points_f, z_f, directions, directions, ids, cfg, draws.get('noise_fine'))
+    fine = render_samples(sd, 'fine', points_f, z_f, directions, directions, ids, cfg, draws.get('noise_fine'),
+                          render_opts=render_opts)                                    # fine level only, models.py:768
     fine['z_vals'] = z_f
     fine['pdf_inds'] = inds
     return {'coarse': coarse, 'fine': fine}

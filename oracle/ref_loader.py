@@ -102,7 +102,7 @@ class _DrawTape:
         torch.rand, torch.randn = self._rand, self._randn
 
 
-def run_reference(model, rays, draws=None, taps=None):
+def run_reference(model, rays, draws=None, taps=None, **forward_kwargs):
     """Forward of the unmodified reference NerfModel on ray rows (B,9).  draws: list of tensors to replay in call
     order (None = draw fresh and record).  taps: optional dict that receives the stage taps z_coarse / z_fine
     (the reference does not return its depth samples).  Returns (outputs, list_of_draws)."""
@@ -124,7 +124,7 @@ def run_reference(model, rays, draws=None, taps=None):
     ref_mu.sample_along_rays, ref_mu.sample_pdf = sar, pdf
     try:
         with _DrawTape(draws) as tape:
-            out = model(ref_mu.prepare_ray_dict(rays), dict(EXTRA))
+            out = model(ref_mu.prepare_ray_dict(rays), dict(EXTRA), **forward_kwargs)
     finally:
         ref_mu.sample_along_rays, ref_mu.sample_pdf = orig_sar, orig_pdf
     return out, tape.tape

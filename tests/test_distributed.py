@@ -97,3 +97,62 @@ def test_shard_bounds_partition(n, world):
     for a, b in zip(spans, spans[1:]):
         assert a[1] == b[0]
     assert all(lo <= hi for lo, hi in spans)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# hardware: 2 NCCL ranks, the real model.  Skips cleanly on a 1-GPU box; run with `gpurun --gpus 2`.
+# ------------------------------------------------------------------------------------------------------------------------
+def _nccl_worker(rank, world, port, n_rays, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from hypernerf_torch_b200 import synthetic
+        from hypernerf_torch_b200.models import NerfModel
+        from oracle import ref_loader
+        model = NerfModel(ref_loader.EMBEDDINGS, **ref_loader.cfg1_kwargs(n_fine=64, noise_std=1.0))
+        model.load_state_dict(synthetic.make_state_dict(model, seed=0, boosted=True))
+        model = model.to(dev)
+        fg = hn_train.FlatGrads(model.parameters())
+        model.attach_flat_grads(fg)
+        rays, rgbs = synthetic.train_rays(n_rays, seed=2, device=dev)
+        rel = hn_train.dp_parity_check(model, fg, rays, rgbs, tol=1e-4)
+        q.put((rank, rel))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_train_step_equals_one_gpu_step():
+    """train.train_step on the two halves of a 4 096-ray batch (globally drawn, rank-sliced u / noise tensors, one flat
+    NCCL all-reduce) == the 1-GPU step on the whole batch, to 1e-4 relative."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, 4096, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    print("2-GPU vs 1-GPU flat gradient, relative L2:", got)
+    assert all(rel <= 1e-4 for _, rel in got)
+
+
+@pytest.mark.gpu
+def test_dp_parity_check_single_rank_is_exact():
+    """The helper itself on one GPU (world 1): sharded == whole by construction, to accumulation-order noise."""
+    from hypernerf_torch_b200 import synthetic
+    from hypernerf_torch_b200.models import NerfModel
+    from oracle import ref_loader
+    model = NerfModel(ref_loader.EMBEDDINGS, **ref_loader.cfg1_kwargs(n_fine=64, noise_std=1.0))
+    model.load_state_dict(synthetic.make_state_dict(model, seed=0, boosted=True))
+    model = model.to("cuda")
+    fg = hn_train.FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+    rays, rgbs = synthetic.train_rays(2048, seed=2, device="cuda")
+    assert hn_train.dp_parity_check(model, fg, rays, rgbs, tol=1e-5) <= 1e-5

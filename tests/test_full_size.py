@@ -175,6 +175,35 @@ def test_fit_loop_learns_and_checkpoints_like_lightning(tmp_path):
         assert torch.equal(a, b), k
 
 
+def test_render_rays_driver_matches_model_forward():
+    """train.render_rays (chunk-free eval driver; eval.py:77-103 batched_inference): the fine-level
+    rgb / depth it returns are exactly what NerfModel.forward returns chunk by chunk with the same draws, whatever the
+    chunk size, and nothing else is materialised."""
+    model = _model(noise_std=None, n_fine=128).eval()
+    rays = synthetic.frame_rays(image_id=1, seed=0, device=DEV, h=63, w=84)          # 5 292 rays
+    N = rays.shape[0]
+    g = torch.Generator(device=DEV).manual_seed(3)
+    u_c, u_f = torch.rand(N, 64, device=DEV, generator=g), torch.rand(N, 128, device=DEV, generator=g)
+
+    def draws_for(chunk):
+        out = []
+        for i in range(0, N, chunk):
+            out += [u_c[i:i + chunk], u_f[i:i + chunk]]
+        return out
+
+    with ref_loader._DrawTape(draws_for(2000)):
+        a = hn_train.render_rays(model, rays, chunk=2000)
+    with ref_loader._DrawTape(draws_for(N)):
+        b = hn_train.render_rays(model, rays, chunk=N, keys=('rgb', 'depth', 'acc'))
+    with torch.no_grad(), ref_loader._DrawTape(draws_for(N)):
+        full = model(mu.prepare_ray_dict(rays), dict(H.EXTRA))['fine']
+    assert set(a) == {'rgb', 'depth'} and set(b) == {'rgb', 'depth', 'acc'}
+    assert a['rgb'].shape == (N, 3) and a['depth'].shape == (N,)
+    for k in ('rgb', 'depth'):
+        assert torch.equal(a[k], full[k]) and torch.equal(b[k], full[k]), k
+    assert not a['rgb'].requires_grad
+
+
 def test_full_frame_render_psnr_matches_oracle():
     """BASELINE.json north_star / SURVEY.md §8(d) cfg3: one 1008 x 756 frame (762 048 rays, 64 + 128 samples, no_grad,
     noise off, reference-initialised weights).  The fp32 oracle runs on the GPU in torch eager (timing is not the point

@@ -156,6 +156,41 @@ def test_configurations_match_reference_golden(name):
     assert not bad, bad
 
 
+RENDER_OPTS = {'dust_threshold': 0.6, 'bounding_box': (-0.8, 0.9, -0.7, 0.8, -1.0, -0.2)}
+
+
+@pytest.mark.parametrize("opts", [RENDER_OPTS, {'dust_threshold': 0.55}, {'bounding_box': RENDER_OPTS['bounding_box']}])
+def test_render_opts_filter_sigma(opts):
+    """filter_sigma (models.py:35-63) runs in hn_filter_sigma and reaches the fine level only (models.py:768); outputs
+    and gradients against the oracle (pinned to the live reference for these options by tests/test_oracle.py)."""
+    from hypernerf_torch_b200 import synthetic
+    sd = synthetic.make_state_dict(H.cfg1_shapes(), seed=9, boosted=True)
+    model = H.make_model(n_fine=64, noise_std=1.0, sd=sd)
+    rays, rgbs = synthetic.train_rays(64, seed=5, device=DEV)
+    with ref_loader._DrawTape() as tape:
+        out = model(mu.prepare_ray_dict(rays), dict(H.EXTRA), render_opts=opts)
+    with ref_loader._DrawTape(tape.tape):
+        plain = model(mu.prepare_ray_dict(rays), dict(H.EXTRA))
+    assert torch.equal(out['coarse']['weights'], plain['coarse']['weights'])
+    assert (out['fine']['weights'] - plain['fine']['weights']).abs().max() > 1e-3
+    # stage isolation: the oracle's fine level at the depths the product resampled (recovered from the sample points)
+    z_fine = (out['fine']['points'][..., 2] - rays[:, None, 2]) / rays[:, None, 5]
+    sd_d = {k: v.to(DEV).requires_grad_(True) for k, v in sd.items()}
+    ref = H.orc.forward(sd_d, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), ref_loader.draws_to_dict(tape.tape),
+                        H.orc.default_cfg(), fine_z=z_fine.detach(), render_opts=opts)
+    for k in ("rgb", "depth", "acc", "weights"):
+        err = (out['fine'][k] - ref['fine'][k]).abs().max().item()
+        print(f"render_opts {sorted(opts)} fine {k} max_abs_err {err:.3e}")
+        # a sample whose sigma sits within bf16 error of the dust threshold is kept on one side and dropped on the other:
+        # bounded by the boosted-weights tolerance on all but those rays
+        bad = ((out['fine'][k] - ref['fine'][k]).abs().reshape(64, -1).max(-1).values > BOOSTED_TOL).sum().item()
+        assert bad <= (2 if 'dust_threshold' in opts else 0), (k, err, bad)
+    loss = torch.nn.functional.mse_loss(out['fine']['rgb'], rgbs)
+    loss.backward()                                      # the masked gradient path runs (hn_filter_sigma backward)
+    g = model.nerf_mlps_fine.alpha_mlp.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
 def test_state_dict_keys_match_reference_layout():
     model = H.make_model()
     shapes = H.cfg1_shapes()

@@ -124,6 +124,30 @@ def test_oracle_matches_live_reference():
     assert (samples - ref_samples).abs().max() < 5e-6
 
 
+RENDER_OPTS = {'dust_threshold': 0.6, 'bounding_box': (-0.8, 0.9, -0.7, 0.8, -1.0, -0.2)}
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_oracle_filter_sigma_matches_live_reference():
+    """render_opts (dust threshold + bounding box, models.py:35-63) reach the fine level only (models.py:768)."""
+    from hypernerf_torch_b200 import synthetic
+    model = ref_loader.build_reference_model(seed=0)
+    sd = synthetic.make_state_dict(model, seed=9, boosted=True)
+    model.load_state_dict(sd)
+    rays, _ = synthetic.train_rays(16, seed=5)
+    torch.manual_seed(7)
+    taps = {}
+    ref_out, tape = ref_loader.run_reference(model, rays, taps=taps, render_opts=RENDER_OPTS)
+    plain, _ = ref_loader.run_reference(model, rays, draws=tape)
+    assert (ref_out['fine']['weights'] - plain['fine']['weights']).abs().max() > 1e-3      # the options do something
+    assert torch.equal(ref_out['coarse']['weights'], plain['coarse']['weights'])            # ... to the fine level only
+    out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), ref_loader.draws_to_dict(tape), orc.default_cfg(),
+                      fine_z=taps['z_fine'], render_opts=RENDER_OPTS)
+    for lvl in ("coarse", "fine"):
+        for k in KEYS:
+            torch.testing.assert_close(out[lvl][k], ref_out[lvl][k].detach(), rtol=2e-5, atol=2e-6, msg=f"{lvl} {k}")
+
+
 def test_synthetic_rays_are_llff_shaped():
     from hypernerf_torch_b200 import synthetic
     rays, rgbs = synthetic.train_rays(4096, seed=0)
