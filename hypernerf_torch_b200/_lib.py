@@ -85,14 +85,14 @@ def lib():
     L.hn_mse_loss.argtypes = [vp, vp, vp, i64, f32, vp, vp, vp, vp]
     L.hn_make_ndc_rays.argtypes = [i32, i32, f32, C.POINTER(C.c_float), f32, f32, i32, vp, vp]
     L.hn_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]
-    L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]
-    L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32,
+    L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp, vp, vp]
+    L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, i32,
                              C.POINTER(C.c_int64), vp, vp, vp]
     L.hn_mlp_bwd_data.argtypes = L.hn_mlp_bwd.argtypes
     L.hn_mlp_bwd_weights.argtypes = [C.POINTER(ModelDesc), vp, i64, i32, i32, C.POINTER(C.c_int64), vp, vp, vp]
-    L.hn_mlp_fwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp]
-    L.hn_mlp_bwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, C.POINTER(C.c_int64),
-                                   vp, vp, vp, vp]
+    L.hn_mlp_fwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp, vp, vp]
+    L.hn_mlp_bwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, i32,
+                                   C.POINTER(C.c_int64), vp, vp, vp, vp]
     L.hn_mlp_bwd_trunk_data.argtypes = L.hn_mlp_bwd_trunk.argtypes
     L.hn_mlp_bwd_trunk_weights.argtypes = L.hn_mlp_bwd_weights.argtypes
     if hasattr(L, "hn_debug_set_timing_buffer"):   # role-timing builds only (make timing; HN_LIB selects them)

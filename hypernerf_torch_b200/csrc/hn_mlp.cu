@@ -137,6 +137,10 @@ struct FwdParams {
   const float* glo;         // (E, G) fp32 copy of the GLO table
   const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
   const float* warped_in;   // trunk-only program (hn_mlp_fwd_trunk): (n, 3 + H) warped points + hyper coordinates, else NULL
+  // Scattered rows: launch row j of ray b reads its point / noise and writes its outputs at position pos[b * S + j] of a
+  // (B, S_full) row; NULL = the launch rows ARE the output rows (S_full == S).  The stash stays in launch order.
+  const int32_t* pos;
+  int S_full;
   float noise_std;
   int view_freqs;           // hyper model: posenc_orig frequencies of the view direction (<= kMaxViewFreqs), run time
   int mflags;               // MF_*
@@ -162,6 +166,8 @@ struct BwdParams {
   const float* sigma; const float* rgb; const float* warped;
   const float* g_sigma; const float* g_rgb; const float* g_warped;
   float* g_warped_out;      // trunk-only program: (n, 3 + H) gradient w.r.t. warped_in, written by the last layer; else NULL
+  const int32_t* pos;       // scattered rows (see FwdParams): sigma / rgb / g_sigma / g_rgb / g_warped (and, outside the
+  int S_full;               // trunk-only program, warped) are indexed at pos[b * S + j] of (B, S_full) rows
   const uint8_t* saved;     // forward stash (X slabs; only its gate-word region is read here)
   const uint32_t* gates;    // ReLU gate words written by the forward: [half tile][g_total][64 rows]
   int g_total;
@@ -779,6 +785,8 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       const bool valid = g < p.n;
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
+      // where this row lives in the caller's (B, S_full) tensors (points, noise, sigma, rgb, warped)
+      const int64_t gq = p.pos != nullptr ? ray * p.S_full + __ldg(p.pos + gc) : gc;
       uint4* save_row = nullptr;
       uint32_t* gate_row = nullptr;   // this row's column of the half tile's gate words
       if (p.saved != nullptr) {
@@ -792,7 +800,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         dir[i] = __ldg(p.viewdirs + ray * 3 + i);
-        pt[i] = trunk_only ? 0.f : __ldg(p.points + gc * 3 + i);
+        pt[i] = trunk_only ? 0.f : __ldg(p.points + gq * 3 + i);
       }
       if (trunk_only) {
         // trunk-only program: the warped point / hyper coordinates of this row were computed by another launch (the
@@ -801,6 +809,10 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         if constexpr (!C::STATIC) {
 #pragma unroll
           for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped_in + gc * C::NWARPED + i);
+          if (valid && p.warped != nullptr) {   // the given point is also this row's entry of the level's warped_points
+#pragma unroll
+            for (int i = 0; i < C::NWARPED; ++i) p.warped[gq * C::NWARPED + i] = wp[i];
+          }
           store_trunk_input<C>(wp, act_row, inb_row, save_row, p.x_in_t);
           if constexpr (C::TIN_ACT) store_ones_only<C>(inb_row); else store_ones_pair<C, C::KT>(inb_row);
         }
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           }
           if (valid && p.warped != nullptr) {
 #pragma unroll
-            for (int i = 0; i < C::NWARPED; ++i) p.warped[g * C::NWARPED + i] = wp[i];
+            for (int i = 0; i < C::NWARPED; ++i) p.warped[gq * C::NWARPED + i] = wp[i];
           }
           store_trunk_input<C>(wp, act_row, inb_row, save_row, L.save_chunk);
           }
@@ -872,8 +884,8 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tmem_ld16(tlane, r);
           tmem_ld_wait();
           float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, 0);
-          if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;
-          if (valid) p.sigma[g] = fmaxf(a, 0.f);
+          if (p.noise != nullptr) a += __ldg(p.noise + gq) * p.noise_std;
+          if (valid) p.sigma[gq] = fmaxf(a, 0.f);
         } else if (L.epi == FE_BOTT) {
           fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, nullptr);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
@@ -902,8 +914,8 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
           float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, kRgbW);
-          if (p.noise != nullptr) a += __ldg(p.noise + gc) * p.noise_std;  // noise_regularize, model_utils.py:312-316
-          if (valid) p.sigma[g] = softplus_f(a);                          // models.py:491
+          if (p.noise != nullptr) a += __ldg(p.noise + gq) * p.noise_std;  // noise_regularize, model_utils.py:312-316
+          if (valid) p.sigma[gq] = softplus_f(a);                         // models.py:491
           }
         } else {  // FE_RGBHEAD
           uint32_t r[16];
@@ -911,7 +923,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) p.rgb[g * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
+            for (int i = 0; i < 3; ++i) p.rgb[gq * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
           }
         }
         if (li + 1 < prog.nlayers) {
@@ -1092,6 +1104,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       const bool valid = g < p.n;
       const int64_t gc = valid ? g : p.n - 1;
       const int64_t ray = gc / p.S;
+      const int64_t gq = p.pos != nullptr ? ray * p.S_full + __ldg(p.pos + gc) : gc;   // row in the (B, S_full) tensors
       const size_t half = (size_t)tile * (2 * kSubTiles) + sub * 2 + (row >> 6);
       const uint32_t* gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
       uint4* save_row = reinterpret_cast<uint4*>(p.dsaved + half * (size_t)p.d_total * kHalfChunkBytes) + (row & 63);
@@ -1104,8 +1117,8 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            float y = __ldg(p.rgb + g * 3 + i);
-            f[i] = __ldg(p.g_rgb + g * 3 + i) * y * (1.f - y);
+            float y = __ldg(p.rgb + gq * 3 + i);
+            f[i] = __ldg(p.g_rgb + gq * 3 + i) * y * (1.f - y);
           }
         }
         store_features<16>(f, act_row, save_row, p.d_rgbhead);
@@ -1114,7 +1127,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           // as the A operand of the sigma^T op that accumulates onto final^T, and stashed for the weight gradient
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
-          if (valid && __ldg(p.sigma + g) > 0.f) f[0] = __ldg(p.g_sigma + g);
+          if (valid && __ldg(p.sigma + gq) > 0.f) f[0] = __ldg(p.g_sigma + gq);
           store_features<16>(f, inb_row, save_row, p.d_sigma);
         }
       }
@@ -1139,7 +1152,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
-          if (valid) f[0] = __ldg(p.g_sigma + g) * (-expm1f(-__ldg(p.sigma + g)));
+          if (valid) f[0] = __ldg(p.g_sigma + gq) * (-expm1f(-__ldg(p.sigma + gq)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
           fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
           continue;
@@ -1171,7 +1184,10 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           // straight from the fp32 accumulator and the two vectors are added: nothing is parked in shared memory.
           float wp[C::NWARPED], gx[C::NWARPED];
 #pragma unroll
-          for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped + gc * C::NWARPED + i);
+          // trunk-only program: `warped` is warped_in, in launch order; otherwise the level's warped_points output
+          const int64_t gw = p.g_warped_out != nullptr ? gc : gq;
+#pragma unroll
+          for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped + gw * C::NWARPED + i);
           trunk_in_bwd<C>(tlane, wp, gx);
           if (L.epi == BE_SKIPSTORE) {
 #pragma unroll
@@ -1180,7 +1196,12 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
             // trunk-only program: this is the last layer; the gradient goes back to whoever produced warped_in
             if (valid) {
 #pragma unroll
-              for (int i = 0; i < C::NWARPED; ++i) p.g_warped_out[g * C::NWARPED + i] = gx[i] + gx_skip[i];
+              for (int i = 0; i < C::NWARPED; ++i) {
+                float v = gx[i] + gx_skip[i];
+                // the given point is also an entry of the level's warped_points output: its upstream gradient passes through
+                if (p.g_warped != nullptr) v += __ldg(p.g_warped + gq * C::NWARPED + i);
+                p.g_warped_out[g * C::NWARPED + i] = v;
+              }
             }
           } else if constexpr (!C::NOWARP) {
           float f[16];
@@ -1190,7 +1211,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
 #pragma unroll
             for (int i = 0; i < C::NWARPED; ++i) {
               f[i] = gx[i] + gx_skip[i];
-              if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + g * C::NWARPED + i);
+              if (p.g_warped != nullptr) f[i] += __ldg(p.g_warped + gq * C::NWARPED + i);
             }
           }
           if constexpr (C::H == C::G) {
@@ -1714,9 +1735,10 @@ static int shape_of(const hn_model_desc& d) {
 // warped_in != NULL: trunk-only program (hn_mlp_fwd_trunk; always the case for a model without warp: warped_in = points)
 static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const float* points, const float* warped_in,
                         const float* viewdirs, const int64_t* ids, const float* noise, float noise_std, int64_t B, int S,
-                        float* sigma, float* rgb, float* warped, void* saved, void* stream) {
+                        const int32_t* pos, int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
   if (!desc || !packed || (!points && !warped_in) || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
+  if (pos != nullptr && S_full < S) return set_error(-1, "hn_mlp_fwd: scattered rows need S_full >= S");
   if (int rc = validate_desc(*desc)) return rc;
   const bool stat = is_static(*desc);
   const int mflags = stat ? 0 : model_flags(*desc);
@@ -1739,6 +1761,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
   fp.n = B * S; fp.S = S; fp.n_embed = desc->num_embeddings;
   fp.view_freqs = desc->view_freqs; fp.mflags = mflags;
+  fp.pos = pos; fp.S_full = pos != nullptr ? S_full : S;
   int64_t nt = tiles_of(fp.n);
   if (nt > 0x7fffffff) return set_error(-1, "hn_mlp_fwd: too many samples");
   fp.n_tiles = (int)nt;
@@ -1764,24 +1787,26 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
 }
 
 extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
-                          const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
-                          float* rgb, float* warped, void* saved, void* stream) {
+                          const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
+                          int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
   if (!points) return set_error(-2, "hn_mlp_fwd: null pointer");
-  return mlp_fwd_impl(desc, packed, points, nullptr, viewdirs, ids, noise, noise_std, B, S, sigma, rgb, warped, saved, stream);
+  return mlp_fwd_impl(desc, packed, points, nullptr, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
+                      saved, stream);
 }
 
 extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
-                                const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma,
-                                float* rgb, void* saved, void* stream) {
+                                const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
+                                int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
   if (!warped_in) return set_error(-2, "hn_mlp_fwd_trunk: null pointer");
-  return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, ids, noise, noise_std, B, S, sigma, rgb, nullptr, saved,
-                      stream);
+  return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
+                      saved, stream);
 }
 
 static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                         const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
-                        const float* g_warped, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
-                        void* workspace, void* stream, bool do_data, bool do_weights, bool trunk = false,
+                        const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
+                        const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream, bool do_data,
+                        bool do_weights, bool trunk = false,
                         float* g_warped_out = nullptr) {   // trunk: trunk-only programs (hn_mlp_bwd_trunk*)
   if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
   const bool stat = desc && is_static(*desc);
@@ -1819,6 +1844,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
       bp.glo_grad = flat_grad + param_offsets[plan.info.glo_param];
     }
     bp.mflags = mflags;
+    bp.pos = pos; bp.S_full = pos != nullptr ? S_full : S;
     bp.n = n; bp.S = S; bp.n_embed = desc->num_embeddings;
     bp.n_tiles = (int)nt;
     bp.x_total = plan.info.x_total; bp.d_total = plan.info.d_total;
@@ -1853,46 +1879,48 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
 
 extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                           const float* rgb, const float* warped, const void* saved, const float* g_sigma,
-                          const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
+                          const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
                           const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, level, param_offsets,
-                      flat_grad, workspace, stream, true, true);
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
+                      param_offsets, flat_grad, workspace, stream, true, true);
 }
 
 extern "C" int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                                const float* rgb, const float* warped, const void* saved, const float* g_sigma,
-                               const float* g_rgb, const float* g_warped, int64_t B, int S, int level,
-                               const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, level, param_offsets,
-                      flat_grad, workspace, stream, true, false);
+                               const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full,
+                               int level, const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
+                      param_offsets, flat_grad, workspace, stream, true, false);
 }
 
 extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                                   const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
-                      param_offsets, flat_grad, (void*)workspace, stream, false, true);
+  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, nullptr, 0,
+                      level, param_offsets, flat_grad, (void*)workspace, stream, false, true);
 }
 
 extern "C" int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                                 const float* rgb, const float* warped_in, const void* saved, const float* g_sigma,
-                                const float* g_rgb, int64_t B, int S, int level, const int64_t* param_offsets, float* flat_grad,
-                                float* g_warped_in, void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
-                      flat_grad, workspace, stream, true, true, true, g_warped_in);
+                                const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full,
+                                int level, const int64_t* param_offsets, float* flat_grad, float* g_warped_in, void* workspace,
+                                void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
+                      param_offsets, flat_grad, workspace, stream, true, true, true, g_warped_in);
 }
 
 extern "C" int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                                      const float* rgb, const float* warped_in, const void* saved, const float* g_sigma,
-                                     const float* g_rgb, int64_t B, int S, int level, const int64_t* param_offsets,
-                                     float* flat_grad, float* g_warped_in, void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, nullptr, B, S, level, param_offsets,
-                      flat_grad, workspace, stream, true, false, true, g_warped_in);
+                                     const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos,
+                                     int S_full, int level, const int64_t* param_offsets, float* flat_grad, float* g_warped_in,
+                                     void* workspace, void* stream) {
+  return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped_in, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
+                      param_offsets, flat_grad, workspace, stream, true, false, true, g_warped_in);
 }
 
 extern "C" int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                                         const int64_t* param_offsets, float* flat_grad, const void* workspace, void* stream) {
-  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, level,
-                      param_offsets, flat_grad, (void*)workspace, stream, false, true, true, nullptr);
+  return mlp_bwd_impl(desc, nullptr, nullptr, nullptr, nullptr, nullptr, saved, nullptr, nullptr, nullptr, B, S, nullptr, 0,
+                      level, param_offsets, flat_grad, (void*)workspace, stream, false, true, true, nullptr);
 }
 
 #if HN_ROLE_TIMING

@@ -28,29 +28,43 @@ def sample_along_rays(origins, directions, num_coarse_samples, near, far, use_st
     """Stratified sampling along the rays (model_utils.py:6-41).  Returns (z_vals (B,Nc), points (B,Nc,3))."""
     B = origins.shape[0]
     dev = origins.device
-    # the Nc stratum bounds are computed with the reference's own torch expressions (bit-identical linspace)
-    t_vals = torch.linspace(0., 1., num_coarse_samples, device=dev)
-    if not use_linear_disparity:
-        z_vals = near * (1. - t_vals) + far * t_vals
-    else:
-        z_vals = 1. / (1. / near * (1. - t_vals) + 1. / far * t_vals)
     o, d = _f32c(origins), _f32c(directions)
     z = torch.empty(B, num_coarse_samples, device=dev, dtype=torch.float32)
     pts = torch.empty(B, num_coarse_samples, 3, device=dev, dtype=torch.float32)
+    lower, upper, depths = _stratum_bounds(num_coarse_samples, float(near), float(far), bool(use_linear_disparity), dev)
     if use_stratified_sampling:
-        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-        upper = torch.cat([mids, z_vals[..., -1:]], dim=-1).contiguous()
-        lower = torch.cat([z_vals[..., :1], mids], dim=-1).contiguous()
         t_rand = torch.rand([B, num_coarse_samples], device=dev)
         check(lib().hn_sample_coarse(ptr(o), ptr(d), ptr(t_rand), ptr(lower), ptr(upper), B, num_coarse_samples,
                                      ptr(z), ptr(pts), stream()), "hn_sample_coarse")
         _lib.count(1)
     else:
-        zc = z_vals.contiguous()
-        check(lib().hn_sample_coarse(ptr(o), ptr(d), None, ptr(zc), ptr(zc), B, num_coarse_samples, ptr(z), ptr(pts),
+        check(lib().hn_sample_coarse(ptr(o), ptr(d), None, ptr(depths), ptr(depths), B, num_coarse_samples, ptr(z), ptr(pts),
                                      stream()), "hn_sample_coarse")
         _lib.count(1)
     return z, pts
+
+
+_bounds_cache = {}
+
+
+def _stratum_bounds(n, near, far, disparity, dev):
+    """(lower, upper) stratum bounds of model_utils.py:25-33 (non-stratified: lower = the depths themselves), computed once
+    per (n, near, far, device) with the reference's own torch expressions (bit-identical linspace) and cached: they do not
+    depend on the rays."""
+    key = (n, near, far, disparity, str(dev))
+    hit = _bounds_cache.get(key)
+    if hit is None:
+        t_vals = torch.linspace(0., 1., n, device=dev)
+        if not disparity:
+            z_vals = near * (1. - t_vals) + far * t_vals
+        else:
+            z_vals = 1. / (1. / near * (1. - t_vals) + 1. / far * t_vals)
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], dim=-1).contiguous()
+        lower = torch.cat([z_vals[..., :1], mids], dim=-1).contiguous()
+        hit = (lower, upper, z_vals.contiguous())
+        _bounds_cache[key] = hit
+    return hit
 
 
 def _sample_pdf_impl(bins, weights, origins, directions, z_vals, n_new, use_stratified_sampling, want_points=True,
@@ -92,7 +106,7 @@ def sample_pdf(bins, weights, origins, directions, z_vals, num_coarse_samples, u
 
 def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None, want_inds=False, want_ranks=False):
     """models.py:752-755 in one launch: bins = .5*(z[1:]+z[:-1]) and weights[...,1:-1] are formed in-kernel.
-    want_ranks: also return (pos_coarse (B,Nc), pos_new (B,n_new)) int64 — where the merge put every coarse depth and
+    want_ranks: also return (pos_coarse (B,Nc), pos_new (B,n_new)) int32 — where the merge put every coarse depth and
     the i-th smallest new sample in the sorted row (a permutation of 0..Nc+n_new-1 per ray)."""
     B, Nc = z_vals.shape
     dev = z_vals.device
@@ -112,7 +126,7 @@ def sample_pdf_fused(z_vals, coarse_weights, origins, directions, n_new, u=None,
         check(lib().hn_sample_pdf_ranks(ptr(zc), None, wptr, Nc, ptr(u), ptr(o), ptr(d), B, Nc, Nc - 2, n_new, ptr(z_fine),
                                         ptr(pts), ptr(inds), ptr(pos_c), ptr(pos_n), stream()), "hn_sample_pdf_ranks")
         _lib.count(1)
-        ranks = (pos_c.long(), pos_n.long())
+        ranks = (pos_c, pos_n)     # int32 position tables: consumed as they are by hn_mlp_fwd / hn_mlp_fwd_trunk
         return (z_fine, pts, inds, ranks) if want_inds else (z_fine, pts, ranks)
     check(lib().hn_sample_pdf(ptr(zc), None, wptr, Nc, ptr(u), ptr(o), ptr(d), B, Nc, Nc - 2, n_new, ptr(z_fine),
                               ptr(pts), ptr(inds), stream()), "hn_sample_pdf")
@@ -187,7 +201,9 @@ def prepare_ray_dict(rays: torch.Tensor) -> dict:
     idx = torch.ones((B, 1), dtype=torch.long, device=rays.device)
     if use_meta:
         idx = rays[:, 8].type(torch.long)
-    metadata = {'warp': idx.clone(), 'camera': idx.clone(), 'appearance': idx.clone(), 'time': idx.clone()}
+    # the reference hands out four clones of the id column (model_utils.py:392-401); nothing on the path writes to them, so
+    # the four keys share one tensor here (4 fewer launches per chunk)
+    metadata = {'warp': idx, 'camera': idx, 'appearance': idx, 'time': idx}
     return {"origins": rays[:, :3], "directions": rays[:, 3:6], "viewdirs": None, "metadata": metadata}
 
 

@@ -106,7 +106,7 @@ class _FusedMlp(torch.autograd.Function):
             saved = torch.empty(sizes.saved_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_fwd", B * S):
             check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise),
-                                   float(noise_std), B, S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()),
+                                   float(noise_std), B, S, None, 0, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()),
                   "hn_mlp_fwd")
         _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
@@ -138,7 +138,7 @@ class _FusedMlp(torch.autograd.Function):
         work = torch.empty(sizes.workspace_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_dgrad", B * S):
             check(lib().hn_mlp_bwd_data(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped),
-                                        ptr(saved), ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, level, offs,
+                                        ptr(saved), ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, None, 0, level, offs,
                                         ptr(flat_grad), ptr(work), stream()), "hn_mlp_bwd_data")
         with _lib.timed("mlp_wgrad", B * S):
             check(lib().hn_mlp_bwd_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad), ptr(work),
@@ -175,7 +175,7 @@ class _FusedTrunk(torch.autograd.Function):
             saved = torch.empty(model._sizes(B * S).saved_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_fwd_trunk", B * S):
             check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(wi), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
-                                         B, S, ptr(sigma), ptr(rgb), ptr(saved), stream()), "hn_mlp_fwd_trunk")
+                                         B, S, None, 0, ptr(sigma), ptr(rgb), None, ptr(saved), stream()), "hn_mlp_fwd_trunk")
         _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
         ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
@@ -205,8 +205,8 @@ class _FusedTrunk(torch.autograd.Function):
         g_wi = torch.empty_like(wi) if (ctx.needs_input_grad[2] or model.use_warp) else None
         with _lib.timed("mlp_dgrad_trunk", B * S):
             check(lib().hn_mlp_bwd_trunk_data(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(wi),
-                                              ptr(saved), ptr(g_sigma), ptr(g_rgb), B, S, level, offs, ptr(flat_grad),
-                                              ptr(g_wi), ptr(work), stream()), "hn_mlp_bwd_trunk_data")
+                                              ptr(saved), ptr(g_sigma), ptr(g_rgb), None, B, S, None, 0, level, offs,
+                                              ptr(flat_grad), ptr(g_wi), ptr(work), stream()), "hn_mlp_bwd_trunk_data")
         with _lib.timed("mlp_wgrad_trunk", B * S):
             check(lib().hn_mlp_bwd_trunk_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad),
                                                  ptr(work), stream()), "hn_mlp_bwd_trunk_weights")
@@ -215,6 +215,92 @@ class _FusedTrunk(torch.autograd.Function):
         if direct:
             return head + (None,) * len(ctx.param_meta)
         return head + tuple(_param_grads(ctx, model, level, flat_grad, offs, 7))
+
+
+class _FusedFineLevel(torch.autograd.Function):
+    """One autograd node for the fine level when it reuses the coarse pass's warp / sheet outputs (`reuse_coarse_warp`):
+    the full network (hn_mlp_fwd) on the depths sample_pdf added and the template alone (hn_mlp_fwd_trunk) on the inherited
+    ones, both launches writing straight into the sorted (B, S) rows through their position tables (hn_sample_pdf_ranks),
+    and the backward launches reading the upstream gradients through the same tables — no gather / scatter / cat passes."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, level, points, viewdirs, ids, noise, noise_std, known_warped, pos_known, pos_new, *params):
+        B, S = points.shape[0], points.shape[1]
+        Sk, Sn = pos_known.shape[1], pos_new.shape[1]
+        dev = points.device
+        desc = model._desc
+        packed = model._packed_weights(level)
+        pts = points.detach().to(torch.float32).contiguous()
+        vd = viewdirs.detach().to(torch.float32).contiguous()
+        kw = known_warped.detach().to(torch.float32).contiguous()
+        ids = ids.reshape(-1).to(torch.int64).contiguous()
+        if ids.numel() != B:
+            raise ValueError(f"metadata ids must have one entry per ray, got {tuple(ids.shape)} for {B} rays")
+        if noise is not None:
+            noise = noise.detach().to(torch.float32).contiguous()
+        sigma = torch.empty(B, S, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
+        warped = torch.empty(B, S, 3 + desc.hyper_dim, device=dev, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[7] or any(ctx.needs_input_grad[10:])
+        saved_n = saved_k = None
+        if need_grad:
+            saved_n = torch.empty(model._sizes(B * Sn).saved_bytes, device=dev, dtype=torch.uint8)
+            saved_k = torch.empty(model._sizes(B * Sk).saved_bytes, device=dev, dtype=torch.uint8)
+        with _lib.timed("mlp_fwd", B * Sn):
+            check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise), float(noise_std), B, Sn,
+                                   ptr(pos_new), S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_n), stream()), "hn_mlp_fwd")
+        with _lib.timed("mlp_fwd_trunk", B * Sk):
+            check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(kw), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
+                                         B, Sk, ptr(pos_known), S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_k), stream()),
+                  "hn_mlp_fwd_trunk")
+        _lib.count(2)
+        ctx.model, ctx.level, ctx.shape = model, level, (B, S, Sk, Sn)
+        ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
+        ctx.save_for_backward(ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new)
+        ctx.set_materialize_grads(False)
+        return sigma, rgb, warped
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g_sigma, g_rgb, g_warped):
+        ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new = ctx.saved_tensors
+        model, level = ctx.model, ctx.level
+        B, S, Sk, Sn = ctx.shape
+        if saved_n is None:
+            raise RuntimeError("hn_mlp_bwd needs the activation stash; forward ran without grad enabled")
+        dev = sigma.device
+        g_sigma = torch.zeros_like(sigma) if g_sigma is None else g_sigma.to(torch.float32).contiguous()
+        g_rgb = torch.zeros_like(rgb) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
+        g_warped = None if g_warped is None else g_warped.to(torch.float32).contiguous()
+        direct = model._flat_grads is not None and model._flat_grads.flat.device == dev
+        if direct:
+            offs, flat_grad = model._flat_offsets(), model._flat_grads.flat
+        else:
+            offs, total = model._grad_offsets()
+            flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        d = C.byref(model._desc)
+        work = torch.empty(model._sizes(B * max(Sk, Sn)).workspace_bytes, device=dev, dtype=torch.uint8)
+        g_kw = torch.empty_like(kw)
+        with _lib.timed("mlp_dgrad", B * Sn):
+            check(lib().hn_mlp_bwd_data(d, ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_n), ptr(g_sigma),
+                                        ptr(g_rgb), ptr(g_warped), B, Sn, ptr(pos_new), S, level, offs, ptr(flat_grad),
+                                        ptr(work), stream()), "hn_mlp_bwd_data")
+        with _lib.timed("mlp_wgrad", B * Sn):
+            check(lib().hn_mlp_bwd_weights(d, ptr(saved_n), B, Sn, level, offs, ptr(flat_grad), ptr(work), stream()),
+                  "hn_mlp_bwd_weights")
+        with _lib.timed("mlp_dgrad_trunk", B * Sk):
+            check(lib().hn_mlp_bwd_trunk_data(d, ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(kw), ptr(saved_k), ptr(g_sigma),
+                                              ptr(g_rgb), ptr(g_warped), B, Sk, ptr(pos_known), S, level, offs, ptr(flat_grad),
+                                              ptr(g_kw), ptr(work), stream()), "hn_mlp_bwd_trunk_data")
+        with _lib.timed("mlp_wgrad_trunk", B * Sk):
+            check(lib().hn_mlp_bwd_trunk_weights(d, ptr(saved_k), B, Sk, level, offs, ptr(flat_grad), ptr(work), stream()),
+                  "hn_mlp_bwd_trunk_weights")
+        _lib.count(4)
+        head = (None,) * 7 + (g_kw if ctx.needs_input_grad[7] else None, None, None)
+        if direct:
+            return head + (None,) * len(ctx.param_meta)
+        return head + tuple(_param_grads(ctx, model, level, flat_grad, offs, 10))
 
 
 class NerfModel(PackedWeights, nn.Module):
@@ -516,19 +602,8 @@ class NerfModel(PackedWeights, nn.Module):
             sigma, rgb, warped_points = _FusedMlp.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
         else:
             known_warped, pos_known, pos_new = _inherited
-            pts_new = torch.gather(points, 1, pos_new[..., None].expand(-1, -1, 3))
-            noise_new = noise_known = None
-            if noise is not None:
-                noise_new = torch.gather(noise, 1, pos_new[..., None])
-                noise_known = torch.gather(noise, 1, pos_known[..., None])
-            s_new, c_new, w_new = _FusedMlp.apply(self, lvl, pts_new, viewdirs, ids, noise_new, noise_std, *params)
-            s_known, c_known = _FusedTrunk.apply(self, lvl, known_warped, viewdirs, ids, noise_known, noise_std, *params)
-            pos = torch.cat([pos_new, pos_known], 1)                               # a permutation of 0..S-1 per ray
-            sigma = torch.empty_like(z_vals).scatter(1, pos, torch.cat([s_new, s_known], 1))
-            rgb = points.new_empty(B, S, 3).scatter(1, pos[..., None].expand(-1, -1, 3), torch.cat([c_new, c_known], 1))
-            wcat = torch.cat([w_new, known_warped], 1)
-            warped_points = wcat.new_empty(B, S, wcat.shape[-1]).scatter(
-                1, pos[..., None].expand(-1, -1, wcat.shape[-1]), wcat)
+            sigma, rgb, warped_points = _FusedFineLevel.apply(self, lvl, points, viewdirs, ids, noise, noise_std, known_warped,
+                                                              pos_known, pos_new, *params)
         sigma = filter_sigma(points, sigma, render_opts)
         out['warped_points'] = warped_points
         comp = model_utils.volumetric_rendering(rgb, sigma, z_vals, directions,
@@ -553,8 +628,9 @@ class NerfModel(PackedWeights, nn.Module):
     def _forward(self, rays_dict, extra_params, metadata_encoded, use_warp, return_points, return_weights,
                  return_warp_jacobian, near, far, use_sample_at_infinity, render_opts, deterministic):
         use_warp = self.use_warp and use_warp
-        origins = rays_dict['origins']
-        directions = rays_dict['directions']
+        # column slices of the (B,9) ray rows are strided views: one contiguous copy each, reused by every stage below
+        origins = rays_dict['origins'].contiguous()
+        directions = rays_dict['directions'].contiguous()
         metadata = rays_dict['metadata']
         if 'viewdirs' in rays_dict and rays_dict['viewdirs'] is not None:
             viewdirs = rays_dict['viewdirs']

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 2
+#define HN_ABI_VERSION 3
 
 /* Topology of one NerfModel (reference: hypernerf/models.py:111-309): NerfMLP (modules.py:172-298) with trunk 8x256
  * skip@4 and rgb branch 4x128, optionally conditioned on a GLO embedding, behind one of the working combinations of
@@ -140,18 +140,23 @@ int hn_filter_sigma(const float* points, const float* sigma, const float* values
  * points (B,S,3); viewdirs (B,3) (the reference passes the raw ray directions, models.py:717-720);
  * ids: (B,) int64 row of metadata['time']; noise: (B,S) standard-normal draws or NULL; noise_std scales it.
  * Outputs sigma (B,S) post-softplus, rgb (B,S,3) post-sigmoid, warped (B,S,3+H);
- * saved: activation stash for hn_mlp_bwd (NULL = inference). */
+ * saved: activation stash for hn_mlp_bwd (NULL = inference).
+ * Scattered rows (pos != NULL): the launch evaluates S of the S_full samples of every ray — launch row j of ray b is
+ * sample pos[b*S + j] (int32) of that ray: points / noise are read and sigma / rgb / warped written at that position of
+ * (B,S_full,...) tensors.  The drop-in model evaluates the fine level's new and inherited depths in two launches that
+ * fill one sorted (B,Nc+Nf) row (models.py:752-767).  pos == NULL: S_full is ignored, rows are the launch rows. */
 int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
-               const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, float* sigma, float* rgb,
-               float* warped, void* saved, void* stream);
+               const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos, int S_full,
+               float* sigma, float* rgb, float* warped, void* saved, void* stream);
 
 /* autograd of hn_mlp_fwd: accumulates parameter gradients of `level` (and the shared warp / sheet / GLO
  * gradients) into flat_grad (fp32); grad_offsets: HOST array of HN_NUM_PARAM_TENSORS element offsets into
- * flat_grad.  g_warped may be NULL.  workspace: hn_sizes.workspace_bytes of scratch. */
+ * flat_grad.  g_warped may be NULL.  workspace: hn_sizes.workspace_bytes of scratch.  pos / S_full as in the forward
+ * (sigma, rgb, warped, g_sigma, g_rgb, g_warped are the (B,S_full,...) tensors). */
 int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma, const float* rgb,
                const float* warped, const void* saved, const float* g_sigma, const float* g_rgb, const float* g_warped,
-               int64_t B, int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace,
-               void* stream);
+               int64_t B, int S, const int32_t* pos, int S_full, int level, const int64_t* grad_offsets /* host */,
+               float* flat_grad, void* workspace, void* stream);
 
 /* The two halves of hn_mlp_bwd, separately callable (hn_mlp_bwd == data then weights on the same stream):
  *   hn_mlp_bwd_data     back-propagates through every layer (tcgen05, transposed weights), writes the
@@ -159,32 +164,37 @@ int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids
  *   hn_mlp_bwd_weights  dW = dY^T X and db = sum dY over all samples from `saved` + `workspace`. */
 int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                     const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
-                    const float* g_warped, int64_t B, int S, int level, const int64_t* grad_offsets /* host */,
-                    float* flat_grad, void* workspace, void* stream);
+                    const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
+                    const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace, void* stream);
 int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                        const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
 
-/* Trunk-only evaluation of one level (hyper model only): the template NeRF — positional encoding of the warped point and
- * the hyper coordinates, trunk, bottleneck, rgb / alpha heads (NerfMLP modules.py:172-298, query_template models.py:447-493)
- * — for rows whose (3 + H) warped point / hyper coordinates are given.  NerfModel.forward (models.py:745-767) re-evaluates
- * the shared TranslationField / HyperSheetMLP at the coarse depths the fine level inherits (`sort(cat[z_coarse, z_new])`);
- * the drop-in model takes those rows' warp-field outputs from the coarse pass instead and runs them through this entry
- * point.  Same stash / workspace sizes as hn_mlp_fwd / hn_mlp_bwd (the warp / sheet slabs stay unused).
- *   hn_mlp_fwd_trunk  warped_in (B,S,3+H) -> sigma (B,S), rgb (B,S,3)
+/* Trunk-only evaluation of one level: the template NeRF — positional encoding of the warped point and the hyper
+ * coordinates, trunk, bottleneck, rgb / alpha heads (NerfMLP modules.py:172-298, query_template models.py:447-493) — for
+ * rows whose (3 + H) warped point / hyper coordinates are given.  NerfModel.forward (models.py:745-767) re-evaluates the
+ * shared TranslationField / HyperSheetMLP at the coarse depths the fine level inherits (`sort(cat[z_coarse, z_new])`); the
+ * drop-in model takes those rows' warp-field outputs from the coarse pass instead and runs them through this entry point.
+ * It is also the whole network of a model without warp (warped_in = the raw sample points, models.py:568-569).  Same stash
+ * / workspace sizes as hn_mlp_fwd / hn_mlp_bwd (the warp / sheet slabs stay unused).
+ *   hn_mlp_fwd_trunk  warped_in (B,S,3+H), in launch order -> sigma, rgb (and, if `warped` != NULL, a copy of warped_in)
+ *                     at the rows' positions (pos / S_full as in hn_mlp_fwd)
  *   hn_mlp_bwd_trunk  data + weight gradients of the trunk / heads into flat_grad, and g_warped_in (B,S,3+H) =
- *                     d loss / d warped_in (to be added to the upstream gradient of whoever produced warped_in). */
+ *                     d loss / d warped_in (+ g_warped at the rows' positions when given), to be added to the upstream
+ *                     gradient of whoever produced warped_in.  ids: NULL unless the template is GLO-conditioned. */
 int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
-                     const int64_t* ids /* NULL unless the template is GLO-conditioned */, const float* noise, float noise_std,
-                     int64_t B, int S, float* sigma, float* rgb, void* saved, void* stream);
+                     const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
+                     int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream);
 int hn_mlp_bwd_trunk(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma, const float* rgb,
-                     const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb, int64_t B, int S,
-                     int level, const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in, void* workspace,
+                     const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb,
+                     const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
+                     const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in, void* workspace,
                      void* stream);
 /* hn_mlp_bwd_trunk split like hn_mlp_bwd_data / hn_mlp_bwd_weights (same workspace hand-off). */
 int hn_mlp_bwd_trunk_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                           const float* rgb, const float* warped_in, const void* saved, const float* g_sigma, const float* g_rgb,
-                          int64_t B, int S, int level, const int64_t* grad_offsets /* host */, float* flat_grad,
-                          float* g_warped_in, void* workspace, void* stream);
+                          const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
+                          const int64_t* grad_offsets /* host */, float* flat_grad, float* g_warped_in, void* workspace,
+                          void* stream);
 int hn_mlp_bwd_trunk_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                              const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
 
