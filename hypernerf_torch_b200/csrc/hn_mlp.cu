@@ -116,7 +116,10 @@ using Smem = SmemPlan<C::INB_CHUNKS, kRingStages>;
 // With 3 stages of 512 cycles of UMMA work a refill (commit -> producer -> L2 -> complete_tx, ~1 100 cycles after the
 // stage's last UMMA retires) lands ~80 cycles after the issuer needs the slot again: 12 % of the issuer's time was
 // spent waiting for stages.
-constexpr int kBwdRingStages = kSubTiles == 2 && !kPair ? 5 : kRingStages;
+#ifndef HN_PAIR_BWD_RING
+#define HN_PAIR_BWD_RING 0   // experiment: give the pair-mode data gradient the deep ring as well
+#endif
+constexpr int kBwdRingStages = kSubTiles == 2 && (!kPair || HN_PAIR_BWD_RING) ? 5 : kRingStages;
 // (the hyper model's data gradient keeps nothing in INB at all: 6 stages)
 template <class C>
 using SmemBwd = SmemPlan<C::STATIC ? 2 : 0, (C::STATIC || kBwdRingStages != 5) ? kBwdRingStages : 6>;
