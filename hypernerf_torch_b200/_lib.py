@@ -29,7 +29,7 @@ EXPORTS = [
 # microbenchmarks / descriptor probes: their own library and header (include/hypernerf_b200_probe.h), not the product ABI
 PROBE_LIB_PATH = os.path.join(_HERE, "libhypernerf_b200_probe.so")
 PROBE_EXPORTS = ["hn_umma_probe", "hn_umma_probe2", "hn_umma_rate", "hn_umma_rate2", "hn_umma_rate3", "hn_umma_rate4",
-                 "hn_epi_rate", "hn_tmem_rate"]
+                 "hn_epi_rate", "hn_tmem_rate", "hn_overlap_rate"]
 
 
 class ModelDesc(C.Structure):
@@ -127,6 +127,7 @@ def probe_lib():
     L.hn_umma_probe2.argtypes = [vp, vp, vp, i32, i32, vp]
     L.hn_umma_rate4.argtypes = [i32] * 5 + [vp, vp]
     L.hn_umma_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.hn_overlap_rate.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     for name in PROBE_EXPORTS:
         getattr(L, name).restype = C.c_int
     _probe = L

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <string.h>
+#include <mutex>
+#include <type_traits>
 #include <unordered_map>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
 #include <cudaTypedefs.h>
@@ -27,6 +29,19 @@
 #include "hn_ptx.cuh"
 
 namespace hn {
+
+// out-of-range metadata id inside the fused kernels (HN_TRAP_IDS): see hn_check_ids
+#ifndef HN_DBG_OLD_BOTT
+#define HN_DBG_OLD_BOTT 0
+#endif
+#ifndef HN_TRAP_IDS
+#define HN_TRAP_IDS 1
+#endif
+#if HN_TRAP_IDS
+#define HN_CHECK_ID(id, n) do { if ((uint64_t)(id) >= (uint64_t)(n)) __trap(); } while (0)
+#else
+#define HN_CHECK_ID(id, n) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // compile-time model shape (cfg-1 family of BASELINE.json)
@@ -80,6 +95,24 @@ using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (->
 #define HN_FOLD_BIAS_TRAIN 0
 #endif
 constexpr bool kFoldBiasTrain = kFoldBias && HN_FOLD_BIAS_TRAIN != 0;
+// HN_CONST_BIAS: where the epilogue takes its biases from when they do not ride in the UMMAs.
+//   0: staged in shared memory per layer (LDS.128 broadcasts)  1: the training forward reads them from constant memory
+//   2: the inference forward too (no bias K steps at all)
+// Measured (profiles/overlap_rate.py): next to a busy tensor pipe the 8 LDS.128 + 32 FADD per 32 columns double a drain
+// (2 380 -> 4 840 cycles per 128 x 256 accumulator) because the broadcasts queue behind the UMMAs' operand reads in the
+// shared-memory pipe; constant-bank loads (LDC, uniform address) do not touch it.
+// HN_LD_MID = k (1..3): the drain issues the next block's TMEM load after k of the 4 chunks of the current block; 0: right
+// after the wait (source order; ptxas then places it)
+#ifndef HN_LD_MID
+#define HN_LD_MID 0
+#endif
+#ifndef HN_CONST_BIAS
+#define HN_CONST_BIAS 0
+#endif
+constexpr int kConstBias = HN_CONST_BIAS;
+constexpr int kMaxBiasFloats = 4608;   // >= the forward bias array of any built configuration (hyper model: 4 144 floats)
+constexpr int kConstSlots = 3;         // blobs whose biases are resident at the same time (coarse, fine, one more model)
+__constant__ float c_bias[kConstSlots * kMaxBiasFloats];
 constexpr bool kPingPongFwdTrain = ((HN_PINGPONG & 1) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongBwd = ((HN_PINGPONG & 2) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongFwdInfer = ((HN_PINGPONG & 4) || kPair) && kSubTiles == 2;
@@ -92,7 +125,14 @@ struct Sched {
 // LAST: the SM's warp arbiter favours the highest warp id, and once a drain loop of one sub-tile runs concurrently with
 // the other sub-tile's UMMAs (ping-pong / pair schedules) low-numbered feeder warps were starved of issue slots
 // (measured: the leader's issuer waited 42 % of its time for the other CTA's relay warp).
-constexpr int kEpiWarps = 4 * kSubTiles;
+constexpr int kEpiWarps = 4 * kSubTiles * kEpiSplit;
+// register budgets after setmaxnreg (65 536 per SM): feeders, primary and secondary epilogue warpgroups
+constexpr int kRegsFeeder = kEpiSplit == 2 ? 40 : (kSubTiles == 2 ? 72 : 40);   // 128 x 72 + 256 x 216 = 64 512 = the launch allocation (384 x 168)
+// (setmaxnreg moves registers inside the CTA's LAUNCH allocation only: 640 threads x 96 = 61 440 with the split epilogue,
+// 384 x 168 = 64 512 without; the budgets below add up to no more than that)
+constexpr int kRegsPrimary = kEpiSplit == 2 ? 144 : (kSubTiles == 2 ? 216 : 208);
+constexpr int kRegsSecondary = 72;
+static_assert(kEpiSplit != 2 || 128 * kRegsFeeder + 256 * kRegsPrimary + 256 * kRegsSecondary <= 640 * 96, "register budget");
 constexpr int kProducerWarp = kEpiWarps, kIssuerWarp = kEpiWarps + 1, kRelayWarp = kEpiWarps + 2;
 
 template <int INB_CHUNKS_, int STAGES_>
@@ -137,6 +177,7 @@ struct FwdParams {
   uint32_t w_row0;          // pair mode: first 16-byte row of `weights` inside the blob the tensor maps cover
   const uint8_t* weights;   // packed blob base + fwd_off
   const float* bias;        // packed blob base + bias_off
+  int cbias;                // first float of this blob's bias array inside c_bias (kConstBias)
   const float* glo;         // (E, G) fp32 copy of the GLO table
   const float* points; const float* viewdirs; const int64_t* ids; const float* noise;
   const float* warped_in;   // trunk-only program (hn_mlp_fwd_trunk): (n, 3 + H) warped points + hyper coordinates, else NULL
@@ -291,6 +332,10 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
 #ifndef HN_PAIR_DIRECT
 #define HN_PAIR_DIRECT 1
 #endif
+// HN_PAIR_MAP2D = 1: the pair mode's tensor maps view the blob as [128-byte line][lines] instead of [block][8 rows][8 bf16]
+#ifndef HN_PAIR_MAP2D
+#define HN_PAIR_MAP2D 1
+#endif
 // Producer of CTA `rank`: per stage, its half (rows [rank N/2, (rank+1) N/2) of every 8-column chunk) of the weights.
 template <class RS>
 __device__ __forceinline__ void produce_tile_pair(const Program& prog, const PairMaps& maps, uint32_t w_row0,
@@ -319,7 +364,11 @@ __device__ __forceinline__ void produce_tile_pair(const Program& prog, const Pai
           uint32_t blk = (w_row0 + row0) >> 3, nblk = bytes >> 7, off = 0;   // 128-byte blocks
           while (nblk) {
             const int i = 31 - __clz(nblk > 256u ? 256u : nblk);             // largest power of two that fits
+#if HN_PAIR_MAP2D
+            tma_g2s_2d_pair(dst + off, &maps.m[i], (int32_t)blk, &full[rs.slot]);
+#else
             tma_g2s_3d_pair(dst + off, &maps.m[i], (int32_t)blk, &full[rs.slot]);
+#endif
             blk += 1u << i; nblk -= 1u << i; off += 128u << i;
           }
 #else
@@ -561,26 +610,36 @@ __device__ __forceinline__ void warp_arrive_leader(uint32_t leader_bar) {
 // named barrier of one chain's epilogue threads (ids 1, 2; barrier 0 is __syncthreads)
 template <bool PP>
 __device__ __forceinline__ void epi_named_barrier(int chain) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * Sched<PP>::SUBS) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + chain), "n"(128 * Sched<PP>::SUBS * kEpiSplit) : "memory");
 }
 
 // bias of a head column: already inside the accumulator when the biases ride in the UMMAs
-template <bool FOLD>
-__device__ __forceinline__ float head_bias(const float* bias_s, int i) { return FOLD ? 0.f : bias_s[i]; }
+// BM: 0 = already inside the accumulator (bias K steps), 1 = shared-memory staging buffer, 2 = constant memory
+template <int BM>
+__device__ __forceinline__ float head_bias(const float* bias_s, int cb, int i) {
+  return BM == 0 ? 0.f : (BM == 2 ? c_bias[cb + i] : bias_s[i]);
+}
 
-template <bool RELU, bool STASH>
-__device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, uint8_t* act_row, uint4* save_row,
-                                            int chunk0, int save_chunk, uint32_t* gate_dst) {
-  uint32_t ge = 0, go = 0;   // sign bits of the even / odd columns of this 32-column block (hn_ptx.cuh: gate_push)
+// chunks [Q0, Q1) of one 32-column block (a chunk = 8 columns): bias, ReLU, bf16 pack, st.shared (+ stash store); ge / go
+// collect the sign bits for the block's gate word
+template <bool RELU, bool STASH, int BM, int Q0, int Q1>
+__device__ __forceinline__ void fwd_store_chunks(const uint32_t* r, const float* bias_s, int cb, uint8_t* act_row, uint4* save_row,
+                                                 int chunk0, int save_chunk, uint32_t& ge, uint32_t& go) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = Q0; q < Q1; ++q) {
     float v[8];
-    if constexpr (kFoldBias && (!STASH || kFoldBiasTrain)) {   // the accumulator already holds W x + b
+    if constexpr (BM == 0) {   // the accumulator already holds W x + b
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * q + j]);
     } else {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * q);       // smem broadcast
-    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * q + 4);
+    float4 b0, b1;
+    if constexpr (BM == 2) {   // constant-bank loads, uniform address
+      b0 = *reinterpret_cast<const float4*>(&c_bias[cb + 8 * q]);
+      b1 = *reinterpret_cast<const float4*>(&c_bias[cb + 8 * q + 4]);
+    } else {                   // smem broadcast
+      b0 = *reinterpret_cast<const float4*>(bias_s + 8 * q);
+      b1 = *reinterpret_cast<const float4*>(bias_s + 8 * q + 4);
+    }
     v[0] = __uint_as_float(r[8 * q + 0]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
     v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
     v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
@@ -601,26 +660,79 @@ __device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias
     *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
     if (STASH) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], o);
   }
+}
+template <bool RELU, bool STASH, int BM>
+__device__ __forceinline__ void fwd_store32(const uint32_t* r, const float* bias_s, int cb, uint8_t* act_row, uint4* save_row,
+                                            int chunk0, int save_chunk, uint32_t* gate_dst) {
+  uint32_t ge = 0, go = 0;   // sign bits of the even / odd columns of this 32-column block (hn_ptx.cuh: gate_push)
+  fwd_store_chunks<RELU, STASH, BM, 0, 4>(r, bias_s, cb, act_row, save_row, chunk0, save_chunk, ge, go);
+  if (RELU && STASH) __stcs(&gate_dst[(chunk0 >> 2) * kHalfRows], gate_word_of(ge, go));
+}
+// the same with the NEXT block's TMEM load issued in the middle of this block's work (HN_LD_MID): where exactly the load
+// sits relative to the stores changes the drain by several percent (ptxas otherwise floats it freely)
+template <bool RELU, bool STASH, int BM>
+__device__ __forceinline__ void fwd_store32_ld(const uint32_t* r, const float* bias_s, int cb, uint8_t* act_row, uint4* save_row,
+                                               int chunk0, int save_chunk, uint32_t* gate_dst, bool more, uint32_t next_taddr,
+                                               uint32_t* next) {
+  uint32_t ge = 0, go = 0;
+  fwd_store_chunks<RELU, STASH, BM, 0, HN_LD_MID>(r, bias_s, cb, act_row, save_row, chunk0, save_chunk, ge, go);
+  asm volatile("" ::: "memory");
+  if (more) tmem_ld32(next_taddr, next);
+  asm volatile("" ::: "memory");
+  fwd_store_chunks<RELU, STASH, BM, HN_LD_MID, 4>(r, bias_s, cb, act_row, save_row, chunk0, save_chunk, ge, go);
   if (RELU && STASH) __stcs(&gate_dst[(chunk0 >> 2) * kHalfRows], gate_word_of(ge, go));
 }
 
 // ncols: multiple of 32
-template <bool RELU, bool STASH>
-__device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, uint8_t* act_row, uint4* save_row,
+template <bool RELU, bool STASH, int BM>
+__device__ __forceinline__ void fwd_cols(uint32_t taddr, const float* bias_s, int cb, uint8_t* act_row, uint4* save_row,
                                          int save_chunk, int ncols, uint32_t* gate_dst) {
+  if constexpr (kEpiSplit == 2) {
+    // two warpgroups per sub-tile overlap each other's TMEM latency: one buffer keeps the secondary warpgroup at 72 registers
+    uint32_t r[32];
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      fwd_store32<RELU, STASH, BM>(r, bias_s + c0, cb + c0, act_row, save_row, c0 >> 3, save_chunk, gate_dst);
+    }
+    return;
+  }
   uint32_t ra[32], rb[32];
   tmem_ld32(taddr, ra);
+#if HN_LD_MID > 0
+  for (int c0 = 0; c0 < ncols; c0 += 64) {
+    tmem_ld_wait();
+    const bool more = c0 + 32 < ncols;
+    fwd_store32_ld<RELU, STASH, BM>(ra, bias_s + c0, cb + c0, act_row, save_row, c0 >> 3, save_chunk, gate_dst, more,
+                                    taddr + c0 + 32, rb);
+    if (more) {
+      tmem_ld_wait();
+      fwd_store32_ld<RELU, STASH, BM>(rb, bias_s + c0 + 32, cb + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk, gate_dst,
+                                      c0 + 64 < ncols, taddr + c0 + 64, ra);
+    }
+  }
+  return;
+#endif
   for (int c0 = 0; c0 < ncols; c0 += 64) {
     tmem_ld_wait();
     const bool more = c0 + 32 < ncols;
     if (more) tmem_ld32(taddr + c0 + 32, rb);
-    fwd_store32<RELU, STASH>(ra, bias_s + c0, act_row, save_row, c0 >> 3, save_chunk, gate_dst);
+    fwd_store32<RELU, STASH, BM>(ra, bias_s + c0, cb + c0, act_row, save_row, c0 >> 3, save_chunk, gate_dst);
     if (more) {
       tmem_ld_wait();
       if (c0 + 64 < ncols) tmem_ld32(taddr + c0 + 64, ra);
-      fwd_store32<RELU, STASH>(rb, bias_s + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk, gate_dst);
+      fwd_store32<RELU, STASH, BM>(rb, bias_s + c0 + 32, cb + c0 + 32, act_row, save_row, (c0 + 32) >> 3, save_chunk, gate_dst);
     }
   }
+}
+
+// the column share of one of the kEpiSplit warpgroups that drain a sub-tile (hn_mlp_program.h: HN_EPI_SPLIT)
+template <bool RELU, bool STASH, int BM>
+__device__ __forceinline__ void fwd_cols_share(int share, uint32_t taddr, const float* bias_s, int cb, uint8_t* act_row,
+                                               uint4* save_row, int save_chunk, int ncols, uint32_t* gate_dst) {
+  const int n = ncols / kEpiSplit, c0 = share * n;
+  fwd_cols<RELU, STASH, BM>(taddr + c0, bias_s + c0, cb + c0, act_row + (c0 >> 3) * kChunkBytes, save_row,
+                            save_chunk + (c0 >> 3), n, gate_dst != nullptr ? gate_dst + (c0 >> 5) * kHalfRows : nullptr);
 }
 
 // backward: ReLU gates from the gate words the forward wrote (one uint32 per row per 32 columns, hn_ptx.cuh), so the
@@ -655,6 +767,16 @@ __device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t w, uint8
 // NCOLS: multiple of 32 (<= 256), compile time so that gw[] and both row buffers stay in registers
 template <bool MASK, int NCOLS>
 __device__ __forceinline__ void bwd_cols(uint32_t taddr, const uint32_t* gw, uint8_t* dst_row, uint4* save_row, int save_chunk) {
+  if constexpr (kEpiSplit == 2) {
+    uint32_t r[32];
+#pragma unroll
+    for (int b = 0; b < NCOLS / 32; ++b) {
+      tmem_ld32(taddr + b * 32, r);
+      tmem_ld_wait();
+      bwd_store32<MASK>(r, MASK ? gw[b] : 0u, dst_row, save_row, b * 4, save_chunk);
+    }
+    return;
+  }
   uint32_t r[2][32];
   tmem_ld32(taddr, r[0]);
 #pragma unroll
@@ -675,6 +797,23 @@ __device__ __forceinline__ void bwd_masked_layer(uint32_t tlane, const uint32_t*
   bwd_cols<true, NCOLS>(tlane, gw, dst_row, save_row, save_chunk);
 }
 
+// the column share of one of the kEpiSplit warpgroups of a sub-tile (hn_mlp_program.h: HN_EPI_SPLIT)
+template <int NCOLS>
+__device__ __forceinline__ void bwd_masked_share(int share, uint32_t tlane, const uint32_t* __restrict__ gate_row, int gate_word,
+                                                 uint8_t* dst_row, uint4* save_row, int save_chunk, uint64_t* acc_full,
+                                                 uint32_t& ph_acc, long long& t_acc) {
+  constexpr int N = NCOLS / kEpiSplit;
+  const int c0 = share * N;
+  bwd_masked_layer<N>(tlane + c0, gate_row, gate_word + (c0 >> 5), dst_row + (c0 >> 3) * kChunkBytes, save_row,
+                      save_chunk + (c0 >> 3), acc_full, ph_acc, t_acc);
+}
+template <int NCOLS>
+__device__ __forceinline__ void bwd_linear_share(int share, uint32_t tlane, uint8_t* dst_row, uint4* save_row, int save_chunk) {
+  constexpr int N = NCOLS / kEpiSplit;
+  const int c0 = share * N;
+  bwd_cols<false, N>(tlane + c0, nullptr, dst_row + (c0 >> 3) * kChunkBytes, save_row, save_chunk + (c0 >> 3));
+}
+
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -687,7 +826,9 @@ template <class C, bool STASH>
 __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SM = Smem<C>;
-  constexpr bool FOLD = kFoldBias && (!STASH || kFoldBiasTrain);   // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS)
+  // biases inside the UMMAs (hn_mlp_program.h: HN_FOLD_BIAS), else from constant memory (HN_CONST_BIAS) or staged in smem
+  constexpr bool FOLD = kFoldBias && (STASH ? kFoldBiasTrain : kConstBias < 2);
+  constexpr int BM = FOLD ? 0 : ((STASH ? kConstBias >= 1 : kConstBias >= 2) ? 2 : 1);
   constexpr bool PP = STASH ? kPingPongFwdTrain : kPingPongFwdInfer;
   uint8_t* act = smem + SM::ACT;
   uint8_t* inb = smem + SM::INB;
@@ -705,7 +846,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     // one arrival per epilogue warp of the chain (pair mode: of both CTAs, the other CTA's arrive remotely)
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * (kPair ? 2 : 1)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * kEpiSplit * (kPair ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == kIssuerWarp) {
@@ -720,7 +861,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
   const Program& prog = p.prog;
 
   if (warp >= kEpiWarps) {
-    setmaxnreg_dec<kSubTiles == 2 ? 56 : 40>();
+    setmaxnreg_dec<kRegsFeeder>();
     if (warp == kProducerWarp && lane == 0) {
       RingState rs;
       long long tw = 0;
@@ -766,11 +907,13 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       }
     }
   } else {
-    setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
-    const int et = threadIdx.x & (128 * Sched<PP>::SUBS - 1);  // index inside this chain's epilogue threads
-    // ---------------- epilogue warps: thread <-> sample row; warps 0..3 sub-tile 0, 4..7 sub-tile 1 ----------------
-    const int sub = warp >> 2;
+    // ---------------- epilogue warps: thread <-> sample row; kEpiSplit warpgroups per sub-tile ----------------
+    const int et = threadIdx.x % (128 * Sched<PP>::SUBS * kEpiSplit);  // index inside this chain's epilogue threads
+    const int sub = warp / (4 * kEpiSplit);
+    const int share = (warp >> 2) % kEpiSplit;   // which column share of the wide drains; share 0 = the primary warpgroup
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    auto epilogue = [&](auto primary_tag) {
+    constexpr bool PRIMARY = decltype(primary_tag)::value;   // primary: per-row work (encodings, heads) + its column share
     const int row = quarter * 32 + lane;     // row inside the sub-tile
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
@@ -797,19 +940,17 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         save_row = reinterpret_cast<uint4*>(p.saved + half * (size_t)p.x_total * kHalfChunkBytes) + (row & 63);
         gate_row = p.gates + half * (size_t)p.g_total * kHalfRows + (row & 63);
       }
-      float pt[3], dir[3];
-      float wp[C::NWARPED + (C::STATIC ? 1 : 0)];  // warped point + hyper coordinates
+      // (the sample point and view direction are re-loaded where they are needed — FE_WSHEAD, FE_BOTT — instead of being
+      // kept in registers across the drain loops; only the wide trunk inputs keep the warped point for FE_SKIPFEED)
+      float wp_keep[C::TIN_ACT ? C::NWARPED : 1];
       const bool trunk_only = !C::STATIC && p.warped_in != nullptr;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        dir[i] = __ldg(p.viewdirs + ray * 3 + i);
-        pt[i] = trunk_only ? 0.f : __ldg(p.points + gq * 3 + i);
-      }
+      if constexpr (PRIMARY) {
       if (trunk_only) {
         // trunk-only program: the warped point / hyper coordinates of this row were computed by another launch (the
         // coarse level's, for the depths the fine level inherits) or are the raw sample point (model without warp); the
         // prologue does what FE_WSHEAD's epilogue does
         if constexpr (!C::STATIC) {
+          float wp[C::NWARPED];
 #pragma unroll
           for (int i = 0; i < C::NWARPED; ++i) wp[i] = __ldg(p.warped_in + gc * C::NWARPED + i);
           if (valid && p.warped != nullptr) {   // the given point is also this row's entry of the level's warped_points
@@ -817,15 +958,26 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
             for (int i = 0; i < C::NWARPED; ++i) p.warped[gq * C::NWARPED + i] = wp[i];
           }
           store_trunk_input<C>(wp, act_row, inb_row, save_row, p.x_in_t);
-          if constexpr (C::TIN_ACT) store_ones_only<C>(inb_row); else store_ones_pair<C, C::KT>(inb_row);
+          if constexpr (C::TIN_ACT) {
+            store_ones_only<C>(inb_row);
+#pragma unroll
+            for (int i = 0; i < C::NWARPED; ++i) wp_keep[i] = wp[i];
+          } else {
+            store_ones_pair<C, C::KT>(inb_row);
+          }
         }
       } else if constexpr (!C::NOWARP) {
       // prologue: [posenc(points, WF) | GLO | 0] -> INB   (static baseline: [Embedding(xyz) | 0], nerf.py:21-38)
         float f[C::KW];
-        posenc<3, C::WF>(pt, f);
+        {
+          float pt[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) pt[i] = __ldg(p.points + gq * 3 + i);
+          posenc<3, C::WF>(pt, f);
+        }
         if constexpr (!C::STATIC) {
           const int64_t id = __ldg(p.ids + ray);
-          if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();   // out-of-range metadata id
+          HN_CHECK_ID(id, p.n_embed);   // out-of-range metadata id
           const float* e = p.glo + id * C::G;
 #pragma unroll
           for (int i = 0; i < C::G; ++i) f[C::PE_W + i] = __ldg(e + i);
@@ -834,6 +986,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         store_features<C::KW>(f, inb_row, save_row, p.x_in_ws);
         store_ones_pair<C, C::KW>(inb_row);
       }
+      }   // PRIMARY
       fence_proxy_async_smem();
       tc_fence_before();
       { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
@@ -845,25 +998,30 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         // a per-block __ldg would go to L2 every time); double-buffered by layer parity
         float* bias = PP ? sbias + chain * 256 : sbias + (li & 1) * 256;
         const long long t_layer = HN_T0();
-        if constexpr (!FOLD) {
+        const int cb = p.cbias + L.bias_off;    // this layer's biases inside c_bias (BM == 2)
+        if constexpr (BM == 1) {
           if (PP) epi_named_barrier<PP>(chain);   // single buffer per chain: everyone is done with the previous layer's bias
-          for (int i = et; i < L.n_out; i += 128 * Sched<PP>::SUBS) bias[i] = __ldg(p.bias + L.bias_off + i);
+          for (int i = et; i < L.n_out; i += 128 * Sched<PP>::SUBS * kEpiSplit) bias[i] = __ldg(p.bias + L.bias_off + i);
           epi_named_barrier<PP>(chain);
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         const long long t_drain = HN_T0();
         if (L.epi == FE_RELU) {
-          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, gate_row + (size_t)L.gate_word * kHalfRows);
+          fwd_cols_share<true, STASH, BM>(share, tlane, bias, cb, act_row, save_row, L.save_chunk, L.n_out,
+                                      STASH ? gate_row + (size_t)L.gate_word * kHalfRows : nullptr);
         } else if (L.epi == FE_WSHEAD) {
-          if constexpr (!C::STATIC && !C::NOWARP) {
+          if constexpr (PRIMARY && !C::STATIC && !C::NOWARP) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
+          float wp[C::NWARPED];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) wp[i] = __ldg(p.points + gq * 3 + i);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 3; ++i) wp[i] = pt[i] + (__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
+          for (int i = 0; i < 3; ++i) wp[i] += __uint_as_float(r[i]) + head_bias<BM>(bias, cb, i);
 #pragma unroll
-          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + head_bias<FOLD>(bias, 3 + i);
+          for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + head_bias<BM>(bias, cb, 3 + i);
           if constexpr (C::H == C::G) {
             if (p.mflags & MF_AXIS) {   // axis-aligned slicing: the hyper point is the GLO vector (models.py:533-534)
               const float* e = p.glo + __ldg(p.ids + ray) * C::G;
@@ -876,24 +1034,33 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
             for (int i = 0; i < C::NWARPED; ++i) p.warped[gq * C::NWARPED + i] = wp[i];
           }
           store_trunk_input<C>(wp, act_row, inb_row, save_row, L.save_chunk);
+          if constexpr (C::TIN_ACT) {
+#pragma unroll
+            for (int i = 0; i < C::NWARPED; ++i) wp_keep[i] = wp[i];
+          }
           }
         } else if (L.epi == FE_SKIPFEED) {
           // hidden part of the skip layer is in the accumulator and stays there; ACT[0, KT) <- the trunk input vector,
           // recomputed from the warped point this thread still holds, for the input part that accumulates on top
-          if constexpr (C::TIN_ACT) store_trunk_input<C>(wp, act_row, inb_row, nullptr, 0);
+          if constexpr (PRIMARY && C::TIN_ACT) store_trunk_input<C>(wp_keep, act_row, inb_row, nullptr, 0);
         } else if (L.epi == FE_SIGMA) {
           // static baseline: raw sigma = Linear(W, 1)(h8) (nerf.py:109); rendering.py:150 uses relu(sigma + noise)
+          if constexpr (PRIMARY) {
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
-          float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, 0);
+          float a = __uint_as_float(r[0]) + head_bias<BM>(bias, cb, 0);
           if (p.noise != nullptr) a += __ldg(p.noise + gq) * p.noise_std;
           if (valid) p.sigma[gq] = fmaxf(a, 0.f);
+          }
         } else if (L.epi == FE_BOTT) {
-          fwd_cols<false, STASH>(tlane, bias, act_row, save_row, L.save_chunk, L.n_out, nullptr);
+          fwd_cols_share<false, STASH, BM>(share, tlane, bias, cb, act_row, save_row, L.save_chunk, L.n_out, nullptr);
           // view-direction condition (models.py:410-419; viewdirs = raw directions, models.py:717-720)
-          float f[C::KV];
-          if constexpr (C::STATIC) {
+          if constexpr (PRIMARY) {
+          float f[C::KV], dir[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) dir[i] = __ldg(p.viewdirs + ray * 3 + i);
+          if constexpr (C::STATIC || HN_DBG_OLD_BOTT) {
             posenc<3, C::VF>(dir, f);
             finish_features<C, C::KV, C::PE_V>(f);
           } else {
@@ -903,30 +1070,34 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
             for (int i = 3 + 6 * kMaxViewFreqs; i < C::KV; ++i) f[i] = 0.f;
             if (p.mflags & MF_COND) {   // get_condition_inputs, models.py:421-434
               const int64_t id = __ldg(p.ids + ray);
-              if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
+              HN_CHECK_ID(id, p.n_embed);
               const float* e = p.glo + id * C::G;
 #pragma unroll
               for (int i = 0; i < C::G; ++i) f[kViewCondCol + i] = __ldg(e + i);
             }
           }
           store_features<C::KV>(f, inb_row, save_row, p.x_in_v);
+          }
         } else if (L.epi == FE_RGB0A) {
           if constexpr (!C::STATIC) {
-          fwd_cols<true, STASH>(tlane, bias, act_row, save_row, L.save_chunk, kRgbW, gate_row + (size_t)L.gate_word * kHalfRows);
+          fwd_cols_share<true, STASH, BM>(share, tlane, bias, cb, act_row, save_row, L.save_chunk, kRgbW,
+                                      STASH ? gate_row + (size_t)L.gate_word * kHalfRows : nullptr);
+          if constexpr (PRIMARY) {
           uint32_t r[16];
           tmem_ld16(tlane + kRgbW, r);
           tmem_ld_wait();
-          float a = __uint_as_float(r[0]) + head_bias<FOLD>(bias, kRgbW);
+          float a = __uint_as_float(r[0]) + head_bias<BM>(bias, cb, kRgbW);
           if (p.noise != nullptr) a += __ldg(p.noise + gq) * p.noise_std;  // noise_regularize, model_utils.py:312-316
           if (valid) p.sigma[gq] = softplus_f(a);                         // models.py:491
           }
-        } else {  // FE_RGBHEAD
+          }
+        } else if constexpr (PRIMARY) {  // FE_RGBHEAD
           uint32_t r[16];
           tmem_ld16(tlane, r);
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) p.rgb[gq * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + head_bias<FOLD>(bias, i));
+            for (int i = 0; i < 3; ++i) p.rgb[gq * 3 + i] = sigmoid_f(__uint_as_float(r[i]) + head_bias<BM>(bias, cb, i));
           }
         }
         if (li + 1 < prog.nlayers) {
@@ -949,6 +1120,10 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
       p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;
       p.dbg[blockIdx.x * 8 + 6] = t_pro; p.dbg[blockIdx.x * 8 + 7] = tt;
     }
+    };   // epilogue
+    // the two kinds of epilogue warpgroups get their own register budgets (setmaxnreg is per warpgroup)
+    if (kEpiSplit == 1 || share == 0) { setmaxnreg_inc<kRegsPrimary>(); epilogue(std::true_type{}); }
+    else { setmaxnreg_dec<kRegsSecondary>(); epilogue(std::false_type{}); }
   }
   tc_fence_before();
   __syncthreads();
@@ -1026,7 +1201,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < SM::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     // one arrival per epilogue warp of the chain (pair mode: of both CTAs, the other CTA's arrive remotely)
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * (kPair ? 2 : 1)); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 4 * Sched<PP>::SUBS * kEpiSplit * (kPair ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == kIssuerWarp) {
@@ -1041,7 +1216,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
   const Program& prog = p.prog;
 
   if (warp >= kEpiWarps) {
-    setmaxnreg_dec<kSubTiles == 2 ? 56 : 40>();
+    setmaxnreg_dec<kRegsFeeder>();
     if (warp == kProducerWarp && lane == 0) {
       Ring rs;
       long long tw = 0;
@@ -1087,9 +1262,11 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       }
     }
   } else {
-    setmaxnreg_inc<kSubTiles == 2 ? 216 : 208>();
-    const int sub = warp >> 2;
+    const int sub = warp / (4 * kEpiSplit);
+    const int share = (warp >> 2) % kEpiSplit;   // column share of the wide layers; share 0 = the primary warpgroup
     const int quarter = warp & 3;
+    auto epilogue = [&](auto primary_tag) {
+    constexpr bool PRIMARY = decltype(primary_tag)::value;   // primary: per-row work (heads, chain rules) + its column share
     const int row = quarter * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * 256;
     uint8_t* act_row = act + sub * SM::ACT_BYTES + row * 16;
@@ -1113,7 +1290,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       uint4* save_row = reinterpret_cast<uint4*>(p.dsaved + half * (size_t)p.d_total * kHalfChunkBytes) + (row & 63);
 
       // prologue: dY of the rgb head = g_rgb * y (1 - y) (Sigmoid, models.py:164)
-      {
+      if constexpr (PRIMARY) {
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = 0.f;
@@ -1143,29 +1320,31 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
         if (L.epi == BE_MASK) {
-          if (L.n_out == kTrunkW) bwd_masked_layer<kTrunkW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
-          else if (L.n_out == kWsW) bwd_masked_layer<kWsW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
-          else bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          if (L.n_out == kTrunkW) bwd_masked_share<kTrunkW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          else if (L.n_out == kWsW) bwd_masked_share<kWsW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          else bwd_masked_share<kRgbW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); } }
           continue;
         }
         if (!C::STATIC && L.epi == BE_RGB1) {
-          bwd_masked_layer<kRgbW>(tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
+          bwd_masked_share<kRgbW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           // alpha column: d softplus(a)/da = sigmoid(a) = 1 - exp(-sigma)
+          if constexpr (PRIMARY) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = 0.f;
           if (valid) f[0] = __ldg(p.g_sigma + gq) * (-expm1f(-__ldg(p.sigma + gq)));
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
+          }
           fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
           continue;
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
         if (L.epi == BE_LINEAR || L.epi == BE_LINCOND) {
-          if (L.n_out == kTrunkW) bwd_cols<false, kTrunkW>(tlane, nullptr, act_row, save_row, L.save_chunk);
-          else bwd_cols<false, kRgbW>(tlane, nullptr, act_row, save_row, L.save_chunk);
-          if constexpr (!C::STATIC) {
+          if (L.n_out == kTrunkW) bwd_linear_share<kTrunkW>(share, tlane, act_row, save_row, L.save_chunk);
+          else bwd_linear_share<kRgbW>(share, tlane, act_row, save_row, L.save_chunk);
+          if constexpr (PRIMARY && !C::STATIC) {
             if (L.epi == BE_LINCOND) {
               // gradient of the GLO condition columns of the view vector (alpha / rgb conditioning, modules.py:283,292),
               // parked in accumulator columns [128, 144) -> gradient of the condition table
@@ -1176,17 +1355,16 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
 #pragma unroll
               for (int i = 0; i < C::G; ++i) v[i] = __uint_as_float(r[i]);
               const int64_t id = __ldg(p.ids + ray);
-              if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
+              HN_CHECK_ID(id, p.n_embed);
               glo_grad_add<C::G>(v, valid, id, p.glo_grad, lane);
             }
           }
-        } else if constexpr (!C::STATIC) {   // (the static program only has BE_MASK / BE_LINEAR layers)
+        } else if constexpr (PRIMARY && !C::STATIC) {   // (the static program only has BE_MASK / BE_LINEAR layers)
         if (L.epi == BE_SKIPSTORE || L.epi == BE_TRUNKIN) {
           // d(trunk input features) arrives twice: from the skip layer and from layer 0.  The chain rule through the
           // positional encoding is linear in it, so each part is pulled back to d(warped point, hyper coordinates)
           // straight from the fp32 accumulator and the two vectors are added: nothing is parked in shared memory.
           float wp[C::NWARPED], gx[C::NWARPED];
-#pragma unroll
           // trunk-only program: `warped` is warped_in, in launch order; otherwise the level's warped_points output
           const int64_t gw = p.g_warped_out != nullptr ? gc : gq;
 #pragma unroll
@@ -1237,7 +1415,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
 #pragma unroll
           for (int i = 0; i < C::G; ++i) v[i] = __uint_as_float(r[i]);
           const int64_t id = __ldg(p.ids + ray);
-          if ((uint64_t)id >= (uint64_t)p.n_embed) __trap();
+          HN_CHECK_ID(id, p.n_embed);
           glo_grad_add<C::G>(v, valid, id, p.glo_grad, lane);
         }
         }
@@ -1253,6 +1431,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;
       p.dbg[blockIdx.x * 8 + 6] = t_pro; p.dbg[blockIdx.x * 8 + 7] = tt;
     }
+    };   // epilogue
+    if (kEpiSplit == 1 || share == 0) { setmaxnreg_inc<kRegsPrimary>(); epilogue(std::true_type{}); }
+    else { setmaxnreg_dec<kRegsSecondary>(); epilogue(std::false_type{}); }
   }
   tc_fence_before();
   __syncthreads();
@@ -1593,6 +1774,19 @@ static int build_pair_maps(const void* blob, int64_t blob_bytes, PairMaps* out) 
       return set_error(-20, "pair mode: cuTensorMapEncodeTiled is not available from this driver");
     enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   }
+#if HN_PAIR_MAP2D
+  // 2-D view [64 bf16 = one 128-byte line][lines]: box = {64, 2^i} is a contiguous run of 2^i lines
+  const cuuint64_t dims[2] = {64, (cuuint64_t)(blob_bytes / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t es[2] = {1, 1};
+  for (int i = 0; i < 9; ++i) {
+    const cuuint32_t box[2] = {64, (cuuint32_t)(1u << i)};
+    CUresult r = enc(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(blob), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-21, "pair mode: cuTensorMapEncodeTiled failed");
+  }
+#else
   const cuuint64_t dims[3] = {8, 8, (cuuint64_t)(blob_bytes / 128)};
   const cuuint64_t strides[2] = {16, 128};
   const cuuint32_t es[3] = {1, 1, 1};
@@ -1603,6 +1797,7 @@ static int build_pair_maps(const void* blob, int64_t blob_bytes, PairMaps* out) 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(-21, "pair mode: cuTensorMapEncodeTiled failed");
   }
+#endif
   cached_blob = blob; cached_bytes = blob_bytes;
   *out = cached;
   return 0;
@@ -1658,6 +1853,52 @@ static ModelPlan& cached_plan(const hn_model_desc& d, int level = -1, const int6
   return c.plan;
 }
 
+// ---- constant-memory bias slots (HN_CONST_BIAS) -------------------------------------------------------------------
+// c_bias holds the forward bias arrays of up to kConstSlots packed blobs per device.  A blob's array is copied in
+// (device to device, stream ordered) the first time a forward launch uses it after it was packed; hn_pack_weights
+// invalidates the slot of the blob it rewrites.  Slots are recycled least-recently-used; a slot last used on another
+// stream is handed over with a synchronisation of that stream (launches of one model on two streams at once are not a use
+// case of this library, but they must not read each other's biases).
+struct ConstSlot { const void* src = nullptr; cudaStream_t stream = nullptr; uint64_t stamp = 0; };
+static std::mutex g_const_mu;
+static ConstSlot g_const_slots[16][kConstSlots];
+static uint64_t g_const_stamp = 0;
+
+static void const_bias_invalidate(const void* src) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  for (auto& sl : g_const_slots[dev]) if (sl.src == src) sl.src = nullptr;
+}
+// returns the float offset of the blob's bias array inside c_bias, uploading it if needed; < 0 on error
+static int const_bias_offset(const float* src, int nfloats, cudaStream_t stream) {
+  if (nfloats > kMaxBiasFloats) return set_error(-22, "bias array larger than a constant-memory slot");
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return -std::abs(set_cuda_error(e, "const bias: cudaGetDevice"));
+  if (dev < 0 || dev >= 16) return set_error(-23, "const bias: device index out of range");
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  ConstSlot* slots = g_const_slots[dev];
+  int hit = -1, victim = 0;
+  for (int i = 0; i < kConstSlots; ++i) {
+    if (slots[i].src == src) hit = i;
+    if (slots[i].stamp < slots[victim].stamp) victim = i;
+  }
+  const int s = hit >= 0 ? hit : victim;
+  if (slots[s].stream != stream && slots[s].stamp != 0) {
+    // kernels of another stream may still be reading (hit) or must not see the overwrite (victim)
+    if (cudaError_t e = cudaStreamSynchronize(slots[s].stream)) { cudaGetLastError(); (void)e; }
+  }
+  if (hit < 0) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_bias, src, (size_t)nfloats * 4, (size_t)s * kMaxBiasFloats * 4,
+                                            cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return -std::abs(set_cuda_error(e, "const bias: cudaMemcpyToSymbolAsync"));
+    slots[s].src = src;
+  }
+  slots[s].stream = stream;
+  slots[s].stamp = ++g_const_stamp;
+  return s * kMaxBiasFloats;
+}
+
 }  // namespace hn
 
 using namespace hn;
@@ -1708,6 +1949,7 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   pp.glo_src = plan.info.glo_param >= 0 ? param_offsets[plan.info.glo_param] : 0;
   if (plan.info.glo_param >= 0 && pp.glo_src < 0) return set_error(-2, "hn_pack_weights: the GLO table of this configuration has no offset");
   pp.glo_floats = plan.info.glo_floats;
+  const_bias_invalidate((const uint8_t*)packed + plan.layout.bias_off);   // the blob's biases are about to change
   dim3 grid(16, plan.pack.nops + 1);
   pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp);
   return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
@@ -1752,14 +1994,21 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   if (B == 0) return 0;
   const ModelPlan& plan = cached_plan(*desc);
   FwdParams fp;
-  // the stash-writing forward keeps its biases in the epilogue
-  const bool nobias_prog = saved != nullptr && !kFoldBiasTrain;
+  // programs without bias K steps: the stash-writing forward (biases in the epilogue) and, with HN_CONST_BIAS = 2, the
+  // inference forward as well
+  const bool nobias_prog = saved != nullptr ? !kFoldBiasTrain : kConstBias >= 2;
   fp.prog = trunk ? (nobias_prog ? plan.fwd_trunk_train : plan.fwd_trunk) : (nobias_prog ? plan.fwd_train : plan.fwd);
   fp.warped_in = warped_in;
   fp.weights = (const uint8_t*)packed + plan.layout.fwd_off;
   fp.w_row0 = (uint32_t)(plan.layout.fwd_off / 16);
   if (int rc = build_pair_maps(packed, plan.layout.total, &fp.maps)) return rc;
   fp.bias = (const float*)((const uint8_t*)packed + plan.layout.bias_off);
+  fp.cbias = 0;
+  if (nobias_prog && kConstBias >= 1) {
+    const int nb = (int)((plan.layout.glo_off - plan.layout.bias_off) / 4);
+    fp.cbias = const_bias_offset(fp.bias, nb, (cudaStream_t)stream);
+    if (fp.cbias < 0) return fp.cbias;
+  }
   fp.glo = (const float*)((const uint8_t*)packed + plan.layout.glo_off);
   fp.points = points; fp.viewdirs = viewdirs; fp.ids = ids; fp.noise = noise; fp.noise_std = noise_std;
   fp.n = B * S; fp.S = S; fp.n_embed = desc->num_embeddings;

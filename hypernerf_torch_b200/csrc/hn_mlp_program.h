@@ -43,7 +43,17 @@ constexpr bool kPair = HN_PAIR && HN_SUBTILES == 2;
 constexpr int kTileRows = 128;   // samples per sub-tile (= UMMA M = TMEM lanes)
 constexpr int kSubTiles = HN_SUBTILES;
 constexpr int kCtasPerSm = kSubTiles == 2 ? 1 : 2;
-constexpr int kMlpThreads = 128 + 128 * kSubTiles;   // warpgroup 0: producer + UMMA issuer; then one epilogue warpgroup per sub-tile
+// HN_EPI_SPLIT = 2: every sub-tile is drained by TWO warpgroups, each taking half of the accumulator columns of the wide
+// (ReLU / linear) layers.  A drain is latency bound per warp (one warp per scheduler issues ~0.2 instructions per clock:
+// TMEM load -> bias -> pack -> st.shared -> st.global chains), and in the out-of-phase schedule only one sub-tile drains at a
+// time, so half of the epilogue warps idled; the second warpgroup per sub-tile doubles the drain's memory-level parallelism.
+// The "primary" warpgroup of a sub-tile also does the per-row work (positional encodings, heads); the "secondary" one only
+// drains its column share and keeps the launch-time 96 registers.
+#ifndef HN_EPI_SPLIT
+#define HN_EPI_SPLIT 1
+#endif
+constexpr int kEpiSplit = HN_EPI_SPLIT;
+constexpr int kMlpThreads = 128 + 128 * kSubTiles * kEpiSplit;   // epilogue warpgroups (kEpiSplit per sub-tile), then the feeder warpgroup: producer + UMMA issuer
 constexpr int kCtaRows = kTileRows * kSubTiles;
 constexpr int kHalfRows = 64;    // granularity of the saved-activation layout and of the wgrad K step
 constexpr int kChunkBytes = kTileRows * 16;      // one 8-column chunk of a 128-row smem operand

@@ -652,3 +652,136 @@ extern "C" int hn_umma_rate4(int N, int nacc, int reps, int inner, int grid, voi
 #undef HN_R4
   return hn::set_cuda_error(e, "hn_umma_rate4");
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// Drain-under-UMMA microbenchmark (test hook): warps 0-3 drain a 128-row x 256-column accumulator (sub-tile 0) `reps`
+// times with a selectable subset of the epilogue's work while, if umma != 0, warp 4 keeps the tensor pipe busy with
+// back-to-back M = 128, N = umma_n, K = 16 UMMAs on sub-tile 1's accumulator from resident shared-memory operands, and, if
+// tma != 0, warp 5 keeps re-loading a 16 KB weight stage from global memory by bulk copies (the weight ring's traffic).
+//   mode bit 0: bf16 pack   bit 1: st.shared of the packed row   bit 2: st.global (stash layout, streaming)
+//        bit 3: bias (8 x LDS.128 + 32 FADD per 32 columns)
+// out[b*4 + 0] = drain cycles, [1] = UMMAs retired while the drain ran, [2] = issuer cycles, [3] = bulk copies completed.
+// ------------------------------------------------------------------------------------------------------
+namespace hn {
+__global__ void __launch_bounds__(256, 1) overlap_rate_kernel(int mode, int umma, int umma_n, int tma, int reps, uint8_t* gout,
+                                                              const uint8_t* gsrc, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: [0, 64 KB) drain target (sub-tile 0 operand rows) | [64 KB, 80 KB) A: 128 x 64 | [80 KB, 112 KB) B: 256 x 64 | [112 KB, 128 KB) weight stage
+  __shared__ uint64_t bar_mma, bar_tma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done;
+  __shared__ __align__(16) float sbias[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  sbias[threadIdx.x] = 0.001f * threadIdx.x;
+  for (int i = threadIdx.x * 16; i < 112 * 1024; i += 256 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (threadIdx.x == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_tma, 1); done = 0; fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* act_row = smem + row * 16;
+    uint4* save_row = reinterpret_cast<uint4*>(gout + ((size_t)blockIdx.x * 2 + (row >> 6)) * 32 * 1024) + (row & 63);
+    uint32_t sink = 0;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t* cur = h ? rb : ra;
+          uint32_t* nxt = h ? ra : rb;
+          tmem_ld_wait();
+          const int c = c0 + 32 * h;
+          if (c + 32 < 256) tmem_ld32(taddr + c + 32, nxt);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(cur[8 * q + j]);
+            if (mode & 8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + 8 * q);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 8 * q + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            uint4 o;
+            if (mode & 1) {
+              o.x = pack_bf16_relu(v[0], v[1]); o.y = pack_bf16_relu(v[2], v[3]);
+              o.z = pack_bf16_relu(v[4], v[5]); o.w = pack_bf16_relu(v[6], v[7]);
+            } else {
+              o.x = __float_as_uint(v[0]) ^ __float_as_uint(v[1]); o.y = __float_as_uint(v[2]) ^ __float_as_uint(v[3]);
+              o.z = __float_as_uint(v[4]) ^ __float_as_uint(v[5]); o.w = __float_as_uint(v[6]) ^ __float_as_uint(v[7]);
+            }
+            if (mode & 2) *reinterpret_cast<uint4*>(act_row + ((c >> 3) + q) * 2048) = o;
+            if (mode & 4) __stcs(&save_row[((c >> 3) + q) * 64], o);
+            sink ^= o.x ^ o.y ^ o.z ^ o.w;
+          }
+        }
+      }
+    }
+    long long t1 = clock64();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) { out[blockIdx.x * 4] = (unsigned long long)(t1 - t0); done = 1; }
+    if (sink == 0x12345678u) out[1] = sink;
+  } else if (warp == 4) {
+    if (umma) {
+      const uint32_t sA = smem_u32(smem) + 65536, sB = sA + 16384;
+      const uint32_t idesc = make_idesc_bf16(128, umma_n, 0, 0);
+      unsigned long long n = 0;
+      uint32_t phase = 0;
+      long long t0 = clock64();
+      while (!done) {
+        if (elect_one_sync()) {
+#pragma unroll 1
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t ad = make_smem_desc(sA + (ks % 4) * 4096, 2048, 128);
+            const uint64_t bd = make_smem_desc(sB + (ks % 4) * 2 * umma_n * 16, umma_n * 16, 128);
+            umma_bf16(tmem_base + 256, ad, bd, idesc, ks > 0);
+          }
+          umma_commit(&bar_mma);
+        }
+        __syncwarp();
+        mbar_wait(&bar_mma, phase);
+        phase ^= 1;
+        n += 16;
+      }
+      if (lane == 0) { out[blockIdx.x * 4 + 1] = n; out[blockIdx.x * 4 + 2] = (unsigned long long)(clock64() - t0); }
+    }
+  } else if (warp == 5) {
+    if (tma && lane == 0) {
+      unsigned long long n = 0;
+      uint32_t phase = 0;
+      while (!done) {
+        mbar_arrive_expect_tx(&bar_tma, 16384);
+        bulk_g2s(smem + 112 * 1024, gsrc + (size_t)((n * 7 + blockIdx.x) % 64) * 16384, 16384, &bar_tma);
+        mbar_wait(&bar_tma, phase);
+        phase ^= 1;
+        ++n;
+      }
+      out[blockIdx.x * 4 + 3] = n;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+}  // namespace hn
+
+extern "C" int hn_overlap_rate(int mode, int umma, int umma_n, int tma, int reps, int grid, void* gout, const void* gsrc,
+                               void* out, void* stream) {
+  if (umma_n < 16 || umma_n > 256 || umma_n % 16) return hn::set_error(-1, "hn_overlap_rate: bad N");
+  const int smem = 128 * 1024 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(hn::overlap_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return hn::set_cuda_error(e, "hn_overlap_rate: smem attr");
+  hn::overlap_rate_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mode, umma, umma_n, tma, reps, (uint8_t*)gout,
+                                                                     (const uint8_t*)gsrc, (unsigned long long*)out);
+  return hn::set_cuda_error(cudaGetLastError(), "hn_overlap_rate");
+}

@@ -100,6 +100,13 @@ __device__ __forceinline__ void tma_g2s_3d_pair(void* smem_dst, const void* tens
                ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar_same_offset) & 0xFEFFFFFFu), "r"(0), "r"(0), "r"(block)
                : "memory");
 }
+// The same over a 2-D view [128-byte row = 64 bf16][rows]: the inner box dimension is a full 128-byte line instead of the
+// 16-byte rows of the 3-D view (which make the TMA engine issue one request per 16 bytes).
+__device__ __forceinline__ void tma_g2s_2d_pair(void* smem_dst, const void* tensor_map, int32_t block, uint64_t* bar_same_offset) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar_same_offset) & 0xFEFFFFFFu), "r"(0), "r"(block)
+               : "memory");
+}
 // bulk L2 prefetch of a contiguous global range (bytes: multiple of 16)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
@@ -294,9 +301,17 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 
 // register re-balancing between warpgroups (all 4 warps of the warpgroup execute it)
 template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void setmaxnreg_inc() {
+#ifndef HN_NO_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
 template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void setmaxnreg_dec() {
+#ifndef HN_NO_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
 
 // pack two fp32 -> bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -40,6 +40,13 @@ int hn_umma_rate4(int N, int nacc, int reps, int inner, int grid, void* out_cycl
 /* test hook: cycles for nwarps warps to read `cols` TMEM columns of their 32 lanes `reps` times (tcgen05.ld.32x32b.x32). */
 int hn_tmem_rate(int nwarps, int cols, int reps, int mode, void* out_cycles, void* stream);
 
+/* test hook: four warps drain a 128 x 256 accumulator `reps` times (mode bits: 1 bf16 pack, 2 st.shared, 4 st.global, 8 bias)
+ * while (umma != 0) another warp issues back-to-back M = 128, N = umma_n UMMAs and (tma != 0) a third keeps re-loading a
+ * 16 KB stage by bulk copies.  gout: grid x 64 KB, gsrc: 1 MB, out: 4 x uint64 per CTA {drain cycles, UMMAs retired,
+ * issuer cycles, bulk copies}. */
+int hn_overlap_rate(int mode, int umma, int umma_n, int tma, int reps, int grid, void* gout, const void* gsrc, void* out,
+                    void* stream);
+
 /* profiling hook: device buffer of 8 x uint64 per CTA filled by the fused MLP kernels with per-role cycle counters
  * (producer wait, UMMA-issuer waits, epilogue wait / work); NULL = off. */
 int hn_debug_set_timing_buffer(void* dev_buffer);
