@@ -11,13 +11,14 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HN_LIB") or os.path.join(_HERE, "libhypernerf_b200.so")  # HN_LIB: profiling build
-HN_NUM_PARAM_TENSORS = 94
+HN_NUM_PARAM_TENSORS = 102
 HN_FLAG_WARP_TRANSLATION = 1
 HN_FLAG_SLICE_BENDY = 2
 HN_FLAG_STATIC_NERF = 4
 HN_FLAG_SLICE_AXIS = 8
 HN_FLAG_ALPHA_COND = 16
 HN_FLAG_RGB_COND = 32
+HN_FLAG_WARP_SE3 = 64
 HN_NUM_STATIC_PARAM_TENSORS = 24
 HN_COMP_WHITE_BKGD = 1
 HN_COMP_ACC_ALL = 2
@@ -85,9 +86,9 @@ def lib():
     L.hn_mse_loss.argtypes = [vp, vp, vp, i64, f32, vp, vp, vp, vp]
     L.hn_make_ndc_rays.argtypes = [i32, i32, f32, C.POINTER(C.c_float), f32, f32, i32, vp, vp]
     L.hn_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]
-    L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp, vp, vp]
+    L.hn_mlp_fwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     L.hn_mlp_bwd.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, i32,
-                             C.POINTER(C.c_int64), vp, vp, vp]
+                             C.POINTER(C.c_int64), vp, vp, vp, vp, vp]
     L.hn_mlp_bwd_data.argtypes = L.hn_mlp_bwd.argtypes
     L.hn_mlp_bwd_weights.argtypes = [C.POINTER(ModelDesc), vp, i64, i32, i32, C.POINTER(C.c_int64), vp, vp, vp]
     L.hn_mlp_fwd_trunk.argtypes = [C.POINTER(ModelDesc), vp, vp, vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp, vp, vp]

@@ -46,13 +46,14 @@ namespace hn {
 // ------------------------------------------------------------------------------------------------------
 // compile-time model shape (cfg-1 family of BASELINE.json)
 // ------------------------------------------------------------------------------------------------------
-template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_, bool STATIC_ = false>
+template <int G_, int H_, int WF_, int SF_, int XF_, int HF_, int VF_, bool STATIC_ = false, bool SE3_ = false>
 struct Shape {
   static constexpr bool STATIC = STATIC_;   // static baseline models/nerf.py: no GLO / warp / sheet / hyper coordinates
   static constexpr bool NOWARP = !STATIC_ && H_ == 0;   // NerfModel(use_warp=False): the template alone on the raw points
+  static constexpr bool SE3 = SE3_;         // warp stage = SE3Field (warping.py:128-240): input posenc(points, 0, WF) alone
   static constexpr int G = G_, H = H_, WF = WF_, SF = SF_, XF = XF_, HF = HF_;
   static constexpr int VF = VF_;            // hyper model: the MAXIMUM view frequency count (run time: FwdParams::view_freqs)
-  static constexpr int PE_W = 3 + 6 * WF, IN_W = PE_W + G, KW = NOWARP ? 0 : pad16(IN_W);
+  static constexpr int PE_W = SE3 ? 6 * WF : 3 + 6 * WF, IN_W = SE3 ? PE_W : PE_W + G, KW = NOWARP ? 0 : pad16(IN_W);
   static constexpr int PE_X = 3 + 6 * XF, PE_H = H * (1 + 2 * HF), IN_T = PE_X + PE_H, KT = pad16(IN_T);
   static constexpr int PE_V = 3 + 6 * VF, KV = STATIC ? pad16(PE_V) : kKV;
   static constexpr bool TIN_ACT = !STATIC && trunk_in_act(KT);   // trunk input vector in ACT (hn_mlp_program.h: kMaxTrunkInInb)
@@ -67,6 +68,7 @@ using CfgH4 = Shape<8, 4, 10, 7, 10, 6, 6>;   // opt.py default hyper_slice_out_
 using CfgH8 = Shape<8, 8, 10, 7, 10, 6, 6>;   // bendy sheet with 8 outputs, or axis-aligned slicing (hyper point = GLO vector)
 using CfgT = Shape<8, 0, 10, 7, 10, 6, 6>;    // no warp: template NeRF on the raw points
 using CfgStatic = Shape<0, 0, 10, 0, 10, 0, 4, true>;   // NeRF(): xyz PE 63 (-> K 64), dir PE 27 (-> K 32)
+using CfgSE3 = Shape<8, 8, kSe3Freqs, 0, 10, 6, 6, false, true>;   // config 5: SE3 warp + axis-aligned slicing (hyper point = GLO vector)
 
 // ------------------------------------------------------------------------------------------------------
 // shared memory plan of the fused kernels
@@ -170,6 +172,7 @@ struct PairMaps { CUtensorMap m[kPair ? 9 : 1]; };
 
 // run-time model flags of the fused kernels (from hn_model_desc::flags)
 enum ModelFlags : int { MF_AXIS = 1, MF_COND = 2 };   // hyper point = GLO vector; GLO condition columns in the view vector
+static bool has_warp(const hn_model_desc& d) { return (d.flags & (HN_FLAG_WARP_TRANSLATION | HN_FLAG_WARP_SE3)) != 0; }
 
 struct FwdParams {
   Program prog;
@@ -195,6 +198,7 @@ struct FwdParams {
   int x_total;              // chunks per half tile of the saved-activation slab
   uint16_t x_in_ws, x_in_t, x_in_v;
   float* sigma; float* rgb; float* warped;
+  float* aux;               // SE3 warp, training: (n, 6) screw parameters (w, v) of every launch row for the data gradient
   uint8_t* saved;
   uint32_t* gates;          // ReLU gate words: [half tile][g_total][64 rows] (inside `saved`, after the X slabs)
   int g_total;
@@ -209,6 +213,7 @@ struct BwdParams {
   const int64_t* ids;
   const float* sigma; const float* rgb; const float* warped;
   const float* g_sigma; const float* g_rgb; const float* g_warped;
+  const float* points; const float* aux;   // SE3 warp: the sample points ((B, S_full) rows) and the forward's (w, v) (launch rows)
   float* g_warped_out;      // trunk-only program: (n, 3 + H) gradient w.r.t. warped_in, written by the last layer; else NULL
   const int32_t* pos;       // scattered rows (see FwdParams): sigma / rgb / g_sigma / g_rgb / g_warped (and, outside the
   int S_full;               // trunk-only program, warped) are indexed at pos[b * S + j] of (B, S_full) rows
@@ -505,6 +510,87 @@ __device__ __forceinline__ void posenc_rt(const float* x, float* out, int nf) {
       float c2 = 1.f - 2.f * s[i] * s[i];
       s[i] = s2; c[i] = c2;
     }
+  }
+}
+
+// posenc(x, 0, NF) of SE3Field (model_utils.py:255-273): scales 2^linspace(0, NF, NF) as torch computes them in fp32 (NF = 8),
+// cos as sin(x s + 0.5 * 3.1415926); per scale [sin x0..2 | "cos" x0..2], no identity columns.  Full-precision sinf: the
+// arguments reach ~400 rad and the reference's shifted-sine form is only reproduced by evaluating exactly that expression.
+__device__ __forceinline__ void posenc_se3(const float* x, float* out) {
+  constexpr float kScale[kSe3Freqs] = {0x1.000000p+0f, 0x1.1aa59cp+1f, 0x1.381148p+2f, 0x1.588ceep+3f,
+                                       0x1.7c6a1ap+4f, 0x1.a40302p+5f, 0x1.cfbb04p+6f, 0x1.000000p+8f};
+#pragma unroll
+  for (int k = 0; k < kSe3Freqs; ++k) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float xb = x[i] * kScale[k];
+      out[6 * k + i] = sinf(xb);
+      out[6 * k + 3 + i] = sinf(xb + 1.5707963f);
+    }
+  }
+}
+
+// se(3) exponential of the screw (w, v) applied to a point (warping.py:229-238, rigid_body.py:55-83), written with the
+// un-normalised w, v so that theta -> 0 is a removable singularity:
+//   y = x + v + A (w x x) + B (w x (w x x) + w x v) + C (w x (w x v)),
+//   A = sin t / t, B = (1 - cos t) / t^2, C = (t - sin t) / t^3, t = |w|
+// (= R x + G(t) v / t with R = I + sin t [w/t] + (1 - cos t) [w/t]^2, Modern Robotics Eq. 3.88).  Below t = 0.25 the
+// coefficients and their derivative factors X'(t) / t come from their Taylor series in t^2 (next term < 1e-10).
+struct Se3Coefs { float A, B, C, Ap, Bp, Cp; };
+template <bool GRAD>
+__device__ __forceinline__ Se3Coefs se3_coefs(float t2) {
+  Se3Coefs c;
+  if (t2 < 0.0625f) {
+    c.A = 1.f + t2 * (-1.f / 6 + t2 * (1.f / 120 - t2 * (1.f / 5040)));
+    c.B = 0.5f + t2 * (-1.f / 24 + t2 * (1.f / 720 - t2 * (1.f / 40320)));
+    c.C = 1.f / 6 + t2 * (-1.f / 120 + t2 * (1.f / 5040 - t2 * (1.f / 362880)));
+    if (GRAD) {
+      c.Ap = -1.f / 3 + t2 * (1.f / 30 + t2 * (-1.f / 840 + t2 * (1.f / 45360)));
+      c.Bp = -1.f / 12 + t2 * (1.f / 180 + t2 * (-1.f / 6720 + t2 * (1.f / 453600)));
+      c.Cp = -1.f / 60 + t2 * (1.f / 1260 + t2 * (-1.f / 60480 + t2 * (1.f / 4989600)));
+    }
+  } else {
+    const float t = sqrtf(t2), it2 = 1.f / t2;
+    float sn, cs;
+    sincosf(t, &sn, &cs);
+    float sh, ch;
+    sincosf(0.5f * t, &sh, &ch);
+    c.A = sn / t;
+    c.B = 2.f * sh * sh * it2;              // (1 - cos t) / t^2 without the cancellation
+    c.C = (t - sn) * it2 / t;
+    if (GRAD) { c.Ap = (cs - c.A) * it2; c.Bp = (c.A - 2.f * c.B) * it2; c.Cp = (c.B - 3.f * c.C) * it2; }
+  }
+  return c;
+}
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void se3_apply(const float* x, const float* w, const float* v, float* y) {
+  const Se3Coefs c = se3_coefs<false>(dot3(w, w));
+  float wx[3], wwx[3], wv[3], wwv[3];
+  cross3(w, x, wx); cross3(w, wx, wwx); cross3(w, v, wv); cross3(w, wv, wwv);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = x[i] + v[i] + c.A * wx[i] + c.B * (wwx[i] + wv[i]) + c.C * wwv[i];
+}
+// pull-back of g = dL/dy to the head outputs (w, v); the sample point itself takes no gradient
+__device__ __forceinline__ void se3_apply_bwd(const float* x, const float* w, const float* v, const float* g, float* gw, float* gv) {
+  const Se3Coefs c = se3_coefs<true>(dot3(w, w));
+  float wx[3], wwx[3], wv[3], wwv[3], gxw[3], t0[3], t1[3], t2[3], t3[3], t4[3], t5[3];
+  cross3(w, x, wx); cross3(w, wx, wwx); cross3(w, v, wv); cross3(w, wv, wwv);
+  cross3(g, w, gxw);
+  cross3(gxw, w, t0);
+  cross3(x, g, t1); cross3(wx, g, t2); cross3(x, gxw, t3); cross3(v, g, t4); cross3(wv, g, t5);
+  float t6[3];
+  cross3(v, gxw, t6);
+  float s[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s[i] = wwx[i] + wv[i];
+  const float k = c.Ap * dot3(g, wx) + c.Bp * dot3(g, s) + c.Cp * dot3(g, wwv);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gv[i] = g[i] + c.B * gxw[i] + c.C * t0[i];
+    gw[i] = c.A * t1[i] + c.B * (t2[i] + t3[i] + t4[i]) + c.C * (t5[i] + t6[i]) + k * w[i];
   }
 }
 
@@ -973,9 +1059,9 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           float pt[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) pt[i] = __ldg(p.points + gq * 3 + i);
-          posenc<3, C::WF>(pt, f);
+          if constexpr (C::SE3) posenc_se3(pt, f); else posenc<3, C::WF>(pt, f);
         }
-        if constexpr (!C::STATIC) {
+        if constexpr (!C::STATIC && !C::SE3) {
           const int64_t id = __ldg(p.ids + ray);
           HN_CHECK_ID(id, p.n_embed);   // out-of-range metadata id
           const float* e = p.glo + id * C::G;
@@ -1018,13 +1104,29 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
 #pragma unroll
           for (int i = 0; i < 3; ++i) wp[i] = __ldg(p.points + gq * 3 + i);
           tmem_ld_wait();
+          if constexpr (C::SE3) {
+            // head columns 0..2 = w, 3..5 = v: rigid transform of the sample point by exp of the screw (warping.py:229-238)
+            float wv[6], x[3];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) wv[i] = __uint_as_float(r[i]) + head_bias<BM>(bias, cb, i);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] = wp[i];
+            se3_apply(x, wv, wv + 3, wp);
+            if (valid && p.aux != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 6; ++i) p.aux[g * 6 + i] = wv[i];
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 3; ++i) wp[i] += __uint_as_float(r[i]) + head_bias<BM>(bias, cb, i);
 #pragma unroll
           for (int i = 0; i < C::H; ++i) wp[3 + i] = __uint_as_float(r[3 + i]) + head_bias<BM>(bias, cb, 3 + i);
+          }
           if constexpr (C::H == C::G) {
             if (p.mflags & MF_AXIS) {   // axis-aligned slicing: the hyper point is the GLO vector (models.py:533-534)
-              const float* e = p.glo + __ldg(p.ids + ray) * C::G;
+              const int64_t id = __ldg(p.ids + ray);
+              HN_CHECK_ID(id, p.n_embed);
+              const float* e = p.glo + id * C::G;
 #pragma unroll
               for (int i = 0; i < C::G; ++i) wp[3 + i] = __ldg(e + i);
             }
@@ -1043,6 +1145,8 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           // hidden part of the skip layer is in the accumulator and stays there; ACT[0, KT) <- the trunk input vector,
           // recomputed from the warped point this thread still holds, for the input part that accumulates on top
           if constexpr (PRIMARY && C::TIN_ACT) store_trunk_input<C>(wp_keep, act_row, inb_row, nullptr, 0);
+        } else if (L.epi == FE_LINEAR) {
+          fwd_cols_share<false, STASH, BM>(share, tlane, bias, cb, act_row, save_row, L.save_chunk, L.n_out, nullptr);
         } else if (L.epi == FE_SIGMA) {
           // static baseline: raw sigma = Linear(W, 1)(h8) (nerf.py:109); rendering.py:150 uses relu(sigma + noise)
           if constexpr (PRIMARY) {
@@ -1404,6 +1508,15 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
 #pragma unroll
               for (int i = 0; i < C::G; ++i) f[3 + i] = 0.f;
             }
+          }
+          if constexpr (C::SE3) {
+            // d(warped xyz) -> d(w, v) through the exp map; columns 0..2 / 3..5 of the head's pre-activation gradient
+            float x[3], wv[6], gy[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { x[i] = __ldg(p.points + gq * 3 + i); gy[i] = f[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) wv[i] = __ldg(p.aux + gc * 6 + i);
+            se3_apply_bwd(x, wv, wv + 3, gy, f, f + 3);
           }
           store_features<16>(f, act_row, save_row, L.save_chunk);
           }
@@ -1923,7 +2036,10 @@ extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* 
   }
   // parameters of the canonical slots this configuration has (include/hypernerf_b200.h)
   int64_t cnt = plan.info.glo_floats;
-  if (!m.nowarp) {
+  if (m.se3) {
+    cnt += lin(kSe3W, m.in_w) + 4 * lin(kSe3W, kSe3W) + lin(kSe3W, kSe3W + m.in_w) + lin(kSe3W, kSe3W) +
+           2 * (lin(kSe3W, kSe3W) + lin(3, kSe3W));
+  } else if (!m.nowarp) {
     if (!m.axis) cnt += lin(kSheetW, m.in_s) + 4 * lin(kSheetW, kSheetW) + lin(kSheetW, kSheetW + m.in_s) + lin(m.H, kSheetW);
     cnt += lin(kWarpW, m.in_w) + 4 * lin(kWarpW, kWarpW) + lin(kWarpW, kWarpW + m.in_w) + lin(3, kWarpW);
   }
@@ -1962,10 +2078,11 @@ static int model_flags(const hn_model_desc& d) {
   if (d.flags & (HN_FLAG_ALPHA_COND | HN_FLAG_RGB_COND)) f |= MF_COND;
   return f;
 }
-// which compile-time shape serves a descriptor: 0 static, 1 hyper_dim 2, 2 hyper_dim 4, 3 hyper_dim 8, 4 no warp
+// which compile-time shape serves a descriptor: 0 static, 1 hyper_dim 2, 2 hyper_dim 4, 3 hyper_dim 8, 4 no warp, 5 SE3 warp
 static int shape_of(const hn_model_desc& d) {
   if (is_static(d)) return 0;
-  if (!(d.flags & HN_FLAG_WARP_TRANSLATION)) return 4;
+  if (d.flags & HN_FLAG_WARP_SE3) return 5;
+  if (!has_warp(d)) return 4;
   return d.hyper_dim == 2 ? 1 : d.hyper_dim == 4 ? 2 : 3;
 }
 #define HN_DISPATCH_SHAPE(shape, MACRO) \
@@ -1974,21 +2091,25 @@ static int shape_of(const hn_model_desc& d) {
     case 1: MACRO(Cfg1); break;         \
     case 2: MACRO(CfgH4); break;        \
     case 3: MACRO(CfgH8); break;        \
+    case 5: MACRO(CfgSE3); break;       \
     default: MACRO(CfgT); break;        \
   }
 
 // warped_in != NULL: trunk-only program (hn_mlp_fwd_trunk; always the case for a model without warp: warped_in = points)
 static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const float* points, const float* warped_in,
                         const float* viewdirs, const int64_t* ids, const float* noise, float noise_std, int64_t B, int S,
-                        const int32_t* pos, int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
+                        const int32_t* pos, int S_full, float* sigma, float* rgb, float* warped, void* saved, float* aux,
+                        void* stream) {
   if (!desc || !packed || (!points && !warped_in) || !viewdirs || !sigma || !rgb) return set_error(-2, "hn_mlp_fwd: null pointer");
   if (B < 0 || S <= 0) return set_error(-1, "hn_mlp_fwd: bad B/S");
   if (pos != nullptr && S_full < S) return set_error(-1, "hn_mlp_fwd: scattered rows need S_full >= S");
   if (int rc = validate_desc(*desc)) return rc;
   const bool stat = is_static(*desc);
   const int mflags = stat ? 0 : model_flags(*desc);
-  if (!stat && !(desc->flags & HN_FLAG_WARP_TRANSLATION) && !warped_in) { warped_in = points; warped = nullptr; }
+  if (!stat && !has_warp(*desc) && !warped_in) { warped_in = points; warped = nullptr; }
   const bool trunk = warped_in != nullptr;
+  if (!stat && (desc->flags & HN_FLAG_WARP_SE3) && !trunk && saved != nullptr && !aux)
+    return set_error(-2, "hn_mlp_fwd: the SE3 warp needs the aux buffer when the stash is written");
   if (trunk && stat) return set_error(-13, "hn_mlp_fwd_trunk: the static model has no warp / sheet stage to skip");
   if (!stat && !ids && (!trunk || (mflags & MF_COND))) return set_error(-2, "hn_mlp_fwd: null ids");
   if (B == 0) return 0;
@@ -2020,6 +2141,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.x_total = plan.info.x_total;
   fp.x_in_ws = plan.info.x_in0; fp.x_in_t = plan.info.x_in_t; fp.x_in_v = plan.info.x_in_v;
   fp.sigma = sigma; fp.rgb = rgb; fp.warped = warped; fp.saved = (uint8_t*)saved;
+  fp.aux = saved != nullptr ? aux : nullptr;
   fp.g_total = plan.info.g_total;
   fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
@@ -2040,10 +2162,10 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
 
 extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
                           const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
-                          int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
+                          int S_full, float* sigma, float* rgb, float* warped, void* saved, float* aux, void* stream) {
   if (!points) return set_error(-2, "hn_mlp_fwd: null pointer");
   return mlp_fwd_impl(desc, packed, points, nullptr, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
-                      saved, stream);
+                      saved, aux, stream);
 }
 
 extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
@@ -2051,7 +2173,7 @@ extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, c
                                 int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
   if (!warped_in) return set_error(-2, "hn_mlp_fwd_trunk: null pointer");
   return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
-                      saved, stream);
+                      saved, nullptr, stream);
 }
 
 static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
@@ -2059,10 +2181,13 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
                         const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
                         const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream, bool do_data,
                         bool do_weights, bool trunk = false,
-                        float* g_warped_out = nullptr) {   // trunk: trunk-only programs (hn_mlp_bwd_trunk*)
+                        float* g_warped_out = nullptr,     // trunk: trunk-only programs (hn_mlp_bwd_trunk*)
+                        const float* points = nullptr, const float* aux = nullptr) {   // SE3 warp, full program only
   if (!desc || !saved || !param_offsets || !flat_grad || !workspace) return set_error(-2, "hn_mlp_bwd: null pointer");
   const bool stat = desc && is_static(*desc);
-  const bool nowarp = !stat && !(desc->flags & HN_FLAG_WARP_TRANSLATION);
+  const bool nowarp = !stat && !has_warp(*desc);
+  if (!stat && (desc->flags & HN_FLAG_WARP_SE3) && !trunk && do_data && (!points || !aux))
+    return set_error(-2, "hn_mlp_bwd: the SE3 warp needs the sample points and the forward's aux buffer");
   const int mflags = stat ? 0 : model_flags(*desc);
   if (nowarp) trunk = true;   // a model without warp only has the template: `warped` are the raw sample points
   if (trunk && do_data && !g_warped_out && !nowarp) return set_error(-2, "hn_mlp_bwd_trunk: null pointer");
@@ -2087,6 +2212,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     if (int rc = build_pair_maps(packed, plan.layout.total, &bp.maps)) return rc;
     bp.ids = ids; bp.sigma = sigma; bp.rgb = rgb; bp.warped = warped;
     bp.g_sigma = g_sigma; bp.g_rgb = g_rgb; bp.g_warped = g_warped;
+    bp.points = points; bp.aux = aux;
     bp.saved = (const uint8_t*)saved; bp.dsaved = (uint8_t*)workspace;
     bp.g_total = plan.info.g_total;
     bp.gates = (const uint32_t*)((const uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes);
@@ -2132,17 +2258,19 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
 extern "C" int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                           const float* rgb, const float* warped, const void* saved, const float* g_sigma,
                           const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
-                          const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+                          const int64_t* param_offsets, float* flat_grad, void* workspace, const float* points,
+                          const float* aux, void* stream) {
   return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
-                      param_offsets, flat_grad, workspace, stream, true, true);
+                      param_offsets, flat_grad, workspace, stream, true, true, false, nullptr, points, aux);
 }
 
 extern "C" int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                                const float* rgb, const float* warped, const void* saved, const float* g_sigma,
                                const float* g_rgb, const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full,
-                               int level, const int64_t* param_offsets, float* flat_grad, void* workspace, void* stream) {
+                               int level, const int64_t* param_offsets, float* flat_grad, void* workspace,
+                               const float* points, const float* aux, void* stream) {
   return mlp_bwd_impl(desc, packed, ids, sigma, rgb, warped, saved, g_sigma, g_rgb, g_warped, B, S, pos, S_full, level,
-                      param_offsets, flat_grad, workspace, stream, true, false);
+                      param_offsets, flat_grad, workspace, stream, true, false, false, nullptr, points, aux);
 }
 
 extern "C" int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,

@@ -12,7 +12,10 @@ int validate_desc(const hn_model_desc& d) {
       return set_error(-11, "hn_model_desc: the static NeRF kernels are instantiated for xyz / dir freqs 10 / 4 (models/nerf.py defaults)");
     return 0;
   }
-  const bool warp = (d.flags & HN_FLAG_WARP_TRANSLATION) != 0;
+  const bool se3 = (d.flags & HN_FLAG_WARP_SE3) != 0;
+  const bool warp = (d.flags & HN_FLAG_WARP_TRANSLATION) != 0 || se3;
+  if (se3 && (d.flags & HN_FLAG_WARP_TRANSLATION))
+    return set_error(-10, "hn_model_desc: the warp field is either a TranslationField or an SE3Field");
   const bool bendy = (d.flags & HN_FLAG_SLICE_BENDY) != 0, axis = (d.flags & HN_FLAG_SLICE_AXIS) != 0;
   const bool cond = (d.flags & (HN_FLAG_ALPHA_COND | HN_FLAG_RGB_COND)) != 0;
   if (warp && (bendy == axis))
@@ -22,7 +25,11 @@ int validate_desc(const hn_model_desc& d) {
     return set_error(-10, "hn_model_desc: without warp map_points returns the raw points (models.py:568-569): pass no slicing flag");
   if (d.xyz_freqs != 10 || d.view_freqs < 0 || d.view_freqs > kMaxViewFreqs)
     return set_error(-11, "hn_model_desc: kernels are instantiated for xyz freqs 10 and view freqs <= 6");
-  if (warp) {
+  if (se3) {
+    if (!axis || d.glo_dim != 8 || d.hyper_dim != 8 || d.hyper_freqs != 6 || d.warp_freqs != kSe3Freqs)
+      return set_error(-11, "hn_model_desc: the SE3 warp is instantiated for axis_aligned_plane slicing with G = hyper_dim = 8, "
+                            "hyper freqs 6 and posenc(points, 0, 8) (warp_freqs = 8; warping.py:150-151)");
+  } else if (warp) {
     if (d.glo_dim != 8 || d.hyper_freqs != 6 || d.warp_freqs != 10 || d.sheet_freqs != 7)
       return set_error(-11, "hn_model_desc: kernels are instantiated for G=8, hyper freqs 6 (warp 10, sheet 7); add an "
                             "instantiation in hn_mlp.cu for other shapes");
@@ -171,7 +178,26 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     if (kFoldBias) b.ones_col = m.ones_col;
     plan->fwd.flags = m.t_in_act ? PF_TIN_ACT : 0;
     int bias = 0;
-    if (!m.nowarp) {
+    if (m.se3) {
+      // SE3Field.warp (warping.py:212-227): trunk on posenc(points) alone, logit layer, merged w / v hidden layer, 6-output head
+      b.begin_layer(FE_RELU, kSe3W, bias, s.x_hws[0], kNone, s.g_hws[0]);
+      b.add_op(kSe3W, m.KW, SRC_INB, 0, 0, SRC_ACT, 0, 0);
+      bias += kSe3W;
+      for (int l = 1; l < kWsDepth; ++l) {
+        b.begin_layer(FE_RELU, kSe3W, bias, s.x_hws[l], kNone, s.g_hws[l]);
+        b.add_op(kSe3W, kSe3W, SRC_ACT, 0, l == kSkip + 1 ? m.KW : 0, SRC_INB, 0, 0);
+        bias += kSe3W;
+      }
+      b.begin_layer(FE_LINEAR, kSe3W, bias, s.x_se_logit, kNone);
+      b.add_op(kSe3W, kSe3W, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      bias += kSe3W;
+      b.begin_layer(FE_RELU, 2 * kSe3W, bias, s.x_se_wv, kNone, s.g_se_wv);
+      b.add_op(2 * kSe3W, kSe3W, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      bias += 2 * kSe3W;
+      b.begin_layer(FE_WSHEAD, 16, bias, s.x_in_t, kNone);
+      b.add_op(16, 2 * kSe3W, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      bias += 16;
+    } else if (!m.nowarp) {
       // warp + sheet, merged to one 192-wide net sharing the input buffer (axis-aligned slicing has no sheet MLP: its
       // part of the operand images stays zero)
       b.begin_layer(FE_RELU, kWsW, bias, s.x_hws[0], kNone, s.g_hws[0]);
@@ -266,7 +292,19 @@ void build_plan(const hn_model_desc& d, ModelPlan* plan) {
     b.begin_layer(BE_TRUNKIN, m.KT, 0, m.nowarp ? kNone : s.d_wshead, kNone);
     b.add_op(m.KT, kTrunkW, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
     const int n_trunk_layers = plan->bwd.nlayers;
-    if (!m.nowarp) {
+    if (m.se3) {
+      // head^T: A = d(w, v) (16 columns, written by BE_TRUNKIN's exp-map chain rule), gated by the w / v hidden ReLUs
+      b.begin_layer(BE_MASK, 2 * kSe3W, 0, s.d_se_wv, s.x_se_wv, s.g_se_wv);
+      b.add_op(2 * kSe3W, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      // (w hidden | v hidden)^T -> gradient of the logit layer's output (no activation)
+      b.begin_layer(BE_LINEAR, kSe3W, 0, s.d_se_logit, kNone);
+      b.add_op(kSe3W, 2 * kSe3W, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      // logit^T, then trunk layers 5..1 (the skip layer's input part is posenc(points): no gradient wanted)
+      for (int l = kWsDepth; l >= 1; --l) {
+        b.begin_layer(BE_MASK, kSe3W, 0, s.d_ws[l - 1], s.x_hws[l - 1], s.g_hws[l - 1]);
+        b.add_op(kSe3W, kSe3W, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
+      }
+    } else if (!m.nowarp) {
       // warp/sheet head^T
       b.begin_layer(BE_MASK, kWsW, 0, s.d_ws[kWsDepth - 1], s.x_hws[kWsDepth - 1], s.g_hws[kWsDepth - 1]);
       b.add_op(kWsW, 16, SRC_ACT, 0, 0, SRC_ACT, 0, 0);
@@ -314,7 +352,28 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   // (modules.py:283,292); inside the operand the view vector is [PE padded to 40 | GLO] (hn_mlp_program.h: kViewCondCol)
   const int ld_rgb0 = kRgbW + m.pe_v + (m.cond_r ? m.G : 0), ld_alpha = kRgbW + (m.cond_a ? m.G : 0);
   const int k_cond = kRgbW + kViewCondCol;
-  if (!m.nowarp) {
+  const int ld_se5 = kSe3W + m.in_w;
+  if (m.se3) {
+    pk.op(F.ops[oi++]);
+    pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kSe3W, 0, m.in_w);
+    pk.bias_rows(P_WARP_B(0), 0, kSe3W);
+    for (int l = 1; l <= kWsDepth; ++l) {   // l == kWsDepth: the trunk's logit layer
+      const int ld = l == kSkip + 1 ? ld_se5 : kSe3W;
+      pk.op(F.ops[oi++]);
+      pk.block(P_WARP_W(l), 0, ld, 1, 0, kSe3W, 0, ld);
+      pk.bias_rows(P_WARP_B(l), 0, kSe3W);
+    }
+    pk.op(F.ops[oi++]);  // rows [0, 128) w_net.linears.0, [128, 256) v_net.linears.0
+    pk.block(P_SE3_W(SE3_W_HID), 0, kSe3W, 1, 0, kSe3W, 0, kSe3W);
+    pk.block(P_SE3_W(SE3_V_HID), 0, kSe3W, 1, kSe3W, kSe3W, 0, kSe3W);
+    pk.bias_rows(P_SE3_B(SE3_W_HID), 0, kSe3W);
+    pk.bias_rows(P_SE3_B(SE3_V_HID), kSe3W, kSe3W);
+    pk.op(F.ops[oi++]);  // head: rows 0..2 = w_net.logit_layer on the w hidden columns, rows 3..5 = v_net.logit_layer on the v ones
+    pk.block(P_SE3_W(SE3_W_OUT), 0, kSe3W, 1, 0, 3, 0, kSe3W);
+    pk.block(P_SE3_W(SE3_V_OUT), 0, kSe3W, 1, 3, 3, kSe3W, kSe3W);
+    pk.bias_rows(P_SE3_B(SE3_W_OUT), 0, 3);
+    pk.bias_rows(P_SE3_B(SE3_V_OUT), 3, 3);
+  } else if (!m.nowarp) {
     // fwd ws0
     pk.op(F.ops[oi++]);
     pk.block(P_WARP_W(0), 0, m.in_w, 1, 0, kWarpW, 0, m.in_w);
@@ -402,7 +461,18 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   }
   bop();  // trunk 0^T
   pk.block(P_TRUNK_W(level, 0), 0, 1, m.in_t, 0, m.in_t, 0, kTrunkW);
-  if (!m.nowarp) {
+  if (m.se3) {
+    bop();  // head^T: n < 128 <- w_net.logit_layer (k < 3); n = 128 + j <- v_net.logit_layer (k = 3 + i)
+    pk.block(P_SE3_W(SE3_W_OUT), 0, 1, kSe3W, 0, kSe3W, 0, 3);
+    pk.block(P_SE3_W(SE3_V_OUT), 0, 1, kSe3W, kSe3W, kSe3W, 3, 3);
+    bop();  // (w hidden | v hidden)^T: dest(n, k < 128) = Wwh[k][n], dest(n, 128 + k) = Wvh[k][n]
+    pk.block(P_SE3_W(SE3_W_HID), 0, 1, kSe3W, 0, kSe3W, 0, kSe3W);
+    pk.block(P_SE3_W(SE3_V_HID), 0, 1, kSe3W, 0, kSe3W, kSe3W, kSe3W);
+    for (int l = kWsDepth; l >= 1; --l) {
+      bop();
+      pk.block(P_WARP_W(l), 0, 1, l == kSkip + 1 ? ld_se5 : kSe3W, 0, kSe3W, 0, kSe3W);
+    }
+  } else if (!m.nowarp) {
     bop();  // ws head^T: n < 128 <- warp logit (k < 3); n = 128 + j <- sheet logit (k = 3 + h)
     pk.block(P_WARP_W(kWsDepth), 0, 1, kWarpW, 0, kWarpW, 0, 3);
     pk.block(P_SHEET_W(kWsDepth), 0, 1, kSheetW, kWarpW, kSheetW, 3, m.H);
@@ -425,7 +495,15 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
 
   // biases, in forward layer order
   int bo = 0;
-  if (!m.nowarp) {
+  if (m.se3) {
+    for (int l = 0; l <= kWsDepth; ++l) { pk.bias(P_WARP_B(l), bo, kSe3W); bo += kSe3W; }
+    pk.bias(P_SE3_B(SE3_W_HID), bo, kSe3W);
+    pk.bias(P_SE3_B(SE3_V_HID), bo + kSe3W, kSe3W);
+    bo += 2 * kSe3W;
+    pk.bias(P_SE3_B(SE3_W_OUT), bo, 3);
+    pk.bias(P_SE3_B(SE3_V_OUT), bo + 3, 3);
+    bo += 16;
+  } else if (!m.nowarp) {
     for (int l = 0; l < kWsDepth; ++l) {
       pk.bias(P_WARP_B(l), bo, kWarpW);
       pk.bias(P_SHEET_B(l), bo + kWarpW, kSheetW);
@@ -469,7 +547,38 @@ void build_tables(const hn_model_desc& d, int level, const int64_t* off, ModelPl
   };
   // a job none of whose outputs exists (the sheet MLP with axis-aligned slicing) is dropped again
   auto keep = [&](WgradJob& j) { if (j.nflush == 0 && j.nbias == 0) { memset(&j, 0, sizeof(j)); --w.njobs; } };
-  if (!m.nowarp) {
+  if (m.se3) {
+    {
+      WgradJob& j = job(s.d_ws[0], kSe3W, s.x_in_ws, m.KW, 0, 0);
+      flush(j, P_WARP_W(0), 0, m.in_w, 0, kSe3W, 0, m.in_w);
+      bseg(j, P_WARP_B(0), 0, kSe3W);
+    }
+    for (int l = 1; l < kWsDepth; ++l) {
+      const bool skip = (l == kSkip + 1);
+      WgradJob& j = job(s.d_ws[l], kSe3W, s.x_hws[l - 1], kSe3W, s.x_in_ws, skip ? m.KW : 0);
+      flush(j, P_WARP_W(l), 0, skip ? ld_se5 : kSe3W, 0, kSe3W, 0, skip ? ld_se5 : kSe3W);
+      bseg(j, P_WARP_B(l), 0, kSe3W);
+    }
+    {
+      WgradJob& j = job(s.d_se_logit, kSe3W, s.x_hws[kWsDepth - 1], kSe3W, 0, 0);
+      flush(j, P_WARP_W(kWsDepth), 0, kSe3W, 0, kSe3W, 0, kSe3W);
+      bseg(j, P_WARP_B(kWsDepth), 0, kSe3W);
+    }
+    {
+      WgradJob& j = job(s.d_se_wv, 2 * kSe3W, s.x_se_logit, kSe3W, 0, 0);
+      flush(j, P_SE3_W(SE3_W_HID), 0, kSe3W, 0, kSe3W, 0, kSe3W);
+      flush(j, P_SE3_W(SE3_V_HID), 0, kSe3W, kSe3W, kSe3W, 0, kSe3W);
+      bseg(j, P_SE3_B(SE3_W_HID), 0, kSe3W);
+      bseg(j, P_SE3_B(SE3_V_HID), kSe3W, kSe3W);
+    }
+    {
+      WgradJob& j = job(s.d_wshead, 16, s.x_se_wv, 2 * kSe3W, 0, 0);
+      flush(j, P_SE3_W(SE3_W_OUT), 0, kSe3W, 0, 3, 0, kSe3W);
+      flush(j, P_SE3_W(SE3_V_OUT), 0, kSe3W, 3, 3, kSe3W, kSe3W);
+      bseg(j, P_SE3_B(SE3_W_OUT), 0, 3);
+      bseg(j, P_SE3_B(SE3_V_OUT), 3, 3);
+    }
+  } else if (!m.nowarp) {
     // warp / sheet layer 0
     {
       WgradJob& j = job(s.d_ws[0], kWarpW, s.x_in_ws, m.KW, 0, 0);

@@ -8,7 +8,7 @@
 // a kernel parameter.
 //
 // Topology source: hypernerf/modules.py:99-127 (MLP), :220-252 (NerfMLP), :302-337 (HyperSheetMLP),
-// hypernerf/warping.py:74-88 (TranslationField), hypernerf/models.py:404-493 (conditioning, template query).
+// hypernerf/warping.py:74-88 (TranslationField), :128-240 (SE3Field), hypernerf/models.py:404-493 (conditioning, template query).
 #pragma once
 #include <stdint.h>
 #include "../../include/hypernerf_b200.h"
@@ -81,7 +81,7 @@ constexpr int kStageBytes = HN_STAGE_BYTES;
 constexpr bool kFoldBias = HN_FOLD_BIAS != 0;
 constexpr bool ones_fit_in_pad(int kmax, int k, int in) { return k < kmax || in <= kmax - 2; }
 constexpr int kMaxOps = 64;
-constexpr int kMaxLayers = 24;
+constexpr int kMaxLayers = 28;
 constexpr int kMaxJobs = 40;
 constexpr uint16_t kNone = 0xFFFF;
 
@@ -90,6 +90,10 @@ constexpr int pad16(int x) { return (x + 15) / 16 * 16; }
 // Fixed cfg-1 family widths (models.py:137-141, warping.py:61, modules.py:303).
 constexpr int kTrunkW = 256, kTrunkDepth = 8, kRgbW = 128, kRgbDepth = 4;
 constexpr int kWarpW = 128, kSheetW = 64, kWsDepth = 6, kWsW = kWarpW + kSheetW, kSkip = 4;
+// SE3Field (warping.py:128-272): trunk depth 6 / width 128 / skip 4 on posenc(points, 0, 8) (8 scales x (sin, cos) x 3 = 48
+// columns, no identity, no metadata), a 128 -> 128 logit layer without activation, then the w / v heads: one hidden 128 ReLU
+// layer each (run as one 256-wide layer) and 3 outputs each (one 16-row head: rows 0..2 = w, 3..5 = v).
+constexpr int kSe3W = 128, kSe3Freqs = 8;
 
 // View-direction condition vector of the template (hyper model): [posenc_orig(viewdirs, view_freqs <= 6) zero-padded to 40
 // columns | GLO condition (8 columns, zero without template conditioning)] = 48 columns, whatever view_freqs is, so that
@@ -120,6 +124,8 @@ constexpr int inb_chunks_of(int KW, int in_w, int KT, int in_t, int KV, int in_v
 struct Dims {
   int G, H;
   bool nowarp, axis, cond_a, cond_r;   // no warp / sheet stage; hyper point = GLO vector; template GLO conditioning
+  bool se3;                            // the warp stage is an SE3Field (no sheet MLP, no GLO input) instead of warp + sheet
+  int ws_w;                            // width of the warp-stage hidden layers: 192 (warp 128 | sheet 64) or 128 (SE3 trunk)
   int pe_w, pe_s, in_w, in_s, KW;  // warp / sheet inputs, shared padded input width (KW = 0 without warp)
   int pe_x, pe_h, in_t, KT;        // trunk input
   int pe_v, KV;                    // view-direction condition: pe_v real posenc columns inside the kKV-wide vector
@@ -130,12 +136,16 @@ struct Dims {
 };
 inline Dims make_dims(const hn_model_desc& d) {
   Dims m{};
-  m.nowarp = (d.flags & HN_FLAG_WARP_TRANSLATION) == 0;
+  m.se3 = (d.flags & HN_FLAG_WARP_SE3) != 0;
+  m.nowarp = (d.flags & (HN_FLAG_WARP_TRANSLATION | HN_FLAG_WARP_SE3)) == 0;
+  m.ws_w = m.se3 ? kSe3W : kWsW;
   m.axis = (d.flags & HN_FLAG_SLICE_AXIS) != 0;
   m.cond_a = (d.flags & HN_FLAG_ALPHA_COND) != 0; m.cond_r = (d.flags & HN_FLAG_RGB_COND) != 0;
   m.G = d.glo_dim; m.H = m.nowarp ? 0 : d.hyper_dim;
   m.pe_w = 3 + 6 * d.warp_freqs; m.pe_s = 3 + 6 * d.sheet_freqs;
-  m.in_w = m.pe_w + m.G; m.in_s = m.pe_s + m.G; m.KW = m.nowarp ? 0 : pad16(m.in_w);
+  m.in_w = m.pe_w + m.G; m.in_s = m.pe_s + m.G;
+  if (m.se3) { m.pe_w = 6 * d.warp_freqs; m.in_w = m.pe_w; m.pe_s = 0; m.in_s = 0; }
+  m.KW = m.nowarp ? 0 : pad16(m.in_w);
   m.pe_x = 3 + 6 * d.xyz_freqs; m.pe_h = m.H * (1 + 2 * d.hyper_freqs);
   m.in_t = m.pe_x + m.pe_h; m.KT = pad16(m.in_t);
   m.pe_v = 3 + 6 * d.view_freqs; m.KV = kKV;
@@ -162,25 +172,33 @@ inline int P_RGB_B(int level, int l) { return P_LEVEL(level) + 21 + 2 * l; }
 inline int P_ALPHA_W(int level) { return P_LEVEL(level) + 30; }
 inline int P_ALPHA_B(int level) { return P_LEVEL(level) + 31; }
 constexpr int P_COND_GLO = 93;   // nerf_embed.embed.weight: the condition table without warp
+// SE3Field: its trunk (linears 0..5, logit_layer) takes the P_WARP_* slots; the heads follow the condition table
+enum Se3Head { SE3_W_HID = 0, SE3_W_OUT = 1, SE3_V_HID = 2, SE3_V_OUT = 3 };
+inline int P_SE3_W(int h) { return 94 + 2 * h; }
+inline int P_SE3_B(int h) { return 95 + 2 * h; }
 
 // ---- saved-activation (forward) and pre-activation-gradient (backward) slab offsets, in 8-col chunks ---
 struct SlabMap {
   // forward activations X (inputs of every linear layer)
   uint16_t x_in_ws, x_hws[kWsDepth], x_in_t, x_t[kTrunkDepth + 1], x_bott, x_in_v, x_r[kRgbDepth];
+  uint16_t x_se_logit, x_se_wv;   // SE3: output of the trunk's logit layer (input of the w / v hidden layer), that layer's output
   uint16_t x_total;
   // gradients w.r.t. every layer's pre-activation output
   uint16_t d_ws[kWsDepth], d_wshead, d_t[kTrunkDepth + 1], d_bott, d_rgb0a, d_r[kRgbDepth] /* [0] unused */, d_rgbhead;
+  uint16_t d_se_logit, d_se_wv;
   uint16_t d_total;
   // ReLU gate words (one uint32 per row per 32 output columns of every ReLU layer), written by the forward epilogue
   // next to the X slabs and read by the data gradient instead of the activations themselves
   uint16_t g_hws[kWsDepth], g_t[kTrunkDepth + 1], g_r[kRgbDepth];
+  uint16_t g_se_wv;
   uint16_t g_total;
 };
 inline SlabMap make_slabs(const Dims& m) {
   SlabMap s{};
   uint16_t c = 0;
   s.x_in_ws = c; c += m.KW / 8;
-  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.x_hws[l] = c; c += kWsW / 8; }
+  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.x_hws[l] = c; c += m.ws_w / 8; }
+  if (m.se3) { s.x_se_logit = c; c += kSe3W / 8; s.x_se_wv = c; c += 2 * kSe3W / 8; }
   s.x_in_t = c; c += m.KT / 8;
   for (int l = 0; l <= kTrunkDepth; ++l) { s.x_t[l] = c; c += kTrunkW / 8; }
   s.x_bott = c; c += kRgbW / 8;
@@ -189,7 +207,8 @@ inline SlabMap make_slabs(const Dims& m) {
   s.x_total = c;
   c = 0;
   if (!m.nowarp) {
-    for (int l = 0; l < kWsDepth; ++l) { s.d_ws[l] = c; c += kWsW / 8; }
+    for (int l = 0; l < kWsDepth; ++l) { s.d_ws[l] = c; c += m.ws_w / 8; }
+    if (m.se3) { s.d_se_logit = c; c += kSe3W / 8; s.d_se_wv = c; c += 2 * kSe3W / 8; }
     s.d_wshead = c; c += 2;
   }
   for (int l = 0; l <= kTrunkDepth; ++l) { s.d_t[l] = c; c += kTrunkW / 8; }
@@ -200,7 +219,8 @@ inline SlabMap make_slabs(const Dims& m) {
   s.d_rgbhead = c; c += 2;
   s.d_total = c;
   c = 0;
-  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.g_hws[l] = c; c += kWsW / 32; }
+  if (!m.nowarp) for (int l = 0; l < kWsDepth; ++l) { s.g_hws[l] = c; c += m.ws_w / 32; }
+  if (m.se3) { s.g_se_wv = c; c += 2 * kSe3W / 32; }
   for (int l = 0; l <= kTrunkDepth; ++l) { s.g_t[l] = c; c += kTrunkW / 32; }
   for (int l = 0; l < kRgbDepth; ++l) { s.g_r[l] = c; c += kRgbW / 32; }
   s.g_total = c;
@@ -231,7 +251,8 @@ struct LogicalOp {
 
 // FE_SKIPFEED: no drain — the accumulator keeps the hidden part of the skip layer; the epilogue re-fills ACT with the trunk
 // input vector for the input part (see kMaxTrunkInInb).  BE_LINCOND: BE_LINEAR + the GLO-condition columns (-> table gradient).
-enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD, FE_SIGMA, FE_SKIPFEED };
+// FE_LINEAR: plain linear layer (bias, no activation, stashed): the SE3 trunk's logit layer.
+enum FwdEpi : uint8_t { FE_RELU = 0, FE_WSHEAD, FE_BOTT, FE_RGB0A, FE_RGBHEAD, FE_SIGMA, FE_SKIPFEED, FE_LINEAR };
 enum BwdEpi : uint8_t { BE_MASK = 0, BE_LINEAR, BE_RGB1, BE_SKIPSTORE, BE_TRUNKIN, BE_GLO, BE_LINCOND };
 enum ProgFlags : int32_t { PF_TIN_ACT = 1 };   // Program::flags
 

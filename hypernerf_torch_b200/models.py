@@ -100,25 +100,27 @@ class _FusedMlp(torch.autograd.Function):
         rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
         warped = torch.empty(B, S, 3 + desc.hyper_dim, device=dev, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad[7:])  # grad mode is off inside forward(); autograd tells us here
-        saved = None
+        saved = aux = None
         if need_grad:
             sizes = model._sizes(B * S)
             saved = torch.empty(sizes.saved_bytes, device=dev, dtype=torch.uint8)
+            if model._se3:   # the screw parameters (w, v) of every sample, for the exp map's chain rule
+                aux = torch.empty(B, S, 6, device=dev, dtype=torch.float32)
         with _lib.timed("mlp_fwd", B * S):
             check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise),
-                                   float(noise_std), B, S, None, 0, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), stream()),
-                  "hn_mlp_fwd")
+                                   float(noise_std), B, S, None, 0, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), ptr(aux),
+                                   stream()), "hn_mlp_fwd")
         _lib.count(1)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S)
         ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
-        ctx.save_for_backward(ids, sigma, rgb, warped, saved, packed)
+        ctx.save_for_backward(ids, sigma, rgb, warped, saved, packed, pts if aux is not None else None, aux)
         ctx.set_materialize_grads(False)
         return sigma, rgb, warped
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_sigma, g_rgb, g_warped):
-        ids, sigma, rgb, warped, saved, packed = ctx.saved_tensors
+        ids, sigma, rgb, warped, saved, packed, pts, aux = ctx.saved_tensors
         model, level = ctx.model, ctx.level
         B, S = ctx.shape
         if saved is None:
@@ -139,7 +141,7 @@ class _FusedMlp(torch.autograd.Function):
         with _lib.timed("mlp_dgrad", B * S):
             check(lib().hn_mlp_bwd_data(C.byref(model._desc), ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped),
                                         ptr(saved), ptr(g_sigma), ptr(g_rgb), ptr(g_warped), B, S, None, 0, level, offs,
-                                        ptr(flat_grad), ptr(work), stream()), "hn_mlp_bwd_data")
+                                        ptr(flat_grad), ptr(work), ptr(pts), ptr(aux), stream()), "hn_mlp_bwd_data")
         with _lib.timed("mlp_wgrad", B * S):
             check(lib().hn_mlp_bwd_weights(C.byref(model._desc), ptr(saved), B, S, level, offs, ptr(flat_grad), ptr(work),
                                            stream()), "hn_mlp_bwd_weights")
@@ -243,13 +245,16 @@ class _FusedFineLevel(torch.autograd.Function):
         rgb = torch.empty(B, S, 3, device=dev, dtype=torch.float32)
         warped = torch.empty(B, S, 3 + desc.hyper_dim, device=dev, dtype=torch.float32)
         need_grad = ctx.needs_input_grad[7] or any(ctx.needs_input_grad[10:])
-        saved_n = saved_k = None
+        saved_n = saved_k = aux = None
         if need_grad:
             saved_n = torch.empty(model._sizes(B * Sn).saved_bytes, device=dev, dtype=torch.uint8)
             saved_k = torch.empty(model._sizes(B * Sk).saved_bytes, device=dev, dtype=torch.uint8)
+            if model._se3:
+                aux = torch.empty(B, Sn, 6, device=dev, dtype=torch.float32)
         with _lib.timed("mlp_fwd", B * Sn):
             check(lib().hn_mlp_fwd(C.byref(desc), ptr(packed), ptr(pts), ptr(vd), ptr(ids), ptr(noise), float(noise_std), B, Sn,
-                                   ptr(pos_new), S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_n), stream()), "hn_mlp_fwd")
+                                   ptr(pos_new), S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_n), ptr(aux), stream()),
+                  "hn_mlp_fwd")
         with _lib.timed("mlp_fwd_trunk", B * Sk):
             check(lib().hn_mlp_fwd_trunk(C.byref(desc), ptr(packed), ptr(kw), ptr(vd), ptr(ids), ptr(noise), float(noise_std),
                                          B, Sk, ptr(pos_known), S, ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_k), stream()),
@@ -257,14 +262,15 @@ class _FusedFineLevel(torch.autograd.Function):
         _lib.count(2)
         ctx.model, ctx.level, ctx.shape = model, level, (B, S, Sk, Sn)
         ctx.param_meta = [(slot, p.shape, p.numel()) for slot, p in zip(model._slots_present(), params)]
-        ctx.save_for_backward(ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new)
+        ctx.save_for_backward(ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new,
+                              pts if aux is not None else None, aux)
         ctx.set_materialize_grads(False)
         return sigma, rgb, warped
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_sigma, g_rgb, g_warped):
-        ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new = ctx.saved_tensors
+        ids, sigma, rgb, warped, kw, saved_n, saved_k, packed, pos_known, pos_new, pts, aux = ctx.saved_tensors
         model, level = ctx.model, ctx.level
         B, S, Sk, Sn = ctx.shape
         if saved_n is None:
@@ -285,7 +291,7 @@ class _FusedFineLevel(torch.autograd.Function):
         with _lib.timed("mlp_dgrad", B * Sn):
             check(lib().hn_mlp_bwd_data(d, ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped), ptr(saved_n), ptr(g_sigma),
                                         ptr(g_rgb), ptr(g_warped), B, Sn, ptr(pos_new), S, level, offs, ptr(flat_grad),
-                                        ptr(work), stream()), "hn_mlp_bwd_data")
+                                        ptr(work), ptr(pts), ptr(aux), stream()), "hn_mlp_bwd_data")
         with _lib.timed("mlp_wgrad", B * Sn):
             check(lib().hn_mlp_bwd_weights(d, ptr(saved_n), B, Sn, level, offs, ptr(flat_grad), ptr(work), stream()),
                   "hn_mlp_bwd_weights")
@@ -310,6 +316,7 @@ class NerfModel(PackedWeights, nn.Module):
       use_warp + hyper_slice_method='bendy_sheet'          TranslationField + HyperSheetMLP, hyper_slice_out_dim in {2, 4, 8}
       use_warp + 'axis_aligned_plane'                      hyper point = the GLO vector, hyper_slice_out_dim == GLO_dim == 8
       use_warp=False (any slicing argument)                the template NeRF on the raw points (models.py:568-569)
+      use_warp + 'axis_aligned_plane' + warp_field_type='se3'   SE3Field warp (restated; the reference never instantiates it)
     each with or without template GLO conditioning (use_nerf_embed + use_alpha_cond [+ use_rgb_cond], models.py:404-445),
     view_fourier_dim <= 6, xyz / hyper fourier dims 10 / 6, GLO_dim 8.  Combinations that fail inside the reference's
     forward (use_warp with slicing 'none'; use_nerf_embed without use_alpha_cond; use_rgb_cond without use_nerf_embed:
@@ -337,7 +344,12 @@ class NerfModel(PackedWeights, nn.Module):
                  share_GLO: bool = True,
                  xyz_fourier_dim: int = 10,
                  hyper_fourier_dim: int = 6,
-                 view_fourier_dim: int = 4):
+                 view_fourier_dim: int = 4,
+                 warp_field_type: str = 'translation'):
+        """`warp_field_type` is the one argument the reference's constructor does not have: there the warp field class is
+        the attribute `warp_field_cls` (models.py:195, "SE3 untested") and the instantiation is hard-coded to
+        TranslationField (models.py:234).  'se3' builds warping.SE3Field (warping.py:128-272) in its place — BASELINE.json
+        config 5 —, evaluated batched as DESIGN.md §"SE3 warp" restates it (the reference's own exp map only takes one point)."""
         super().__init__()
         self.embeddings_dict = embeddings_dict
         self.near, self.far = near, far
@@ -386,8 +398,12 @@ class NerfModel(PackedWeights, nn.Module):
             if not self.hyper_use_warp_embed:
                 self.hyper_embed = modules.GLOEmbed(num_embeddings=n_embed(self.hyper_embed_key), embedding_dim=GLO_dim)
             self.hyper_sheet_mlp = modules.HyperSheetMLP(out_ch=self.hyper_sheet_out_dim, in_ch_embed=GLO_dim)
+        if warp_field_type not in ('translation', 'se3'):
+            raise ValueError(f"Unknown warp field type {warp_field_type}.")
+        self._se3 = self.use_warp and warp_field_type == 'se3'
+        self.warp_field_cls = modules.SE3Field if warp_field_type == 'se3' else modules.TranslationField
         if self.use_warp:
-            self.warp_field = modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
+            self.warp_field = modules.SE3Field(in_ch=3) if self._se3 else modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
         self.alpha_default = 0.0
         self.nerf_in_ch_pos = modules.posenc_channels(3, self.xyz_freq)
         self.nerf_cond_ch_rgb = modules.posenc_channels(3, self.dir_freq)
@@ -425,6 +441,9 @@ class NerfModel(PackedWeights, nn.Module):
             self._forward_error = "use_rgb_cond without use_nerf_embed: rgb_mlp expects the GLO columns (models.py:269-272)"
         elif self.hyper_slice_method not in ('none', 'bendy_sheet', 'axis_aligned_plane'):
             self._forward_error = f'Unknown hyper slice method {self.hyper_slice_method}.'   # models.py:394-396
+        elif self._se3 and self.hyper_slice_method != 'axis_aligned_plane':
+            self._forward_error = ("warp_field_type 'se3' is built for hyper_slice_method 'axis_aligned_plane' "
+                                   "(BASELINE.json config 5)")
 
         # ---- the kernels' view of the model ---------------------------------------------------------------------------
         cond_a = self.use_nerf_embed and self.use_alpha_condition
@@ -432,15 +451,15 @@ class NerfModel(PackedWeights, nn.Module):
         flags = (_lib.HN_FLAG_ALPHA_COND if cond_a else 0) | (_lib.HN_FLAG_RGB_COND if cond_r else 0)
         self._ids_key, n_rows = None, 0
         if self.use_warp:
-            flags |= _lib.HN_FLAG_WARP_TRANSLATION
+            flags |= _lib.HN_FLAG_WARP_SE3 if self._se3 else _lib.HN_FLAG_WARP_TRANSLATION
             flags |= _lib.HN_FLAG_SLICE_AXIS if self.hyper_slice_method == 'axis_aligned_plane' else _lib.HN_FLAG_SLICE_BENDY
             self._ids_key, n_rows = self.warp_embed_key, n_embed(self.warp_embed_key)
         elif cond_a or cond_r:
             # without warp the condition comes from nerf_embed[metadata['warp']] (models.py:425-430)
             self._ids_key, n_rows = self.nerf_embed_key, n_embed(self.nerf_embed_key)
         self._desc = _lib.ModelDesc(GLO_dim, hyper_slice_out_dim if self.use_warp else 0, xyz_fourier_dim, hyper_fourier_dim,
-                                    view_fourier_dim, modules.TranslationField.n_freq, modules.HyperSheetMLP.n_freq, n_rows,
-                                    flags)
+                                    view_fourier_dim, modules.SE3Field.max_deg if self._se3 else modules.TranslationField.n_freq,
+                                    modules.HyperSheetMLP.n_freq, n_rows, flags)
         self._slot_cache = None
         self._pack_levels = 2
         self._init_packing()
@@ -476,7 +495,12 @@ class NerfModel(PackedWeights, nn.Module):
             out[0] = self.warp_embed.embed.weight
             if bendy:
                 put(1, list(self.hyper_sheet_mlp.mlp.linears) + [self.hyper_sheet_mlp.mlp.logit_layer])
-            put(15, list(self.warp_field.mlp.linears) + [self.warp_field.mlp.logit_layer])
+            if self._se3:
+                wf = self.warp_field
+                put(15, list(wf.trunk.linears) + [wf.trunk.logit_layer])
+                put(94, [wf.w_net.linears[0], wf.w_net.logit_layer, wf.v_net.linears[0], wf.v_net.logit_layer])
+            else:
+                put(15, list(self.warp_field.mlp.linears) + [self.warp_field.mlp.logit_layer])
         elif self.use_nerf_embed:
             out[93] = self.nerf_embed.embed.weight
         for level, nm in enumerate((self.nerf_mlps_coarse, self.nerf_mlps_fine)):

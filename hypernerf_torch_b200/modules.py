@@ -89,3 +89,20 @@ class TranslationField(_FusedOnly):
         self.in_ch = posenc_channels(in_ch, self.n_freq) + in_ch_embed
         self.mlp = MLP(self.in_ch, 3, depth=depth, width=hidden_channels, skips=[4] if skips is None else skips,
                        hidden_init=nn.init.xavier_normal_, output_init=functools.partial(nn.init.uniform_, b=1e-4))
+
+
+class SE3Field(_FusedOnly):
+    """warping.py:128-209: trunk MLP 6x128 (skip@4, 128 outputs, no output activation) on posenc(points, 0, 8) — 48 channels,
+    the metadata embedding is not an input (warping.py:223-224) —, then w_net / v_net: depth 0 in the reference's MLP still
+    builds ONE hidden 128 layer (modules.py:95-98) + 3 outputs initialised uniform(0, 1e-4)."""
+
+    min_deg, max_deg = 0, 8
+
+    def __init__(self, in_ch=3, out_ch=1):
+        super().__init__()
+        self.out_ch = out_ch   # unused, as in the reference
+        self.in_ch = 2 * in_ch * (self.max_deg - self.min_deg)
+        self.trunk = MLP(self.in_ch, 128, depth=6, width=128, skips=(4,), hidden_init=nn.init.xavier_normal_)
+        head_init = functools.partial(nn.init.uniform_, b=1e-4)
+        self.w_net = MLP(128, 3, depth=0, width=128, hidden_init=nn.init.xavier_normal_, output_init=head_init)
+        self.v_net = MLP(128, 3, depth=0, width=128, hidden_init=nn.init.xavier_normal_, output_init=head_init)

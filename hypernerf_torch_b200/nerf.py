@@ -58,7 +58,8 @@ class _FusedStatic(torch.autograd.Function):
             saved = torch.empty(model._sizes(B * S).saved_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_fwd", B * S):
             check(lib().hn_mlp_fwd(C.byref(model._desc), ptr(packed), ptr(pts), ptr(vd), None, ptr(noise),
-                                   float(noise_std), B, S, None, 0, ptr(sigma), ptr(rgb), None, ptr(saved), stream()), "hn_mlp_fwd")
+                                   float(noise_std), B, S, None, 0, ptr(sigma), ptr(rgb), None, ptr(saved), None, stream()),
+                  "hn_mlp_fwd")
         _lib.count(1)
         ctx.model, ctx.shape = model, (B, S)
         ctx.param_meta = [(p.shape, p.numel()) for p in params]
@@ -82,7 +83,8 @@ class _FusedStatic(torch.autograd.Function):
         work = torch.empty(model._sizes(B * S).workspace_bytes, device=dev, dtype=torch.uint8)
         with _lib.timed("mlp_dgrad", B * S):
             check(lib().hn_mlp_bwd_data(C.byref(model._desc), ptr(packed), None, ptr(sigma), ptr(rgb), None, ptr(saved),
-                                        ptr(g_sigma), ptr(g_rgb), None, B, S, None, 0, 0, offs, ptr(flat_grad), ptr(work), stream()),
+                                        ptr(g_sigma), ptr(g_rgb), None, B, S, None, 0, 0, offs, ptr(flat_grad), ptr(work), None, None,
+                                        stream()),
                   "hn_mlp_bwd_data")
         with _lib.timed("mlp_wgrad", B * S):
             check(lib().hn_mlp_bwd_weights(C.byref(model._desc), ptr(saved), B, S, 0, offs, ptr(flat_grad), ptr(work),

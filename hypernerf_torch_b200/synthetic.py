@@ -81,6 +81,11 @@ def make_state_dict(module_or_shapes, seed=0, boosted=False):
             wt = (torch.rand(shape, generator=g) * 2 - 1) * bound
             if name == "warp_field.mlp.logit_layer.weight":
                 wt = wt * 0.05 if boosted is True else torch.rand(shape, generator=g) * 1e-4
+            if name in ("warp_field.w_net.logit_layer.weight", "warp_field.v_net.logit_layer.weight"):
+                # SE3Field heads (warping.py:167-168: U(0, 1e-4)); boosted: rotations of ~0.1-1 rad (both branches of the
+                # kernels' exp-map coefficients), translations ~0.05
+                scale = 0.6 if ".w_net." in name else 0.1
+                wt = wt * scale if boosted is True else torch.rand(shape, generator=g) * 1e-4
             if name == "hyper_sheet_mlp.mlp.logit_layer.weight":
                 wt = wt * 0.3 if boosted is True else torch.randn(shape, generator=g) * 1e-5
             out[name] = wt

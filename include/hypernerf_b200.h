@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 3
+#define HN_ABI_VERSION 4
 
 /* Topology of one NerfModel (reference: hypernerf/models.py:111-309): NerfMLP (modules.py:172-298) with trunk 8x256
  * skip@4 and rgb branch 4x128, optionally conditioned on a GLO embedding, behind one of the working combinations of
@@ -48,6 +48,10 @@ typedef struct hn_model_desc {
 #define HN_FLAG_SLICE_AXIS 8        /* hyper_slice_method == 'axis_aligned_plane': hyper point = GLO vector (models.py:533-534) */
 #define HN_FLAG_ALPHA_COND 16       /* use_nerf_embed + use_alpha_cond: alpha head input [bottleneck | GLO] (modules.py:283)   */
 #define HN_FLAG_RGB_COND 32         /* use_nerf_embed + use_rgb_cond: rgb branch input [bottleneck | view PE | GLO] (:292)     */
+#define HN_FLAG_WARP_SE3 64         /* SE3Field warp (warping.py:128-272, rigid_body.py:55-83) instead of TranslationField; set
+                                       together with HN_FLAG_WARP_TRANSLATION's place taken: flags = WARP_SE3 | SLICE_AXIS.  The
+                                       reference never instantiates SE3Field and its exp map is not runnable batched
+                                       (SURVEY.md App. B.1): parity for this flag is against the batched restatement in oracle/ */
 #define HN_FLAG_STATIC_NERF 4       /* static baseline models/nerf.py:41-123 (one NeRF per blob; xyz_freqs 10,
                                        view_freqs 4; glo/hyper/warp/sheet fields ignored).  hn_mlp_fwd then returns
                                        sigma = relu(raw + noise * noise_std) (rendering.py:150) and rgb; ids / warped
@@ -64,10 +68,12 @@ typedef struct hn_model_desc {
  *                          rgb linears 0..3 + logit (10), alpha (2)
  *   93                     nerf_embed.embed.weight (E,G): the condition table when there is no warp (models.py:425-430;
  *                          with a warp the condition is warp_embed, slot 0, models.py:421-423)
+ *   94..101                SE3Field only: w_net.linears.0, w_net.logit_layer, v_net.linears.0, v_net.logit_layer
+ *                          {weight,bias}; its trunk (linears 0..5 + logit_layer) takes slots 15..28
  * Offsets tables give the element offset of tensor i relative to a base pointer; the tensors need not be
  * contiguous with each other (the Python shim passes base = lowest parameter address).  A tensor the configuration
  * does not have (sheet MLP with axis-aligned slicing, warp MLP without warp, ...) has a NEGATIVE offset. */
-#define HN_NUM_PARAM_TENSORS 94
+#define HN_NUM_PARAM_TENSORS 102
 
 typedef struct hn_sizes {
   int64_t packed_bytes;       /* one level's packed bf16 weights (forward + transposed) + fp32 biases */
@@ -144,19 +150,22 @@ int hn_filter_sigma(const float* points, const float* sigma, const float* values
  * Scattered rows (pos != NULL): the launch evaluates S of the S_full samples of every ray — launch row j of ray b is
  * sample pos[b*S + j] (int32) of that ray: points / noise are read and sigma / rgb / warped written at that position of
  * (B,S_full,...) tensors.  The drop-in model evaluates the fine level's new and inherited depths in two launches that
- * fill one sorted (B,Nc+Nf) row (models.py:752-767).  pos == NULL: S_full is ignored, rows are the launch rows. */
+ * fill one sorted (B,Nc+Nf) row (models.py:752-767).  pos == NULL: S_full is ignored, rows are the launch rows.
+ * aux: SE3 warp only, training only: (B,S,6) fp32 scratch that receives the screw parameters (w, v) of every launch row for
+ * the backward pass; NULL otherwise. */
 int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
                const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos, int S_full,
-               float* sigma, float* rgb, float* warped, void* saved, void* stream);
+               float* sigma, float* rgb, float* warped, void* saved, float* aux, void* stream);
 
 /* autograd of hn_mlp_fwd: accumulates parameter gradients of `level` (and the shared warp / sheet / GLO
  * gradients) into flat_grad (fp32); grad_offsets: HOST array of HN_NUM_PARAM_TENSORS element offsets into
  * flat_grad.  g_warped may be NULL.  workspace: hn_sizes.workspace_bytes of scratch.  pos / S_full as in the forward
- * (sigma, rgb, warped, g_sigma, g_rgb, g_warped are the (B,S_full,...) tensors). */
+ * (sigma, rgb, warped, g_sigma, g_rgb, g_warped are the (B,S_full,...) tensors).  points / aux: SE3 warp only (the sample
+ * points the forward saw and the (w, v) it wrote), NULL otherwise. */
 int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma, const float* rgb,
                const float* warped, const void* saved, const float* g_sigma, const float* g_rgb, const float* g_warped,
                int64_t B, int S, const int32_t* pos, int S_full, int level, const int64_t* grad_offsets /* host */,
-               float* flat_grad, void* workspace, void* stream);
+               float* flat_grad, void* workspace, const float* points, const float* aux, void* stream);
 
 /* The two halves of hn_mlp_bwd, separately callable (hn_mlp_bwd == data then weights on the same stream):
  *   hn_mlp_bwd_data     back-propagates through every layer (tcgen05, transposed weights), writes the
@@ -165,7 +174,8 @@ int hn_mlp_bwd(const hn_model_desc* desc, const void* packed, const int64_t* ids
 int hn_mlp_bwd_data(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                     const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
                     const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
-                    const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace, void* stream);
+                    const int64_t* grad_offsets /* host */, float* flat_grad, void* workspace, const float* points,
+                    const float* aux, void* stream);
 int hn_mlp_bwd_weights(const hn_model_desc* desc, const void* saved, int64_t B, int S, int level,
                        const int64_t* grad_offsets /* host */, float* flat_grad, const void* workspace, void* stream);
 

@@ -26,6 +26,57 @@ def posenc_orig(x, n_freqs):
     return torch.cat(out, -1)
 
 
+def posenc_scaled(x, min_deg, max_deg):
+    """hypernerf/model_utils.py:255-273 with use_identity=False: scales 2**linspace(min_deg, max_deg, max_deg - min_deg) (NOT
+    integer octaves: 1, 2.208, ..., 256 for (0, 8)), cos as sin(x + 0.5 * 3.1415926), the alpha window commented out in the
+    reference (:262-265).  Channel order (*, F, 2, C) flattened: per scale [sin(s x_0..2), sin(s x_0..2 + pi/2)]."""
+    scales = 2. ** torch.linspace(min_deg, max_deg, steps=max_deg - min_deg, device=x.device)
+    xb = x[..., None, :] * scales[:, None]
+    four = torch.sin(torch.stack((xb, xb + 0.5 * 3.1415926), dim=-2))
+    return four.reshape(*x.shape[:-1], -1)
+
+
+def _skew(w):
+    """rigid_body.py:24-38 (Modern Robotics Eq. 3.30), batched."""
+    z = torch.zeros_like(w[..., 0])
+    return torch.stack([torch.stack([z, -w[..., 2], w[..., 1]], -1),
+                        torch.stack([w[..., 2], z, -w[..., 0]], -1),
+                        torch.stack([-w[..., 1], w[..., 0], z], -1)], -2)
+
+
+def se3_transform(points, w, v):
+    """SE3Field.warp's tail (warping.py:229-238) with the closed forms of rigid_body.py:55-83, batched over the leading
+    dimensions: theta = |w|; the screw axis is (w, v) / theta; R = I + sin(theta) W + (1 - cos(theta)) W^2 (Rodrigues);
+    p = (theta I + (1 - cos(theta)) W + (theta - sin(theta)) W^2) v (Modern Robotics Eq. 3.88); warped = R x + p (the
+    homogeneous divide of rigid_body.py:91-93 is by 1).  RESTATEMENT, parity unpinned by the reference: rigid_body.skew only
+    accepts one point, returns constants and severs autograd, so this is what the reference code
+    says, batched, not what it runs.  Like the reference there is no epsilon: theta == 0 gives NaN here (the CUDA path
+    evaluates the same map through its removable-singularity form and returns x + v there)."""
+    theta = torch.norm(w, dim=-1)
+    wh = w / theta[..., None]
+    vh = v / theta[..., None]
+    W = _skew(wh)
+    th = theta[..., None, None]
+    eye = torch.eye(3, dtype=points.dtype, device=points.device)
+    WW = W @ W
+    R = eye + torch.sin(th) * W + (1.0 - torch.cos(th)) * WW
+    G = th * eye + (1.0 - torch.cos(th)) * W + (th - torch.sin(th)) * WW
+    return (R @ points[..., None])[..., 0] + (G @ vh[..., None])[..., 0]
+
+
+def se3_field(sd, points, q=None, gates=None):
+    """SE3Field.warp, warping.py:212-240: trunk MLP (depth 6, width 128, skip 4, out 128 without activation) on
+    posenc(points, 0, 8) — the metadata embedding is NOT an input (:223-224) —, w_net / v_net (depth 0 => ONE hidden 128 ReLU
+    layer + 3 outputs each, modules.py:95-98), exp map.  Returns (warped xyz, w, v)."""
+    g = gates or {}
+    q = q or _ident
+    feat = q(posenc_scaled(points, 0, 8))
+    trunk = q(mlp(sd, "warp_field.trunk", feat, 6, q=q, gates=g.get('warp')))
+    w = mlp(sd, "warp_field.w_net", trunk, 1, skips=(), q=q, gates=g.get('w_net'))
+    v = mlp(sd, "warp_field.v_net", trunk, 1, skips=(), q=q, gates=g.get('v_net'))
+    return se3_transform(points, w, v), w, v
+
+
 def _ident(x):
     return x
 
@@ -142,7 +193,8 @@ def sample_pdf(bins, weights, origins, directions, z, u):
 def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None, gates=None):
     """map_points + query_template (hypernerf/models.py:545-581, 447-493).  cfg['slice'] in {'bendy_sheet' (default),
     'axis_aligned_plane', 'none'}, cfg['use_warp'] (default True), cfg['cond_alpha'] / cfg['cond_rgb'] (template GLO
-    conditioning, models.py:404-445).  ids: dict of metadata id rows {'time', 'warp'} or a single row used for both.
+    conditioning, models.py:404-445), cfg['warp_field'] in {'translation' (what models.py:234 hard-codes), 'se3' (config 5: the
+    SE3Field the reference defines but never instantiates — restated, see se3_transform)}.  ids: dict of metadata id rows {'time', 'warp'} or a single row used for both.
     Returns (rgb (B,S,3), sigma (B,S), warped_points (B,S,3[+H]), raw alpha)."""
     B, S, _ = points.shape
     q = bf16_ste if cfg.get('emulate_bf16') else _ident
@@ -154,9 +206,12 @@ def query_fields(sd, level, points, viewdirs, ids, cfg, noise=None, gates=None):
     if use_warp:
         embed_b = sd["warp_embed.embed.weight"][ids['time'].reshape(-1)]   # GLOEmbed, modules.py:155-167; key 'time'
         embed = embed_b[:, None, :].expand(B, S, embed_b.shape[-1])        # models.py:627-632
-        # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
-        warp_in = q(torch.cat([posenc_orig(points, 10), embed], -1))
-        warped = points + mlp(sd, "warp_field.mlp", warp_in, 6, q=q, gates=g.get('warp'))
+        if cfg.get('warp_field', 'translation') == 'se3':
+            warped, _, _ = se3_field(sd, points, q=q, gates=g)
+        else:
+            # TranslationField.warp, warping.py:90-96 (n_freq hard-coded 10)
+            warp_in = q(torch.cat([posenc_orig(points, 10), embed], -1))
+            warped = points + mlp(sd, "warp_field.mlp", warp_in, 6, q=q, gates=g.get('warp'))
         if slice_method == 'bendy_sheet':
             # HyperSheetMLP on the UNWARPED points, modules.py:331-337 (n_freq 7), models.py:571-572
             sheet_in = q(torch.cat([posenc_orig(points, 7), embed], -1))
@@ -233,7 +288,8 @@ def forward(sd, origins, directions, ids, draws, cfg, fine_z=None, render_opts=N
 
 def default_cfg(n_fine=64, noise_std=1.0, emulate_bf16=False, **over):
     cfg = dict(near=0., far=1., n_coarse=64, n_fine=n_fine, noise_std=noise_std, xyz_freq=10, hyper_freq=6,
-               view_freq=6, emulate_bf16=emulate_bf16, use_warp=True, slice='bendy_sheet', cond_alpha=False, cond_rgb=False)
+               view_freq=6, emulate_bf16=emulate_bf16, use_warp=True, slice='bendy_sheet', cond_alpha=False, cond_rgb=False,
+               warp_field='translation')
     cfg.update(over)
     return cfg
 
@@ -247,7 +303,8 @@ def cfg_from_kwargs(kw, emulate_bf16=False):
                        view_freq=kw.get('view_fourier_dim', 4), use_warp=kw.get('use_warp', True),
                        slice=kw.get('hyper_slice_method') or 'none',
                        cond_alpha=nerf_embed and kw.get('use_alpha_cond', True),
-                       cond_rgb=nerf_embed and kw.get('use_rgb_cond', False))
+                       cond_rgb=nerf_embed and kw.get('use_rgb_cond', False),
+                       warp_field=kw.get('warp_field_type', 'translation'))
 
 
 def mse_loss(out, target):

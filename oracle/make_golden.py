@@ -169,7 +169,36 @@ def make_ndc_rays():
     print('ndc_rays', [tuple(c['rays'].shape) for c in cases])
 
 
+def make_se3_net():
+    """What of config 5 the reference CAN run: SE3Field's networks.  warping.SE3Field(in_ch=3) is instantiated from the
+    unmodified reference, loaded with synthetic weights, and its own posenc / trunk / w_net / v_net are evaluated on a batch
+    of points (warping.py:212-227); only rigid.exp_se3 (rigid_body.py:59-83, single point, constants, no autograd) is left
+    out.  Pins oracle.se3_field up to the exp map; the exp map itself is checked against torch.linalg.matrix_exp."""
+    from hypernerf_torch_b200 import synthetic
+    ref_loader.load_reference()
+    from hypernerf import warping as ref_warping, model_utils as ref_mu
+    torch.manual_seed(0)
+    field = ref_warping.SE3Field(in_ch=3)
+    shapes = {f"warp_field.{k}": tuple(v.shape) for k, v in field.state_dict().items()}
+    sd = synthetic.make_state_dict(shapes, seed=21, boosted=True)
+    field.load_state_dict({k[len("warp_field."):]: v for k, v in sd.items()})
+    g = torch.Generator().manual_seed(5)
+    points = torch.cat([(torch.rand(4, 64, 2, generator=g) - 0.5) * 3.0, -torch.rand(4, 64, 1, generator=g)], -1)
+    with torch.no_grad():
+        feat = ref_mu.posenc(points, min_deg=field.min_deg, max_deg=field.max_deg, use_identity=field.use_posenc_identity,
+                             alpha=None)
+        trunk = field.trunk(feat)
+        w, v = field.w_net(trunk), field.v_net(trunk)
+    fix = dict(shapes=shapes, weight_seed=21, points=points, feat=feat, trunk=trunk, w=w, v=v,
+               weight_checksum=float(sum(t.double().abs().sum() for t in sd.values())))
+    torch.save(fix, os.path.join(ROOT, "tests", "golden", "se3_net_ref.pt"))
+    print("se3_net_ref", tuple(w.shape), float(w.norm(dim=-1).min()), float(w.norm(dim=-1).max()))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'se3net':
+        make_se3_net()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'configs':
         for name in (sys.argv[2:] or CONFIGS):
             make_config(name)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().hn_abi_version() == 3
+    assert _lib.lib().hn_abi_version() == 4
     # the product ABI carries no test / microbenchmark hooks: those live in libhypernerf_b200_probe.so with their own header
     assert not any(n.startswith(("hn_umma", "hn_epi", "hn_tmem", "hn_debug")) for n in declared)
     for n in ("hn_umma_probe", "hn_epi_rate", "hn_debug_set_timing_buffer"):
@@ -67,7 +67,7 @@ def test_errors_are_reported_not_crashed():
     # shape / null checks happen before any launch, so they are testable without a GPU
     assert L.hn_sample_pdf(None, None, None, 0, None, None, None, 4, 64, 62, 64, None, None, None, None) < 0
     assert L.hn_composite_fwd(None, None, None, None, 4, 1000, 0, 1e-5, 1e7, None, None, None, None, None, None, None) < 0
-    assert L.hn_mlp_fwd(C.byref(_desc()), None, None, None, None, None, 0.0, 4, 64, None, 0, None, None, None, None, None) < 0
+    assert L.hn_mlp_fwd(C.byref(_desc()), None, None, None, None, None, 0.0, 4, 64, None, 0, None, None, None, None, None, None) < 0
     with pytest.raises(_lib.NativeLibraryError):
         _lib.check(-1, "probe")
 

@@ -148,6 +148,71 @@ def test_oracle_filter_sigma_matches_live_reference():
             torch.testing.assert_close(out[lvl][k], ref_out[lvl][k].detach(), rtol=2e-5, atol=2e-6, msg=f"{lvl} {k}")
 
 
+# ------------------------------------------------------------------------------------------------------------------------
+# config 5: SE3Field + axis-aligned slicing.  The reference never instantiates SE3Field and its exp map cannot run batched
+# (SURVEY.md §8(c)): the restatement is pinned in two halves — the networks against the reference's own modules, the exp
+# map against the matrix exponential of the twist — and "parity unpinned by the reference" stays true for the composition.
+# ------------------------------------------------------------------------------------------------------------------------
+def test_se3_networks_match_reference_golden():
+    """posenc(points, 0, 8), trunk, w_net, v_net of the UNMODIFIED warping.SE3Field (oracle/make_golden.py se3net)."""
+    from hypernerf_torch_b200 import synthetic
+    fix = load_golden("se3_net_ref")
+    sd = synthetic.make_state_dict(fix['shapes'], seed=fix['weight_seed'], boosted=True)
+    chk = float(sum(v.double().abs().sum() for v in sd.values()))
+    assert abs(chk - fix['weight_checksum']) <= 1e-6 * abs(chk)
+    assert torch.equal(orc.posenc_scaled(fix['points'], 0, 8), fix['feat'])
+    _, w, v = orc.se3_field(sd, fix['points'])
+    torch.testing.assert_close(w, fix['w'], rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(v, fix['v'], rtol=2e-5, atol=2e-6)
+
+
+def test_se3_transform_is_the_matrix_exponential_of_the_twist():
+    """se3_transform (Rodrigues + Modern Robotics Eq. 3.88, rigid_body.py:55-83 batched) == expm([[skew(w), v], [0, 0]])
+    applied to the homogeneous point, in fp64, for rotation angles from 1e-3 to beyond pi."""
+    g = torch.Generator().manual_seed(3)
+    n = 512
+    axis = torch.nn.functional.normalize(torch.randn(n, 3, generator=g, dtype=torch.float64), dim=-1)
+    theta = torch.logspace(-3, 0.6, n, dtype=torch.float64)           # 1e-3 .. ~4 rad
+    w = axis * theta[:, None]
+    v = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    twist = torch.zeros(n, 4, 4, dtype=torch.float64)
+    twist[:, :3, :3] = orc._skew(w)
+    twist[:, :3, 3] = v
+    T = torch.linalg.matrix_exp(twist)
+    want = (T[:, :3, :3] @ x[..., None])[..., 0] + T[:, :3, 3]
+    got = orc.se3_transform(x, w, v)
+    torch.testing.assert_close(got, want, rtol=1e-9, atol=1e-9)
+    # a rigid map: distances between points are preserved
+    x2 = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    d0 = (x - x2).norm(dim=-1)
+    d1 = (got - orc.se3_transform(x2, w, v)).norm(dim=-1)
+    torch.testing.assert_close(d0, d1, rtol=1e-9, atol=1e-9)
+
+
+def test_se3_config_forward_runs_and_differentiates():
+    """The restated config-5 forward end to end on CPU: shapes of the reference's output dictionary, finite gradients for
+    every SE3 tensor, none for the unused hyper_embed table."""
+    from hypernerf_torch_b200 import synthetic
+    from hypernerf_torch_b200.models import NerfModel
+    kw = dict(n_samples_coarse=64, n_samples_fine=64, noise_std=1.0, use_warp=True, use_nerf_embed=False,
+              hyper_slice_method='axis_aligned_plane', hyper_slice_out_dim=8, view_fourier_dim=6, warp_field_type='se3')
+    model = NerfModel(ref_loader.EMBEDDINGS, **kw)     # parameter containers only: constructs without a GPU
+    sd = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_state_dict(model, seed=1, boosted=True).items()}
+    rays, rgbs = synthetic.train_rays(8, seed=4)
+    g = torch.Generator().manual_seed(0)
+    draws = [torch.rand(8, 64, generator=g), torch.randn(8, 64, 1, generator=g), torch.rand(8, 64, generator=g),
+             torch.randn(8, 128, 1, generator=g)]
+    out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), ref_loader.draws_to_dict(draws), orc.cfg_from_kwargs(kw))
+    assert out['fine']['warped_points'].shape == (8, 128, 11) and out['fine']['rgb'].shape == (8, 3)
+    orc.mse_loss(out, rgbs).backward()
+    for k, v in sd.items():
+        if k.startswith("hyper_embed"):
+            assert v.grad is None
+        else:
+            assert v.grad is not None and torch.isfinite(v.grad).all() and float(v.grad.abs().max()) > 0, k
+
+
 def test_synthetic_rays_are_llff_shaped():
     from hypernerf_torch_b200 import synthetic
     rays, rgbs = synthetic.train_rays(4096, seed=0)
