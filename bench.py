@@ -27,6 +27,12 @@ sys.path.insert(0, ROOT)
 
 GLOBAL_RAYS = 65536
 N_COARSE, N_FINE = 64, 64
+SE3_FLOP_PER_EVAL = 2 * 857728            # SE3Field 144 128 + template (167-wide input) 713 600 MAC
+SE3_TRUNK_FLOP_PER_EVAL = 2 * 713600
+EMB = {'warp': list(range(100)), 'camera': [0], 'appearance': list(range(100)), 'time': list(range(100))}
+SE3_KW = dict(near=0., far=1., n_samples_coarse=128, n_samples_fine=128, noise_std=1.0, use_warp=True, use_nerf_embed=False,
+              use_alpha_cond=False, use_rgb_cond=False, hyper_slice_method='axis_aligned_plane', hyper_slice_out_dim=8,
+              GLO_dim=8, share_GLO=True, xyz_fourier_dim=10, hyper_fourier_dim=6, view_fourier_dim=6, warp_field_type='se3')
 FWD_FLOP_PER_EVAL = 2 * 801536            # 801 536 MAC per sample evaluation (unpadded)
 TRUNK_FLOP_PER_EVAL = 2 * 673664          # the same without TranslationField (100 480) and HyperSheetMLP (27 392)
 EVALS_PER_RAY = N_COARSE + (N_COARSE + N_FINE)
@@ -58,15 +64,32 @@ def _draws(n_rays, n_fine, it, noise=True):
 
 def cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="train"):
     """rays/s of the reference path on the host CPU.  workload: 'train' (cfg2 shape: 64+64, fwd + loss + bwd), 'render'
-    (cfg3: 64+128, no_grad forward), 'static' (cfg4: models/nerf.py x2 + render_rays, 128+128, fwd + bwd)."""
+    (cfg3: 64+128, no_grad forward), 'static' (cfg4: models/nerf.py x2 + render_rays, 128+128, fwd + bwd), 'se3' (cfg5:
+    SE3Field + axis-aligned slicing, 128+128, fwd + loss + bwd — always the restatement: the reference cannot run it)."""
     from hypernerf_torch_b200 import synthetic
     from oracle import hypernerf_oracle as orc
     from oracle import ref_loader, static_oracle
     cores, live = _cpu_setup()
     kind = "reference" if live else "port"
     rays, rgbs = synthetic.train_rays(n_rays, seed=0)
-    n_fine = {"train": N_FINE, "render": 128, "static": 128}[workload]
-    if workload == "static":
+    n_fine = {"train": N_FINE, "render": 128, "static": 128, "se3": 128}[workload]
+    if workload == "se3":
+        from hypernerf_torch_b200.models import NerfModel
+        live, kind = False, "port"
+        shapes = {k: tuple(v.shape) for k, v in NerfModel(EMB, **SE3_KW).state_dict().items()}   # parameter containers only
+        sd = {k: v.clone().requires_grad_(True) for k, v in synthetic.make_state_dict(shapes, seed=0, boosted=False).items()}
+        cfg = orc.cfg_from_kwargs(SE3_KW)
+
+        def step(it):
+            for v in sd.values():
+                v.grad = None
+            g = torch.Generator().manual_seed(it)
+            draws = dict(u_coarse=torch.rand(n_rays, 128, generator=g), noise_coarse=torch.randn(n_rays, 128, 1, generator=g),
+                         u_fine=torch.rand(n_rays, 128, generator=g), noise_fine=torch.randn(n_rays, 256, 1, generator=g))
+            out = orc.forward(sd, rays[:, :3], rays[:, 3:6], rays[:, 8].long(), draws, cfg)
+            orc.mse_loss(out, rgbs).backward()
+        what = "cfg5 SE3 warp + axis-aligned slicing (128+128 samples, fwd+loss+bwd; batched restatement)"
+    elif workload == "static":
         sds = [synthetic.make_state_dict(synthetic.static_state_dict_shapes(), seed=i) for i in range(2)]
         if live:
             ref_loader.load_reference()
@@ -132,6 +155,8 @@ def cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="train"):
         if it >= warmup:
             best = min(best, dt)
     impl = "the unmodified reference imported in place" if live else "oracle port of the reference (a Python reference cannot travel to the GPU box)"
+    if workload == "se3":
+        impl = "batched restatement under oracle/ (the reference defines SE3Field but cannot run it: SURVEY.md §8(c))"
     return {"value": n_rays / best, "unit": "rays/s", "cores": cores, "kind": kind,
             "sample": f"{n_rays} rays of {what}, fp32 torch on {cores} CPU threads, {impl}, best of {repeats}"}
 
@@ -330,7 +355,7 @@ def run_gpu_arm(args):
     except Exception:
         pass
 
-    emb = {'warp': list(range(100)), 'camera': [0], 'appearance': list(range(100)), 'time': list(range(100))}
+    emb = EMB
     model = NerfModel(emb, near=0., far=1., n_samples_coarse=N_COARSE, n_samples_fine=N_FINE, noise_std=1.0,
                       hyper_slice_method='bendy_sheet', hyper_slice_out_dim=2, use_warp=True, use_nerf_embed=False,
                       use_alpha_cond=False, use_rgb_cond=False, GLO_dim=8, share_GLO=True, xyz_fourier_dim=10,
@@ -513,10 +538,55 @@ def run_gpu_arm(args):
                   "workload": "cfg4: static NeRF baseline, 262144-ray batch, perturb=1, noise_std=1, fwd+bwd"}
         del smodels, srays, srgbs
 
+    # ---------------------------------------------------------------------------------------------------------------
+    # secondary workload (BASELINE.json configs[4]): SE3Field warp + axis-aligned slicing (H = G = 8), 131 072-ray batch
+    # sharded over the ranks, 128+128 samples, noise_std=1, forward + loss + backward + Adam, 4 096-ray chunks
+    # ---------------------------------------------------------------------------------------------------------------
+    se3 = None
+    if not args.no_se3:
+        n_se3 = 131072
+        m5 = NerfModel(emb, **SE3_KW)
+        m5.load_state_dict(synthetic.make_state_dict(m5, seed=0, boosted=False))
+        m5 = m5.to(dev)
+        fg5 = hn_train.FlatGrads(m5.parameters())
+        m5.attach_flat_grads(fg5)
+        opt5 = hn_train.FusedAdam(fg5, lr=5e-4, eps=1e-8)
+        lo5, hi5 = hn_train.shard_bounds(n_se3, rank, world)
+        r5, c5 = synthetic.train_rays(n_se3, seed=11)
+        r5_h, c5_h = r5[lo5:hi5].contiguous().pin_memory(), c5[lo5:hi5].contiguous().pin_memory()
+        r5_d, c5_d = r5_h.to(dev), c5_h.to(dev)
+
+        def se3_step(rays_in=None, rgbs_in=None):
+            return hn_train.train_step(m5, r5_d if rays_in is None else rays_in, c5_d if rgbs_in is None else rgbs_in, fg5,
+                                       global_rays=n_se3, chunk=4096, optimizer=opt5)
+
+        def se3_e2e():
+            loss = se3_step(r5_h.to(dev, non_blocking=True), c5_h.to(dev, non_blocking=True))
+            loss_h.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        se3_step()
+        steps5 = max(3, args.se3_steps)
+        secs_5, launches_5, prof_5 = timed_loop(se3_step, steps5, profile=True)
+        se3_e2e()
+        secs_5e, _, _ = timed_loop(se3_e2e, steps5)
+        k5, exec5 = kernel_table(prof_5, secs_5, SE3_FLOP_PER_EVAL, SE3_TRUNK_FLOP_PER_EVAL)
+        se3 = {"value": n_se3 * steps5 / secs_5, "unit": "rays/s", "rays_per_step": n_se3, "samples": "128+128",
+               "ms_per_step": 1e3 * secs_5 / steps5, "steps_timed": steps5,
+               "e2e": {"value": n_se3 * steps5 / secs_5e, "unit": "rays/s",
+                       "h2d_bytes_per_step": int(r5_h.numel() * 4 + c5_h.numel() * 4), "d2h_bytes_per_step": 4},
+               "gpu_launches": launches_5, "roofline": roofline_of(k5, exec5, secs_5, peaks, {}),
+               "workload": "cfg5: SE3Field warp + axis-aligned slicing (hyper point = GLO vector, H = G = 8), 131072-ray batch, "
+                           "128+128 samples, noise_std=1, fwd+loss+bwd+Adam; parity is against the batched restatement "
+                           "(the reference never instantiates SE3Field)"}
+        del m5, fg5, opt5, r5_d, c5_d
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="train")
+            if se3 is not None:
+                se3["cpu_baseline"] = cpu_reference_rate(n_rays=256, repeats=1, warmup=1, workload="se3")
             if render is not None:
                 render["cpu_baseline"] = cpu_reference_rate(n_rays=1024, repeats=2, warmup=1, workload="render")
             if static is not None:
@@ -536,6 +606,7 @@ def run_gpu_arm(args):
             "e2e": {"value": GLOBAL_RAYS * args.steps / secs_e2e, "unit": "rays/s",
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render, "static_nerf": static,
+            "se3_axis": se3,
         }
         emit(line)
     if world > 1:
@@ -571,6 +642,8 @@ def main():
     ap.add_argument("--no-static", action="store_true", help="skip the secondary static-NeRF (cfg4) measurement")
     ap.add_argument("--render-frames", type=int, default=5, help="timed frames of the render leg (>= 5)")
     ap.add_argument("--static-steps", type=int, default=3, help="timed steps of the static-NeRF leg (>= 3)")
+    ap.add_argument("--no-se3", action="store_true", help="skip the secondary SE3 + axis-aligned (cfg5) measurement")
+    ap.add_argument("--se3-steps", type=int, default=3, help="timed steps of the cfg5 leg (>= 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
