@@ -115,6 +115,11 @@ constexpr int kConstBias = HN_CONST_BIAS;
 constexpr int kMaxBiasFloats = 4608;   // >= the forward bias array of any built configuration (hyper model: 4 144 floats)
 constexpr int kConstSlots = 3;         // blobs whose biases are resident at the same time (coarse, fine, one more model)
 __constant__ float c_bias[kConstSlots * kMaxBiasFloats];
+// HN_WS = 1: lock-step schedules issue weight-stationary UMMAs (hn_ptx.cuh: umma_ws_*): one shared-memory read of every
+// weight stage per CTA instead of one per sub-tile.
+#ifndef HN_WS
+#define HN_WS 0
+#endif
 constexpr bool kPingPongFwdTrain = ((HN_PINGPONG & 1) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongBwd = ((HN_PINGPONG & 2) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongFwdInfer = ((HN_PINGPONG & 4) || kPair) && kSubTiles == 2;
@@ -316,8 +321,17 @@ __device__ __forceinline__ void issue_layer(const Program& prog, const Layer& L,
         uint32_t acc = (c > 0) | acc0;
         for (uint32_t j = 0; j < cnt; j += 2) {
           const uint64_t bd = desc64(b_lo);
+#if HN_WS
+          // lock step: the second sub-tile takes the weights from the collector buffer (.ws only exists for N = 64 / 128 / 256)
+          if (Sched<PP>::SUBS == 2 && (n == 64 || n == 128 || n == 256)) {
+            umma_ws_fill_bf16(d0, desc64(a_lo), bd, idesc, acc);
+            umma_ws_lastuse_bf16(d0 + 256, desc64(a_lo + a_sub), bd, idesc, acc);
+          } else
+#endif
+          {
 #pragma unroll
           for (int sub = 0; sub < Sched<PP>::SUBS; ++sub) umma_bf16(d0 + sub * 256, desc64(a_lo + sub * a_sub), bd, idesc, acc);
+          }
           a_lo += 2 * (kChunkBytes >> 4);
           b_lo += 2 * n;
           acc = 1;
