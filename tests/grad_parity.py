@@ -41,7 +41,7 @@ def oracle_grads(sd, rays, rgbs, draws, cfg, mode, z_fine=None, chunk=1024):
                    ((out['fine']['rgb'].float() - rgbs[sl]) ** 2).sum() / (3.0 * B)
         (loss * scale).backward()
         total += float(loss.detach())
-    return {k: v.grad.detach() / scale for k, v in sd.items()}, total
+    return {k: (None if v.grad is None else v.grad.detach() / scale) for k, v in sd.items()}, total
 
 
 def product_grads(model, fg, rays, rgbs, chunk):
@@ -79,7 +79,7 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
 
 
-def compare(model, rays, rgbs, chunk=8192, noise_std=1.0, n_fine=64):
+def compare(model, rays, rgbs, chunk=8192, noise_std=1.0, n_fine=64, cfg=None):
     from hypernerf_torch_b200 import train as hn_train
     fg = hn_train.FlatGrads(model.parameters())
     model.attach_flat_grads(fg)
@@ -88,12 +88,13 @@ def compare(model, rays, rgbs, chunk=8192, noise_std=1.0, n_fine=64):
     finally:
         model.attach_flat_grads(None)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    cfg = orc.default_cfg(n_fine=n_fine, noise_std=noise_std)
+    cfg = orc.default_cfg(n_fine=n_fine, noise_std=noise_std) if cfg is None else cfg
     rows, losses = {}, {'kernel': loss_k}
     g32, losses['f32'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'f32')
     g32_iso, _ = oracle_grads(sd, rays, rgbs, draws, cfg, 'f32', z_fine=z_fine)
     g16, losses['amp16'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'amp16')
     gbf, losses['bf16'] = oracle_grads(sd, rays, rgbs, draws, cfg, 'bf16')
+    g_k = {k: v for k, v in g_k.items() if g32[k] is not None}   # tables no configuration path reaches (hyper_embed)
     for k in g_k:
         rows[k] = dict(norm=float(g32[k].double().norm()), numel=g32[k].numel(), kernel=rel(g_k[k], g32[k]),
                        kernel_iso=rel(g_k[k], g32_iso[k]), amp16=rel(g16[k], g32[k]), bf16=rel(gbf[k], g32[k]),
@@ -107,11 +108,15 @@ def compare(model, rays, rgbs, chunk=8192, noise_std=1.0, n_fine=64):
     return rows, whole, losses
 
 
-def setup(n_rays=8192, adam_steps=0, seed=0, device="cuda"):
+SE3_KW = dict(n_samples_coarse=64, n_samples_fine=64, noise_std=1.0, use_warp=True, use_nerf_embed=False,
+              hyper_slice_method='axis_aligned_plane', hyper_slice_out_dim=8, view_fourier_dim=6, warp_field_type='se3')
+
+
+def setup(n_rays=8192, adam_steps=0, seed=0, device="cuda", kw=None):
     from hypernerf_torch_b200 import synthetic
     from hypernerf_torch_b200 import train as hn_train
     from hypernerf_torch_b200.models import NerfModel
-    model = NerfModel(ref_loader.EMBEDDINGS, **ref_loader.cfg1_kwargs(n_fine=64, noise_std=1.0))
+    model = NerfModel(ref_loader.EMBEDDINGS, **(ref_loader.cfg1_kwargs(n_fine=64, noise_std=1.0) if kw is None else kw))
     model.load_state_dict(synthetic.make_state_dict(model, seed=seed, boosted=False))
     model = model.to(device)
     rays, rgbs = synthetic.train_rays(n_rays, seed=seed + 3, device=device)
@@ -152,13 +157,18 @@ if __name__ == "__main__":
           "`torch.autocast(float16)`, i.e. the precision the reference trains in (train.py:217-218); `bf16-emulating oracle`",
           "rounds where the kernels hold bf16 operands.  `kernel (fine depths shared)` evaluates the oracle's fine level at the",
           "depths the product resampled (stage isolation: removes the effect of coarse-weight differences on `sample_pdf`).", ""]
+    se3 = len(sys.argv) > 2 and sys.argv[2] == "se3"
+    if se3:
+        md[0] = "# Gradient parity at a training-size batch — config 5 (SE3Field warp + axis-aligned slicing)"
+        md.insert(2, "The oracle here is the batched RESTATEMENT of SE3Field (parity unpinned by the reference, DESIGN.md §2a); "
+                     f"`python tests/grad_parity.py {n} se3`.")
     for title, steps in (("reference-init weights", 0), ("after 50 FusedAdam steps (lr 5e-4)", 50)):
-        model, rays, rgbs = setup(n_rays=n, adam_steps=steps)
-        rows, whole, losses = compare(model, rays, rgbs)
+        model, rays, rgbs = setup(n_rays=n, adam_steps=steps, kw=SE3_KW if se3 else None)
+        rows, whole, losses = compare(model, rays, rgbs, cfg=orc.cfg_from_kwargs(SE3_KW) if se3 else None)
         md += table(title, rows, whole, losses) + [""]
         print(title, whole, losses)
         worst = sorted(rows.items(), key=lambda kv: -kv[1]['kernel'])[:8]
         for k, r in worst:
             print(f"  {k:55s} kernel {r['kernel']:.2e} iso {r['kernel_iso']:.2e} amp16 {r['amp16']:.2e} bf16 {r['bf16']:.2e} k_vs_bf16 {r['kernel_vs_bf16']:.2e} |g| {r['norm']:.2e}")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    open(os.path.join(ROOT, "gpurun_out", "grad_parity.md"), "w").write("\n".join(md) + "\n")
+    open(os.path.join(ROOT, "gpurun_out", "grad_parity_se3.md" if se3 else "grad_parity.md"), "w").write("\n".join(md) + "\n")
