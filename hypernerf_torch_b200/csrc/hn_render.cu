@@ -3,6 +3,8 @@
 // global loads are contiguous across the warp and scans are lane-local + one shuffle scan.
 //
 // Reference semantics (cited per kernel): hypernerf/model_utils.py of songrise/HyperNeRF-torch.
+#include <stdint.h>
+#include <stdlib.h>
 #include "hn_api_internal.h"
 
 namespace hn {
@@ -534,6 +536,231 @@ sample_pdf_kernel(const float* __restrict__ zc, const float* __restrict__ bins_i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path of hn_sample_pdf for the shapes the model uses: in-kernel mid-point bins, Nc = 32 CP coarse depths,
+// Nf = 32 FP new samples (CP, FP in {2, 4}).  Same arithmetic contract, different organisation:
+//   * the draws u are sorted FIRST (plain keys on registers); the inverse CDF is monotone, so the samples come out
+//     ascending and every sample still knows its CDF bin k.  (If rounding ever breaks the order by an ulp — checked —
+//     the generic merge below takes over; the multiset of samples is the same either way.)
+//   * the bins are the mid-points of the ascending coarse depths, so a sample of bin k lies between mid(z_k, z_k+1) and
+//     mid(z_k+1, z_k+2): its rank among the coarse depths is k + 1 + [z_k+1 <= s], corrected by a (normally empty)
+//     linear fix-up loop instead of a binary search;
+//   * the coarse depths take the slots the samples left free: a bit mask of the taken slots + popcounts, no second search;
+//   * depths and points leave as 16-byte vectors (a lane owns 4 consecutive samples = 48 contiguous bytes of points).
+// ------------------------------------------------------------------------------------------------
+template <int CP, int FP>
+__global__ void __launch_bounds__(4 * 32)
+sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__ wc, int64_t w_stride,
+                       const float* __restrict__ u_g, const float* __restrict__ o, const float* __restrict__ d, int64_t B,
+                       float* __restrict__ zf, float* __restrict__ pts, int32_t* __restrict__ bin_idx,
+                       int32_t* __restrict__ pos_c, int32_t* __restrict__ pos_n) {
+  constexpr int Nc = 32 * CP, Nf = 32 * FP, nb = Nc - 2, ncdf = nb + 1, S = Nc + Nf, NW = S / 32;
+  __shared__ float sm_all[4][3 * Nc + Nf + S];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + wid;
+  if (ray >= B) return;
+  float* zc = sm_all[wid];          // [Nc] coarse depths (ascending, or sorted below)
+  float* bins = zc + Nc;            // [Nc - 1]
+  float* cdf = bins + Nc;           // [Nc - 1]
+  float* smp = cdf + Nc;            // [Nf]
+  float* merged = smp + Nf;         // [S]
+  const float eps = 1e-5f;
+
+  // coarse depths, mid-point bins
+  bool c_sorted = true;
+#pragma unroll
+  for (int r = 0; r < CP; ++r) zc[r * 32 + lane] = __ldg(zc_g + ray * Nc + r * 32 + lane);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < CP; ++r) {
+    const int i = r * 32 + lane;
+    if (i < ncdf) {
+      bins[i] = __fmul_rn(0.5f, __fadd_rn(zc[i + 1], zc[i]));
+      c_sorted &= zc[i] <= zc[i + 1];
+    }
+  }
+  c_sorted = __all_sync(kFull, c_sorted);
+
+  // pdf and its inclusive prefix: lane owns bins [lane CP, lane CP + CP); sums carried in fp64 (exact)
+  float wl[CP];
+  double part = 0.0;
+#pragma unroll
+  for (int j = 0; j < CP; ++j) {
+    const int i = lane * CP + j;
+    wl[j] = i < nb ? __fadd_rn(__ldg(wc + ray * w_stride + i), eps) : 0.f;
+    part += (double)wl[j];
+  }
+  const float Ssum = (float)warp_sum_d(part);
+  double loc[CP];
+  double run = 0.0;
+#pragma unroll
+  for (int j = 0; j < CP; ++j) {
+    const int i = lane * CP + j;
+    if (i < nb) run += (double)__fdiv_rn(wl[j], Ssum);
+    loc[j] = run;
+  }
+  double inc = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t = __shfl_up_sync(kFull, inc, off);
+    if (lane >= off) inc += t;
+  }
+  const double excl = inc - run;
+  if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+  for (int j = 0; j < CP; ++j) {
+    const int i = lane * CP + j;
+    if (i < nb) cdf[i + 1] = (float)(excl + loc[j]);
+  }
+
+  // draws: sorted unless they arrive ascending (deterministic linspace draws)
+  float uu[FP];
+  bool ordered = true;
+#pragma unroll
+  for (int r = 0; r < FP; ++r) {
+    uu[r] = __ldg(u_g + ray * Nf + r * 32 + lane);
+    smp[r * 32 + lane] = uu[r];
+  }
+  __syncwarp();
+  if (bin_idx != nullptr) {   // (parity tests) bin of every draw in its original order
+#pragma unroll
+    for (int r = 0; r < FP; ++r) {
+      int pos = 0;
+#pragma unroll
+      for (int st = Nc / 2; st > 0; st >>= 1)
+        if (cdf[pos + st - 1] <= uu[r]) pos += st;
+      bin_idx[ray * Nf + r * 32 + lane] = pos;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < FP; ++r) {
+    const int e = r * 32 + lane;
+    if (e > 0) ordered &= smp[e - 1] <= uu[r];
+  }
+  if (!__all_sync(kFull, ordered)) {
+    __syncwarp();
+    bitonic_sort_regs<FP>(smp, lane);
+#pragma unroll
+    for (int r = 0; r < FP; ++r) uu[r] = smp[r * 32 + lane];
+  }
+  __syncwarp();
+
+  // inverse CDF of the sorted draws; sample e = r 32 + lane keeps its bin
+  float sv[FP];
+  int kb[FP];
+#pragma unroll
+  for (int r = 0; r < FP; ++r) {
+    int pos = 0;   // searchsorted(cdf, u, right=True): entries <= u among the Nc - 1
+#pragma unroll
+    for (int st = Nc / 2; st > 0; st >>= 1)
+      if (cdf[pos + st - 1] <= uu[r]) pos += st;
+    const int below = max(pos - 1, 0), above = min(pos, nb);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float g0 = bins[below], g1 = bins[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < eps) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(uu[r], c0), denom);
+    sv[r] = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
+    kb[r] = below;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < FP; ++r) smp[r * 32 + lane] = sv[r];
+  __syncwarp();
+  ordered = true;
+#pragma unroll
+  for (int r = 0; r < FP; ++r) {
+    const int e = r * 32 + lane;
+    if (e > 0) ordered &= smp[e - 1] <= sv[r];
+  }
+  ordered = __all_sync(kFull, ordered);
+
+  if (ordered && c_sorted) {
+    // ranks from the bins: a new sample goes after the coarse depths <= it; mask[t] = slots [32 t, 32 t + 32) taken by
+    // new samples (warp-wide OR reductions, every lane ends up with all words)
+    uint32_t mask[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) mask[t] = 0u;
+#pragma unroll
+    for (int r = 0; r < FP; ++r) {
+      const int e = r * 32 + lane;
+      const float v = sv[r];
+      int c = kb[r] + 1;
+      while (c < Nc && zc[c] <= v) ++c;
+      while (c > 0 && zc[c - 1] > v) --c;
+      const int p = e + c;
+      merged[p] = v;
+      if (pos_n != nullptr) pos_n[ray * Nf + e] = p;
+      // sample e = 32 r + lane lands in [32 r, 32 r + Nc + 32): only those words can receive its bit
+#pragma unroll
+      for (int t = r; t < NW && t <= r + CP; ++t)
+        mask[t] |= __reduce_or_sync(kFull, (p >> 5) == t ? (1u << (p & 31)) : 0u);
+    }
+    // the coarse depths fill the free slots in order
+    int before = 0;
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const uint32_t word = mask[t];
+      if (!((word >> lane) & 1u)) {
+        const int q = t * 32 + lane;
+        const int i = q - (before + __popc(word & ((1u << lane) - 1u)));
+        merged[q] = zc[i];
+        if (pos_c != nullptr) pos_c[ray * Nc + i] = q;
+      }
+      before += __popc(word);
+    }
+  } else {
+    // generic merge (sample_pdf_kernel): sort what is not ascending, ranks by binary search
+    if (!ordered) bitonic_sort_regs<FP>(smp, lane);
+    if (!c_sorted) bitonic_sort_regs<CP>(zc, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < CP; ++r) {
+      const int i = r * 32 + lane;
+      const float v = zc[i];
+      int lo = 0, hi = Nf;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
+      merged[i + lo] = v;
+      if (pos_c != nullptr) pos_c[ray * Nc + i] = i + lo;
+    }
+#pragma unroll
+    for (int r = 0; r < FP; ++r) {
+      const int i = r * 32 + lane;
+      const float v = smp[i];
+      int lo = 0, hi = Nc;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= v) lo = mid + 1; else hi = mid; }
+      merged[i + lo] = v;
+      if (pos_n != nullptr) pos_n[ray * Nf + i] = i + lo;
+    }
+  }
+  __syncwarp();
+
+  // depths and points: a lane owns 4 consecutive samples
+  float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+  if (pts != nullptr) {
+    ox = __ldg(o + ray * 3); oy = __ldg(o + ray * 3 + 1); oz = __ldg(o + ray * 3 + 2);
+    dx = __ldg(d + ray * 3); dy = __ldg(d + ray * 3 + 1); dz = __ldg(d + ray * 3 + 2);
+  }
+  for (int g = lane; g < S / 4; g += 32) {
+    const float4 z4 = *reinterpret_cast<const float4*>(merged + 4 * g);
+    reinterpret_cast<float4*>(zf + ray * S)[g] = z4;
+    if (pts != nullptr) {
+      const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+      float pv[12];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pv[3 * j] = __fadd_rn(ox, __fmul_rn(zz[j], dx));
+        pv[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zz[j], dy));
+        pv[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zz[j], dz));
+      }
+      float4* dst = reinterpret_cast<float4*>(pts + (ray * S + 4 * g) * 3);
+      dst[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      dst[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+      dst[2] = make_float4(pv[8], pv[9], pv[10], pv[11]);
+    }
+  }
+}
+
 template <int C>
 static int launch_comp_fwd(bool exact, dim3 g, cudaStream_t st, const float* sigma, const float* rgb, const float* z,
                            const float* dirs, int64_t B, int S, int flags, float eps, float ld, float* o_rgb,
@@ -576,6 +803,12 @@ extern "C" int hn_sample_coarse(const float* origins, const float* dirs, const f
   return set_cuda_error(cudaGetLastError(), "hn_sample_coarse");
 }
 
+// HN_SAMPLE_PDF_GENERIC=1 in the environment forces the generic kernel (A/B measurements, tests of both paths)
+static bool sample_pdf_fast_enabled() {
+  static const bool on = [] { const char* e = getenv("HN_SAMPLE_PDF_GENERIC"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 static int sample_pdf_impl(const float* z_coarse, const float* bins, const float* weights, int64_t w_stride,
                            const float* u, const float* origins, const float* dirs, int64_t B, int Nc, int nb, int Nf,
                            float* z_fine, float* points, int32_t* bin_idx, int32_t* pos_coarse, int32_t* pos_new,
@@ -586,6 +819,20 @@ static int sample_pdf_impl(const float* z_coarse, const float* bins, const float
   if (!z_coarse || !weights || !u || !z_fine) return set_error(-2, "hn_sample_pdf: null pointer");
   if (points && (!origins || !dirs)) return set_error(-2, "hn_sample_pdf: points need origins and dirs");
   if (B == 0) return 0;
+  // the model's shapes (in-kernel bins, 64 / 128 coarse depths, 64 / 128 new samples) take the fast kernel
+  const bool aligned = (reinterpret_cast<uintptr_t>(z_fine) & 15) == 0 && (!points || (reinterpret_cast<uintptr_t>(points) & 15) == 0);
+  if (bins == nullptr && aligned && (Nc == 64 || Nc == 128) && (Nf == 64 || Nf == 128) && sample_pdf_fast_enabled()) {
+    const unsigned blocks4 = (unsigned)((B + 3) / 4);
+#define HN_PDF_FAST(CP, FP)                                                                                                 \
+    sample_pdf_fast_kernel<CP, FP><<<blocks4, 128, 0, (cudaStream_t)stream>>>(z_coarse, weights, w_stride, u, origins, dirs, B, \
+                                                                              z_fine, points, bin_idx, pos_coarse, pos_new)
+    if (Nc == 64 && Nf == 64) HN_PDF_FAST(2, 2);
+    else if (Nc == 64) HN_PDF_FAST(2, 4);
+    else if (Nf == 64) HN_PDF_FAST(4, 2);
+    else HN_PDF_FAST(4, 4);
+#undef HN_PDF_FAST
+    return set_cuda_error(cudaGetLastError(), "hn_sample_pdf");
+  }
   int n2 = 1, n2c = 1;   // new samples and coarse depths are sorted on their own (padded to powers of two), then merged
   while (n2 < Nf) n2 <<= 1;
   while (n2c < Nc) n2c <<= 1;

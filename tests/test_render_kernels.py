@@ -80,7 +80,8 @@ def test_composite_rgb_only_gradient():
     assert (rgb.grad - r2.grad).abs().max() <= 2e-4 * r2.grad.abs().max() + 1e-7
 
 
-@pytest.mark.parametrize("B,Nc,Nf", [(1, 64, 64), (37, 64, 64), (512, 64, 128), (19, 128, 128), (4, 16, 5), (3, 200, 300)])
+@pytest.mark.parametrize("B,Nc,Nf", [(1, 64, 64), (37, 64, 64), (512, 64, 128), (19, 128, 128), (9, 128, 64), (4, 16, 5),
+                                     (3, 200, 300)])
 def test_sample_pdf_bit_exact(B, Nc, Nf):
     o, d = _rays(B, seed=6)
     g = torch.Generator(device=DEV).manual_seed(Nc + Nf)
@@ -106,6 +107,44 @@ def test_sample_pdf_bit_exact(B, Nc, Nf):
     u2 = torch.rand(B, Nf, device=DEV)
     z_ref2, _, _ = orc.sample_pdf(bins, w[..., 1:-1], o, d, z, u2)
     assert torch.equal(z_g, z_ref2)
+
+
+@pytest.mark.parametrize("B,Nc,Nf", [(37, 64, 64), (130, 64, 128), (9, 128, 64), (19, 128, 128), (5, 96, 40)])
+@pytest.mark.parametrize("case", ["random", "sorted_u", "unsorted_coarse", "ties", "peaked"])
+def test_sample_pdf_rank_tables(B, Nc, Nf, case):
+    """hn_sample_pdf_ranks: where the merge put every coarse depth / the i-th smallest new sample (consumed as they are by
+    hn_mlp_fwd / hn_mlp_fwd_trunk).  Fast kernel (64 / 128 shapes: ranks from the CDF bins + bit mask; its generic-merge
+    branch for non-ascending coarse depths) and generic kernel (96 + 40) against the oracle's merge; the tie rule is the
+    reference's stable torch.sort of cat([z_vals, z_samples]) (model_utils.py:227): coarse depths first."""
+    o, d = _rays(B, seed=3)
+    g = torch.Generator(device=DEV).manual_seed(Nc * 7 + Nf)
+    z, _ = torch.sort(torch.rand(B, Nc, device=DEV, generator=g), -1)
+    w = torch.rand(B, Nc, device=DEV, generator=g)
+    u = torch.rand(B, Nf, device=DEV, generator=g)
+    if case == "sorted_u":
+        u = torch.linspace(0., 1. - torch.finfo(torch.float32).eps, Nf, device=DEV).expand(B, Nf).contiguous()
+    elif case == "unsorted_coarse":
+        z = z[:, torch.randperm(Nc, device=DEV, generator=g)].contiguous()
+    elif case == "ties":
+        w[:, 3:-3] = 0.0          # many new samples collapse onto bin edges; duplicates among the draws
+        u[:, 1::2] = u[:, 0::2][:, :u[:, 1::2].shape[1]]
+    elif case == "peaked":
+        w = w ** 8                # a trained model's distribution: most samples in a handful of bins
+    z_f, pts, inds, (pos_c, pos_n) = mu.sample_pdf_fused(z, w, o, d, Nf, u=u, want_inds=True, want_ranks=True)
+    bins = .5 * (z[..., 1:] + z[..., :-1])
+    z_ref, pts_ref, inds_ref = orc.sample_pdf(bins, w[..., 1:-1], o, d, z, u)
+    assert torch.equal(z_f, z_ref) and torch.equal(pts, pts_ref) and torch.equal(inds.long(), inds_ref)
+    pc, pn = pos_c.long(), pos_n.long()
+    both = torch.cat([pc, pn], -1)
+    assert torch.equal(torch.sort(both, -1).values, torch.arange(Nc + Nf, device=DEV).expand(B, -1)), "not a permutation"
+    zs = torch.sort(z, -1).values
+    assert torch.equal(torch.gather(z_f, 1, pc), zs)                       # coarse depth i sits at pos_c[i]
+    assert (pc[:, 1:] > pc[:, :-1]).all() and (pn[:, 1:] > pn[:, :-1]).all()   # both tables ascending
+    new_sorted = torch.gather(z_f, 1, pn)                                 # the new samples, ascending
+    assert (new_sorted[:, 1:] >= new_sorted[:, :-1]).all()
+    # tie rule: a coarse depth precedes the new samples equal to it  <=>  #(new < coarse_i) == pos_c[i] - i
+    cnt = (new_sorted[:, None, :] < zs[:, :, None]).sum(-1)
+    assert torch.equal(cnt, pc - torch.arange(Nc, device=DEV))
 
 
 @pytest.mark.parametrize("case", ["sorted_u", "unsorted_coarse", "ties"])

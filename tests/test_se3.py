@@ -153,6 +153,28 @@ def test_se3_backward_parameter_gradients(B, S, level, boosted):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("B,S", [(1, 7), (3, 33), (2, 257), (5, 128)])
+def test_se3_forward_ragged_shapes(B, S):
+    """One level through hn_mlp_fwd at sample counts that do not fill a 256-row CTA tile (and one that spills into a second
+    one), inference and training kernels, against the restatement in bf16-emulation mode."""
+    from hypernerf_torch_b200.models import _FusedMlp
+    model, sd, kw = _model(7, True)
+    rays, _ = synthetic.train_rays(B, seed=9, device=DEV)
+    o, d, ids = rays[:, :3].contiguous(), rays[:, 3:6].contiguous(), rays[:, 8].long()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    z, _ = torch.sort(torch.rand(B, S, device=DEV, generator=g), -1)
+    pts = (o[:, None, :] + z[..., None] * d[:, None, :]).contiguous()
+    rgb_r, sigma_r, wp_r, _ = orc.query_fields(sd, 'coarse', pts, d, ids, orc.cfg_from_kwargs(kw, emulate_bf16=True))
+    params = model._canonical_params()
+    for train in (False, True):
+        ps = params if train else [q.detach() for q in params]
+        sigma, rgb, warped = _FusedMlp.apply(model, 0, pts, d, ids, None, 0.0, *ps)
+        assert sigma.shape == (B, S) and rgb.shape == (B, S, 3) and warped.shape == (B, S, 11)
+        assert (rgb.detach() - rgb_r).abs().max().item() < 2e-3
+        assert (warped.detach() - wp_r).abs().max().item() < 2e-3
+        assert H.rel_err(sigma.detach(), sigma_r) < 1e-2
+
+
 # Gradients against fp32 autograd of the restatement at reference-init weights, 512 rays.  What separates a bf16 from an
 # fp32 forward is ReLU gates that flip (profiles/grad_parity.md): at 8 192 rays the translation field's tensors sit at
 # 5-12 % and the template's at 0.5-3 %; at 512 rays that noise is ~4x larger, and the bias of the v head is a sum with
