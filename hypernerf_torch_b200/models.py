@@ -13,6 +13,7 @@ the import.  What runs where:
 Random draws use the same torch generator calls, in the same order and shapes as the reference
 (SURVEY.md App. A.5), and are handed to the kernels as tensors.
 """
+import copy
 import ctypes as C
 import os
 from typing import Any, Dict, Optional
@@ -576,6 +577,42 @@ class NerfModel(PackedWeights, nn.Module):
         return max(self.embeddings_dict[self.hyper_embed_key]) + 1
 
     @property
+    def nerf_embeds(self):
+        return torch.tensor(self.embeddings_dict[self.nerf_embed_key])
+
+    @property
+    def warp_embeds(self):
+        return torch.tensor(self.embeddings_dict[self.warp_embed_key])
+
+    @property
+    def hyper_embeds(self):
+        return torch.tensor(self.embeddings_dict[self.hyper_embed_key])
+
+    @staticmethod
+    def _encode_embed(embed, embed_fn):
+        """models.py:352-374: a (*, 1) id, or (*, 3) = (left id, right id, progression) blended linearly."""
+        if embed.shape[-1] == 3:
+            left, right, progression = torch.split(embed, 1, dim=-1)   # (the reference's split size 3 returns one chunk
+            left = embed_fn(left.type(torch.int32))                    #  and cannot unpack: :368; one column each is meant)
+            right = embed_fn(right.type(torch.int32))
+            return (1.0 - progression) * left + progression * right
+        return embed_fn(embed)
+
+    def encode_hyper_embed(self, metadata):
+        """models.py:376-396."""
+        if self.hyper_slice_method in ('axis_aligned_plane', 'bendy_sheet'):
+            if self.hyper_use_warp_embed:
+                return self._encode_embed(metadata[self.warp_embed_key], self.warp_embed)
+            return self._encode_embed(metadata[self.hyper_embed_key], self.hyper_embed)
+        raise RuntimeError(f'Unknown hyper slice method {self.hyper_slice_method}.')
+
+    def encode_nerf_embed(self, metadata):
+        return self._encode_embed(metadata[self.nerf_embed_key], self.nerf_embed)
+
+    def encode_warp_embed(self, metadata):
+        return self._encode_embed(metadata[self.warp_embed_key], self.warp_embed)
+
+    @property
     def has_hyper(self):
         return self.hyper_slice_method != 'none'
 
@@ -587,15 +624,130 @@ class NerfModel(PackedWeights, nn.Module):
     def has_embeds(self):
         return self.has_hyper_embed or self.use_warp or self.use_nerf_embed
 
+    # ------------------------------------------------------------------------------------------------------
+    # pre-encoded embeddings and the pieces of render_samples (models.py:447-585)
+    # ------------------------------------------------------------------------------------------------------
+    def _embed_view(self, embed):
+        """This model with its GLO table replaced by per-ray embedding vectors: `embed` (B, G), (B, 1, G) or the broadcast
+        (B, S, G) of models.py:627-632 (row 0 of the sample axis is taken: embeddings are per ray).  A shallow copy that
+        shares every parameter; its table slot is `embed` itself, so the kernels read ray b's vector at id b, weights are
+        packed per view, and the gradient of the table slot is the gradient with respect to `embed`."""
+        if self._ids_key is None:
+            raise RuntimeError("this configuration takes no metadata embedding")
+        e = embed[:, 0, :] if embed.dim() == 3 else embed
+        if e.dim() != 2 or e.shape[1] != self.GLO_dim:
+            raise ValueError(f"embedding must be (B, {self.GLO_dim}) or (B, S, {self.GLO_dim}), got {tuple(embed.shape)}")
+        e = e.to(torch.float32).contiguous()
+        view = copy.copy(self)                      # shares _parameters / _modules with self
+        d = self._desc
+        view._desc = _lib.ModelDesc(d.glo_dim, d.hyper_dim, d.xyz_freqs, d.hyper_freqs, d.view_freqs, d.warp_freqs,
+                                    d.sheet_freqs, e.shape[0], d.flags)
+        slots = list(self._slot_params())
+        slots[0 if self.use_warp else 93] = e
+        view._slot_cache = slots
+        view._init_packing()
+        view._flat_grads, view._flat_off_cache, view._grad_off_cache, view._size_cache = None, None, None, {}
+        sizes = _lib.Sizes()
+        check(lib().hn_query(C.byref(view._desc), 0, C.byref(sizes)), "hn_query")
+        view._packed_bytes = sizes.packed_bytes
+        return view
+
+    def _encoded_view(self, metadata):
+        """metadata_encoded=True (models.py:605-625, 420-421): 'encoded_warp' / 'encoded_hyper' / 'encoded_nerf' hold the
+        embedding vectors themselves.  The kernels take ONE vector per ray for the warp field, the hyper sheet / hyper point
+        and the template condition (the reference shares them too: models.py:167-182, 421-423), so the entries this
+        configuration reads must be the same tensor."""
+        keys = []
+        if self.use_warp:
+            keys.append('encoded_warp')
+            if self.has_hyper_embed:
+                keys.append('encoded_hyper')
+        if self.use_nerf_embed:
+            keys.append('encoded_nerf')
+        tensors = [metadata[k] for k in keys]
+        first = tensors[0]
+        for k, t in zip(keys[1:], tensors[1:]):
+            if t is not first and not (t.shape == first.shape and t.data_ptr() == first.data_ptr()):
+                raise NotImplementedError(f"metadata_encoded with '{k}' different from '{keys[0]}' is not built: the fused "
+                                          "kernels share one embedding per ray between warp, slicing and conditioning")
+        return self._embed_view(first)
+
+    def _zero_dirs(self, points):
+        return torch.zeros(points.shape[0], 3, device=points.device, dtype=torch.float32)
+
+    def apply_warp(self, points, warp_embed, extra_params):
+        """models.py:583-585: `warp_embed` holds metadata IDS here (the method embeds them itself); returns
+        {'warped_points': (B, S, 3)}.  Runs the fused level-0 network and keeps the warp stage's output."""
+        if not self.use_warp:
+            raise AttributeError("'NerfModel' object has no attribute 'warp_field'")   # as in the reference
+        params = self._canonical_params() if torch.is_grad_enabled() else [q.detach() for q in self._canonical_params()]
+        _, _, warped = _FusedMlp.apply(self, 0, points, self._zero_dirs(points), warp_embed, None, 0.0, *params)
+        return {'warped_points': warped[..., :3]}
+
+    def map_points(self, points, warp_embed, hyper_embed, extra_params, use_warp=True, return_warp_jacobian=False,
+                   hyper_point_override=None):
+        """models.py:545-581: embedding VECTORS in ((B, S, G) broadcasts of per-ray rows), (warped points (B, S, 3 + H),
+        None) out.  One launch of the fused network on a view whose table is the given vectors."""
+        if not (self.use_warp and use_warp):
+            return points, None
+        if return_warp_jacobian:
+            raise NotImplementedError  # warping.py:121-122
+        if hyper_point_override is not None:
+            raise NotImplementedError('hyper_point_override is not implemented.')
+        if self._forward_error is not None:
+            raise RuntimeError(self._forward_error)
+        if hyper_embed is not None and hyper_embed is not warp_embed and hyper_embed.data_ptr() != warp_embed.data_ptr():
+            raise NotImplementedError("distinct warp / hyper embeddings are not built (one embedding per ray)")
+        view = self._embed_view(warp_embed)
+        ids = torch.arange(points.shape[0], device=points.device, dtype=torch.int64)
+        params = view._canonical_params() if torch.is_grad_enabled() else [q.detach() for q in view._canonical_params()]
+        _, _, warped = _FusedMlp.apply(view, 0, points, self._zero_dirs(points), ids, None, 0.0, *params)
+        return warped, None
+
+    def map_spatial_points(self, points, warp_embed, extra_params, use_warp=True, return_warp_jacobian=False):
+        """models.py:495-512."""
+        if not (self.use_warp and use_warp):
+            return points, None
+        warped, _ = self.map_points(points, warp_embed, None, extra_params, use_warp, return_warp_jacobian)
+        return warped[..., :3], None
+
+    def map_hyper_points(self, points, hyper_embed, extra_params, hyper_point_override=None):
+        """models.py:514-543: the hyper coordinates (B, S, H); None without slicing."""
+        if hyper_point_override is not None:
+            raise NotImplementedError('hyper_point_override is not implemented.')
+        if self.hyper_slice_method not in ('axis_aligned_plane', 'bendy_sheet') or not self.use_warp:
+            return None
+        warped, _ = self.map_points(points, hyper_embed, hyper_embed, extra_params)
+        return warped[..., 3:]
+
+    def query_template(self, level, points, viewdirs, metadata, extra_params, metadata_encoded=False):
+        """models.py:447-493: the template NeRF of one level on (warped) points (B, S, 3 [+ H]) -> (rgb (B, S, 3),
+        sigma (B, S)), with the density noise of model_utils.py:300-317 when the model has one."""
+        if self._forward_error is not None:
+            raise RuntimeError(self._forward_error)
+        B, S = points.shape[0], points.shape[1]
+        owner, ids = self, None
+        if self._ids_key is not None and metadata_encoded:
+            owner = self._encoded_view(metadata)
+            ids = torch.arange(B, device=points.device, dtype=torch.int64)
+        elif self._ids_key is not None:
+            ids = metadata[self._ids_key]
+        noise, noise_std = None, 0.0
+        if (self.noise_std is not None) and self.noise_std > 0.0 and self.use_stratified_sampling:
+            noise = torch.randn((B, S, 1), device=points.device, dtype=torch.float32)
+            noise_std = float(self.noise_std)
+        params = owner._canonical_params() if torch.is_grad_enabled() else [q.detach() for q in owner._canonical_params()]
+        with owner.packed_frozen():
+            sigma, rgb = _FusedTrunk.apply(owner, 1 if level == 'fine' else 0, points, viewdirs, ids, noise, noise_std, *params)
+        return rgb, sigma
+
     def render_samples(self, level, points, z_vals, directions, viewdirs, metadata, extra_params, use_warp=True,
                        metadata_encoded=False, return_warp_jacobian=False, use_sample_at_infinity=False,
-                       render_opts=None, _inherited=None):
+                       render_opts=None, _inherited=None, _view=None):
         """models.py:587-671.  _inherited = (warped points of the inherited depths (B,Ni,3+H), their positions (B,Ni) and
         the positions (B,S-Ni) of the remaining depths in the sorted row): see `reuse_coarse_warp`."""
         if self._forward_error is not None:
             raise RuntimeError(self._forward_error)
-        if metadata_encoded:
-            raise NotImplementedError("metadata_encoded=True is not built (callers pass ids; train.py:102, eval.py:86)")
         if return_warp_jacobian:
             raise NotImplementedError  # warping.py:121-122
         if self.use_warp and not use_warp:
@@ -605,14 +757,20 @@ class NerfModel(PackedWeights, nn.Module):
         if metadata.get('hyper_point') is not None:
             raise NotImplementedError('hyper_point_override is not implemented.')  # models.py:528-529
         out = {'points': points}
-        ids = metadata[self._ids_key] if self._ids_key is not None else None
         B, S = points.shape[0], points.shape[1]
+        owner, ids = self, None
+        if self._ids_key is not None and metadata_encoded:
+            # pre-encoded metadata (models.py:605-625, 420-421): the kernels read ray b's embedding from row b of a table
+            owner = _view if _view is not None else self._encoded_view(metadata)
+            ids = torch.arange(B, device=points.device, dtype=torch.int64)
+        elif self._ids_key is not None:
+            ids = metadata[self._ids_key]
         noise, noise_std = None, 0.0
         if (self.noise_std is not None) and self.noise_std > 0.0 and self.use_stratified_sampling:
             # noise_regularize (model_utils.py:300-317): same draw, same shape, applied inside the kernel
             noise = torch.randn((B, S, 1), device=points.device, dtype=torch.float32)
             noise_std = float(self.noise_std)
-        params = self._canonical_params()
+        params = owner._canonical_params()
         if not torch.is_grad_enabled():
             # autograd.Function reports needs_input_grad for parameters even under no_grad; detached parameters make
             # the eval path (eval.py:77 @torch.no_grad) take the inference kernel, which writes no activation stash
@@ -620,13 +778,13 @@ class NerfModel(PackedWeights, nn.Module):
         lvl = 1 if level == 'fine' else 0
         if not self.use_warp:
             # map_points returns the raw points (models.py:568-569): the template alone
-            sigma, rgb = _FusedTrunk.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
+            sigma, rgb = _FusedTrunk.apply(owner, lvl, points, viewdirs, ids, noise, noise_std, *params)
             warped_points = points
         elif _inherited is None:
-            sigma, rgb, warped_points = _FusedMlp.apply(self, lvl, points, viewdirs, ids, noise, noise_std, *params)
+            sigma, rgb, warped_points = _FusedMlp.apply(owner, lvl, points, viewdirs, ids, noise, noise_std, *params)
         else:
             known_warped, pos_known, pos_new = _inherited
-            sigma, rgb, warped_points = _FusedFineLevel.apply(self, lvl, points, viewdirs, ids, noise, noise_std, known_warped,
+            sigma, rgb, warped_points = _FusedFineLevel.apply(owner, lvl, points, viewdirs, ids, noise, noise_std, known_warped,
                                                               pos_known, pos_new, *params)
         sigma = filter_sigma(points, sigma, render_opts)
         out['warped_points'] = warped_points
@@ -665,12 +823,13 @@ class NerfModel(PackedWeights, nn.Module):
         if use_sample_at_infinity is None:
             use_sample_at_infinity = self.use_sample_at_infinity
 
+        view = self._encoded_view(metadata) if (metadata_encoded and self._ids_key is not None) else None
         z_vals, points = model_utils.sample_along_rays(origins, directions, self.num_coarse_samples, near, far,
                                                        self.use_stratified_sampling, self.use_linear_disparity)
         coarse_ret = self.render_samples('coarse', points, z_vals, directions, viewdirs, metadata, extra_params,
                                          use_warp=use_warp, metadata_encoded=metadata_encoded,
                                          return_warp_jacobian=return_warp_jacobian,
-                                         use_sample_at_infinity=self.use_sample_at_infinity)
+                                         use_sample_at_infinity=self.use_sample_at_infinity, _view=view)
         out = {'coarse': coarse_ret}
         if self.num_fine_samples > 0:
             inherited = None
@@ -689,5 +848,5 @@ class NerfModel(PackedWeights, nn.Module):
                                               use_warp=use_warp, metadata_encoded=metadata_encoded,
                                               return_warp_jacobian=return_warp_jacobian,
                                               use_sample_at_infinity=use_sample_at_infinity, render_opts=render_opts,
-                                              _inherited=inherited)
+                                              _inherited=inherited, _view=view)
         return out

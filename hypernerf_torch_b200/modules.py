@@ -42,14 +42,21 @@ class MLP(_FusedOnly):
         output_init(self.logit_layer.weight)
 
 
-class GLOEmbed(_FusedOnly):
-    """modules.py:131-167."""
+class GLOEmbed(nn.Module):
+    """modules.py:131-167.  Inside NerfModel.forward the lookup happens in the fused kernels (ids in, table in the packed
+    blob); the module's own forward — a row gather, used by the reference's encode_*_embed helpers (models.py:352-402) —
+    is the plain table lookup."""
 
     def __init__(self, num_embeddings, embedding_dim):
         super().__init__()
         self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
         self.embed = nn.Embedding(num_embeddings, embedding_dim)
         nn.init.normal_(self.embed.weight, std=0.1 / embedding_dim)
+
+    def forward(self, inputs):
+        if inputs.shape[-1] == 1:     # modules.py:164-165
+            inputs = torch.squeeze(inputs, dim=-1)
+        return self.embed(inputs)
 
 
 class NerfMLP(_FusedOnly):
