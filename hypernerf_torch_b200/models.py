@@ -13,7 +13,6 @@ the import.  What runs where:
 Random draws use the same torch generator calls, in the same order and shapes as the reference
 (SURVEY.md App. A.5), and are handed to the kernels as tensors.
 """
-import copy
 import ctypes as C
 import os
 from typing import Any, Dict, Optional
@@ -405,6 +404,7 @@ class NerfModel(PackedWeights, nn.Module):
         self.warp_field_cls = modules.SE3Field if warp_field_type == 'se3' else modules.TranslationField
         if self.use_warp:
             self.warp_field = modules.SE3Field(in_ch=3) if self._se3 else modules.TranslationField(in_ch=3, in_ch_embed=GLO_dim)
+        self._bind_sub_modules()
         self.alpha_default = 0.0
         self.nerf_in_ch_pos = modules.posenc_channels(3, self.xyz_freq)
         self.nerf_cond_ch_rgb = modules.posenc_channels(3, self.dir_freq)
@@ -476,6 +476,17 @@ class NerfModel(PackedWeights, nn.Module):
             if n_params != sizes.flat_param_floats:
                 raise _lib.NativeLibraryError(f"parameter layout mismatch: module has {n_params} kernel-visible parameters, "
                                               f"library expects {sizes.flat_param_floats}")
+
+    def _bind_sub_modules(self):
+        """Lets `self.warp_field(...)` / `self.hyper_sheet_mlp(...)` be called on their own (modules._FusedOnly._bind)."""
+        if self.use_warp:
+            self.warp_field._bind(self)
+        if 'hyper_sheet_mlp' in self._modules:
+            self.hyper_sheet_mlp._bind(self)
+
+    def __setstate__(self, state):       # copy.deepcopy / pickle
+        super().__setstate__(state)
+        self._bind_sub_modules()
 
     # ------------------------------------------------------------------------------------------------------
     # native plumbing
@@ -638,7 +649,8 @@ class NerfModel(PackedWeights, nn.Module):
         if e.dim() != 2 or e.shape[1] != self.GLO_dim:
             raise ValueError(f"embedding must be (B, {self.GLO_dim}) or (B, S, {self.GLO_dim}), got {tuple(embed.shape)}")
         e = e.to(torch.float32).contiguous()
-        view = copy.copy(self)                      # shares _parameters / _modules with self
+        view = object.__new__(type(self))           # shallow: shares _parameters / _modules (and the sub-modules'
+        view.__dict__.update(self.__dict__)         # back references, which keep pointing at self)
         d = self._desc
         view._desc = _lib.ModelDesc(d.glo_dim, d.hyper_dim, d.xyz_freqs, d.hyper_freqs, d.view_freqs, d.warp_freqs,
                                     d.sheet_freqs, e.shape[0], d.flags)

@@ -6,6 +6,7 @@ These modules own parameters only.  The arithmetic of the hot path runs in the f
 `NerfModel.forward`; calling a sub-module on its own is not part of the hot path and is not implemented.
 """
 import functools
+import weakref
 
 import torch
 import torch.nn as nn
@@ -21,6 +22,26 @@ class _FusedOnly(nn.Module):
         raise NotImplementedError(
             f"{type(self).__name__} holds parameters for the fused B200 kernels; evaluate it through "
             "NerfModel.forward (hn_mlp_fwd).  There is no stand-alone / CPU path.")
+
+    # The warp field and the hyper sheet of a NerfModel can be called on their own like in the reference: the call is
+    # served by the model's fused network (NerfModel.map_spatial_points / map_hyper_points).  The back reference is weak
+    # and bypasses nn.Module's attribute registration (a registered parent would make the module tree cyclic).
+    def _bind(self, model):
+        object.__setattr__(self, "_owner_ref", weakref.ref(model))
+
+    def __getstate__(self):            # deepcopy / pickle: the back reference is re-made by NerfModel.__setstate__
+        state = self.__dict__.copy()
+        state.pop("_owner_ref", None)
+        return state
+
+    def _owner(self):
+        ref = getattr(self, "_owner_ref", None)
+        model = ref() if ref is not None else None
+        if model is None:
+            raise NotImplementedError(
+                f"a {type(self).__name__} outside a NerfModel cannot be evaluated: the fused B200 kernels run the whole "
+                "per-sample network and need the model it belongs to.  There is no stand-alone / CPU path.")
+        return model
 
 
 class MLP(_FusedOnly):
@@ -85,6 +106,10 @@ class HyperSheetMLP(_FusedOnly):
         self.mlp = MLP(self.in_ch, out_ch, depth=depth, width=width, skips=[4] if skips is None else skips,
                        output_init=functools.partial(nn.init.normal_, std=1e-5))
 
+    def forward(self, pts, embed, alpha=None):
+        """modules.py:331-337: hyper coordinates (B, S, out_ch) for points (B, S, 3) and embedding vectors (B, S, G)."""
+        return self._owner().map_hyper_points(pts, embed, {'hyper_sheet_alpha': alpha})
+
 
 class TranslationField(_FusedOnly):
     """warping.py:28-125: input [posenc_orig(points, 10) | embed], 6x128, skip@4, output uniform(0, 1e-4)."""
@@ -96,6 +121,12 @@ class TranslationField(_FusedOnly):
         self.in_ch = posenc_channels(in_ch, self.n_freq) + in_ch_embed
         self.mlp = MLP(self.in_ch, 3, depth=depth, width=hidden_channels, skips=[4] if skips is None else skips,
                        hidden_init=nn.init.xavier_normal_, output_init=functools.partial(nn.init.uniform_, b=1e-4))
+
+    def forward(self, points, metadata, extra_params, return_jacobian=False):
+        """warping.py:98-125: `metadata` = embedding vectors (B, S, G); returns {'warped_points': (B, S, 3)}."""
+        if return_jacobian:
+            raise NotImplementedError   # warping.py:121-122
+        return {'warped_points': self._owner().map_spatial_points(points, metadata, extra_params)[0]}
 
 
 class SE3Field(_FusedOnly):
@@ -113,3 +144,10 @@ class SE3Field(_FusedOnly):
         head_init = functools.partial(nn.init.uniform_, b=1e-4)
         self.w_net = MLP(128, 3, depth=0, width=128, hidden_init=nn.init.xavier_normal_, output_init=head_init)
         self.v_net = MLP(128, 3, depth=0, width=128, hidden_init=nn.init.xavier_normal_, output_init=head_init)
+
+    def forward(self, points, metadata, extra_params, return_jacobian=False):
+        """warping.py:242-272 (the metadata is not an input of this field, :223-224, but selects the hyper point that the
+        fused network evaluates alongside)."""
+        if return_jacobian:
+            raise NotImplementedError   # warping.py:266-271
+        return {'warped_points': self._owner().map_spatial_points(points, metadata, extra_params)[0]}

@@ -48,6 +48,10 @@ def test_pieces_compose_to_render_samples(kw):
         assert torch.equal(sp, warped[..., :3])
         assert torch.equal(model.map_hyper_points(pts, embed, dict(H.EXTRA)), warped[..., 3:])
         assert torch.equal(model.apply_warp(pts, ids, dict(H.EXTRA))['warped_points'], warped[..., :3])
+        # the sub-modules called on their own, as the reference's map_* methods call them (warping.py:98-125, modules.py:331-337)
+        assert torch.equal(model.warp_field(pts, embed, dict(H.EXTRA))['warped_points'], warped[..., :3])
+        if model.hyper_slice_method == 'bendy_sheet':
+            assert torch.equal(model.hyper_sheet_mlp(pts, embed, alpha=None), warped[..., 3:])
         rgb, sigma = model.query_template('coarse', warped, d, meta, dict(H.EXTRA))
         assert rgb.shape == (B, S, 3) and sigma.shape == (B, S)
         comp = mu.volumetric_rendering(rgb, sigma, z, d, False, sample_at_infinity=True)
@@ -110,3 +114,17 @@ def test_metadata_encoded_equals_ids_path(kw):
         other = dict(enc_dict)
         other['metadata'] = {'encoded_warp': enc, 'encoded_hyper': enc.detach().clone(), 'encoded_nerf': enc}
         model(other, dict(H.EXTRA), metadata_encoded=True)
+
+
+def test_sub_modules_outside_a_model_fail_loudly():
+    from hypernerf_torch_b200 import modules
+    pts = torch.zeros(2, 4, 3, device=DEV)
+    emb = torch.zeros(2, 4, 8, device=DEV)
+    for mod, args in ((modules.TranslationField(), (pts, emb, {})), (modules.HyperSheetMLP(out_ch=2), (pts, emb)),
+                      (modules.SE3Field(), (pts, emb, {})), (modules.NerfMLP(89), (pts,))):
+        with pytest.raises(NotImplementedError):
+            mod.to(DEV)(*args)
+    # a model survives deep copies / device moves with its back references in place (no cyclic module tree)
+    import copy
+    m = copy.deepcopy(_model())
+    assert m.warp_field._owner() is not None and 'warp_field._owner_ref' not in m.state_dict()
