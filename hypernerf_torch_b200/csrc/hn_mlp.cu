@@ -3,7 +3,8 @@
 // positional encodings computed in-kernel.
 //
 //   mlp_fwd_kernel    render_samples -> query_template (models.py:587-650, :447-493): GLO lookup, posenc_orig,
-//                     TranslationField, HyperSheetMLP, NerfMLP, noise_regularize, Softplus / Sigmoid.
+//                     TranslationField (or SE3Field: posenc(0, 8), w / v heads, fp32 exp map), HyperSheetMLP (or the
+//                     axis-aligned hyper point), NerfMLP, noise_regularize, Softplus / Sigmoid.
 //   mlp_dgrad_kernel  the autograd of the above w.r.t. every layer's pre-activation (and the GLO table).
 //   mlp_wgrad_kernel  dW = dY^T X and db = sum dY over all samples, accumulated into the flat gradient.
 //   pack_kernel       fp32 (out,in) nn.Linear weights -> bf16 operand images (forward and transposed).
