@@ -121,6 +121,18 @@ __constant__ float c_bias[kConstSlots * kMaxBiasFloats];
 #ifndef HN_WS
 #define HN_WS 0
 #endif
+// HN_TMA_STASH = 1: the wide layers' stash slabs (activations in the training forward, pre-activation gradients in the data
+// gradient) are not stored by the epilogue threads: the bf16 tile the epilogue writes into ACT for the next layer's UMMAs IS
+// the slab (ACT chunk c, rows [64 h, 64 h + 64) = 1 KB = half tile h's chunk c), so one lane per epilogue warp hands it to the
+// copy engine in 1 KB bulk copies (cp.async.bulk shared -> global, evict-first) once the sub-tile's drain is complete.
+// Timing-only builds that drop the stores altogether bound what this could buy: forward 2.50 -> 2.24 ms, data gradient
+// 2.30 -> 2.00 ms per 1 M samples.  Measured with the copies in place (parity tests green): forward 2.50 -> 2.62 ms, data
+// gradient 2.30 -> 2.28 ms — the cost of the stash is not the epilogue's store instructions but the traffic itself (the copy
+// engine's shared-memory reads compete with the UMMAs' operand reads like the stores' did with the drain).  Off.
+#ifndef HN_TMA_STASH
+#define HN_TMA_STASH 0
+#endif
+constexpr bool kTmaStash = HN_TMA_STASH != 0 && kEpiSplit == 1 && !kPair;
 constexpr bool kPingPongFwdTrain = ((HN_PINGPONG & 1) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongBwd = ((HN_PINGPONG & 2) || kPair) && kSubTiles == 2;
 constexpr bool kPingPongFwdInfer = ((HN_PINGPONG & 4) || kPair) && kSubTiles == 2;
@@ -759,7 +771,7 @@ __device__ __forceinline__ void fwd_store_chunks(const uint32_t* r, const float*
       o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
     }
     *reinterpret_cast<uint4*>(act_row + (chunk0 + q) * kChunkBytes) = o;
-    if (STASH) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], o);
+    if (STASH && !kTmaStash) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], o);
   }
 }
 template <bool RELU, bool STASH, int BM>
@@ -862,7 +874,7 @@ __device__ __forceinline__ void bwd_store32(const uint32_t* r, uint32_t w, uint8
   for (int q = 0; q < 4; ++q) {
     const uint4 v = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     *reinterpret_cast<uint4*>(dst_row + (chunk0 + q) * kChunkBytes) = v;
-    if (save_row != nullptr) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], v);
+    if (save_row != nullptr && !kTmaStash) stash_store(&save_row[(save_chunk + chunk0 + q) * (kHalfChunkBytes / 16)], v);
   }
 }
 // NCOLS: multiple of 32 (<= 256), compile time so that gw[] and both row buffers stay in registers
@@ -913,6 +925,21 @@ __device__ __forceinline__ void bwd_linear_share(int share, uint32_t tlane, uint
   constexpr int N = NCOLS / kEpiSplit;
   const int c0 = share * N;
   bwd_cols<false, N>(tlane + c0, nullptr, dst_row + (c0 >> 3) * kChunkBytes, save_row, save_chunk + (c0 >> 3));
+}
+
+// HN_TMA_STASH: chunks [0, nchunks) of sub-tile `sub`'s ACT tile -> slab `slab_chunk` of its two half tiles.  Called by every
+// epilogue warp of the sub-tile after a barrier that follows the drain; lane 0 of warp quarter q takes chunks q, q + 4, ...
+__device__ __forceinline__ void stash_tile_bulk(const uint8_t* act_sub, uint8_t* stash, size_t half0, int total_chunks, int slab_chunk,
+                                                int nchunks, int quarter, int lane, uint64_t policy) {
+  if (lane == 0) {
+    for (int c = quarter; c < nchunks; c += 4) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        bulk_s2g_hint(stash + ((half0 + h) * (size_t)total_chunks + slab_chunk + c) * kHalfChunkBytes,
+                      act_sub + c * kChunkBytes + h * kHalfChunkBytes, kHalfChunkBytes, policy);
+    }
+    bulk_commit_group();
+  }
 }
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -1026,6 +1053,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
     uint32_t ph_acc = 0;
     long long t_acc = 0, t_pro = 0;
     const long long t_begin = HN_T0();
+    const uint64_t stash_policy = (STASH && kTmaStash) ? l2_policy_evict_first() : 0;   // like st.global.cs: see stash_store
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long t_tile = HN_T0();
       const int64_t g = (int64_t)tile * kCtaRows + sub * kTileRows + row;
@@ -1107,6 +1135,12 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
         tc_fence_after();
+        if constexpr (STASH && kTmaStash) {
+          // the copy engine has had this layer's UMMA phase to read the previous layer's tile out of ACT; nobody overwrites
+          // it before the lanes that issued those copies have seen them complete
+          bulk_wait_read_all();
+          epi_named_barrier<PP>(chain);
+        }
         const long long t_drain = HN_T0();
         if (L.epi == FE_RELU) {
           fwd_cols_share<true, STASH, BM>(share, tlane, bias, cb, act_row, save_row, L.save_chunk, L.n_out,
@@ -1224,6 +1258,16 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           tc_fence_before();
           { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
         }
+        if constexpr (STASH && kTmaStash) {
+          // the tile this layer left in ACT for the next layer's UMMAs is its stash slab: hand it to the copy engine
+          const bool wide = L.epi == FE_RELU || L.epi == FE_BOTT || L.epi == FE_LINEAR || L.epi == FE_RGB0A;
+          if (wide && L.save_chunk != kNone) {
+            if (li + 1 == prog.nlayers) fence_proxy_async_smem();
+            epi_named_barrier<PP>(chain);   // every row of the sub-tile is written (and fenced towards the async proxy)
+            stash_tile_bulk(act + sub * SM::ACT_BYTES, p.saved, (size_t)tile * (2 * kSubTiles) + sub * 2, p.x_total, L.save_chunk,
+                            (L.epi == FE_RGB0A ? kRgbW : (int)L.n_out) >> 3, quarter, lane, stash_policy);
+          }
+        }
 #if HN_ROLE_TIMING
         // per-layer profile of CTA 0 (profiles/role_timing.py): [wait for the accumulator, drain] after the 8 role counters
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1234,6 +1278,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
         (void)t_layer; (void)t_drain;
       }
     }
+    if constexpr (STASH && kTmaStash) bulk_wait_all();   // the slabs are in global memory before the CTA retires
     if (p.dbg && threadIdx.x == 0) {
       const long long tt = HN_T0() - t_begin;
       p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;
@@ -1397,6 +1442,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
     uint32_t ph_acc = 0;
     long long t_acc = 0, t_pro = 0;
     const long long t_begin = HN_T0();
+    const uint64_t stash_policy = kTmaStash ? l2_policy_evict_first() : 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long t_tile = HN_T0();
       const int64_t g = (int64_t)tile * kCtaRows + sub * kTileRows + row;
@@ -1436,13 +1482,27 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
       t_pro += HN_T0() - t_tile;
 
       float gx_skip[C::STATIC ? 1 : C::NWARPED] = {};   // skip-layer part of d(warped point, hyper coordinates)
+      // HN_TMA_STASH: the gradient tile a wide layer leaves in ACT is its dY slab (see stash_tile_bulk)
+      auto stash_tile = [&](const Layer& L, int ncols) {
+        if constexpr (kTmaStash) {
+          epi_named_barrier<PP>(chain);   // every row of the sub-tile is written (and fenced towards the async proxy)
+          stash_tile_bulk(act + sub * SM::ACT_BYTES, p.dsaved, (size_t)tile * (2 * kSubTiles) + sub * 2, p.d_total, L.save_chunk,
+                          ncols >> 3, quarter, lane, stash_policy);
+        }
+      };
       for (int li = 0; li < prog.nlayers; ++li) {
         const Layer& L = prog.layers[li];
+        if constexpr (kTmaStash) {   // the copy engine is done reading ACT before this layer's drain overwrites it
+          bulk_wait_read_all();
+          epi_named_barrier<PP>(chain);
+        }
         if (L.epi == BE_MASK) {
           if (L.n_out == kTrunkW) bwd_masked_share<kTrunkW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           else if (L.n_out == kWsW) bwd_masked_share<kWsW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
           else bwd_masked_share<kRgbW>(share, tlane, gate_row, L.gate_word, act_row, save_row, L.save_chunk, my_acc, ph_acc, t_acc);
-          if (li + 1 < prog.nlayers) { fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); } }
+          fence_proxy_async_smem();
+          if (li + 1 < prog.nlayers) { tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); } }
+          stash_tile(L, L.n_out);
           continue;
         }
         if (!C::STATIC && L.epi == BE_RGB1) {
@@ -1456,6 +1516,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           store_features<16>(f, act_row + (kRgbW / 8) * kChunkBytes, save_row, L.save_chunk + kRgbW / 8);
           }
           fence_proxy_async_smem(); tc_fence_before(); { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
+          stash_tile(L, kRgbW);
           continue;
         }
         { long long t0 = HN_T0(); mbar_wait(my_acc, ph_acc); ph_acc ^= 1; t_acc += HN_T0() - t0; }
@@ -1552,8 +1613,13 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_dgrad_kernel(cons
           tc_fence_before();
           { if (kPair) warp_arrive_leader(leader_ready); else warp_arrive(my_ready); }
         }
+        if (L.epi == BE_LINEAR || L.epi == BE_LINCOND) {
+          if (li + 1 == prog.nlayers) fence_proxy_async_smem();
+          stash_tile(L, L.n_out);
+        }
       }
     }
+    if constexpr (kTmaStash) bulk_wait_all();   // the slabs are in global memory before the CTA retires
     if (p.dbg && threadIdx.x == 0) {
       const long long tt = HN_T0() - t_begin;
       p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = tt - t_acc - t_pro;

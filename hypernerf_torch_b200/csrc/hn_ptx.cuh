@@ -91,6 +91,17 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
+// shared -> global bulk copy (the copy engine reads shared memory; no per-thread store instructions), bulk-group completion
+__device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (the global writes may still be in flight)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed entirely (before the kernel's shared memory goes away)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Tensor-map TMA load of a contiguous run of 128-byte blocks (3-D view [block][8 rows][8 bf16], box = 2^i blocks) into this CTA's shared memory whose completion (complete_tx) is signalled
 // on the LEADER CTA's mbarrier: the cta_group::2 form accepts the barrier of the pair's other CTA (bit 24 of the
 // shared::cluster address selects the CTA; cute/arch/copy_sm100_tma.hpp, SM100_TMA_2SM_LOAD_2D).  The plain
