@@ -131,3 +131,80 @@ def test_backward_parameter_gradients(B, S, level, boosted):
         if e_g > lim:
             bad.append((name, e_g, e_emu, e_f32))
     assert not bad, bad
+
+
+# dY slab map of the cfg-1 shape (hn_mlp_program.h make_slabs), in 8-column chunks
+D_WS, D_WSHEAD, D_T, D_BOTT, D_RGB0A, D_R1, D_RGBHEAD, D_TOTAL = 0, 144, 146, 434, 450, 468, 516, 518
+
+
+@pytest.mark.parametrize("B", [2048, 333])
+def test_weight_gradient_equals_its_own_operands(B):
+    """The weight-gradient kernel against dW = dY^T X and db = sum dY computed by torch FROM THE TWO STASHES IT READ
+    (decoded slabs of the forward's X stash and the data gradient's dY stash).  Both sides multiply the same bf16 values
+    and accumulate in fp32, so they agree to summation order (1e-4) — unless a pipeline stage was consumed stale or
+    overwritten early: the ring of the kernel wraps ~100 times per CTA here (4 job groups at B = 2048, one at 333), the
+    tensor-core reads are released by the UMMA commit and the bias warps' shared-memory reads by their own arrivals on the
+    stage's `empty` barrier — the hand-off compute-sanitizer's racecheck cannot model (profiles/README.md)."""
+    import ctypes as C
+    from hypernerf_torch_b200 import _lib
+    from hypernerf_torch_b200._lib import check, lib, ptr, stream
+    S, level = 64, 0
+    model, sd, pts, d, ids = _setup(B, S, boosted=True, seed=11)
+    n = B * S
+    g = torch.Generator(device=DEV).manual_seed(1)
+    g_sigma = torch.randn(B, S, device=DEV, generator=g)
+    g_rgb = torch.randn(B, S, 3, device=DEV, generator=g)
+    sizes = model._sizes(n)
+    packed = model._packed_weights(level)
+    sigma = torch.empty(B, S, device=DEV); rgb = torch.empty(B, S, 3, device=DEV); warped = torch.empty(B, S, 5, device=DEV)
+    saved = torch.empty(sizes.saved_bytes, device=DEV, dtype=torch.uint8)
+    work = torch.empty(sizes.workspace_bytes, device=DEV, dtype=torch.uint8)
+    offs, total = model._grad_offsets()
+    desc = C.byref(model._desc)
+    check(lib().hn_mlp_fwd(desc, ptr(packed), ptr(pts), ptr(d), ptr(ids), None, 0.0, B, S, None, 0, ptr(sigma), ptr(rgb),
+                           ptr(warped), ptr(saved), None, stream()), "hn_mlp_fwd")
+    flat0 = torch.zeros(total, device=DEV)
+    check(lib().hn_mlp_bwd_data(desc, ptr(packed), ptr(ids), ptr(sigma), ptr(rgb), ptr(warped), ptr(saved), ptr(g_sigma),
+                                ptr(g_rgb), None, B, S, None, 0, level, offs, ptr(flat0), ptr(work), None, None, stream()),
+          "hn_mlp_bwd_data")
+
+    def x_slab(chunk, ncols):
+        return H.decode_slab(saved, n, chunk, ncols)
+
+    def d_slab(chunk, ncols):
+        return H.decode_slab(work, n, chunk, ncols, total_chunks=D_TOTAL)
+
+    names = {k: i for i, (k, _) in enumerate(model.named_parameters())}
+    params = model._canonical_params()
+    slots = model._slots_present()
+    off_of = {id(p): offs[s] for s, p in zip(slots, params)}
+    for rep in range(3):                      # a stale stage would not reproduce
+        flat = torch.zeros(total, device=DEV)
+        check(lib().hn_mlp_bwd_weights(desc, ptr(saved), B, S, level, offs, ptr(flat), ptr(work), stream()), "hn_mlp_bwd_weights")
+        torch.cuda.synchronize()
+
+        def grad_of(name):
+            p = dict(model.named_parameters())[name]
+            o = off_of[id(p)]
+            return flat[o:o + p.numel()].view(p.shape)
+
+        cases = []
+        for l in range(1, 9):                 # trunk layers 1..7 and the logit layer (8); 5 is the skip layer
+            w = f"nerf_mlps_coarse.trunk_mlp.linears.{l}" if l < 8 else "nerf_mlps_coarse.trunk_mlp.logit_layer"
+            x = x_slab(H.X_T + 32 * (l - 1), 256)
+            if l == 5:
+                x = torch.cat([x, x_slab(H.X_IN_T, 96)[:, :89]], 1)
+            cases.append((w, d_slab(D_T + 32 * l, 256), x))
+        cases.append(("nerf_mlps_coarse.bottleneck_mlp", d_slab(D_BOTT, 128), x_slab(H.X_T + 32 * 8, 256)))
+        for l in range(1, 4):
+            cases.append((f"nerf_mlps_coarse.rgb_mlp.linears.{l}", d_slab(D_R1 + 16 * (l - 1), 128), x_slab(H.X_R + 16 * (l - 1), 128)))
+        for l in range(1, 6):                 # warp field layers 1..5 (5 = skip: [hidden | posenc(points) | GLO])
+            x = x_slab(H.X_HWS + 24 * (l - 1), 192)[:, :128]
+            if l == 5:
+                x = torch.cat([x, x_slab(H.X_IN_WS, 96)[:, :71]], 1)
+            cases.append((f"warp_field.mlp.linears.{l}", d_slab(D_WS + 24 * l, 192)[:, :128], x))
+        for name, dy, x in cases:
+            want_w, want_b = dy.t() @ x, dy.sum(0)
+            got_w, got_b = grad_of(name + ".weight"), grad_of(name + ".bias")
+            assert H.rel_err(got_w, want_w) < 1e-4, (rep, name, H.rel_err(got_w, want_w))
+            assert (got_b - want_b).abs().max() <= 1e-4 * want_b.abs().max() + 1e-6, (rep, name)
