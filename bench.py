@@ -462,7 +462,7 @@ def run_gpu_arm(args):
         flo, fhi = hn_train.shard_bounds(n_frame, rank, world)
         frame_d = synthetic.frame_rays(image_id=3, seed=0)[flo:fhi].contiguous().to(dev)
         frames = max(5, args.render_frames)
-        hn_train.render_rays(rmodel, frame_d[:32768], chunk=32768)       # warm-up
+        hn_train.render_rays(rmodel, frame_d, chunk=32768)               # warm-up: one whole frame (allocator, clocks)
         secs_r, launches_r, prof_r = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=32768), frames, profile=True)
         img_h = torch.empty(fhi - flo, 3, dtype=torch.float32).pin_memory()
         poses = [torch.tensor([[1., 0., 0., 0.02 * i], [0., 1., 0., -0.01 * i], [0., 0., 1., 0.0]]) for i in range(frames)]
