@@ -198,6 +198,8 @@ def prepare_ray_dict(rays: torch.Tensor) -> dict:
     if len(rays.shape) > 2:
         rays = rays.view(-1, 8)
     B = rays.shape[0]
+    if B == 0:   # the reference reads rays[0, 6] / rays[0, 7] here (model_utils.py:389-390): same exception for an empty batch
+        raise IndexError("index 0 is out of bounds for dimension 0 with size 0")
     idx = torch.ones((B, 1), dtype=torch.long, device=rays.device)
     if use_meta:
         idx = rays[:, 8].type(torch.long)

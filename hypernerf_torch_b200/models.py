@@ -815,6 +815,8 @@ class NerfModel(PackedWeights, nn.Module):
         """models.py:673-780.  Returns {'coarse': {...}, 'fine': {...}} with the reference's keys."""
         if self._forward_error is not None:
             raise RuntimeError(self._forward_error)
+        if rays_dict['origins'].shape[0] == 0:
+            raise ValueError("NerfModel.forward: empty ray batch (the reference fails on it too: model_utils.py:389, models.py:668)")
         with self.packed_frozen():   # re-packs the bf16 weight blobs unless an enclosing block froze them (_packing.py)
             return self._forward(rays_dict, extra_params, metadata_encoded, use_warp, return_points, return_weights,
                                  return_warp_jacobian, near, far, use_sample_at_infinity, render_opts, deterministic)

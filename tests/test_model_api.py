@@ -60,3 +60,16 @@ def test_embedding_helpers_match_live_reference():
     for prop in ("num_nerf_embeds", "num_warp_embeds", "num_hyper_embeds", "has_hyper", "has_hyper_embed", "has_embeds"):
         assert getattr(ref, prop) == getattr(m, prop), prop
     assert torch.equal(ref.warp_embeds, m.warp_embeds)
+
+
+def test_empty_ray_batch_raises_like_the_reference():
+    from hypernerf_torch_b200 import model_utils as mu
+    with pytest.raises(IndexError):
+        mu.prepare_ray_dict(torch.zeros(0, 9))
+    if ref_loader.reference_available():
+        _, ref_mu = ref_loader.load_reference()
+        with pytest.raises(IndexError):
+            ref_mu.prepare_ray_dict(torch.zeros(0, 9))
+    m = _model()
+    with pytest.raises(ValueError):
+        m({'origins': torch.zeros(0, 3), 'directions': torch.zeros(0, 3), 'metadata': {'time': torch.zeros(0, dtype=torch.long)}}, {})
