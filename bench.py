@@ -462,8 +462,8 @@ def run_gpu_arm(args):
         flo, fhi = hn_train.shard_bounds(n_frame, rank, world)
         frame_d = synthetic.frame_rays(image_id=3, seed=0)[flo:fhi].contiguous().to(dev)
         frames = max(5, args.render_frames)
-        hn_train.render_rays(rmodel, frame_d, chunk=32768)               # warm-up: one whole frame (allocator, clocks)
-        secs_r, launches_r, prof_r = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=32768), frames, profile=True)
+        hn_train.render_rays(rmodel, frame_d, chunk=args.render_chunk)       # warm-up: one whole frame (allocator, clocks)
+        secs_r, launches_r, prof_r = timed_loop(lambda: hn_train.render_rays(rmodel, frame_d, chunk=args.render_chunk), frames, profile=True)
         img_h = torch.empty(fhi - flo, 3, dtype=torch.float32).pin_memory()
         poses = [torch.tensor([[1., 0., 0., 0.02 * i], [0., 1., 0., -0.01 * i], [0., 0., 1., 0.0]]) for i in range(frames)]
         it = iter(range(10 ** 9))
@@ -471,7 +471,7 @@ def run_gpu_arm(args):
         def render_e2e():
             c2w = poses[next(it) % frames]
             rows = ray_utils.frame_rays_ndc(Hh, Ww, synthetic.FOCAL, c2w, image_id=3, device=dev)[flo:fhi]
-            out = hn_train.render_rays(rmodel, rows, chunk=32768, keys=('rgb',))
+            out = hn_train.render_rays(rmodel, rows, chunk=args.render_chunk, keys=('rgb',))
             img_h.copy_(out['rgb'], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -540,7 +540,7 @@ def run_gpu_arm(args):
 
     # ---------------------------------------------------------------------------------------------------------------
     # secondary workload (BASELINE.json configs[4]): SE3Field warp + axis-aligned slicing (H = G = 8), 131 072-ray batch
-    # sharded over the ranks, 128+128 samples, noise_std=1, forward + loss + backward + Adam, 4 096-ray chunks
+    # sharded over the ranks, 128+128 samples, noise_std=1, forward + loss + backward + Adam, chunks of --chunk / 2 rays
     # ---------------------------------------------------------------------------------------------------------------
     se3 = None
     if not args.no_se3:
@@ -558,7 +558,7 @@ def run_gpu_arm(args):
 
         def se3_step(rays_in=None, rgbs_in=None):
             return hn_train.train_step(m5, r5_d if rays_in is None else rays_in, c5_d if rgbs_in is None else rgbs_in, fg5,
-                                       global_rays=n_se3, chunk=4096, optimizer=opt5)
+                                       global_rays=n_se3, chunk=max(1024, args.chunk // 2), optimizer=opt5)
 
         def se3_e2e():
             loss = se3_step(r5_h.to(dev, non_blocking=True), c5_h.to(dev, non_blocking=True))
@@ -636,11 +636,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk", type=int, default=8192, help="rays per forward/backward chunk on one GPU")
+    ap.add_argument("--chunk", type=int, default=32768,
+                    help="rays per forward/backward chunk on one GPU (64+64 samples: 2.1 M samples per launch, ~75 GB of "
+                         "stashes alive per chunk; 8192 costs 2.5 %% of the step in launch tails)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary full-frame render measurement")
     ap.add_argument("--no-static", action="store_true", help="skip the secondary static-NeRF (cfg4) measurement")
     ap.add_argument("--render-frames", type=int, default=5, help="timed frames of the render leg (>= 5)")
+    ap.add_argument("--render-chunk", type=int, default=131072, help="rays per chunk of the render leg")
     ap.add_argument("--static-steps", type=int, default=3, help="timed steps of the static-NeRF leg (>= 3)")
     ap.add_argument("--no-se3", action="store_true", help="skip the secondary SE3 + axis-aligned (cfg5) measurement")
     ap.add_argument("--se3-steps", type=int, default=3, help="timed steps of the cfg5 leg (>= 3)")
