@@ -428,10 +428,24 @@ def run_gpu_arm(args):
     # end to end: host rows in, loss out, every step
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
+    # The end-to-end caller synchronises every step (it reads the loss), so the host's ~45 launches per chunk are exposed
+    # once a step is short (N = 8: 11 ms): the chunk loop is captured in a CUDA graph (train.GraphedTrainStep); the exchange
+    # and the optimizer launch stay eager.  Falls back to the eager step if the capture is refused.
+    gstep, graph_note = None, "eager"
+    if not args.no_graph:
+        try:
+            gstep = hn_train.GraphedTrainStep(model, fg, hi - lo, GLOBAL_RAYS, chunk)
+            gstep(rays_d, rgbs_d, opt)
+            torch.cuda.synchronize()
+            graph_note = f"chunk loop replayed from a CUDA graph ({gstep.launches} captured launches)"
+        except Exception as e:   # noqa: BLE001 - any capture failure: measure eagerly and say so
+            gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+
     def e2e_step():
         r = rays_h.to(dev, non_blocking=True)
         c = rgbs_h.to(dev, non_blocking=True)
-        loss = step(r, c)
+        loss = gstep(r, c, opt) if gstep is not None else step(r, c)
         loss_h.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -604,7 +618,8 @@ def run_gpu_arm(args):
                                           "the shared warp / sheet nets: 874.3 MFLOP per ray instead of the reference's 923.4)",
                        "dp_parity": dp_parity},
             "e2e": {"value": GLOBAL_RAYS * args.steps / secs_e2e, "unit": "rays/s",
-                    "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": int(rays_h.numel() * 4 + rgbs_h.numel() * 4), "d2h_bytes_per_step": 4,
+                    "launch": graph_note},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render, "static_nerf": static,
             "se3_axis": se3,
         }
@@ -646,6 +661,7 @@ def main():
     ap.add_argument("--render-chunk", type=int, default=131072, help="rays per chunk of the render leg")
     ap.add_argument("--static-steps", type=int, default=3, help="timed steps of the static-NeRF leg (>= 3)")
     ap.add_argument("--no-se3", action="store_true", help="skip the secondary SE3 + axis-aligned (cfg5) measurement")
+    ap.add_argument("--no-graph", action="store_true", help="end-to-end path: launch the chunk loop eagerly instead of from a CUDA graph")
     ap.add_argument("--se3-steps", type=int, default=3, help="timed steps of the cfg5 leg (>= 3)")
     args = ap.parse_args()
     if args.impl == "reference":

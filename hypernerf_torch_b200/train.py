@@ -11,7 +11,7 @@ ShardedDDP gradient reduction (train.py:224-229) do, without Lightning.
 import torch
 import torch.distributed as dist
 
-from . import losses, model_utils
+from . import _lib, losses, model_utils
 
 EXTRA_PARAMS = {'nerf_alpha': None, 'warp_alpha': None, 'hyper_alpha': None, 'hyper_sheet_alpha': None}
 
@@ -115,7 +115,8 @@ def shard_bounds(n, rank, world):
     return lo, min(lo + per, n)
 
 
-def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, optimizer=None, return_stats=False):
+def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, optimizer=None, return_stats=False,
+               _exchange=True):
     """One data-parallel training step on this rank's ray rows (B,9) / target colours (B,3).
     Returns the local contribution to the global-mean loss (sum over ranks = the reference's loss); with
     return_stats, training_step's log entries {'train/loss', 'train/psnr'} (train.py:147-163; psnr of the fine level
@@ -137,12 +138,64 @@ def train_step(model, rays, rgbs, flat_grads, global_rays=None, chunk=8192, opti
             total += loss.detach()
             if return_stats:
                 fine_sq = sums[1] if fine_sq is None else fine_sq + sums[1]
-    flat_grads.all_reduce()
+    if _exchange:
+        flat_grads.all_reduce()
     if optimizer is not None:
         optimizer.step()
     if return_stats:
         return {'train/loss': total, 'train/psnr': -10.0 * torch.log10(fine_sq / (3.0 * B))}
     return total
+
+
+class GraphedTrainStep:
+    """`train_step` for a fixed per-rank batch shape with its per-chunk launches (zeroing, weight packing, both levels'
+    forward / loss / backward: ~45 launches per 8 192-ray chunk) captured ONCE in a CUDA graph and replayed, so a step costs
+    the host one graph launch + the gradient exchange + the optimizer launch.  That matters where a step is short (N = 8:
+    11 ms) and the caller synchronises every step (the end-to-end path: rays in, loss out).  The random draws are made by
+    the captured torch.rand / torch.randn calls (graph-safe Philox: every replay advances the generator), the exchange and
+    the optimizer stay outside the graph (NCCL's own stream; Adam's lr / step number are launch arguments).
+
+        step = GraphedTrainStep(model, flat_grads, n_rays, global_rays, chunk)
+        loss = step(rays, rgbs, optimizer)          # first call captures"""
+
+    def __init__(self, model, flat_grads, n_rays, global_rays=None, chunk=8192):
+        dev = flat_grads.flat.device
+        self.model, self.fg = model, flat_grads
+        self.global_rays = n_rays if global_rays is None else global_rays
+        self.chunk = chunk
+        self.rays = torch.zeros(n_rays, 9, device=dev, dtype=torch.float32)
+        self.rgbs = torch.zeros(n_rays, 3, device=dev, dtype=torch.float32)
+        self.graph, self.loss, self.launches = None, None, 0
+
+    def _local(self):
+        return train_step(self.model, self.rays, self.rgbs, self.fg, global_rays=self.global_rays, chunk=self.chunk,
+                          _exchange=False)
+
+    def _capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # warm-up off the capture: allocator pools, plan caches, kernel attributes
+            for _ in range(2):
+                self._local()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = _lib.launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.loss = self._local()
+        self.graph, self.launches = graph, _lib.launches - before
+
+    def __call__(self, rays, rgbs, optimizer=None):
+        self.rays.copy_(rays, non_blocking=True)
+        self.rgbs.copy_(rgbs, non_blocking=True)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        _lib.count(self.launches)
+        self.fg.all_reduce()
+        if optimizer is not None:
+            optimizer.step()
+        return self.loss
 
 
 class _Replay:

@@ -279,3 +279,35 @@ def test_reusing_the_coarse_warp_outputs_changes_nothing(n_fine, noise_std):
     for name, off, n in zip(names, offs, numels):
         x, y = ga[off:off + n], gb[off:off + n]
         assert (x - y).norm() <= 2e-2 * x.norm() + 1e-9, (name, ((x - y).norm() / x.norm()).item())
+
+
+def test_graphed_train_step_matches_eager():
+    """train.GraphedTrainStep (the chunk loop captured in a CUDA graph) against train.train_step on the same weights and
+    rays: same loss and flat gradient up to the different random draws being excluded (noise off, deterministic u)."""
+    from hypernerf_torch_b200 import synthetic
+    from hypernerf_torch_b200 import train as hn_train
+    from hypernerf_torch_b200.models import NerfModel
+    from oracle import ref_loader
+    kw = ref_loader.cfg1_kwargs(n_fine=64, noise_std=None)
+    model = NerfModel(ref_loader.EMBEDDINGS, **kw)
+    model.load_state_dict(synthetic.make_state_dict(model, seed=0, boosted=False))
+    model = model.to(DEV)
+    model.use_stratified_sampling = False        # no draws at all: linspace depths, deterministic resampling (models.py:146)
+    fg = hn_train.FlatGrads(model.parameters())
+    model.attach_flat_grads(fg)
+    rays, rgbs = synthetic.train_rays(4096, seed=3, device=DEV)
+    loss_e = hn_train.train_step(model, rays, rgbs, fg, chunk=2048)
+    flat_e = fg.flat.clone()
+    step = hn_train.GraphedTrainStep(model, fg, 4096, chunk=2048)
+    for _ in range(3):                            # capture, then two replays
+        loss_g = step(rays, rgbs)
+        torch.cuda.synchronize()
+        assert abs(float(loss_g) - float(loss_e)) < 1e-6
+        rel = ((fg.flat - flat_e).norm() / flat_e.norm()).item()
+        assert rel < 1e-4, rel                    # atomics order only
+    assert step.launches > 0
+    # new inputs go through the static buffers
+    rays2, rgbs2 = synthetic.train_rays(4096, seed=4, device=DEV)
+    loss2_g = float(step(rays2, rgbs2))
+    loss2_e = float(hn_train.train_step(model, rays2, rgbs2, fg, chunk=2048))
+    assert abs(loss2_g - loss2_e) < 1e-6
