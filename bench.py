@@ -434,10 +434,12 @@ def run_gpu_arm(args):
     gstep, graph_note = None, "eager"
     if not args.no_graph:
         try:
-            gstep = hn_train.GraphedTrainStep(model, fg, hi - lo, GLOBAL_RAYS, chunk)
+            # (8 192-ray chunks inside the graph: a replay has no launch gaps to amortise, and the graph's private memory
+            # pool — every stash of a chunk stays allocated for the graph's lifetime — is 19 GB instead of 75 GB)
+            gstep = hn_train.GraphedTrainStep(model, fg, hi - lo, GLOBAL_RAYS, min(chunk, 8192))
             gstep(rays_d, rgbs_d, opt)
             torch.cuda.synchronize()
-            graph_note = f"chunk loop replayed from a CUDA graph ({gstep.launches} captured launches)"
+            graph_note = f"chunk loop replayed from a CUDA graph ({gstep.launches} captured launches, {min(chunk, 8192)}-ray chunks)"
         except Exception as e:   # noqa: BLE001 - any capture failure: measure eagerly and say so
             gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__})"
             torch.cuda.synchronize()
@@ -451,6 +453,9 @@ def run_gpu_arm(args):
 
     e2e_step()
     secs_e2e, _, _ = timed_loop(e2e_step, args.steps)
+    use_graph = gstep is not None
+    gstep = None                      # the graph's private pool goes back before the other legs allocate
+    torch.cuda.empty_cache()
     kernels, executed = kernel_table(prof, secs, FWD_FLOP_PER_EVAL, TRUNK_FLOP_PER_EVAL)
     roof = roofline_of(kernels, executed, secs, peaks, traffic_json)
     if roof:
@@ -500,6 +505,7 @@ def run_gpu_arm(args):
                   "gpu_launches": launches_r, "roofline": roofline_of(rk, rexec, secs_r, peaks, traffic_json),
                   "workload": "cfg3: full-frame eval render 1008x756, random-init weights, no_grad"}
         del rmodel, frame_d
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------------------------------------------------------
     # secondary workload (BASELINE.json configs[3]): static NeRF baseline (models/nerf.py x2 + render_rays), 262 144-ray
@@ -551,6 +557,7 @@ def run_gpu_arm(args):
                   "gpu_launches": launches_s, "roofline": roofline_of(sk, sexec, secs_s, peaks, {}),
                   "workload": "cfg4: static NeRF baseline, 262144-ray batch, perturb=1, noise_std=1, fwd+bwd"}
         del smodels, srays, srgbs
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------------------------------------------------------
     # secondary workload (BASELINE.json configs[4]): SE3Field warp + axis-aligned slicing (H = G = 8), 131 072-ray batch
@@ -574,8 +581,19 @@ def run_gpu_arm(args):
             return hn_train.train_step(m5, r5_d if rays_in is None else rays_in, c5_d if rgbs_in is None else rgbs_in, fg5,
                                        global_rays=n_se3, chunk=max(1024, args.chunk // 2), optimizer=opt5)
 
+        g5 = None
+        if use_graph:
+            try:
+                g5 = hn_train.GraphedTrainStep(m5, fg5, hi5 - lo5, n_se3, min(max(1024, args.chunk // 2), 4096))
+                g5(r5_d, c5_d, opt5)
+                torch.cuda.synchronize()
+            except Exception:   # noqa: BLE001
+                g5 = None
+                torch.cuda.synchronize()
+
         def se3_e2e():
-            loss = se3_step(r5_h.to(dev, non_blocking=True), c5_h.to(dev, non_blocking=True))
+            r, c = r5_h.to(dev, non_blocking=True), c5_h.to(dev, non_blocking=True)
+            loss = g5(r, c, opt5) if g5 is not None else se3_step(r, c)
             loss_h.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -593,8 +611,11 @@ def run_gpu_arm(args):
                "workload": "cfg5: SE3Field warp + axis-aligned slicing (hyper point = GLO vector, H = G = 8), 131072-ray batch, "
                            "128+128 samples, noise_std=1, fwd+loss+bwd+Adam; parity is against the batched restatement "
                            "(the reference never instantiates SE3Field)"}
-        del m5, fg5, opt5, r5_d, c5_d
+        se3["e2e"]["launch"] = "CUDA graph" if g5 is not None else "eager"
+        del m5, fg5, opt5, r5_d, c5_d, g5
+        torch.cuda.empty_cache()
 
+    print(f"[bench] rank {rank}: peak device memory reserved {torch.cuda.max_memory_reserved() / 2**30:.1f} GiB", file=sys.stderr)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -651,9 +672,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk", type=int, default=32768,
-                    help="rays per forward/backward chunk on one GPU (64+64 samples: 2.1 M samples per launch, ~75 GB of "
-                         "stashes alive per chunk; 8192 costs 2.5 %% of the step in launch tails)")
+    ap.add_argument("--chunk", type=int, default=16384,
+                    help="rays per forward/backward chunk on one GPU (64+64 samples: 1 M samples per launch, ~38 GB of "
+                         "stashes alive per chunk; 8192 costs 1.5 %% of the step in launch gaps, 32768 gains another 1 %% "
+                         "for twice the memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary full-frame render measurement")
     ap.add_argument("--no-static", action="store_true", help="skip the secondary static-NeRF (cfg4) measurement")
