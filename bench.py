@@ -529,10 +529,11 @@ def run_gpu_arm(args):
             for m in smodels:
                 m.zero_grad(set_to_none=True)
             total = torch.zeros((), device=dev)
-            for i in range(0, r_in.shape[0], 32768):
-                out = static_render_rays(smodels, semb, r_in[i:i + 32768], N_samples=128, perturb=1.0, noise_std=1.0,
+            sc = 16384    # rays per chunk: 128 + 256 samples per ray, ~50 GB of stashes alive per chunk
+            for i in range(0, r_in.shape[0], sc):
+                out = static_render_rays(smodels, semb, r_in[i:i + sc], N_samples=128, perturb=1.0, noise_std=1.0,
                                          N_importance=128)
-                tgt = t_in[i:i + 32768]
+                tgt = t_in[i:i + sc]
                 loss = (torch.nn.functional.mse_loss(out['rgb_coarse'], tgt, reduction='sum') +
                         torch.nn.functional.mse_loss(out['rgb_fine'], tgt, reduction='sum')) / (3.0 * n_static)
                 loss.backward()
