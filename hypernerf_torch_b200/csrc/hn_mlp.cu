@@ -1650,13 +1650,15 @@ struct WgSmem {
 };
 // Job groups: CTAs of group g run only the jobs with WgradJob::group == g, over 1/(CTAs per group) of the half tiles
 // each.  Jobs are spread over the groups by their operand bytes per half tile (the kernel is HBM-bound), largest first.
-static int wgrad_groups() {
+// HN_WGRAD_GROUPS overrides; default 8 groups for the ~30-job tables of the hyper model (measured at 0.5 / 1 / 2 M samples per
+// launch: 8 groups beat 4 by 5 / 2.5 / 3 %, 12 and 16 lose to load imbalance) and 4 for the short tables (static NeRF: 12 jobs,
+// 4 groups 502 k against 497 k rays/s with 8).
+static int wgrad_groups(int njobs) {
   static const int g = [] {
     const char* e = getenv("HN_WGRAD_GROUPS");
-    int v = e ? atoi(e) : 4;
-    return std::max(1, std::min(v, 16));
+    return e ? std::max(1, std::min(atoi(e), 16)) : 0;
   }();
-  return g;
+  return g ? g : (njobs >= 24 ? 8 : 4);
 }
 static void assign_wgrad_groups(WgradTable& t, int groups) {
   int order[kMaxJobs];
@@ -2328,7 +2330,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.x_total = plan.info.x_total; wp.d_total = plan.info.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
     int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
-    wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? wgrad_groups() : 1;
+    wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? wgrad_groups(wp.tab.njobs) : 1;
     assign_wgrad_groups(wp.tab, wp.groups);
     mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
     if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch")) return rc;

@@ -1,5 +1,5 @@
 """Per-kernel CUDA-event times of one 8 192-ray chunk (fine level: 1 M samples): forward in inference and training
-mode, data gradient, weight gradient."""
+mode, data gradient, weight gradient.  python profiles/kernel_times.py [samples per ray]"""
 import os
 import sys
 
@@ -17,7 +17,7 @@ model = NerfModel(emb, near=0., far=1., n_samples_coarse=64, n_samples_fine=64, 
                   hyper_fourier_dim=6, view_fourier_dim=6)
 model.load_state_dict(synthetic.make_state_dict(model, seed=0))
 model = model.to(dev)
-B, S = 8192, 128
+B, S = 8192, int(sys.argv[1]) if len(sys.argv) > 1 else 128     # samples per ray: 128 = 1 M samples per launch
 rays, _ = synthetic.train_rays(B, seed=0, device=dev)
 o, d, ids = rays[:, :3].contiguous(), rays[:, 3:6].contiguous(), rays[:, 8].long()
 z, _ = torch.sort(torch.rand(B, S, device=dev), -1)
