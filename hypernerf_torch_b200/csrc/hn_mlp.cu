@@ -32,9 +32,6 @@
 namespace hn {
 
 // out-of-range metadata id inside the fused kernels (HN_TRAP_IDS): see hn_check_ids
-#ifndef HN_DBG_OLD_BOTT
-#define HN_DBG_OLD_BOTT 0
-#endif
 #ifndef HN_TRAP_IDS
 #define HN_TRAP_IDS 1
 #endif
@@ -1213,7 +1210,7 @@ __global__ void __launch_bounds__(kMlpThreads, kCtasPerSm) mlp_fwd_kernel(const 
           float f[C::KV], dir[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) dir[i] = __ldg(p.viewdirs + ray * 3 + i);
-          if constexpr (C::STATIC || HN_DBG_OLD_BOTT) {
+          if constexpr (C::STATIC) {
             posenc<3, C::VF>(dir, f);
             finish_features<C, C::KV, C::PE_V>(f);
           } else {
