@@ -156,20 +156,21 @@ class GraphedTrainStep:
     the optimizer stay outside the graph (NCCL's own stream; Adam's lr / step number are launch arguments).
 
         step = GraphedTrainStep(model, flat_grads, n_rays, global_rays, chunk)
-        loss = step(rays, rgbs, optimizer)          # first call captures"""
+        loss = step(rays, rgbs, optimizer)          # first call captures; the result lives in a static buffer that the
+                                                    # next call overwrites (a dict of such with return_stats=True)"""
 
-    def __init__(self, model, flat_grads, n_rays, global_rays=None, chunk=8192):
+    def __init__(self, model, flat_grads, n_rays, global_rays=None, chunk=8192, return_stats=False):
         dev = flat_grads.flat.device
         self.model, self.fg = model, flat_grads
         self.global_rays = n_rays if global_rays is None else global_rays
-        self.chunk = chunk
+        self.chunk, self.return_stats = chunk, return_stats
         self.rays = torch.zeros(n_rays, 9, device=dev, dtype=torch.float32)
         self.rgbs = torch.zeros(n_rays, 3, device=dev, dtype=torch.float32)
         self.graph, self.loss, self.launches = None, None, 0
 
     def _local(self):
         return train_step(self.model, self.rays, self.rgbs, self.fg, global_rays=self.global_rays, chunk=self.chunk,
-                          _exchange=False)
+                          return_stats=self.return_stats, _exchange=False)
 
     def _capture(self):
         side = torch.cuda.Stream()
@@ -278,14 +279,15 @@ def save_ckpt(model, path, epoch=0, global_step=0, optimizer=None, module_name='
 
 
 def fit(model, rays, rgbs, num_epochs=1, batch_size=1024, lr=5e-4, weight_decay=0.0, decay_step=(20,), decay_gamma=0.1,
-        chunk=8192, seed=0, ckpt_path=None, log_every=0):
+        chunk=8192, seed=0, ckpt_path=None, log_every=0, cuda_graph=False):
     """Minimal stand-in for `Trainer.fit(NeRFSystem)` (train.py:35-233) on a ray pool that is already on the device:
     per epoch one shuffled pass over (rays (P,9), rgbs (P,3)) in batches of `batch_size` (train_dataloader,
     train.py:133-138: shuffle=True; the last short batch is kept, as DataLoader's drop_last=False does), each batch
     = train_step + Adam (get_optimizer, utils/__init__.py:22-41), MultiStepLR(decay_step, decay_gamma) stepped per epoch
     (get_scheduler 'steplr', utils/__init__.py:43-47; opt.py:62-75 defaults).  Under torch.distributed every rank
     passes its own shard of the pool; gradients are all-reduced inside train_step.
-    Returns a list of per-step dicts {'epoch', 'step', 'lr', 'train/loss', 'train/psnr'} (training_step's log)."""
+    cuda_graph: replay the full-size batches from one CUDA graph (GraphedTrainStep); the last short batch of an epoch runs
+    eagerly.  Returns a list of per-step dicts {'epoch', 'step', 'lr', 'train/loss', 'train/psnr'} (training_step's log)."""
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     fg = FlatGrads(model.parameters())
     model.attach_flat_grads(fg)
@@ -302,6 +304,7 @@ def fit(model, rays, rgbs, num_epochs=1, batch_size=1024, lr=5e-4, weight_decay=
         P = int(n.item())
     gen = torch.Generator(device=rays.device).manual_seed(seed)
     step, log = 0, []
+    graphed = None
     for epoch in range(num_epochs):
         opt.param_groups[0]['lr'] = lr * decay_gamma ** sum(1 for m in decay_step if epoch >= m)
         order = torch.randperm(rays.shape[0], device=rays.device, generator=gen)[:P]
@@ -310,8 +313,13 @@ def fit(model, rays, rgbs, num_epochs=1, batch_size=1024, lr=5e-4, weight_decay=
             r, t = rays[idx], rgbs[idx]
             # every rank holds P rows and the same batch boundaries, so the global batch is world * local
             world = dist.get_world_size() if distributed else 1
-            stats = train_step(model, r, t, fg, global_rays=world * r.shape[0], chunk=chunk, optimizer=opt,
-                               return_stats=True)
+            if cuda_graph and r.shape[0] == batch_size:
+                if graphed is None:
+                    graphed = GraphedTrainStep(model, fg, batch_size, world * batch_size, chunk, return_stats=True)
+                stats = {k: v.clone() for k, v in graphed(r, t, opt).items()}
+            else:
+                stats = train_step(model, r, t, fg, global_rays=world * r.shape[0], chunk=chunk, optimizer=opt,
+                                   return_stats=True)
             step += 1
             log.append({'epoch': epoch, 'step': step, 'lr': opt.param_groups[0]['lr'], **stats})
             if log_every and step % log_every == 0:

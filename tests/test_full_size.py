@@ -150,9 +150,11 @@ def test_training_with_fused_adam_tracks_torch_adam():
         assert abs(x - y) <= 2e-3 * abs(y), (a, b)
 
 
-def test_fit_loop_learns_and_checkpoints_like_lightning(tmp_path):
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_fit_loop_learns_and_checkpoints_like_lightning(tmp_path, cuda_graph):
     """train.fit (stand-in for Trainer.fit(NeRFSystem), train.py:35-233): shuffled epochs, Adam + MultiStepLR per epoch,
-    training_step's log entries, and a checkpoint that utils.load_ckpt(model, path, 'nerf') reads back."""
+    training_step's log entries, and a checkpoint that utils.load_ckpt(model, path, 'nerf') reads back; eagerly and with the
+    full-size batches replayed from a CUDA graph."""
     from hypernerf_torch_b200 import utils as hn_utils
     P = 4096
     rays, _ = synthetic.train_rays(P, seed=31, device=DEV)
@@ -160,7 +162,7 @@ def test_fit_loop_learns_and_checkpoints_like_lightning(tmp_path):
     model = _model()
     torch.manual_seed(7)
     log = hn_train.fit(model, rays, rgbs, num_epochs=3, batch_size=1000, lr=5e-4, decay_step=(2,), decay_gamma=0.1,
-                       ckpt_path=str(tmp_path / "epoch={epoch}.ckpt"))
+                       ckpt_path=str(tmp_path / "epoch={epoch}.ckpt"), cuda_graph=cuda_graph)
     assert len(log) == 3 * 5 and log[-1]['step'] == 15                   # 4 full batches + the short one per epoch
     assert [round(e['lr'], 8) for e in log[::5]] == [5e-4, 5e-4, 5e-5]   # MultiStepLR(milestones=[2], gamma=0.1)
     first, last = float(log[0]['train/loss']), float(log[-1]['train/loss'])
