@@ -1653,7 +1653,7 @@ struct WgSmem {
 static int wgrad_groups(int njobs) {
   static const int g = [] {
     const char* e = getenv("HN_WGRAD_GROUPS");
-    return e ? std::max(1, std::min(atoi(e), 16)) : 0;
+    return (e && atoi(e) > 0) ? std::min(atoi(e), 16) : 0;   // unset, empty or 0: the rule below
   }();
   return g ? g : (njobs >= 24 ? 8 : 4);
 }
