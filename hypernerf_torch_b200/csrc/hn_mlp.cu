@@ -2225,7 +2225,7 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   fp.g_total = plan.info.g_total;
   fp.gates = saved ? (uint32_t*)((uint8_t*)saved + (size_t)(2 * kSubTiles) * nt * plan.info.x_total * kHalfChunkBytes) : nullptr;
   fp.dbg = g_dbg;
-  int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
+  int grid = (int)std::min<int64_t>(nt, (int64_t)mlp_grid_cap() * kCtasPerSm);
 #define HN_LAUNCH_FWD(CFG)                                                                                                   \
   do {                                                                                                                       \
     if (saved != nullptr) {                                                                                                  \
@@ -2308,7 +2308,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     bp.x_total = plan.info.x_total; bp.d_total = plan.info.d_total;
     bp.d_rgbhead = plan.info.d_rgbhead; bp.d_sigma = plan.info.d_sigma;
     bp.dbg = g_dbg;
-    int grid = (int)std::min<int64_t>(nt, (int64_t)num_sms() * kCtasPerSm);
+    int grid = (int)std::min<int64_t>(nt, (int64_t)mlp_grid_cap() * kCtasPerSm);
 #define HN_LAUNCH_BWD(CFG)                                                                                                  \
   do {                                                                                                                      \
     if (int rc = set_smem(mlp_dgrad_kernel<CFG>, SmemBwd<CFG>::TOTAL, "hn_mlp_bwd: dgrad smem attr")) return rc;            \
@@ -2326,7 +2326,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.n_half = 2 * kSubTiles * nt;
     wp.x_total = plan.info.x_total; wp.d_total = plan.info.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
-    int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)num_sms());
+    int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)wgrad_grid_cap());
     wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? wgrad_groups(wp.tab.njobs) : 1;
     assign_wgrad_groups(wp.tab, wp.groups);
     mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
