@@ -2327,7 +2327,7 @@ static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int
     wp.x_total = plan.info.x_total; wp.d_total = plan.info.d_total;
     if (int rc = set_smem(mlp_wgrad_kernel, WgSmem::TOTAL, "hn_mlp_bwd: wgrad smem attr")) return rc;
     int wgrid = (int)std::min<int64_t>(wp.n_half, (int64_t)wgrad_grid_cap());
-    wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? wgrad_groups(wp.tab.njobs) : 1;
+    wp.groups = wp.n_half >= 8 * (int64_t)wgrid ? std::min(wgrad_groups(wp.tab.njobs), wgrid) : 1;
     assign_wgrad_groups(wp.tab, wp.groups);
     mlp_wgrad_kernel<<<wgrid, 192, WgSmem::TOTAL, (cudaStream_t)stream>>>(wp);
     if (int rc = set_cuda_error(cudaGetLastError(), "hn_mlp_bwd: wgrad launch")) return rc;
