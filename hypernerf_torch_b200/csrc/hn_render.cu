@@ -653,6 +653,7 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
                        int32_t* __restrict__ pos_c, int32_t* __restrict__ pos_n) {
   constexpr int Nc = 32 * CP, Nf = 32 * FP, nb = Nc - 2, ncdf = nb + 1, S = Nc + Nf, NW = S / 32;
   __shared__ float sm_all[4][3 * Nc + Nf + S];
+  __shared__ int sm_cnt[4][Nf];     // bucket counts / bucket starts of the draw sort
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * 4 + wid;
   if (ray >= B) return;
@@ -735,8 +736,71 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
     if (e > 0) ordered &= smp[e - 1] <= uu[r];
   }
   if (!__all_sync(kFull, ordered)) {
+    // Bucket sort: torch.rand draws are uniform on [0, 1) whatever the weights look like, so bucket floor(u Nf) holds one
+    // draw on average (Poisson): count per bucket (shared-memory atomics hand out arrival numbers), exclusive prefix,
+    // then every draw ranks itself among the few members of its own bucket.  floor(u Nf) is monotone in u, so the
+    // result is the ascending order of the draws (equal draws are interchangeable).  A crowded bucket (> 8 members:
+    // draws that are not uniform) sends the ray through the bitonic network instead.
+    int* cnt = sm_cnt[wid];
+#pragma unroll
+    for (int r = 0; r < FP; ++r) cnt[r * 32 + lane] = 0;
     __syncwarp();
-    bitonic_sort_regs<FP>(smp, lane);
+    int bk[FP], arr[FP];
+#pragma unroll
+    for (int r = 0; r < FP; ++r) {
+      bk[r] = min(max((int)(uu[r] * (float)Nf), 0), Nf - 1);
+      arr[r] = atomicAdd(&cnt[bk[r]], 1);
+    }
+    __syncwarp();
+    int c[FP], tot = 0, cmax = 0;
+#pragma unroll
+    for (int j = 0; j < FP; ++j) {
+      c[j] = cnt[lane * FP + j];
+      tot += c[j];
+      cmax = max(cmax, c[j]);
+    }
+    int inc = tot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, off);
+      if (lane >= off) inc += t;
+    }
+    const int m = __reduce_max_sync(kFull, cmax);   // fullest bucket of the ray (warp-uniform)
+    if (m > 8) {
+      bitonic_sort_regs<FP>(smp, lane);
+    } else {
+      int ex = inc - tot;
+#pragma unroll
+      for (int j = 0; j < FP; ++j) { cnt[lane * FP + j] = ex; ex += c[j]; }   // counts -> bucket starts
+      float* tmp = merged;   // free until the merge; [Nf] draws grouped by bucket + 8 x +inf
+      if (lane < 8) tmp[Nf + lane] = __int_as_float(0x7f800000);
+      __syncwarp();
+      int s0[FP];
+#pragma unroll
+      for (int r = 0; r < FP; ++r) {
+        s0[r] = cnt[bk[r]];
+        tmp[s0[r] + arr[r]] = uu[r];
+      }
+      __syncwarp();
+      // rank inside the bucket: members below the draw, equal members that arrived earlier.  The m entries from the
+      // bucket's start cover the bucket; what follows it belongs to later buckets (strictly larger) or is the padding.
+      int rank[FP];
+#pragma unroll
+      for (int r = 0; r < FP; ++r) rank[r] = s0[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j >= m) break;
+#pragma unroll
+        for (int r = 0; r < FP; ++r) {
+          const float v = tmp[s0[r] + j];
+          rank[r] += (v < uu[r]) ? 1 : 0;
+          rank[r] += (v == uu[r] && j < arr[r]) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < FP; ++r) smp[rank[r]] = uu[r];
+      __syncwarp();
+    }
 #pragma unroll
     for (int r = 0; r < FP; ++r) uu[r] = smp[r * 32 + lane];
   }
@@ -782,9 +846,12 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
     for (int r = 0; r < FP; ++r) {
       const int e = r * 32 + lane;
       const float v = sv[r];
-      int c = kb[r] + 1;
-      while (c < Nc && zc[c] <= v) ++c;
-      while (c > 0 && zc[c - 1] > v) --c;
+      int c = kb[r] + 1;                       // 1 .. Nc - 1
+      if (zc[c] <= v) ++c;
+      if ((c < Nc && zc[min(c, Nc - 1)] <= v) || zc[c - 1] > v) {   // (normally not taken)
+        while (c < Nc && zc[c] <= v) ++c;
+        while (c > 0 && zc[c - 1] > v) --c;
+      }
       const int p = e + c;
       merged[p] = v;
       if (pos_n != nullptr) pos_n[ray * Nf + e] = p;

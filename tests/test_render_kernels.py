@@ -110,7 +110,7 @@ def test_sample_pdf_bit_exact(B, Nc, Nf):
 
 
 @pytest.mark.parametrize("B,Nc,Nf", [(37, 64, 64), (130, 64, 128), (9, 128, 64), (19, 128, 128), (5, 96, 40)])
-@pytest.mark.parametrize("case", ["random", "sorted_u", "unsorted_coarse", "ties", "peaked"])
+@pytest.mark.parametrize("case", ["random", "sorted_u", "unsorted_coarse", "ties", "peaked", "crowded_u", "edge_u"])
 def test_sample_pdf_rank_tables(B, Nc, Nf, case):
     """hn_sample_pdf_ranks: where the merge put every coarse depth / the i-th smallest new sample (consumed as they are by
     hn_mlp_fwd / hn_mlp_fwd_trunk).  Fast kernel (64 / 128 shapes: ranks from the CDF bins + bit mask; its generic-merge
@@ -130,6 +130,14 @@ def test_sample_pdf_rank_tables(B, Nc, Nf, case):
         u[:, 1::2] = u[:, 0::2][:, :u[:, 1::2].shape[1]]
     elif case == "peaked":
         w = w ** 8                # a trained model's distribution: most samples in a handful of bins
+    elif case == "crowded_u":     # draws that are not uniform: the fast kernel's bucket sort hands the ray to its bitonic network
+        u = 0.5 + 0.01 * u
+        u[1::2] = torch.rand(u[1::2].shape, device=DEV, generator=g) ** 6      # skewed: some buckets crowded, some rays not
+    elif case == "edge_u":        # first / last bucket: 0, the largest float below 1, and a few equal draws
+        u[:, 0] = 0.0
+        u[:, 1] = 1.0 - 2.0 ** -24
+        u[:, 2] = u[:, 1]
+        u[:, 3] = 2.0 ** -30
     z_f, pts, inds, (pos_c, pos_n) = mu.sample_pdf_fused(z, w, o, d, Nf, u=u, want_inds=True, want_ranks=True)
     bins = .5 * (z[..., 1:] + z[..., :-1])
     z_ref, pts_ref, inds_ref = orc.sample_pdf(bins, w[..., 1:-1], o, d, z, u)
