@@ -774,6 +774,8 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
       for (int j = 0; j < FP; ++j) { cnt[lane * FP + j] = ex; ex += c[j]; }   // counts -> bucket starts
       float* tmp = merged;   // free until the merge; [Nf] draws grouped by bucket + 8 x +inf
       if (lane < 8) tmp[Nf + lane] = __int_as_float(0x7f800000);
+#pragma unroll
+      for (int r = 0; r < FP; ++r) smp[r * 32 + lane] = __int_as_float(0x7fc00000);   // NaN: "slot not written yet"
       __syncwarp();
       int s0[FP];
 #pragma unroll
@@ -782,8 +784,9 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
         tmp[s0[r] + arr[r]] = uu[r];
       }
       __syncwarp();
-      // rank inside the bucket: members below the draw, equal members that arrived earlier.  The m entries from the
-      // bucket's start cover the bucket; what follows it belongs to later buckets (strictly larger) or is the padding.
+      // rank = bucket start + members below the draw.  The m entries from the bucket's start cover the bucket; what
+      // follows it belongs to later buckets (strictly larger) or is the padding.  Equal draws inside one bucket (1e-4 of
+      // the rays with torch.rand's 24-bit draws) get the same rank and leave a slot unwritten: detected below.
       int rank[FP];
 #pragma unroll
       for (int r = 0; r < FP; ++r) rank[r] = s0[r];
@@ -791,15 +794,21 @@ sample_pdf_fast_kernel(const float* __restrict__ zc_g, const float* __restrict__
       for (int j = 0; j < 8; ++j) {
         if (j >= m) break;
 #pragma unroll
-        for (int r = 0; r < FP; ++r) {
-          const float v = tmp[s0[r] + j];
-          rank[r] += (v < uu[r]) ? 1 : 0;
-          rank[r] += (v == uu[r] && j < arr[r]) ? 1 : 0;
-        }
+        for (int r = 0; r < FP; ++r) rank[r] += (tmp[s0[r] + j] < uu[r]) ? 1 : 0;
       }
 #pragma unroll
       for (int r = 0; r < FP; ++r) smp[rank[r]] = uu[r];
       __syncwarp();
+      bool hole = false;
+#pragma unroll
+      for (int r = 0; r < FP; ++r) { const float v = smp[r * 32 + lane]; hole |= v != v; }
+      if (__any_sync(kFull, hole)) {
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < FP; ++r) smp[r * 32 + lane] = uu[r];
+        __syncwarp();
+        bitonic_sort_regs<FP>(smp, lane);
+      }
     }
 #pragma unroll
     for (int r = 0; r < FP; ++r) uu[r] = smp[r * 32 + lane];
