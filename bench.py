@@ -434,12 +434,14 @@ def run_gpu_arm(args):
     gstep, graph_note = None, "eager"
     if not args.no_graph:
         try:
-            # (8 192-ray chunks inside the graph: a replay has no launch gaps to amortise, and the graph's private memory
-            # pool — every stash of a chunk stays allocated for the graph's lifetime — is 19 GB instead of 75 GB)
-            gstep = hn_train.GraphedTrainStep(model, fg, hi - lo, GLOBAL_RAYS, min(chunk, 8192))
+            # (the graph's private memory pool keeps every stash of a chunk allocated for the graph's lifetime: the eager
+            # leg's pool is released first; 16 384-ray chunks: 0.3 % behind the eager `value` on one box, 8 192: 0.7 %)
+            gchunk = min(chunk, args.graph_chunk)
+            torch.cuda.empty_cache()          # the eager leg's pool goes back before the graph builds its own
+            gstep = hn_train.GraphedTrainStep(model, fg, hi - lo, GLOBAL_RAYS, gchunk)
             gstep(rays_d, rgbs_d, opt)
             torch.cuda.synchronize()
-            graph_note = f"chunk loop replayed from a CUDA graph ({gstep.launches} captured launches, {min(chunk, 8192)}-ray chunks)"
+            graph_note = f"chunk loop replayed from a CUDA graph ({gstep.launches} captured launches, {gchunk}-ray chunks)"
         except Exception as e:   # noqa: BLE001 - any capture failure: measure eagerly and say so
             gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__})"
             torch.cuda.synchronize()
@@ -684,6 +686,7 @@ def main():
     ap.add_argument("--render-chunk", type=int, default=131072, help="rays per chunk of the render leg")
     ap.add_argument("--static-steps", type=int, default=3, help="timed steps of the static-NeRF leg (>= 3)")
     ap.add_argument("--no-se3", action="store_true", help="skip the secondary SE3 + axis-aligned (cfg5) measurement")
+    ap.add_argument("--graph-chunk", type=int, default=16384, help="rays per chunk inside the CUDA graph of the end-to-end path")
     ap.add_argument("--no-graph", action="store_true", help="end-to-end path: launch the chunk loop eagerly instead of from a CUDA graph")
     ap.add_argument("--se3-steps", type=int, default=3, help="timed steps of the cfg5 leg (>= 3)")
     args = ap.parse_args()
