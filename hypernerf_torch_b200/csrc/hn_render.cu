@@ -34,6 +34,42 @@ __global__ void sample_coarse_kernel(const float* __restrict__ o, const float* _
   }
 }
 
+// Nc % 4 == 0 and 16-byte aligned rows: a thread owns 4 consecutive depths of one ray (same arithmetic; one 16-byte load of
+// the draws, one 16-byte store of the depths and three of the 48 contiguous bytes of points instead of 16 scalar accesses)
+__global__ void __launch_bounds__(256) sample_coarse_v4_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                                               const float4* __restrict__ u, const float4* __restrict__ lower,
+                                                               const float4* __restrict__ upper, int64_t n4, int Nc4,
+                                                               float4* __restrict__ z, float4* __restrict__ pts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int64_t b = i / Nc4;
+  const int s = (int)(i - b * Nc4);
+  const float4 lo = __ldg(lower + s);
+  float zz[4] = {lo.x, lo.y, lo.z, lo.w};
+  if (u != nullptr) {
+    const float4 up = __ldg(upper + s), uu = __ldg(u + i);
+    zz[0] = __fadd_rn(lo.x, __fmul_rn(__fsub_rn(up.x, lo.x), uu.x));
+    zz[1] = __fadd_rn(lo.y, __fmul_rn(__fsub_rn(up.y, lo.y), uu.y));
+    zz[2] = __fadd_rn(lo.z, __fmul_rn(__fsub_rn(up.z, lo.z), uu.z));
+    zz[3] = __fadd_rn(lo.w, __fmul_rn(__fsub_rn(up.w, lo.w), uu.w));
+  }
+  z[i] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  if (pts != nullptr) {
+    const float ox = __ldg(o + b * 3), oy = __ldg(o + b * 3 + 1), oz = __ldg(o + b * 3 + 2);
+    const float dx = __ldg(d + b * 3), dy = __ldg(d + b * 3 + 1), dz = __ldg(d + b * 3 + 2);
+    float pv[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pv[3 * j] = __fadd_rn(ox, __fmul_rn(zz[j], dx));
+      pv[3 * j + 1] = __fadd_rn(oy, __fmul_rn(zz[j], dy));
+      pv[3 * j + 2] = __fadd_rn(oz, __fmul_rn(zz[j], dz));
+    }
+    pts[i * 3] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    pts[i * 3 + 1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+    pts[i * 3 + 2] = make_float4(pv[8], pv[9], pv[10], pv[11]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // warp scans
 // ------------------------------------------------------------------------------------------------
@@ -970,6 +1006,14 @@ extern "C" int hn_sample_coarse(const float* origins, const float* dirs, const f
   if (B == 0) return 0;
   int64_t n = B * Nc;
   int threads = 256;
+  auto aligned16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (Nc % 4 == 0 && aligned16(u) && aligned16(lower) && aligned16(upper) && aligned16(z) && aligned16(points)) {
+    const int64_t n4 = n / 4;
+    sample_coarse_v4_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        origins, dirs, reinterpret_cast<const float4*>(u), reinterpret_cast<const float4*>(lower),
+        reinterpret_cast<const float4*>(upper), n4, Nc / 4, reinterpret_cast<float4*>(z), reinterpret_cast<float4*>(points));
+    return set_cuda_error(cudaGetLastError(), "hn_sample_coarse");
+  }
   int64_t blocks = (n + threads - 1) / threads;
   sample_coarse_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(origins, dirs, u, lower, upper, n, Nc,
                                                                               z, points);
