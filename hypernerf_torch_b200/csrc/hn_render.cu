@@ -466,6 +466,97 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
   }
 }
 
+// S == 64: two rays per warp (16 lanes x 4 consecutive samples), like composite_fwd_s64_kernel; 16-byte loads / stores.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_s64_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ z,
+                         const float* __restrict__ dirs, int64_t B, int flags, float eps, float last_delta,
+                         const float* __restrict__ g_out_rgb, const float* __restrict__ g_depth,
+                         const float* __restrict__ g_acc, const float* __restrict__ g_weights,
+                         float* __restrict__ g_sigma, float* __restrict__ g_rgb) {
+  constexpr int C = 4, S = 64, W = 16;
+  const int lane = threadIdx.x & 31, sub = lane & (W - 1), half = lane >> 4;
+  const int64_t ray_w = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 2;
+  if (ray_w >= B) return;
+  const bool live = ray_w + half < B;
+  const int64_t ray = live ? ray_w + half : ray_w;
+  const int base = sub * C;
+  float sg[C], zz[C];
+  load_run<C>(sigma + ray * S + base, sg);
+  load_run<C>(z + ray * S + base, zz);
+  const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float znext = __shfl_down_sync(kFull, zz[0], 1, W);
+  float alpha[C], T[C], dist[C];
+  float run = 1.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int s = base + j;
+    const float zn = (j + 1 < C) ? zz[j + 1] : znext;
+    const float dl = (s == S - 1) ? last_delta : (zn - zz[j]);
+    dist[j] = dl * dnorm;
+    const float a = 1.f - expf(-sg[j] * dist[j]);
+    alpha[j] = a;
+    T[j] = run;
+    run *= 1.f - a + eps;
+  }
+  float inc = run;                               // exclusive product over the lanes of this half
+#pragma unroll
+  for (int o = 1; o < W; o <<= 1) {
+    const float t = __shfl_up_sync(kFull, inc, o, W);
+    if (sub >= o) inc *= t;
+  }
+  float pre = __shfl_up_sync(kFull, inc, 1, W);
+  if (sub == 0) pre = 1.f;
+  float col[3 * C];
+  load_run<3 * C>(rgb + (ray * S + base) * 3, col);
+  float gr = 0.f, gg = 0.f, gb = 0.f;
+  if (g_out_rgb != nullptr) {
+    gr = __ldg(g_out_rgb + ray * 3); gg = __ldg(g_out_rgb + ray * 3 + 1); gb = __ldg(g_out_rgb + ray * 3 + 2);
+  }
+  const float gd = g_depth ? __ldg(g_depth + ray) : 0.f;
+  const float ga = g_acc ? __ldg(g_acc + ray) : 0.f;
+  const float gbg = (flags & HN_COMP_WHITE_BKGD) ? -(gr + gg + gb) : 0.f;
+  float gw[C];
+  if (g_weights != nullptr) {
+    load_run<C>(g_weights + ray * S + base, gw);
+  } else {
+#pragma unroll
+    for (int j = 0; j < C; ++j) gw[j] = 0.f;
+  }
+  float w[C], G[C], Gw[C];
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    T[j] *= pre;
+    w[j] = alpha[j] * T[j];
+    float g = gr * col[3 * j] + gg * col[3 * j + 1] + gb * col[3 * j + 2] + gd * zz[j] + gw[j] + gbg;
+    if ((flags & HN_COMP_ACC_ALL) || base + j < S - 1) g += ga;
+    G[j] = g;
+    Gw[j] = g * w[j];
+    tot += Gw[j];
+  }
+  float rinc = tot;                              // sum over the later lanes of this half
+#pragma unroll
+  for (int o = 1; o < W; o <<= 1) {
+    const float t = __shfl_down_sync(kFull, rinc, o, W);
+    if (sub + o < W) rinc += t;
+  }
+  float suf = __shfl_down_sync(kFull, rinc, 1, W);
+  if (sub == W - 1) suf = 0.f;
+  float gs[C], gc[3 * C];
+#pragma unroll
+  for (int j = C - 1; j >= 0; --j) {
+    const float p = 1.f - alpha[j] + eps;
+    const float dalpha = G[j] * T[j] - suf / p;
+    gs[j] = dalpha * dist[j] * (1.f - alpha[j]);
+    suf += Gw[j];
+    gc[3 * j] = w[j] * gr; gc[3 * j + 1] = w[j] * gg; gc[3 * j + 2] = w[j] * gb;
+  }
+  if (!live) return;
+  store_run<C>(g_sigma + ray * S + base, gs);
+  store_run<3 * C>(g_rgb + (ray * S + base) * 3, gc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // hn_sample_pdf — model_utils.py:160-232 (+ the slicing at models.py:752-755).
 // Arithmetic contract (DESIGN.md "resampling"): w' = fl32(w + 1e-5); S = fl32(sum w') and
@@ -1129,6 +1220,12 @@ extern "C" int hn_composite_bwd(const float* sigma, const float* rgb, const floa
   if (B == 0) return 0;
   int C = comp_c(S);
   bool exact = (S == 32 * C);
+  if (S == 64) {
+    dim3 g2((unsigned)((B + 2 * kWarpsPerBlock - 1) / (2 * kWarpsPerBlock)));
+    composite_bwd_s64_kernel<<<g2, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(sigma, rgb, z, dirs, B, flags, eps, last_delta,
+                                                                                   g_out_rgb, g_depth, g_acc, g_weights, g_sigma, g_rgb);
+    return set_cuda_error(cudaGetLastError(), "hn_composite_bwd");
+  }
   dim3 g((unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock));
   HN_DISPATCH_C(launch_comp_bwd, exact, g, (cudaStream_t)stream, sigma, rgb, z, dirs, B, S, flags, eps, last_delta,
                 g_out_rgb, g_depth, g_acc, g_weights, g_sigma, g_rgb);
