@@ -386,7 +386,7 @@ composite_fwd_s64_kernel(const float* __restrict__ sigma, const float* __restric
 //   dL/dsigma_i = dL/dalpha_i * dist_i * (1 - alpha_i) ;  dL/dc_i = w_i g_rgb
 // ------------------------------------------------------------------------------------------------
 template <int C, bool EXACT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, C <= 4 ? 6 : 1)
 composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb, const float* __restrict__ z,
                      const float* __restrict__ dirs, int64_t B, int S, int flags, float eps, float last_delta,
                      const float* __restrict__ g_out_rgb, const float* __restrict__ g_depth,
