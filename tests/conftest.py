@@ -23,6 +23,18 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _seed_per_test(request):
+    """Every test starts from its own fixed generator state (a hash of its node id): tests that draw with torch.rand /
+    torch.randn without seeding are reproducible and independent of which tests ran before them."""
+    import zlib
+    seed = zlib.crc32(request.node.nodeid.encode())
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    yield
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
 
