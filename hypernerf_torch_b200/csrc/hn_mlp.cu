@@ -29,6 +29,29 @@
 #include "hn_mlp_program.h"
 #include "hn_ptx.cuh"
 
+// This file is compiled twice into libhypernerf_b200.so (Makefile).  The second compilation (hn_mlp_fv.o:
+// -DHN_MLP_FWD_VARIANT=1 -DHN_EPI_SPLIT=2 + register budgets) holds the FORWARD kernels with two epilogue warpgroups per
+// sub-tile, in their own namespace, and exports only hn_mlp_fwd_fv / hn_mlp_fwd_trunk_fv, which the first compilation's
+// hn_mlp_fwd / hn_mlp_fwd_trunk call for INFERENCE launches (HN_FWD_VARIANT_LINKED; HN_FWD_VARIANT = 0 / 1 / 2 in the
+// environment: never / every forward / inference only, the default).  Measured per 1 M samples in isolation: inference
+// forward 2.03 -> 1.93 ms, training forward 2.50 -> 2.42 ms, data gradient +2 % (hence per kernel, not a global switch);
+// a full-frame render goes from 2.27 to 2.40 Mrays/s, while inside the power-capped training step the split training
+// forward is a wash (690 k against 691 k rays/s over three alternating runs, the trunk-only launch 3 % slower), so training
+// keeps the single-warpgroup kernels.  The stash / gate-word layout does not depend on the epilogue split (all GPU tests pass
+// with HN_FWD_VARIANT=1: the backward kernels of the first compilation read what these forwards wrote).
+#ifndef HN_FWD_VARIANT_DEFAULT
+#define HN_FWD_VARIANT_DEFAULT 2
+#endif
+#ifdef HN_MLP_FWD_VARIANT
+namespace hn_fv { using namespace hn; }
+#define hn hn_fv
+#define hn_mlp_fwd hn_mlp_fwd_fv
+#define hn_mlp_fwd_trunk hn_mlp_fwd_trunk_fv
+#define HN_FV_HIDDEN __attribute__((visibility("hidden")))
+#else
+#define HN_FV_HIDDEN
+#endif
+
 namespace hn {
 
 // out-of-range metadata id inside the fused kernels (HN_TRAP_IDS): see hn_check_ids
@@ -143,12 +166,24 @@ struct Sched {
 // the other sub-tile's UMMAs (ping-pong / pair schedules) low-numbered feeder warps were starved of issue slots
 // (measured: the leader's issuer waited 42 % of its time for the other CTA's relay warp).
 constexpr int kEpiWarps = 4 * kSubTiles * kEpiSplit;
+// split-epilogue register budgets after setmaxnreg (feeder / primary / secondary warpgroups; 128 F + 256 P + 256 S <= 640 x 96).
+// The first split build (40 / 144 / 72) starved the weight producer (it spills below 72 registers): forward 2.76 ms per 1 M
+// samples; with 72 / 136 / 64 the split epilogue is the faster forward (Makefile: FV_FLAGS).
+#ifndef HN_SPLIT_FEEDER_REGS
+#define HN_SPLIT_FEEDER_REGS 40
+#endif
+#ifndef HN_SPLIT_PRIMARY_REGS
+#define HN_SPLIT_PRIMARY_REGS 144
+#endif
+#ifndef HN_SPLIT_SECONDARY_REGS
+#define HN_SPLIT_SECONDARY_REGS 72
+#endif
 // register budgets after setmaxnreg (65 536 per SM): feeders, primary and secondary epilogue warpgroups
-constexpr int kRegsFeeder = kEpiSplit == 2 ? 40 : (kSubTiles == 2 ? 72 : 40);   // 128 x 72 + 256 x 216 = 64 512 = the launch allocation (384 x 168)
+constexpr int kRegsFeeder = kEpiSplit == 2 ? HN_SPLIT_FEEDER_REGS : (kSubTiles == 2 ? 72 : 40);   // 128 x 72 + 256 x 216 = 64 512 = the launch allocation (384 x 168)
 // (setmaxnreg moves registers inside the CTA's LAUNCH allocation only: 640 threads x 96 = 61 440 with the split epilogue,
 // 384 x 168 = 64 512 without; the budgets below add up to no more than that)
-constexpr int kRegsPrimary = kEpiSplit == 2 ? 144 : (kSubTiles == 2 ? 216 : 208);
-constexpr int kRegsSecondary = 72;
+constexpr int kRegsPrimary = kEpiSplit == 2 ? HN_SPLIT_PRIMARY_REGS : (kSubTiles == 2 ? 216 : 208);
+constexpr int kRegsSecondary = HN_SPLIT_SECONDARY_REGS;
 static_assert(kEpiSplit != 2 || 128 * kRegsFeeder + 256 * kRegsPrimary + 256 * kRegsSecondary <= 640 * 96, "register budget");
 constexpr int kProducerWarp = kEpiWarps, kIssuerWarp = kEpiWarps + 1, kRelayWarp = kEpiWarps + 2;
 
@@ -2112,6 +2147,7 @@ static int const_bias_offset(const float* src, int nfloats, cudaStream_t stream)
 
 using namespace hn;
 
+#ifndef HN_MLP_FWD_VARIANT
 extern "C" int hn_query(const hn_model_desc* desc, int64_t n_samples, hn_sizes* out) {
   if (!desc || !out) return set_error(-2, "hn_query: null pointer");
   if (int rc = validate_desc(*desc)) return rc;
@@ -2166,6 +2202,8 @@ extern "C" int hn_pack_weights(const hn_model_desc* desc, const float* flat_para
   pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp);
   return set_cuda_error(cudaGetLastError(), "hn_pack_weights");
 }
+
+#endif  // !HN_MLP_FWD_VARIANT
 
 // run-time model flags of the fused kernels
 static int model_flags(const hn_model_desc& d) {
@@ -2256,22 +2294,42 @@ static int mlp_fwd_impl(const hn_model_desc* desc, const void* packed, const flo
   return set_error(-1, "hn_mlp_fwd: unreachable");
 }
 
-extern "C" int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
+#if defined(HN_FWD_VARIANT_LINKED) && !defined(HN_MLP_FWD_VARIANT)
+extern "C" int hn_mlp_fwd_fv(const hn_model_desc*, const void*, const float*, const float*, const int64_t*, const float*, float,
+                             int64_t, int, const int32_t*, int, float*, float*, float*, void*, float*, void*);
+extern "C" int hn_mlp_fwd_trunk_fv(const hn_model_desc*, const void*, const float*, const float*, const int64_t*, const float*,
+                                   float, int64_t, int, const int32_t*, int, float*, float*, float*, void*, void*);
+// HN_FWD_VARIANT in the environment: 0 = never, 1 = inference and training forward, 2 = inference forward only
+static bool fwd_variant_enabled(bool training) {
+  static const int mode = [] { const char* e = getenv("HN_FWD_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : HN_FWD_VARIANT_DEFAULT; }();
+  return mode == 1 || (mode == 2 && !training);
+}
+#define HN_FWD_VARIANT_CALL(fn, ...) if (fwd_variant_enabled(saved != nullptr)) return fn(__VA_ARGS__)
+#else
+#define HN_FWD_VARIANT_CALL(fn, ...)
+#endif
+
+extern "C" HN_FV_HIDDEN int hn_mlp_fwd(const hn_model_desc* desc, const void* packed, const float* points, const float* viewdirs,
                           const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
                           int S_full, float* sigma, float* rgb, float* warped, void* saved, float* aux, void* stream) {
+  HN_FWD_VARIANT_CALL(hn_mlp_fwd_fv, desc, packed, points, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
+                      saved, aux, stream);
   if (!points) return set_error(-2, "hn_mlp_fwd: null pointer");
   return mlp_fwd_impl(desc, packed, points, nullptr, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
                       saved, aux, stream);
 }
 
-extern "C" int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
+extern "C" HN_FV_HIDDEN int hn_mlp_fwd_trunk(const hn_model_desc* desc, const void* packed, const float* warped_in, const float* viewdirs,
                                 const int64_t* ids, const float* noise, float noise_std, int64_t B, int S, const int32_t* pos,
                                 int S_full, float* sigma, float* rgb, float* warped, void* saved, void* stream) {
+  HN_FWD_VARIANT_CALL(hn_mlp_fwd_trunk_fv, desc, packed, warped_in, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb,
+                      warped, saved, stream);
   if (!warped_in) return set_error(-2, "hn_mlp_fwd_trunk: null pointer");
   return mlp_fwd_impl(desc, packed, nullptr, warped_in, viewdirs, ids, noise, noise_std, B, S, pos, S_full, sigma, rgb, warped,
                       saved, nullptr, stream);
 }
 
+#ifndef HN_MLP_FWD_VARIANT
 static int mlp_bwd_impl(const hn_model_desc* desc, const void* packed, const int64_t* ids, const float* sigma,
                         const float* rgb, const float* warped, const void* saved, const float* g_sigma, const float* g_rgb,
                         const float* g_warped, int64_t B, int S, const int32_t* pos, int S_full, int level,
@@ -2407,3 +2465,4 @@ extern "C" int hn_debug_set_timing_buffer(void* dev_buffer) {
   return 0;
 }
 #endif
+#endif  // !HN_MLP_FWD_VARIANT
