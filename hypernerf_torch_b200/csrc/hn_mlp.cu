@@ -169,6 +169,12 @@ constexpr int kEpiWarps = 4 * kSubTiles * kEpiSplit;
 // split-epilogue register budgets after setmaxnreg (feeder / primary / secondary warpgroups; 128 F + 256 P + 256 S <= 640 x 96).
 // The first split build (40 / 144 / 72) starved the weight producer (it spills below 72 registers): forward 2.76 ms per 1 M
 // samples; with 72 / 136 / 64 the split epilogue is the faster forward (Makefile: FV_FLAGS).
+#ifndef HN_FEEDER_REGS        // single epilogue warpgroup per sub-tile: 128 F + 256 P <= 384 x 168 (88 / 208 and 104 / 200: no gain)
+#define HN_FEEDER_REGS 72
+#endif
+#ifndef HN_PRIMARY_REGS
+#define HN_PRIMARY_REGS 216
+#endif
 #ifndef HN_SPLIT_FEEDER_REGS
 #define HN_SPLIT_FEEDER_REGS 40
 #endif
@@ -179,10 +185,10 @@ constexpr int kEpiWarps = 4 * kSubTiles * kEpiSplit;
 #define HN_SPLIT_SECONDARY_REGS 72
 #endif
 // register budgets after setmaxnreg (65 536 per SM): feeders, primary and secondary epilogue warpgroups
-constexpr int kRegsFeeder = kEpiSplit == 2 ? HN_SPLIT_FEEDER_REGS : (kSubTiles == 2 ? 72 : 40);   // 128 x 72 + 256 x 216 = 64 512 = the launch allocation (384 x 168)
+constexpr int kRegsFeeder = kEpiSplit == 2 ? HN_SPLIT_FEEDER_REGS : (kSubTiles == 2 ? HN_FEEDER_REGS : 40);   // 128 x 72 + 256 x 216 = 64 512 = the launch allocation (384 x 168)
 // (setmaxnreg moves registers inside the CTA's LAUNCH allocation only: 640 threads x 96 = 61 440 with the split epilogue,
 // 384 x 168 = 64 512 without; the budgets below add up to no more than that)
-constexpr int kRegsPrimary = kEpiSplit == 2 ? HN_SPLIT_PRIMARY_REGS : (kSubTiles == 2 ? 216 : 208);
+constexpr int kRegsPrimary = kEpiSplit == 2 ? HN_SPLIT_PRIMARY_REGS : (kSubTiles == 2 ? HN_PRIMARY_REGS : 208);
 constexpr int kRegsSecondary = HN_SPLIT_SECONDARY_REGS;
 static_assert(kEpiSplit != 2 || 128 * kRegsFeeder + 256 * kRegsPrimary + 256 * kRegsSecondary <= 640 * 96, "register budget");
 constexpr int kProducerWarp = kEpiWarps, kIssuerWarp = kEpiWarps + 1, kRelayWarp = kEpiWarps + 2;
